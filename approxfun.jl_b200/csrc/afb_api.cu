@@ -1,0 +1,730 @@
+// extern "C" boundary of libapproxfun_b200.so: status plumbing, twiddle tables, plans, host wrappers.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "afb_internal.h"
+
+namespace afb {
+
+// ---- status --------------------------------------------------------------------------------------
+static thread_local std::string g_err_msg;
+static thread_local int32_t g_err_code = AFB_OK;
+
+void set_error(int32_t code, const std::string& msg) {
+    g_err_code = code;
+    g_err_msg = msg;
+}
+int32_t fail(int32_t code, const std::string& msg) {
+    set_error(code, msg);
+    return code;
+}
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();  // clear sticky-less errors
+    return fail(e == cudaErrorMemoryAllocation ? AFB_OOM : AFB_CUDA_ERROR, buf);
+}
+
+// ---- device ---------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static int g_sm_count = 0;
+static bool g_dev_ok = false;
+
+int32_t ensure_device() {
+    if (g_dev_ok) return AFB_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev_ok) return AFB_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(AFB_NO_DEVICE, "no CUDA device visible: libapproxfun_b200 has no CPU fallback");
+    }
+    int dev = 0;
+    AFB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    AFB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    g_sm_count = prop.multiProcessorCount;
+    g_dev_ok = true;
+    return AFB_OK;
+}
+int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+// ---- tables -----------------------------------------------------------------------------------------
+static std::map<int64_t, cplx*> g_root_tables;
+static std::vector<void*> g_owned;
+
+int32_t upload_table(const std::vector<cplx>& host, cplx** dev) {
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, sizeof(cplx) * std::max<size_t>(host.size(), 1)));
+    cudaError_t e = cudaMemcpy(d, host.data(), sizeof(cplx) * host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "cudaMemcpy(table)", __FILE__, __LINE__); }
+    *dev = reinterpret_cast<cplx*>(d);
+    return AFB_OK;
+}
+
+static inline cplx unit_ld(long double turns_num, long double turns_den, int sign) {
+    // exp(sign * 2 pi i * num/den) with the angle reduced in extended precision
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    const long double a = PI2 * (turns_num / turns_den);
+    return make_double2((double)cosl(a), (double)(sign * sinl(a)));
+}
+
+int32_t root_table(int64_t N, const cplx** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_root_tables.find(N);
+    if (it != g_root_tables.end()) { *out = it->second; return AFB_OK; }
+    std::vector<cplx> h((size_t)N);
+    for (int64_t m = 0; m < N; ++m) h[(size_t)m] = unit_ld((long double)m, (long double)N, -1);
+    cplx* d = nullptr;
+    AFB_TRY(upload_table(h, &d));
+    g_root_tables[N] = d;
+    *out = d;
+    return AFB_OK;
+}
+
+void free_tables() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_root_tables) cudaFree(kv.second);
+    g_root_tables.clear();
+}
+
+}  // namespace afb
+
+using namespace afb;
+
+// =====================================================================================================
+// plans
+// =====================================================================================================
+enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4 };
+
+struct afb_plan_s {
+    int32_t kind = 0;
+    int64_t n = 0, n2 = 0, batch = 0, stride = 0;
+    uint32_t flags = 0;
+    int path = PATH_EMPTY;
+    int elem = 8;  // bytes per element (16 for Laurent)
+    // LINE
+    int Nc = 0;
+    int line_kind = 0;
+    const cplx* tw = nullptr;
+    cplx* aux = nullptr;
+    double scale = 1.0;
+    // DIRECT
+    cplx* dtab = nullptr;
+    // GENERIC (any n): length-n complex FFT engine + pre/post
+    CfftPlan* cfft = nullptr;
+    cplx* qtab = nullptr;      // exp(-i pi k/(2n)), k = 0..n  (Chebyshev)
+    cplx* gwork = nullptr;     // gbatch x n complex
+    int64_t gbatch = 0;
+    // TENSOR2D
+    afb_plan_s* col_plan = nullptr;  // length n,  batch n2
+    afb_plan_s* row_plan = nullptr;  // length n2, batch n
+    double* t2buf = nullptr;
+    // scratch for in-place direct execution
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    // host pipeline
+    static constexpr int NPIPE = 3;
+    cudaStream_t pstream[NPIPE] = {nullptr, nullptr, nullptr};
+    void* pbuf[NPIPE] = {nullptr, nullptr, nullptr};
+    int64_t pchunk = 0;  // transforms per chunk
+    std::mutex mu;
+};
+
+static void plan_free(afb_plan_s* p) {
+    if (!p) return;
+    if (p->aux) cudaFree(p->aux);
+    if (p->dtab) cudaFree(p->dtab);
+    if (p->qtab) cudaFree(p->qtab);
+    if (p->gwork) cudaFree(p->gwork);
+    if (p->cfft) cfft_destroy(p->cfft);
+    if (p->t2buf) cudaFree(p->t2buf);
+    if (p->tmp) cudaFree(p->tmp);
+    for (int i = 0; i < afb_plan_s::NPIPE; ++i) {
+        if (p->pbuf[i]) cudaFree(p->pbuf[i]);
+        if (p->pstream[i]) cudaStreamDestroy(p->pstream[i]);
+    }
+    plan_free(p->col_plan);
+    plan_free(p->row_plan);
+    delete p;
+}
+
+static inline bool kind_is_real(int kind) { return kind <= AFB_FOURIER_INV || kind >= AFB_CHEB1_2D_FWD; }
+
+// fused per-plan tables of the LINE path (see LineOp<> in afb_transform.cu)
+static int32_t build_line_aux(afb_plan_s* p) {
+    const int64_t n = p->n;
+    const int64_t N = p->Nc;
+    std::vector<cplx> h;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    auto w = [&](long double k) {  // exp(-i pi k / (2n))
+        const long double a = PI * k / (2.0L * (long double)n);
+        return std::pair<long double, long double>(cosl(a), -sinl(a));
+    };
+    switch (p->kind) {
+        case AFB_CHEB1_FWD:
+            h.resize((size_t)(N / 2 + 1) * 2);
+            for (int64_t k = 0; k <= N / 2; ++k) {
+                auto a = w((long double)k), b = w((long double)(5 * k));
+                h[2 * k] = make_double2((double)(a.first / n), (double)(a.second / n));
+                // -i (br + i bi) = bi - i br
+                h[2 * k + 1] = make_double2((double)(b.second / n), (double)(-b.first / n));
+            }
+            p->line_kind = ILK_CHEB_FWD;
+            p->scale = 1.0 / (double)n;
+            break;
+        case AFB_CHEB1_INV:
+            h.resize((size_t)(N / 2 + 1) * 2);
+            for (int64_t k = 0; k <= N / 2; ++k) {
+                auto a = w((long double)k), b = w((long double)(4 * k));
+                h[2 * k] = make_double2((double)a.first, (double)(-a.second));
+                h[2 * k + 1] = make_double2((double)b.first, (double)(-b.second));
+            }
+            p->line_kind = ILK_CHEB_INV;
+            break;
+        case AFB_FOURIER_FWD:
+            h.resize((size_t)(N / 2 + 1));
+            for (int64_t k = 0; k <= N / 2; ++k) {
+                auto b = w((long double)(4 * k));  // exp(-2 pi i k / n)
+                h[k] = make_double2((double)(b.second / n), (double)(-b.first / n));
+            }
+            p->line_kind = ILK_FOURIER_FWD;
+            p->scale = 1.0 / (double)n;
+            break;
+        case AFB_FOURIER_INV:
+            h.resize((size_t)(N / 2 + 1));
+            for (int64_t k = 0; k <= N / 2; ++k) {
+                auto b = w((long double)(4 * k));
+                h[k] = make_double2((double)b.first, (double)(-b.second));
+            }
+            p->line_kind = ILK_FOURIER_INV;
+            break;
+        case AFB_LAURENT_FWD:
+            p->line_kind = ILK_LAURENT_FWD;
+            p->scale = 1.0 / (double)n;
+            return AFB_OK;
+        case AFB_LAURENT_INV:
+            p->line_kind = ILK_LAURENT_INV;
+            return AFB_OK;
+        default:
+            return fail(AFB_BAD_ARG, "bad kind for line path");
+    }
+    return upload_table(h, &p->aux);
+}
+
+static int32_t build_direct_tab(afb_plan_s* p) {
+    const int64_t n = p->n;
+    std::vector<cplx> h;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    if (p->kind == AFB_CHEB1_FWD || p->kind == AFB_CHEB1_INV) {
+        h.resize((size_t)(4 * n));
+        for (int64_t m = 0; m < 4 * n; ++m) h[m] = make_double2((double)cosl(PI * m / (2.0L * n)), 0.0);
+    } else {
+        h.resize((size_t)n);
+        for (int64_t m = 0; m < n; ++m) {
+            const long double a = 2.0L * PI * m / (long double)n;
+            h[m] = make_double2((double)cosl(a), (double)(-sinl(a)));
+        }
+    }
+    return upload_table(h, &p->dtab);
+}
+
+static int32_t build_generic(afb_plan_s* p) {
+    const int64_t n = p->n;
+    // sub-batch: keep the complex work buffer below ~256 MiB
+    int64_t gb = std::max<int64_t>(1, (int64_t)(256ll << 20) / (16 * n));
+    gb = std::min<int64_t>(gb, std::max<int64_t>(p->batch, 1));
+    p->gbatch = gb;
+    AFB_TRY(cfft_create(&p->cfft, n, gb));
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, sizeof(cplx) * (size_t)(gb * n)));
+    p->gwork = reinterpret_cast<cplx*>(d);
+    if (p->kind == AFB_CHEB1_FWD || p->kind == AFB_CHEB1_INV) {
+        std::vector<cplx> h((size_t)n + 1);
+        const long double PI = 3.141592653589793238462643383279502884L;
+        for (int64_t k = 0; k <= n; ++k) {
+            const long double a = PI * k / (2.0L * (long double)n);
+            h[k] = make_double2((double)cosl(a), (double)(-sinl(a)));
+        }
+        AFB_TRY(upload_table(h, &p->qtab));
+    }
+    return AFB_OK;
+}
+
+static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t batch, int64_t stride, uint32_t flags) {
+    afb_plan_s* p = new afb_plan_s();
+    p->kind = kind; p->n = n; p->batch = batch; p->stride = stride; p->flags = flags;
+    p->elem = (kind == AFB_LAURENT_FWD || kind == AFB_LAURENT_INV) ? 16 : 8;
+    int32_t st = AFB_OK;
+    if (n == 0 || batch == 0) {
+        p->path = PATH_EMPTY;
+    } else if (n <= DIRECT_MAX) {
+        p->path = PATH_DIRECT;
+        st = build_direct_tab(p);
+    } else {
+        const int64_t Nc = (p->elem == 16) ? n : n / 2;
+        if (is_pow2(n) && Nc >= LINE_MIN_N && Nc <= LINE_MAX_N) {
+            p->path = PATH_LINE;
+            p->Nc = (int)Nc;
+            st = root_table(Nc, &p->tw);
+            if (st == AFB_OK) st = build_line_aux(p);
+        } else {
+            p->path = PATH_GENERIC;
+            st = build_generic(p);
+        }
+    }
+    if (st != AFB_OK) { plan_free(p); return st; }
+    *out = p;
+    return AFB_OK;
+}
+
+static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int64_t batch, int64_t istride,
+                              int64_t ostride, void* stream) {
+    switch (p->path) {
+        case PATH_EMPTY: return AFB_OK;
+        case PATH_DIRECT: {
+            const void* src = d_in;
+            if (d_in == d_out) {  // the O(n^2) kernel is not in-place safe: stage the input
+                const size_t bytes = (size_t)p->elem * (size_t)((batch - 1) * istride + p->n);
+                if (bytes > p->tmp_bytes) {
+                    AFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+                    if (p->tmp) cudaFree(p->tmp);
+                    p->tmp = nullptr; p->tmp_bytes = 0;
+                    AFB_CUDA(cudaMalloc(&p->tmp, bytes));
+                    p->tmp_bytes = bytes;
+                }
+                AFB_CUDA(cudaMemcpyAsync(p->tmp, d_in, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+                src = p->tmp;
+            }
+            return launch_direct(p->kind, (int)p->n, src, d_out, batch, istride, ostride, p->dtab, stream);
+        }
+        case PATH_LINE:
+            return launch_line(p->line_kind, p->Nc, d_in, d_out, batch, istride, ostride, p->tw, p->aux, p->scale, stream);
+        case PATH_GENERIC: {
+            const bool inv = (p->kind & 1) != 0;
+            for (int64_t b0 = 0; b0 < batch; b0 += p->gbatch) {
+                const int64_t nb = std::min(p->gbatch, batch - b0);
+                const char* in = reinterpret_cast<const char*>(d_in) + (size_t)p->elem * (size_t)(b0 * istride);
+                char* out = reinterpret_cast<char*>(d_out) + (size_t)p->elem * (size_t)(b0 * ostride);
+                AFB_TRY(launch_generic_pre(p->kind, p->n, in, istride, p->gwork, nb, p->qtab, stream));
+                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nb, inv, 1.0, stream));
+                AFB_TRY(launch_generic_post(p->kind, p->n, p->gwork, out, ostride, nb, p->qtab, stream));
+            }
+            return AFB_OK;
+        }
+        default: return fail(AFB_BAD_ARG, "plan path");
+    }
+}
+
+static int32_t plan_launch_count(afb_plan_s* p) {
+    switch (p->path) {
+        case PATH_EMPTY: return 0;
+        case PATH_DIRECT: return 1;
+        case PATH_LINE: return 1;
+        case PATH_GENERIC: {
+            const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
+            return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
+        }
+        case PATH_TENSOR2D: return plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan) + 2;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int32_t afb_version(void) { return AFB_VERSION; }
+
+int32_t afb_last_error(char* buf, size_t len) {
+    if (buf && len) {
+        std::strncpy(buf, g_err_msg.c_str(), len - 1);
+        buf[len - 1] = 0;
+    }
+    return g_err_code;
+}
+
+int32_t afb_init(int32_t device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(AFB_NO_DEVICE, "no CUDA device visible: libapproxfun_b200 has no CPU fallback");
+    }
+    if (device >= 0) {
+        if (device >= n) return fail(AFB_BAD_ARG, "device index out of range");
+        AFB_CUDA(cudaSetDevice(device));
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_dev_ok = false;
+    }
+    return ensure_device();
+}
+
+int32_t afb_shutdown(void) {
+    free_tables();
+    return AFB_OK;
+}
+
+int32_t afb_device_info(int32_t* sms, int64_t* hbm_bytes, char* name, size_t name_len) {
+    AFB_TRY(ensure_device());
+    int dev = 0;
+    AFB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    AFB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sms) *sms = prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = (int64_t)prop.totalGlobalMem;
+    if (name && name_len) { std::strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return AFB_OK;
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------
+int32_t afb_malloc(void** dptr, size_t bytes) {
+    if (!dptr) return fail(AFB_BAD_ARG, "afb_malloc: null out pointer");
+    AFB_TRY(ensure_device());
+    AFB_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return AFB_OK;
+}
+int32_t afb_free(void* dptr) { if (dptr) AFB_CUDA(cudaFree(dptr)); return AFB_OK; }
+int32_t afb_host_alloc(void** hptr, size_t bytes) {
+    if (!hptr) return fail(AFB_BAD_ARG, "afb_host_alloc: null out pointer");
+    AFB_TRY(ensure_device());
+    AFB_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return AFB_OK;
+}
+int32_t afb_host_free(void* hptr) { if (hptr) AFB_CUDA(cudaFreeHost(hptr)); return AFB_OK; }
+int32_t afb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return AFB_OK;
+}
+int32_t afb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return AFB_OK;
+}
+int32_t afb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return AFB_OK;
+}
+int32_t afb_stream_sync(void* stream) { AFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return AFB_OK; }
+
+// ---- plans --------------------------------------------------------------------------------------------
+int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int64_t batch, int64_t stride,
+                        uint32_t flags) {
+    if (!out) return fail(AFB_BAD_ARG, "afb_plan_create: null out pointer");
+    *out = nullptr;
+    if (kind < AFB_CHEB1_FWD || kind > AFB_CHEB1_2D_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
+    if (n < 0 || n2 < 0 || batch < 0) return fail(AFB_BAD_SIZE, "afb_plan_create: negative size");
+    AFB_TRY(ensure_device());
+    if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV) {
+        if (batch != 1) return fail(AFB_BAD_SIZE, "afb_plan_create: 2D plans take batch == 1");
+        afb_plan_s* p = new afb_plan_s();
+        p->kind = kind; p->n = n; p->n2 = n2; p->batch = 1; p->stride = n; p->flags = flags;
+        p->path = (n == 0 || n2 == 0) ? PATH_EMPTY : PATH_TENSOR2D;
+        if (p->path == PATH_TENSOR2D) {
+            const int32_t k1 = (kind == AFB_CHEB1_2D_FWD) ? AFB_CHEB1_FWD : AFB_CHEB1_INV;
+            int32_t st = plan_create_1d(&p->col_plan, k1, n, n2, n, flags);
+            if (st == AFB_OK) st = plan_create_1d(&p->row_plan, k1, n2, n, n2, flags);
+            if (st == AFB_OK) {
+                void* d = nullptr;
+                cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)(n * n2));
+                if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(2D transpose buffer)", __FILE__, __LINE__);
+                p->t2buf = reinterpret_cast<double*>(d);
+            }
+            if (st != AFB_OK) { plan_free(p); return st; }
+        }
+        *out = p;
+        return AFB_OK;
+    }
+    if (n2 != 0) return fail(AFB_BAD_SIZE, "afb_plan_create: n2 must be 0 for 1D kinds");
+    if (stride < n) return fail(AFB_BAD_SIZE, "afb_plan_create: stride < n");
+    if ((kind == AFB_CHEB1_FWD || kind == AFB_CHEB1_INV || kind == AFB_FOURIER_FWD || kind == AFB_FOURIER_INV) &&
+        (stride & 1) && batch > 1 && n > DIRECT_MAX && is_pow2(n))
+        return fail(AFB_BAD_SIZE, "afb_plan_create: odd stride breaks 16-byte alignment of the vectorised path");
+    return plan_create_1d(out, kind, n, batch, stride, flags);
+}
+
+int32_t afb_plan_destroy(afb_plan plan) {
+    plan_free(plan);
+    return AFB_OK;
+}
+
+int32_t afb_plan_launches(afb_plan plan, int32_t* launches) {
+    if (!plan || !launches) return fail(AFB_BAD_ARG, "afb_plan_launches: null argument");
+    *launches = plan_launch_count(plan);
+    return AFB_OK;
+}
+
+int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void* stream) {
+    if (!p) return fail(AFB_BAD_ARG, "afb_plan_execute_device: null plan");
+    if (p->path == PATH_EMPTY) return AFB_OK;
+    if (!d_in || !d_out) return fail(AFB_BAD_ARG, "afb_plan_execute_device: null buffer");
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(AFB_BAD_ARG, "afb_plan_execute_device: buffers must be 16-byte aligned");
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->path == PATH_TENSOR2D) {
+        // C = T_x V T_y^T on a column-major n x n2 matrix: columns, transpose, columns, transpose back
+        const int64_t n = p->n, n2 = p->n2;
+        AFB_TRY(exec_1d_device(p->col_plan, d_in, d_out, n2, n, n, stream));
+        AFB_TRY(launch_transpose(reinterpret_cast<const double*>(d_out), p->t2buf, n, n2, stream));
+        AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, n, n2, n2, stream));
+        AFB_TRY(launch_transpose(p->t2buf, reinterpret_cast<double*>(d_out), n2, n, stream));
+        return AFB_OK;
+    }
+    return exec_1d_device(p, d_in, d_out, p->batch, p->stride, p->stride, stream);
+}
+
+int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
+    if (!p) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null plan");
+    if (p->path == PATH_EMPTY) return AFB_OK;
+    if (!in || !out) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null buffer");
+    if (p->path == PATH_TENSOR2D) {
+        const size_t bytes = sizeof(double) * (size_t)(p->n * p->n2);
+        void* d = nullptr;
+        AFB_CUDA(cudaMalloc(&d, bytes));
+        int32_t st = AFB_OK;
+        cudaError_t e = cudaMemcpy(d, in, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) st = cuda_fail(e, "H2D", __FILE__, __LINE__);
+        if (st == AFB_OK) st = afb_plan_execute_device(p, d, d, nullptr);
+        if (st == AFB_OK) {
+            e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+        }
+        cudaFree(d);
+        return st;
+    }
+    std::lock_guard<std::mutex> lk(p->mu);
+    // chunked three-stage pipeline: H2D | kernels | D2H on NPIPE streams, packed (stride = n) on device
+    const int64_t n = p->n;
+    const size_t line_bytes = (size_t)p->elem * (size_t)n;
+    if (p->pchunk == 0) {
+        int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
+        ch = std::min(ch, p->batch);
+        if (p->path == PATH_GENERIC) ch = std::min(ch, p->gbatch);
+        for (int i = 0; i < afb_plan_s::NPIPE; ++i) {
+            AFB_CUDA(cudaStreamCreateWithFlags(&p->pstream[i], cudaStreamNonBlocking));
+            AFB_CUDA(cudaMalloc(&p->pbuf[i], line_bytes * (size_t)ch));
+        }
+        p->pchunk = ch;
+    }
+    const bool generic = p->path == PATH_GENERIC;
+    int64_t c = 0;
+    for (int64_t b0 = 0; b0 < p->batch; b0 += p->pchunk, ++c) {
+        // the generic path shares one work buffer between chunks: keep it on a single stream
+        const int si = generic ? 0 : (int)(c % afb_plan_s::NPIPE);
+        cudaStream_t s = p->pstream[si];
+        const int64_t nb = std::min(p->pchunk, p->batch - b0);
+        const char* src = reinterpret_cast<const char*>(in) + (size_t)p->elem * (size_t)(b0 * p->stride);
+        char* dst = reinterpret_cast<char*>(out) + (size_t)p->elem * (size_t)(b0 * p->stride);
+#ifdef AFB_HOST_EMU
+        for (int64_t b = 0; b < nb; ++b)
+            std::memcpy((char*)p->pbuf[si] + line_bytes * b, src + (size_t)p->elem * (size_t)(b * p->stride), line_bytes);
+#else
+        AFB_CUDA(cudaMemcpy2DAsync(p->pbuf[si], line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes,
+                                   (size_t)nb, cudaMemcpyHostToDevice, s));
+#endif
+        AFB_TRY(exec_1d_device(p, p->pbuf[si], p->pbuf[si], nb, n, n, s));
+#ifdef AFB_HOST_EMU
+        for (int64_t b = 0; b < nb; ++b)
+            std::memcpy(dst + (size_t)p->elem * (size_t)(b * p->stride), (char*)p->pbuf[si] + line_bytes * b, line_bytes);
+#else
+        AFB_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, p->pbuf[si], line_bytes, line_bytes,
+                                   (size_t)nb, cudaMemcpyDeviceToHost, s));
+#endif
+    }
+    for (int i = 0; i < afb_plan_s::NPIPE; ++i) AFB_CUDA(cudaStreamSynchronize(p->pstream[i]));
+    return AFB_OK;
+}
+
+// ---- points -------------------------------------------------------------------------------------------
+int32_t afb_chebpoints_device(double* d_out, int64_t n, double a, double b, void* stream) {
+    if (n < 0) return fail(AFB_BAD_SIZE, "afb_chebpoints: n < 0");
+    if (n == 0) return AFB_OK;
+    if (!d_out) return fail(AFB_BAD_ARG, "afb_chebpoints: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_chebpoints(d_out, n, a, b, stream);
+}
+
+}  // extern "C"
+
+// generic "copy in, run, copy out" helper for the plain-function entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int32_t alloc(size_t bytes) { AFB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); return AFB_OK; }
+    int32_t put(const void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice)); return AFB_OK; }
+    int32_t get(void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost)); return AFB_OK; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+extern "C" {
+
+int32_t afb_chebpoints(double* out, int64_t n, double a, double b) {
+    if (n < 0) return fail(AFB_BAD_SIZE, "afb_chebpoints: n < 0");
+    if (n == 0) return AFB_OK;
+    if (!out) return fail(AFB_BAD_ARG, "afb_chebpoints: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf d;
+    AFB_TRY(d.alloc(sizeof(double) * (size_t)n));
+    AFB_TRY(launch_chebpoints(d.as<double>(), n, a, b, nullptr));
+    return d.get(out, sizeof(double) * (size_t)n);
+}
+
+int32_t afb_fourierpoints(double* out, int64_t n, double a, double b) {
+    if (n < 0) return fail(AFB_BAD_SIZE, "afb_fourierpoints: n < 0");
+    if (n && !out) return fail(AFB_BAD_ARG, "afb_fourierpoints: null buffer");
+    for (int64_t j = 0; j < n; ++j) out[j] = a + (b - a) * (double)j / (double)n;  // O(n) host arithmetic, no GPU analogue
+    return AFB_OK;
+}
+
+// ---- Clenshaw ----------------------------------------------------------------------------------------
+int32_t afb_clenshaw_cheb_device(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !d_c) || !d_x || !d_y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_clenshaw_vec(d_c, N, d_x, d_y, P, stream);
+}
+int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y, int64_t P) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !c) || !x || !y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dx, dy;
+    AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(dx.put(x, 8 * (size_t)P));
+    AFB_TRY(launch_clenshaw_vec(dc.as<double>(), N, dx.as<double>(), dy.as<double>(), P, nullptr));
+    return dy.get(y, 8 * (size_t)P);
+}
+
+int32_t afb_clenshaw_cheb_cols_device(const double* d_C, int64_t N, int64_t ld, const double* d_x, double* d_y,
+                                      int64_t P, void* stream) {
+    if (N < 0 || P < 0 || ld < N) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb_cols: bad sizes (need ld >= N >= 0)");
+    if (P == 0) return AFB_OK;
+    if ((N && !d_C) || !d_x || !d_y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb_cols: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_cols(false, d_C, N, ld, d_x, d_y, P, 0, stream);
+}
+int32_t afb_clenshaw_cheb_cols(const double* C, int64_t N, int64_t ld, const double* x, double* y, int64_t P) {
+    if (N < 0 || P < 0 || ld < N) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb_cols: bad sizes (need ld >= N >= 0)");
+    if (P == 0) return AFB_OK;
+    if ((N && !C) || !x || !y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb_cols: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dx, dy;
+    const size_t cb = 8 * (size_t)(ld * P);
+    AFB_TRY(dc.alloc(cb)); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(C, cb)); AFB_TRY(dx.put(x, 8 * (size_t)P));
+    AFB_TRY(launch_cols(false, dc.as<double>(), N, ld, dx.as<double>(), dy.as<double>(), P, 0, nullptr));
+    return dy.get(y, 8 * (size_t)P);
+}
+
+int32_t afb_clenshaw_cheb_multi_device(const double* d_C, int64_t N, int64_t M, const double* d_x, double* d_Y,
+                                       int64_t P, void* stream) {
+    if (N < 0 || M < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb_multi: negative size");
+    if (P == 0 || M == 0) return AFB_OK;
+    if ((N && !d_C) || !d_x || !d_Y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb_multi: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_multi(d_C, N, M, d_x, d_Y, P, stream);
+}
+int32_t afb_clenshaw_cheb_multi(const double* C, int64_t N, int64_t M, const double* x, double* Y, int64_t P) {
+    if (N < 0 || M < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb_multi: negative size");
+    if (P == 0 || M == 0) return AFB_OK;
+    if ((N && !C) || !x || !Y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb_multi: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dx, dy;
+    AFB_TRY(dc.alloc(8 * (size_t)(N * M))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)(M * P)));
+    AFB_TRY(dc.put(C, 8 * (size_t)(N * M))); AFB_TRY(dx.put(x, 8 * (size_t)P));
+    AFB_TRY(launch_multi(dc.as<double>(), N, M, dx.as<double>(), dy.as<double>(), P, nullptr));
+    return dy.get(Y, 8 * (size_t)(M * P));
+}
+
+// ---- sampling ------------------------------------------------------------------------------------------
+int32_t afb_cheb_normcumsum_device(double* d_C, int64_t N, int64_t ncols, int64_t ld, int32_t grow, void* stream) {
+    if (N < 0 || ncols < 0 || ld < N + (grow ? 1 : 0))
+        return fail(AFB_BAD_SIZE, "afb_cheb_normcumsum: bad sizes (need ld >= N + grow)");
+    if (ncols == 0) return AFB_OK;
+    if (!d_C) return fail(AFB_BAD_ARG, "afb_cheb_normcumsum: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_normcumsum(d_C, N, ncols, ld, grow, stream);
+}
+int32_t afb_cheb_normcumsum(double* C, int64_t N, int64_t ncols, int64_t ld, int32_t grow) {
+    if (N < 0 || ncols < 0 || ld < N + (grow ? 1 : 0))
+        return fail(AFB_BAD_SIZE, "afb_cheb_normcumsum: bad sizes (need ld >= N + grow)");
+    if (ncols == 0) return AFB_OK;
+    if (!C) return fail(AFB_BAD_ARG, "afb_cheb_normcumsum: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf d;
+    const size_t bytes = 8 * (size_t)(ld * ncols);
+    AFB_TRY(d.alloc(bytes)); AFB_TRY(d.put(C, bytes));
+    AFB_TRY(launch_normcumsum(d.as<double>(), N, ncols, ld, grow, nullptr));
+    return d.get(C, bytes);
+}
+
+int32_t afb_cheb_bisect_device(const double* d_c, int64_t N, const double* d_u, double* d_out, int64_t P,
+                               int32_t numits, double a, double b, void* stream) {
+    if (N < 0 || P < 0 || numits < 0) return fail(AFB_BAD_SIZE, "afb_cheb_bisect: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !d_c) || !d_u || !d_out) return fail(AFB_BAD_ARG, "afb_cheb_bisect: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_bisect_vec(d_c, N, d_u, false, 0, 0, d_out, P, numits, a, b, stream);
+}
+static int32_t bisect_host(const double* c, int64_t N, const double* u, double* out, int64_t P, int32_t numits,
+                           double a, double b) {
+    if (N < 0 || P < 0 || numits < 0) return fail(AFB_BAD_SIZE, "afb_cheb_bisect: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !c) || !u || !out) return fail(AFB_BAD_ARG, "afb_cheb_bisect: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, du, dout;
+    AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(du.put(u, 8 * (size_t)P));
+    AFB_TRY(launch_bisect_vec(dc.as<double>(), N, du.as<double>(), false, 0, 0, dout.as<double>(), P, numits, a, b, nullptr));
+    return dout.get(out, 8 * (size_t)P);
+}
+int32_t afb_cheb_bisect(const double* c, int64_t N, const double* u, double* out, int64_t P, int32_t numits) {
+    return bisect_host(c, N, u, out, P, numits, -1.0, 1.0);
+}
+int32_t afb_samplecdf_cheb(const double* cdf_c, int64_t N, double a, double b, const double* u, double* out, int64_t P) {
+    return bisect_host(cdf_c, N, u, out, P, 47, a, b);
+}
+
+int32_t afb_cheb_bisect_cols_device(const double* d_C, int64_t N, int64_t ld, const double* d_u, double* d_out,
+                                    int64_t P, int32_t numits, void* stream) {
+    if (N < 0 || P < 0 || ld < N || numits < 0) return fail(AFB_BAD_SIZE, "afb_cheb_bisect_cols: bad sizes");
+    if (P == 0) return AFB_OK;
+    if ((N && !d_C) || !d_u || !d_out) return fail(AFB_BAD_ARG, "afb_cheb_bisect_cols: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_cols(true, d_C, N, ld, d_u, d_out, P, numits, stream);
+}
+int32_t afb_cheb_bisect_cols(const double* C, int64_t N, int64_t ld, const double* u, double* out, int64_t P,
+                             int32_t numits) {
+    if (N < 0 || P < 0 || ld < N || numits < 0) return fail(AFB_BAD_SIZE, "afb_cheb_bisect_cols: bad sizes");
+    if (P == 0) return AFB_OK;
+    if ((N && !C) || !u || !out) return fail(AFB_BAD_ARG, "afb_cheb_bisect_cols: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, du, dout;
+    const size_t cb = 8 * (size_t)(ld * P);
+    AFB_TRY(dc.alloc(cb)); AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(C, cb)); AFB_TRY(du.put(u, 8 * (size_t)P));
+    AFB_TRY(launch_cols(true, dc.as<double>(), N, ld, du.as<double>(), dout.as<double>(), P, numits, nullptr));
+    return dout.get(out, 8 * (size_t)P);
+}
+
+int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, double b, uint64_t seed, uint64_t offset,
+                               double* d_out, int64_t P, void* stream) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_sample_cheb: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !d_cdf_c) || !d_out) return fail(AFB_BAD_ARG, "afb_sample_cheb: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_bisect_vec(d_cdf_c, N, nullptr, true, seed, offset, d_out, P, 47, a, b, stream);
+}
+int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream) {
+    if (P < 0) return fail(AFB_BAD_SIZE, "afb_philox_uniform: negative size");
+    if (P == 0) return AFB_OK;
+    if (!d_out) return fail(AFB_BAD_ARG, "afb_philox_uniform: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_philox(seed, offset, d_out, P, stream);
+}
+
+}  // extern "C"

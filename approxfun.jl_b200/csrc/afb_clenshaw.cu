@@ -1,0 +1,433 @@
+// FP64 Clenshaw evaluation, Clenshaw bisection (inverse-CDF sampling) and the normalised-cumsum
+// helpers: kernels K6, K7, K9 of SURVEY.md section 2c.
+//
+// Arithmetic is written with explicit __fma_rn/__dsub_rn so that every result is bit-identical to the
+// reference recurrence evaluated with a fused muladd (UPSTREAM AFOP clenshaw; call sites
+// /root/reference/src/Extras/sample.jl:47,56,68,80,94):
+//     x2 = 2x; b1 = b2 = 0; for k = N:-1:2: (b2,b1) = (b1, muladd(x2,b1,c[k]-b2)); muladd(x2/2,b1,c[1]-b2)
+//
+// Roofline: FP64 pipe.  One coefficient step costs one DFMA + one DADD per point (3 flops in two
+// issue slots), so the structural ceiling is 75 % of the 2-flop/slot FMA peak.  Coefficients live in
+// shared memory and are read as broadcast 128-bit loads (two coefficients per LDS); every thread
+// carries R independent points so the DFMA dependency chains overlap.
+#include "afb_common.cuh"
+
+namespace afb {
+
+constexpr int CL_THREADS = 512;        // threads per CTA
+constexpr int CL_R = 4;                // points per thread (independent recurrences)
+constexpr int CL_CHUNK = 12288;        // coefficients staged per shared-memory chunk (96 KB)
+
+// Runs the recurrence over coefficients c[klo..khi) (khi exclusive), from high to low, with klo >= 1.
+// `c` may point to shared or global memory.  (b1, b2) follow the reference naming.
+template <int R>
+__device__ __forceinline__ void clenshaw_span(const double* c, int klo, int khi, const double (&x2)[R],
+                                              double (&b1)[R], double (&b2)[R]) {
+    int k = khi - 1;
+    // peel to make (k - klo + 1) even, then two steps per iteration without register moves
+    if (((k - klo + 1) & 1) && k >= klo) {
+        const double ck = c[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t = __fma_rn(x2[r], b1[r], __dsub_rn(ck, b2[r]));
+            b2[r] = b1[r];
+            b1[r] = t;
+        }
+        --k;
+    }
+    for (; k > klo; k -= 2) {
+        const double ck = c[k], ck1 = c[k - 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            b2[r] = __fma_rn(x2[r], b1[r], __dsub_rn(ck, b2[r]));   // new b1 lives in b2
+            b1[r] = __fma_rn(x2[r], b2[r], __dsub_rn(ck1, b1[r]));  // next step, roles swapped back
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void clenshaw_finish(double c0, const double (&x2)[R], const double (&b1)[R],
+                                                const double (&b2)[R], double (&y)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[r] = __fma_rn(__dmul_rn(x2[r], 0.5), b1[r], __dsub_rn(c0, b2[r]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: y[i] = sum_k c[k] T_k(x[i]),  one CTA loops over tiles of CL_THREADS*R points
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS, 2)
+clenshaw_vec_kernel(const double* __restrict__ c, int64_t N, const double* __restrict__ x,
+                    double* __restrict__ y, int64_t P, int64_t ntiles) {
+    AFB_DYN_SMEM(double, sc);
+    const int tid = threadIdx.x;
+    const int64_t nchunks = (N + CL_CHUNK - 1) / CL_CHUNK;
+    if (nchunks <= 1) {
+        for (int64_t k = tid; k < N; k += CL_THREADS) sc[k] = c[k];
+        __syncthreads();
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * (int64_t)(CL_THREADS * CL_R);
+        double x2[CL_R], b1[CL_R], b2[CL_R], out[CL_R];
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * CL_THREADS;
+            const double xv = (i < P) ? x[i] : 0.0;
+            x2[r] = __dmul_rn(2.0, xv);
+            b1[r] = 0.0;
+            b2[r] = 0.0;
+        }
+        if (N == 0) {
+#pragma unroll
+            for (int r = 0; r < CL_R; ++r) out[r] = 0.0;
+        } else if (nchunks <= 1) {
+            clenshaw_span<CL_R>(sc, 1, (int)N, x2, b1, b2);
+            clenshaw_finish<CL_R>(sc[0], x2, b1, b2, out);
+        } else {
+            double c0 = 0.0;
+            for (int64_t ch = nchunks - 1; ch >= 0; --ch) {
+                const int64_t lo = ch * CL_CHUNK;
+                const int64_t hi = (lo + CL_CHUNK < N) ? lo + CL_CHUNK : N;
+                __syncthreads();  // previous chunk fully consumed
+                for (int64_t k = lo + tid; k < hi; k += CL_THREADS) sc[k - lo] = c[k];
+                __syncthreads();
+                const int klo = (ch == 0) ? 1 : 0;
+                clenshaw_span<CL_R>(sc, klo, (int)(hi - lo), x2, b1, b2);
+                if (ch == 0) c0 = sc[0];
+            }
+            clenshaw_finish<CL_R>(c0, x2, b1, b2, out);
+        }
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * CL_THREADS;
+            if (i < P) y[i] = (N == 1) ? c[0] : out[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011); 53-bit uniforms in [0,1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&ctr)[4], const uint32_t (&key)[2]) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * ctr[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * ctr[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ ctr[1] ^ key[0];
+    const uint32_t n2 = hi0 ^ ctr[3] ^ key[1];
+    ctr[0] = n0; ctr[1] = lo1; ctr[2] = n2; ctr[3] = lo0;
+}
+// two uniforms per 128-bit block; index i uses block i>>1, half i&1
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t index) {
+    const uint64_t blk = index >> 1;
+    uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(ctr, key);
+        key[0] += 0x9E3779B9u;
+        key[1] += 0xBB67AE85u;
+    }
+    const uint64_t w = (index & 1) ? (((uint64_t)ctr[3] << 32) | ctr[2]) : (((uint64_t)ctr[1] << 32) | ctr[0]);
+    return (double)(w >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, double* __restrict__ out, int64_t P) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = philox_uniform(seed, offset + (uint64_t)i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: Clenshaw bisection (src/Extras/sample.jl:58-75), fused with fromcanonical (sample.jl:106)
+//     a=-1,b=1; numits x { m=.5(a+b); v=clenshaw(c,m); (v<=u) ? a=m : b=m }; out = .5(a+b)
+// USE_RNG: uniforms drawn on device (throughput path of `sample`), else read from `u`.
+// ------------------------------------------------------------------------------------------------
+template <bool USE_RNG, bool SMEM_COEF>
+__global__ void __launch_bounds__(CL_THREADS, 2)
+bisect_vec_kernel(const double* __restrict__ c, int64_t N, const double* __restrict__ u, uint64_t seed,
+                  uint64_t offset, double* __restrict__ out, int64_t P, int numits, double da, double db,
+                  int64_t ntiles) {
+    AFB_DYN_SMEM(double, sc);
+    const int tid = threadIdx.x;
+    const double* cc = c;
+    if (SMEM_COEF) {
+        for (int64_t k = tid; k < N; k += CL_THREADS) sc[k] = c[k];
+        __syncthreads();
+        cc = sc;
+    }
+    const double mid = __dmul_rn(__dadd_rn(da, db), 0.5);  // mean(d)
+    const double len = __dsub_rn(db, da);                   // complexlength(d)
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * (int64_t)(CL_THREADS * CL_R);
+        double a[CL_R], b[CL_R], uu[CL_R];
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * CL_THREADS;
+            a[r] = -1.0;
+            b[r] = 1.0;
+            if (USE_RNG) uu[r] = philox_uniform(seed, offset + (uint64_t)i);
+            else uu[r] = (i < P) ? u[i] : 0.0;
+        }
+        for (int it = 0; it < numits; ++it) {
+            double m[CL_R], x2[CL_R], b1[CL_R], b2[CL_R], v[CL_R];
+#pragma unroll
+            for (int r = 0; r < CL_R; ++r) {
+                m[r] = __dmul_rn(0.5, __dadd_rn(a[r], b[r]));
+                x2[r] = __dmul_rn(2.0, m[r]);
+                b1[r] = 0.0;
+                b2[r] = 0.0;
+            }
+            if (N == 0) {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) v[r] = 0.0;
+            } else if (N == 1) {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) v[r] = cc[0];
+            } else {
+                clenshaw_span<CL_R>(cc, 1, (int)N, x2, b1, b2);
+                clenshaw_finish<CL_R>(cc[0], x2, b1, b2, v);
+            }
+#pragma unroll
+            for (int r = 0; r < CL_R; ++r) {
+                if (v[r] <= uu[r]) a[r] = m[r]; else b[r] = m[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * CL_THREADS;
+            const double xm = __dmul_rn(0.5, __dadd_rn(a[r], b[r]));
+            // fromcanonical(d, x) = mean(d) + complexlength(d) x / 2
+            if (i < P) out[i] = __dadd_rn(mid, __dmul_rn(__dmul_rn(len, xm), 0.5));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Matrix-coefficient variants (column j of C at x[j]); src/Extras/sample.jl:80-101.
+// A CTA owns W consecutive columns; when the N x W tile fits in shared memory it is staged there
+// transposed (sm[k*W + col]) with coalesced global reads, else columns are walked in global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int COLS_W = 128;
+constexpr int COLS_LD = COLS_W + 1;  // padded row of the transposed tile (conflict-free both ways)
+
+template <bool BISECT>
+__global__ void __launch_bounds__(COLS_W)
+cols_kernel(const double* __restrict__ C, int64_t N, int64_t ld, const double* __restrict__ xu,
+            double* __restrict__ out, int64_t P, int numits, int use_smem) {
+    AFB_DYN_SMEM(double, sm);
+    const int tid = threadIdx.x;
+    const int64_t col0 = (int64_t)blockIdx.x * COLS_W;
+    const int64_t j = col0 + tid;
+    if (use_smem) {
+        // coalesced: consecutive threads read consecutive k of one column
+        const int64_t ncol = (P - col0 < COLS_W) ? (P - col0) : COLS_W;
+        for (int64_t cidx = 0; cidx < ncol; ++cidx)
+            for (int64_t k = tid; k < N; k += COLS_W) sm[k * COLS_LD + cidx] = C[(col0 + cidx) * ld + k];
+        __syncthreads();
+    }
+    if (j >= P) return;
+    const double* gcol = C + j * ld;
+    auto coef = [&](int64_t k) -> double { return use_smem ? sm[k * COLS_LD + tid] : gcol[k]; };
+    auto eval = [&](double x) -> double {
+        if (N == 0) return 0.0;
+        if (N == 1) return coef(0);
+        const double x2 = __dmul_rn(2.0, x);
+        double b1 = 0.0, b2 = 0.0;
+        for (int64_t k = N - 1; k >= 1; --k) {
+            const double t = __fma_rn(x2, b1, __dsub_rn(coef(k), b2));
+            b2 = b1;
+            b1 = t;
+        }
+        return __fma_rn(__dmul_rn(x2, 0.5), b1, __dsub_rn(coef(0), b2));
+    };
+    if (!BISECT) {
+        out[j] = eval(xu[j]);
+    } else {
+        double a = -1.0, b = 1.0;
+        const double u = xu[j];
+        for (int it = 0; it < numits; ++it) {
+            const double m = __dmul_rn(0.5, __dadd_rn(a, b));
+            if (eval(m) <= u) a = m; else b = m;
+        }
+        out[j] = __dmul_rn(0.5, __dadd_rn(a, b));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-function evaluation  Y[m + M*i] = f_m(x[i])   (evaluate.(f.A, ry'), sample.jl:208)
+// Coefficients (N x M) are staged in shared memory when they fit; all lanes read the same
+// coefficient (broadcast), each thread owns one point and walks the M functions.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+multi_kernel(const double* __restrict__ C, int64_t N, int64_t M, const double* __restrict__ x,
+             double* __restrict__ Y, int64_t P, int use_smem) {
+    AFB_DYN_SMEM(double, sm);
+    const int tid = threadIdx.x;
+    const double* cc = C;
+    if (use_smem) {
+        for (int64_t k = tid; k < N * M; k += blockDim.x) sm[k] = C[k];
+        __syncthreads();
+        cc = sm;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const double xv = x[i];
+        const double x2 = __dmul_rn(2.0, xv);
+        for (int64_t m = 0; m < M; ++m) {
+            const double* c = cc + m * N;
+            double r;
+            if (N == 0) r = 0.0;
+            else if (N == 1) r = c[0];
+            else {
+                double b1 = 0.0, b2 = 0.0;
+                for (int64_t k = N - 1; k >= 1; --k) {
+                    const double t = __fma_rn(x2, b1, __dsub_rn(c[k], b2));
+                    b2 = b1;
+                    b1 = t;
+                }
+                r = __fma_rn(__dmul_rn(x2, 0.5), b1, __dsub_rn(c[0], b2));
+            }
+            Y[m + M * i] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: chebnormalizedcumsum! per column (sample.jl:170-175), sequential per column to keep the
+// reference's summation order; one thread per column.
+// ------------------------------------------------------------------------------------------------
+__global__ void normcumsum_kernel(double* __restrict__ C, int64_t N, int64_t ncols, int64_t ld, int grow) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    double* v = C + j * ld;
+    const int64_t n = N;
+    if (n == 2) {
+        v[1] = __ddiv_rn(v[1], 2.0);
+    } else if (n > 2) {
+        v[0] = __dsub_rn(v[0], __ddiv_rn(v[2], 2.0));
+        for (int64_t q = 1; q <= n - 3; ++q) v[q] = __ddiv_rn(__dsub_rn(v[q], v[q + 2]), 2.0);
+        v[n - 2] = __ddiv_rn(v[n - 2], 2.0);
+        v[n - 1] = __ddiv_rn(v[n - 1], 2.0);
+    }
+    const int64_t L = grow ? n + 1 : n;
+    for (int64_t k = L - 1; k >= 1; --k) v[k] = __ddiv_rn(v[k - 1], (double)k);
+    if (L > 0) v[0] = 0.0;
+    for (int64_t k = 2; k <= L; ++k) v[0] = __dadd_rn(v[0], (k & 1) ? -v[k - 1] : v[k - 1]);
+    double val = 0.0;
+    for (int64_t k = 0; k < L; ++k) val = __dadd_rn(val, v[k]);
+    val = __ddiv_rn(1.0, val);
+    for (int64_t k = 0; k < L; ++k) v[k] = __dmul_rn(v[k], val);
+}
+
+// ------------------------------------------------------------------------------------------------
+// points(::Chebyshev, n), descending (NEWS.md:92): x_k = sinpi((n-2k-1)/(2n)) mapped to [a,b]
+// ------------------------------------------------------------------------------------------------
+__global__ void chebpoints_kernel(double* __restrict__ out, int64_t n, double da, double db) {
+    const double mid = __dmul_rn(__dadd_rn(da, db), 0.5);
+    const double len = __dsub_rn(db, da);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double arg = __ddiv_rn((double)(n - 2 * k - 1), (double)(2 * n));
+        const double xc = sinpi(arg);
+        out[k] = __dadd_rn(mid, __dmul_rn(__dmul_rn(len, xc), 0.5));
+    }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static inline int64_t cl_tiles(int64_t P) { return (P + (int64_t)CL_THREADS * CL_R - 1) / ((int64_t)CL_THREADS * CL_R); }
+
+int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream) {
+    if (P == 0) return AFB_OK;
+    const int64_t ntiles = cl_tiles(P);
+    const int64_t grid = ntiles < 2 * (int64_t)sm_count() ? ntiles : 2 * (int64_t)sm_count();
+    const size_t smem = sizeof(double) * (size_t)((N < CL_CHUNK ? (N > 0 ? N : 1) : CL_CHUNK));
+    auto k = clenshaw_vec_kernel;
+    AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * CL_CHUNK)));
+    AFB_LAUNCH(k, (unsigned)grid, CL_THREADS, smem, stream, d_c, N, d_x, d_y, P, ntiles);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_bisect_vec(const double* d_c, int64_t N, const double* d_u, bool rng, uint64_t seed, uint64_t offset,
+                          double* d_out, int64_t P, int numits, double a, double b, void* stream) {
+    if (P == 0) return AFB_OK;
+    const int64_t ntiles = cl_tiles(P);
+    const int64_t grid = ntiles < 2 * (int64_t)sm_count() ? ntiles : 2 * (int64_t)sm_count();
+    const bool in_smem = N <= CL_CHUNK;
+    const size_t smem = in_smem ? sizeof(double) * (size_t)(N > 0 ? N : 1) : 8;
+#define AFB_BISECT_LAUNCH(RNG, SM)                                                                          \
+    do {                                                                                                    \
+        auto k = bisect_vec_kernel<RNG, SM>;                                                                \
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                      (int)(sizeof(double) * CL_CHUNK)));                                   \
+        AFB_LAUNCH(k, (unsigned)grid, CL_THREADS, smem, stream, d_c, N, d_u, seed, offset, d_out, P, numits, \
+                   a, b, ntiles);                                                                           \
+    } while (0)
+    if (rng) { if (in_smem) AFB_BISECT_LAUNCH(true, true); else AFB_BISECT_LAUNCH(true, false); }
+    else     { if (in_smem) AFB_BISECT_LAUNCH(false, true); else AFB_BISECT_LAUNCH(false, false); }
+#undef AFB_BISECT_LAUNCH
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_philox(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream) {
+    if (P == 0) return AFB_OK;
+    int64_t grid = (P + 255) / 256;
+    if (grid > 8 * (int64_t)sm_count()) grid = 8 * (int64_t)sm_count();
+    auto k = philox_uniform_kernel;
+    AFB_LAUNCH(k, (unsigned)grid, 256, 0, stream, seed, offset, d_out, P);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_cols(bool bisect, const double* d_C, int64_t N, int64_t ld, const double* d_xu, double* d_out,
+                    int64_t P, int numits, void* stream) {
+    if (P == 0) return AFB_OK;
+    const int64_t grid = (P + COLS_W - 1) / COLS_W;
+    const size_t need = sizeof(double) * (size_t)N * COLS_LD;
+    const int use_smem = (N > 0 && need <= 160 * 1024) ? 1 : 0;
+    const size_t smem = use_smem ? need : 8;
+    if (bisect) {
+        auto k = cols_kernel<true>;
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        AFB_LAUNCH(k, (unsigned)grid, COLS_W, smem, stream, d_C, N, ld, d_xu, d_out, P, numits, use_smem);
+    } else {
+        auto k = cols_kernel<false>;
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        AFB_LAUNCH(k, (unsigned)grid, COLS_W, smem, stream, d_C, N, ld, d_xu, d_out, P, numits, use_smem);
+    }
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_multi(const double* d_C, int64_t N, int64_t M, const double* d_x, double* d_Y, int64_t P, void* stream) {
+    if (P == 0 || M == 0) return AFB_OK;
+    const size_t need = sizeof(double) * (size_t)(N * M);
+    const int use_smem = (N * M > 0 && need <= 160 * 1024) ? 1 : 0;
+    int64_t grid = (P + 255) / 256;
+    if (grid > 8 * (int64_t)sm_count()) grid = 8 * (int64_t)sm_count();
+    auto k = multi_kernel;
+    AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    AFB_LAUNCH(k, (unsigned)grid, 256, use_smem ? need : 8, stream, d_C, N, M, d_x, d_Y, P, use_smem);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_normcumsum(double* d_C, int64_t N, int64_t ncols, int64_t ld, int grow, void* stream) {
+    if (ncols == 0) return AFB_OK;
+    auto k = normcumsum_kernel;
+    AFB_LAUNCH(k, (unsigned)((ncols + 127) / 128), 128, 0, stream, d_C, N, ncols, ld, grow);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_chebpoints(double* d_out, int64_t n, double a, double b, void* stream) {
+    if (n == 0) return AFB_OK;
+    int64_t grid = (n + 255) / 256;
+    if (grid > 4 * (int64_t)sm_count()) grid = 4 * (int64_t)sm_count();
+    auto k = chebpoints_kernel;
+    AFB_LAUNCH(k, (unsigned)grid, 256, 0, stream, d_out, n, a, b);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+}  // namespace afb

@@ -1,0 +1,83 @@
+// Shared declarations for libapproxfun_b200.so (sm_100a).  See include/approxfun_b200.h for the ABI.
+#pragma once
+
+#ifdef AFB_HOST_EMU
+#include "afb_emu.h"
+#define AFB_HD
+#else
+#include <cuda_runtime.h>
+#define AFB_HD __host__ __device__
+#define AFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define AFB_DYN_SMEM(T, name)                                          \
+    extern __shared__ __align__(16) unsigned char afb_dyn_smem_raw[];  \
+    T* name = reinterpret_cast<T*>(afb_dyn_smem_raw)
+#endif
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/approxfun_b200.h"
+
+namespace afb {
+
+// ---- status / error plumbing (never throws across the ABI) -------------------------------------
+void set_error(int32_t code, const std::string& msg);
+int32_t fail(int32_t code, const std::string& msg);
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define AFB_CUDA(expr)                                                          \
+    do {                                                                        \
+        cudaError_t afb_e_ = (expr);                                            \
+        if (afb_e_ != cudaSuccess) return afb::cuda_fail(afb_e_, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define AFB_TRY(expr)                         \
+    do {                                      \
+        int32_t afb_s_ = (expr);              \
+        if (afb_s_ != AFB_OK) return afb_s_;  \
+    } while (0)
+#define AFB_KERNEL_CHECK() AFB_CUDA(cudaGetLastError())
+
+int32_t ensure_device();  // AFB_NO_DEVICE unless a CUDA device is usable (no CPU fallback)
+int sm_count();
+
+// ---- complex helpers ----------------------------------------------------------------------------
+typedef double2 cplx;
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx cmul_mi(cplx a) { return make_double2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ cplx cmul_pi(cplx a) { return make_double2(-a.y, a.x); }  // a * (+i)
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+
+__device__ __forceinline__ cplx ldg2(const cplx* p) {
+#ifdef AFB_HOST_EMU
+    return *p;
+#else
+    return __ldg(reinterpret_cast<const double2*>(p));
+#endif
+}
+
+static inline int ilog2(int64_t v) {
+    int l = 0;
+    while ((int64_t(1) << (l + 1)) <= v) ++l;
+    return l;
+}
+static inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ---- twiddle tables (device resident, built once per size, double-double accurate on host) ------
+// root_table(N)[m] = exp(-2 pi i m / N), m = 0..N-1
+int32_t root_table(int64_t N, const cplx** out);
+// half_root_table(n)[k] = exp(-i pi k / (2 n)), k = 0..n   (DCT post/pre twiddles)
+int32_t quarter_table(int64_t n, const cplx** out);
+void free_tables();
+
+}  // namespace afb

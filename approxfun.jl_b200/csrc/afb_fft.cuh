@@ -1,0 +1,201 @@
+// Shared-memory Stockham FFT core (complex FP64, power-of-two length N = 32 .. 8192).
+//
+// One "line" = one length-N complex transform, worked on by T = N / R1 threads that each hold
+// E = N / T complex values (16 for N >= 128) in registers.  A pass of radix R reads E values per
+// thread from the line's shared-memory buffer (stride N/R apart: conflict free), multiplies by the
+// pass twiddles, runs E/R register butterflies and scatters the results (autosort order) back.
+// The buffer is indexed through an XOR swizzle on 16-byte slots so that the first pass' scatter
+// (stride R1 slots between lanes) is conflict free as well.
+//
+// Twiddles: per pass one table load w = exp(-2 pi i k / (NS R)) per butterfly; the R-1 powers are
+// formed in registers with a depth-<=4 product tree (the FP64 pipe has slack, the L1/shared
+// datapath does not).
+#pragma once
+#include "afb_common.cuh"
+
+namespace afb {
+
+// ---- per-length configuration -------------------------------------------------------------------
+template <int N> struct FftCfg;
+#define AFB_FFTCFG(N_, R1_, R2_, R3_, R4_)                          \
+    template <> struct FftCfg<N_> {                                   \
+        static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;  \
+        static constexpr int T = N_ / R1_;                            \
+        static constexpr int E = R1_;                                 \
+        static constexpr int SH = (R1_ == 16) ? 4 : 3;                \
+    }
+AFB_FFTCFG(32, 8, 4, 1, 1);
+AFB_FFTCFG(64, 8, 8, 1, 1);
+AFB_FFTCFG(128, 16, 8, 1, 1);
+AFB_FFTCFG(256, 16, 16, 1, 1);
+AFB_FFTCFG(512, 16, 16, 2, 1);
+AFB_FFTCFG(1024, 16, 16, 4, 1);
+AFB_FFTCFG(2048, 16, 16, 8, 1);
+AFB_FFTCFG(4096, 16, 16, 16, 1);
+AFB_FFTCFG(8192, 16, 16, 16, 2);
+#undef AFB_FFTCFG
+
+// slots per line in shared memory (one pad slot for short lines packed many per CTA)
+template <int N> struct FftLine {
+    static constexpr int STRIDE = (N < 256) ? N + 8 : N;
+};
+
+template <int SH> __device__ __forceinline__ int swz(int i) { return i ^ ((i >> SH) & 7); }
+
+// ---- register butterflies (forward sign, natural-order output) ------------------------------------
+__device__ __forceinline__ void dft2(cplx& a, cplx& b) {
+    const cplx t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+__device__ __forceinline__ void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
+    const cplx t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = cmul_mi(csub(x1, x3));
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    x1 = cadd(t1, t3);
+    x3 = csub(t1, t3);
+}
+
+template <int R> struct Dft;
+template <> struct Dft<2> {
+    static __device__ __forceinline__ void run(cplx* x) { dft2(x[0], x[1]); }
+};
+template <> struct Dft<4> {
+    static __device__ __forceinline__ void run(cplx* x) { dft4(x[0], x[1], x[2], x[3]); }
+};
+template <> struct Dft<8> {
+    static __device__ __forceinline__ void run(cplx* x) {
+        const double h = 0.70710678118654752440;
+        cplx e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
+        cplx o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+        dft4(e0, e1, e2, e3);
+        dft4(o0, o1, o2, o3);
+        // w8^b * o_b
+        const cplx p1 = make_double2((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+        const cplx p2 = cmul_mi(o2);
+        const cplx p3 = make_double2((o3.y - o3.x) * h, -(o3.x + o3.y) * h);
+        x[0] = cadd(e0, o0); x[4] = csub(e0, o0);
+        x[1] = cadd(e1, p1); x[5] = csub(e1, p1);
+        x[2] = cadd(e2, p2); x[6] = csub(e2, p2);
+        x[3] = cadd(e3, p3); x[7] = csub(e3, p3);
+    }
+};
+template <> struct Dft<16> {
+    static __device__ __forceinline__ void run(cplx* x) {
+        const double h = 0.70710678118654752440;
+        const double c1 = 0.92387953251128675613;  // cos(pi/8)
+        const double s1 = 0.38268343236508977173;  // sin(pi/8)
+        cplx y[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            y[a][0] = x[a]; y[a][1] = x[a + 4]; y[a][2] = x[a + 8]; y[a][3] = x[a + 12];
+            dft4(y[a][0], y[a][1], y[a][2], y[a][3]);
+        }
+        // y[a][b] *= w16^(a b)
+        y[1][1] = cmul(y[1][1], make_double2(c1, -s1));
+        y[1][2] = make_double2((y[1][2].x + y[1][2].y) * h, (y[1][2].y - y[1][2].x) * h);
+        y[1][3] = cmul(y[1][3], make_double2(s1, -c1));
+        y[2][1] = make_double2((y[2][1].x + y[2][1].y) * h, (y[2][1].y - y[2][1].x) * h);
+        y[2][2] = cmul_mi(y[2][2]);
+        y[2][3] = make_double2((y[2][3].y - y[2][3].x) * h, -(y[2][3].x + y[2][3].y) * h);
+        y[3][1] = cmul(y[3][1], make_double2(s1, -c1));
+        y[3][2] = make_double2((y[3][2].y - y[3][2].x) * h, -(y[3][2].x + y[3][2].y) * h);
+        y[3][3] = cmul(y[3][3], make_double2(-c1, s1));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            dft4(y[0][b], y[1][b], y[2][b], y[3][b]);
+            x[b] = y[0][b]; x[b + 4] = y[1][b]; x[b + 8] = y[2][b]; x[b + 12] = y[3][b];
+        }
+    }
+};
+
+// multiply x[1..R-1] by w^1..w^(R-1)
+template <int R> __device__ __forceinline__ void apply_powers(cplx* x, cplx w) {
+    if constexpr (R == 2) {
+        x[1] = cmul(x[1], w);
+        return;
+    }
+    cplx p[R];
+    p[1] = w;
+#pragma unroll
+    for (int r = 2; r < R; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);  // depth <= log2 R
+#pragma unroll
+    for (int r = 1; r < R; ++r) x[r] = cmul(x[r], p[r]);
+}
+
+// ---- one Stockham pass on a line -------------------------------------------------------------------
+// x[b*R + r]: butterfly b of this thread, element r.   j_b = t + b*T  in [0, N/R)
+template <int N, int T, int R, int SH>
+__device__ __forceinline__ void pass_load(const cplx* __restrict__ s, int t, cplx* x) {
+    constexpr int B = (N / R) / T;
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[b * R + r] = s[swz<SH>(t + b * T + r * (N / R))];
+}
+
+template <int N, int T, int R, int NS>
+__device__ __forceinline__ void pass_compute(int t, cplx* x, const cplx* __restrict__ tw) {
+    constexpr int B = (N / R) / T;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        if constexpr (NS > 1) {
+            const int k = (t + b * T) & (NS - 1);
+            const cplx w = ldg2(tw + k * (N / (NS * R)));
+            apply_powers<R>(x + b * R, w);
+        }
+        Dft<R>::run(x + b * R);
+    }
+}
+
+template <int N, int T, int R, int NS, int SH>
+__device__ __forceinline__ void pass_store(cplx* __restrict__ s, int t, const cplx* x) {
+    constexpr int B = (N / R) / T;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int j = t + b * T;
+        const int k = j & (NS - 1);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[swz<SH>(base + q * NS)] = x[b * R + q];
+    }
+}
+
+// Full transform of one line.  On entry x[] holds this thread's first-pass inputs
+// (x[r] = input[t + T*r]); on exit the natural-order spectrum is in shared memory (swizzled slots)
+// and a __syncthreads() has been executed, so any thread may read any element.
+template <int N>
+__device__ __forceinline__ void fft_line(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    constexpr int T = C::T, SH = C::SH;
+    pass_compute<N, T, C::R1, 1>(t, x, tw);
+    pass_store<N, T, C::R1, 1, SH>(s, t, x);
+    __syncthreads();
+    if constexpr (C::R2 > 1) {
+        pass_load<N, T, C::R2, SH>(s, t, x);
+        __syncthreads();
+        pass_compute<N, T, C::R2, C::R1>(t, x, tw);
+        pass_store<N, T, C::R2, C::R1, SH>(s, t, x);
+        __syncthreads();
+    }
+    if constexpr (C::R3 > 1) {
+        pass_load<N, T, C::R3, SH>(s, t, x);
+        __syncthreads();
+        pass_compute<N, T, C::R3, C::R1 * C::R2>(t, x, tw);
+        pass_store<N, T, C::R3, C::R1 * C::R2, SH>(s, t, x);
+        __syncthreads();
+    }
+    if constexpr (C::R4 > 1) {
+        pass_load<N, T, C::R4, SH>(s, t, x);
+        __syncthreads();
+        pass_compute<N, T, C::R4, C::R1 * C::R2 * C::R3>(t, x, tw);
+        pass_store<N, T, C::R4, C::R1 * C::R2 * C::R3, SH>(s, t, x);
+        __syncthreads();
+    }
+}
+
+// read element i of the finished (or pre-staged) line
+template <int N> __device__ __forceinline__ cplx line_get(const cplx* s, int i) { return s[swz<FftCfg<N>::SH>(i)]; }
+template <int N> __device__ __forceinline__ void line_put(cplx* s, int i, cplx v) { s[swz<FftCfg<N>::SH>(i)] = v; }
+
+}  // namespace afb

@@ -1,0 +1,57 @@
+// Internal declarations shared by the translation units of libapproxfun_b200.so.
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "afb_common.cuh"
+
+namespace afb {
+
+// line kinds of afb_transform.cu (values must match enum LineKind there)
+enum { ILK_CHEB_FWD = 0, ILK_CHEB_INV = 1, ILK_FOURIER_FWD = 2, ILK_FOURIER_INV = 3, ILK_LAURENT_FWD = 4,
+       ILK_LAURENT_INV = 5, ILK_CFFT = 6 };
+
+constexpr int DIRECT_MAX = 32;      // n <= DIRECT_MAX: O(n^2) kernel
+constexpr int LINE_MIN_N = 32;      // complex FFT lengths served by one CTA in shared memory
+constexpr int LINE_MAX_N = 8192;
+
+// ---- kernels / launchers --------------------------------------------------------------------------
+int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
+                    const cplx* tw, const cplx* aux, double scale, void* stream);
+int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
+                          int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
+                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream);
+int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
+                      const cplx* tab, void* stream);
+
+int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream);
+int32_t launch_bisect_vec(const double* d_c, int64_t N, const double* d_u, bool rng, uint64_t seed, uint64_t offset,
+                          double* d_out, int64_t P, int numits, double a, double b, void* stream);
+int32_t launch_philox(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
+int32_t launch_cols(bool bisect, const double* d_C, int64_t N, int64_t ld, const double* d_xu, double* d_out,
+                    int64_t P, int numits, void* stream);
+int32_t launch_multi(const double* d_C, int64_t N, int64_t M, const double* d_x, double* d_Y, int64_t P, void* stream);
+int32_t launch_normcumsum(double* d_C, int64_t N, int64_t ncols, int64_t ld, int grow, void* stream);
+int32_t launch_chebpoints(double* d_out, int64_t n, double a, double b, void* stream);
+
+// ---- generic complex FFT engine (afb_large.cu): any length, batched, contiguous lines ---------------
+struct CfftPlan;
+int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch);
+void cfft_destroy(CfftPlan* p);
+// out[b*n + k] = scale * sum_j in[b*n + j] exp(-/+ 2 pi i jk/n)   (inverse = +, unnormalised); in == out allowed
+int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale, void* stream);
+int32_t cfft_launches(const CfftPlan* p);
+
+// pre/post kernels mapping the real transforms onto a length-n complex FFT (afb_large.cu)
+int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
+                           const cplx* qtab, void* stream);
+int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, int64_t ostride, int64_t batch,
+                            const cplx* qtab, void* stream);
+
+// ---- 2-D (afb_tensor.cu) -----------------------------------------------------------------------------
+int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, void* stream);
+
+// ---- device table helpers ------------------------------------------------------------------------------
+int32_t upload_table(const std::vector<cplx>& host, cplx** dev);
+
+}  // namespace afb

@@ -1,0 +1,315 @@
+// Any-length batched complex FFT engine and the generic (non fused) real-transform path.
+//
+//   * power-of-two n <= 8192      : one shared-memory line kernel (afb_transform.cu)
+//   * power-of-two n  > 8192      : four-step  n = n1 n2  (kernel K3 of SURVEY.md section 2c):
+//        A: n2 strided lines of length n1 (+ twiddle w_n^(b k1)),  B: n1 contiguous lines of length n2
+//           with a stride-n1 scatter so that X[k1 + n1 k2] lands in natural order
+//   * any other n                 : Bluestein chirp-z through a power-of-two engine of length M >= 2n-1
+//
+// The generic real-transform path (plot-sized or chopped lengths, and n > 16384) maps each kind onto
+// a length-n complex FFT with an element-wise pre and post kernel; it is the correctness path for
+// arbitrary n -- the fused power-of-two kernels of afb_transform.cu are the throughput path.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "afb_internal.h"
+
+namespace afb {
+
+struct CfftPlan {
+    int64_t n = 0, max_batch = 0;
+    int mode = 0;  // 0 line, 1 four-step, 2 Bluestein
+    const cplx* tw = nullptr;
+    // four-step
+    int n1 = 0, n2 = 0;
+    const cplx *tw1 = nullptr, *tw2 = nullptr;
+    cplx *twA = nullptr, *twB = nullptr;
+    cplx* tmp = nullptr;
+    // Bluestein
+    int64_t M = 0;
+    CfftPlan* sub = nullptr;
+    cplx *chirp = nullptr, *bhat = nullptr, *pad = nullptr;
+};
+
+// ---- Bluestein element-wise kernels ------------------------------------------------------------------
+__global__ void blue_pre_kernel(const cplx* __restrict__ in, cplx* __restrict__ pad, int64_t n, int64_t M,
+                                int64_t batch, const cplx* __restrict__ chirp, int conj_in) {
+    const int64_t total = batch * M;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / M, j = g % M;
+        cplx z = make_double2(0.0, 0.0);
+        if (j < n) {
+            z = in[b * n + j];
+            if (conj_in) z.y = -z.y;
+            z = cmul(z, chirp[j]);
+        }
+        pad[g] = z;
+    }
+}
+__global__ void blue_mul_kernel(cplx* __restrict__ pad, int64_t M, int64_t batch, const cplx* __restrict__ bhat) {
+    const int64_t total = batch * M;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
+        pad[g] = cmul(pad[g], bhat[g % M]);
+}
+__global__ void blue_post_kernel(const cplx* __restrict__ pad, cplx* __restrict__ out, int64_t n, int64_t M,
+                                 int64_t batch, const cplx* __restrict__ chirp, int conj_out, double scale) {
+    const int64_t total = batch * n;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / n, k = g % n;
+        cplx z = cscale(cmul(pad[b * M + k], chirp[k]), scale);
+        if (conj_out) z.y = -z.y;
+        out[g] = z;
+    }
+}
+__global__ void fill_bfilter_kernel(cplx* __restrict__ b, int64_t n, int64_t M, const cplx* __restrict__ chirp) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        cplx z = make_double2(0.0, 0.0);
+        if (j < n) z = cconj(chirp[j]);
+        else if (M - j < n) z = cconj(chirp[M - j]);
+        b[j] = z;
+    }
+}
+
+static inline unsigned ew_grid(int64_t total) {
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = 16 * (int64_t)sm_count();
+    return (unsigned)std::max<int64_t>(1, std::min(g, cap));
+}
+
+void cfft_destroy(CfftPlan* p) {
+    if (!p) return;
+    if (p->twA) cudaFree(p->twA);
+    if (p->twB) cudaFree(p->twB);
+    if (p->tmp) cudaFree(p->tmp);
+    if (p->chirp) cudaFree(p->chirp);
+    if (p->bhat) cudaFree(p->bhat);
+    if (p->pad) cudaFree(p->pad);
+    cfft_destroy(p->sub);
+    delete p;
+}
+
+int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
+    CfftPlan* p = new CfftPlan();
+    p->n = n;
+    p->max_batch = std::max<int64_t>(1, max_batch);
+    int32_t st = AFB_OK;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    if (is_pow2(n) && n >= LINE_MIN_N && n <= LINE_MAX_N) {
+        p->mode = 0;
+        st = root_table(n, &p->tw);
+    } else if (is_pow2(n) && n > LINE_MAX_N) {
+        const int lg = ilog2(n);
+        if (lg > 26) { cfft_destroy(p); return fail(AFB_UNSUPPORTED, "complex FFT length above 2^26"); }
+        p->mode = 1;
+        p->n1 = 1 << ((lg + 1) / 2);
+        p->n2 = 1 << (lg / 2);
+        st = root_table(p->n1, &p->tw1);
+        if (st == AFB_OK) st = root_table(p->n2, &p->tw2);
+        if (st == AFB_OK) {
+            std::vector<cplx> hA((size_t)((n + 4095) / 4096)), hB(4096);
+            for (size_t i = 0; i < hA.size(); ++i) {
+                const long double a = 2.0L * PI * (long double)(i * 4096) / (long double)n;
+                hA[i] = make_double2((double)cosl(a), (double)(-sinl(a)));
+            }
+            for (size_t i = 0; i < 4096; ++i) {
+                const long double a = 2.0L * PI * (long double)i / (long double)n;
+                hB[i] = make_double2((double)cosl(a), (double)(-sinl(a)));
+            }
+            st = upload_table(hA, &p->twA);
+            if (st == AFB_OK) st = upload_table(hB, &p->twB);
+        }
+        if (st == AFB_OK) {
+            void* d = nullptr;
+            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)n);
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(four-step tmp)", __FILE__, __LINE__);
+            p->tmp = reinterpret_cast<cplx*>(d);
+        }
+    } else if (n >= 1) {
+        p->mode = 2;
+        int64_t M = 32;
+        while (M < 2 * n - 1) M <<= 1;
+        p->M = M;
+        st = cfft_create(&p->sub, M, p->max_batch);
+        if (st == AFB_OK) {
+            std::vector<cplx> h((size_t)n);
+            for (int64_t j = 0; j < n; ++j) {
+                const int64_t m = (int64_t)(((__int128)j * j) % (2 * n));  // j^2 mod 2n, exact
+                const long double a = PI * (long double)m / (long double)n;
+                h[(size_t)j] = make_double2((double)cosl(a), (double)(-sinl(a)));  // exp(-i pi j^2 / n)
+            }
+            st = upload_table(h, &p->chirp);
+        }
+        if (st == AFB_OK) {
+            void* d = nullptr;
+            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)M);
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(bhat)", __FILE__, __LINE__);
+            p->bhat = reinterpret_cast<cplx*>(d);
+        }
+        if (st == AFB_OK) {
+            void* d = nullptr;
+            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)(M * p->max_batch));
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(bluestein pad)", __FILE__, __LINE__);
+            p->pad = reinterpret_cast<cplx*>(d);
+        }
+        if (st == AFB_OK) {
+            auto k = fill_bfilter_kernel;
+            AFB_LAUNCH(k, ew_grid(M), 256, 0, nullptr, p->bhat, n, M, p->chirp);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) st = cuda_fail(e, "fill_bfilter_kernel", __FILE__, __LINE__);
+            if (st == AFB_OK) st = cfft_exec(p->sub, p->bhat, p->bhat, 1, false, 1.0, nullptr);
+            if (st == AFB_OK) {
+                e = cudaStreamSynchronize(nullptr);
+                if (e != cudaSuccess) st = cuda_fail(e, "sync(bhat)", __FILE__, __LINE__);
+            }
+        }
+    } else {
+        st = fail(AFB_BAD_SIZE, "complex FFT length must be >= 1");
+    }
+    if (st != AFB_OK) { cfft_destroy(p); return st; }
+    *out = p;
+    return AFB_OK;
+}
+
+int32_t cfft_launches(const CfftPlan* p) {
+    if (!p) return 0;
+    switch (p->mode) {
+        case 0: return 1;
+        case 1: return 2;
+        default: return 3 + 2 * cfft_launches(p->sub);
+    }
+}
+
+int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale, void* stream) {
+    if (batch == 0) return AFB_OK;
+    const int64_t n = p->n;
+    if (p->mode == 0) {
+        return launch_cfft_lines((int)n, in, out, batch, n, 1, n, 1, p->tw, inverse, inverse, scale, nullptr, nullptr, 1,
+                                 stream);
+    }
+    if (p->mode == 1) {
+        const int64_t n1 = p->n1, n2 = p->n2;
+        for (int64_t b = 0; b < batch; ++b) {
+            const cplx* src = in + b * n;
+            cplx* dst = out + b * n;
+            // A: for every column b2 (stride-n2 elements): FFT over a, times w_n^(b2 k1), kept in place layout
+            AFB_TRY(launch_cfft_lines((int)n1, src, p->tmp, n2, 1, n2, 1, n2, p->tw1, inverse, false, 1.0, p->twA, p->twB,
+                                      n2, stream));
+            // B: for every row k1 (contiguous n2 elements): FFT over b2, scattered to X[k1 + n1 k2]
+            AFB_TRY(launch_cfft_lines((int)n2, p->tmp, dst, n1, n2, 1, 1, n1, p->tw2, false, inverse, scale, nullptr,
+                                      nullptr, 1, stream));
+        }
+        return AFB_OK;
+    }
+    // Bluestein: X_k = chirp_k * sum_j (x_j chirp_j) conj(chirp)_{k-j}
+    for (int64_t b0 = 0; b0 < batch; b0 += p->max_batch) {
+        const int64_t nb = std::min(p->max_batch, batch - b0);
+        const int64_t M = p->M;
+        auto kpre = blue_pre_kernel;
+        AFB_LAUNCH(kpre, ew_grid(nb * M), 256, 0, stream, in + b0 * n, p->pad, n, M, nb, p->chirp, inverse ? 1 : 0);
+        AFB_KERNEL_CHECK();
+        AFB_TRY(cfft_exec(p->sub, p->pad, p->pad, nb, false, 1.0, stream));
+        auto kmul = blue_mul_kernel;
+        AFB_LAUNCH(kmul, ew_grid(nb * M), 256, 0, stream, p->pad, M, nb, p->bhat);
+        AFB_KERNEL_CHECK();
+        AFB_TRY(cfft_exec(p->sub, p->pad, p->pad, nb, true, 1.0 / (double)M, stream));
+        auto kpost = blue_post_kernel;
+        AFB_LAUNCH(kpost, ew_grid(nb * n), 256, 0, stream, p->pad, out + b0 * n, n, M, nb, p->chirp, inverse ? 1 : 0, scale);
+        AFB_KERNEL_CHECK();
+    }
+    return AFB_OK;
+}
+
+// =====================================================================================================
+// generic pre / post kernels: real transform <-> length-n complex FFT (one thread per element)
+//   qtab[k] = exp(-i pi k / (2n)), k = 0..n   (Chebyshev kinds only)
+// =====================================================================================================
+__global__ void generic_pre_kernel(int kind, int64_t n, const void* __restrict__ in, int64_t istride,
+                                   cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ qtab) {
+    const int64_t total = batch * n;
+    const int64_t nh = (n + 1) / 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / n, j = g % n;
+        cplx z = make_double2(0.0, 0.0);
+        if (kind == AFB_CHEB1_FWD) {
+            const double* v = reinterpret_cast<const double*>(in) + b * istride;
+            z.x = (j < nh) ? v[2 * j] : v[2 * (n - 1 - j) + 1];
+        } else if (kind == AFB_CHEB1_INV) {
+            // X'_k = conj(w^k) (c'_k - i c'_{n-k}) / 2,  c'_0 = 2 c_0, c'_n = 0
+            const double* c = reinterpret_cast<const double*>(in) + b * istride;
+            if (j == 0) z.x = c[0];
+            else {
+                const cplx w = qtab[j];
+                z = cmul(make_double2(0.5 * c[j], -0.5 * c[n - j]), make_double2(w.x, -w.y));
+            }
+        } else if (kind == AFB_FOURIER_FWD) {
+            z.x = (reinterpret_cast<const double*>(in) + b * istride)[j];
+        } else if (kind == AFB_FOURIER_INV) {
+            // F'_0 = c_0 ; F'_k = (a_k - i b_k)/2 (1 <= k < nh) ; F'_{n-k} = conj ; even n: F'_{n/2} = -c_last
+            const double* c = reinterpret_cast<const double*>(in) + b * istride;
+            if (j == 0) z.x = c[0];
+            else if ((n % 2 == 0) && j == n / 2) z.x = -c[n - 1];
+            else if (j < nh) z = make_double2(0.5 * c[2 * j], -0.5 * c[2 * j - 1]);
+            else { const int64_t k = n - j; z = make_double2(0.5 * c[2 * k], 0.5 * c[2 * k - 1]); }
+        } else if (kind == AFB_LAURENT_FWD) {
+            z = (reinterpret_cast<const cplx*>(in) + b * istride)[j];
+        } else {  // AFB_LAURENT_INV: F[m] = c[imap(m)]
+            const cplx* c = reinterpret_cast<const cplx*>(in) + b * istride;
+            const int64_t i = (j < nh) ? 2 * j : 2 * (n - j) - 1;
+            z = c[i];
+        }
+        work[g] = z;
+    }
+}
+
+__global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict__ work, void* __restrict__ out,
+                                    int64_t ostride, int64_t batch, const cplx* __restrict__ qtab) {
+    const int64_t total = batch * n;
+    const int64_t nh = (n + 1) / 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / n, o = g % n;
+        const cplx* W = work + b * n;
+        if (kind == AFB_CHEB1_FWD) {
+            double* c = reinterpret_cast<double*>(out) + b * ostride;
+            const cplx P = cmul(W[o], qtab[o]);
+            c[o] = (o == 0) ? P.x / (double)n : P.x * (2.0 / (double)n);
+        } else if (kind == AFB_CHEB1_INV) {
+            double* v = reinterpret_cast<double*>(out) + b * ostride;
+            v[o] = (o & 1) ? W[n - 1 - (o - 1) / 2].x : W[o / 2].x;
+        } else if (kind == AFB_FOURIER_FWD) {
+            double* c = reinterpret_cast<double*>(out) + b * ostride;
+            const double l = (double)n;
+            if (o == 0) c[o] = W[0].x / l;
+            else if ((n % 2 == 0) && o == n - 1) c[o] = -W[n / 2].x / l;
+            else if (o & 1) c[o] = -W[(o + 1) / 2].y * (2.0 / l);
+            else c[o] = W[o / 2].x * (2.0 / l);
+        } else if (kind == AFB_FOURIER_INV) {
+            (reinterpret_cast<double*>(out) + b * ostride)[o] = W[o].x;
+        } else if (kind == AFB_LAURENT_FWD) {
+            const int64_t m = (o & 1) ? n - ((o + 1) >> 1) : (o >> 1);
+            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[m], 1.0 / (double)n);
+        } else {
+            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = W[o];
+        }
+        (void)nh;
+    }
+}
+
+int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
+                           const cplx* qtab, void* stream) {
+    if (batch == 0) return AFB_OK;
+    auto k = generic_pre_kernel;
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, in, istride, work, batch, qtab);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, int64_t ostride, int64_t batch,
+                            const cplx* qtab, void* stream) {
+    if (batch == 0) return AFB_OK;
+    auto k = generic_post_kernel;
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, work, out, ostride, batch, qtab);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+}  // namespace afb

@@ -1,0 +1,176 @@
+/*
+ * libapproxfun_b200.so -- C ABI of the B200-native ApproxFun transform / evaluate / sample path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / CUDA types), returns
+ * an int32 status (AFB_OK == 0) and never throws, exits or falls back to the CPU: without a usable
+ * CUDA device every compute call returns AFB_NO_DEVICE.  The message of the last failure on the
+ * calling thread is available through afb_last_error().
+ *
+ * "Replaces" lines cite the reference interface each entry point stands in for.  Paths are relative
+ * to /root/reference (ApproxFun.jl v0.13.28); UPSTREAM = package not vendored there (see SURVEY.md
+ * section 8b).  Arrays follow Julia's column-major layout: a batch of B transforms of length n is an
+ * n x B matrix, i.e. B contiguous vectors (`stride` elements apart).
+ *
+ * Ownership: the caller owns every buffer it passes; the library owns device workspaces, twiddle
+ * tables and streams inside the opaque plan.  Host-pointer entry points copy in, compute on the GPU
+ * and copy out before returning.  `*_device` entry points take device pointers plus a CUDA stream
+ * handle (cudaStream_t passed as void*, NULL = legacy default stream) and are asynchronous.
+ *
+ * Threading: plan creation / destruction and table construction are mutex protected; executing
+ * different plans concurrently is allowed; one plan must not be executed concurrently with itself.
+ */
+#ifndef APPROXFUN_B200_H
+#define APPROXFUN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFB_VERSION 100 /* 0.1.0 */
+
+enum afb_status {
+    AFB_OK = 0,
+    AFB_BAD_ARG = 1,     /* null pointer, unknown kind ...            (Julia: ArgumentError)      */
+    AFB_BAD_SIZE = 2,    /* negative / inconsistent sizes             (Julia: DimensionMismatch,
+                            the `@assert size(c)[2] == length(xl)` of src/Extras/sample.jl:85)  */
+    AFB_NO_DEVICE = 3,   /* no CUDA device: there is NO CPU fallback                              */
+    AFB_CUDA_ERROR = 4,
+    AFB_NCCL_ERROR = 5,
+    AFB_OOM = 6,
+    AFB_UNSUPPORTED = 7
+};
+
+/* Transform kinds.  FWD = values -> coefficients (plan_transform), INV = coefficients -> values
+ * (plan_itransform). */
+enum afb_kind {
+    AFB_CHEB1_FWD = 0,   /* plan_transform(Chebyshev(), n):  UPSTREAM FastTransforms
+                            plan_chebyshevtransform(v, Val(1)) = FFTW REDFT10, /n, c0/2
+                            (boundary visible in-tree: ext/ApproxFunDualNumbersExt.jl:10-12,44,49) */
+    AFB_CHEB1_INV = 1,   /* plan_itransform(Chebyshev(), n): plan_ichebyshevtransform(c, Val(1)) =
+                            c0*2, FFTW REDFT01, /2  (ext/ApproxFunDualNumbersExt.jl:45,50)         */
+    AFB_FOURIER_FWD = 2, /* plan_transform(Fourier(), n): R2HC + interlace; in-tree twin
+                            src/Extras/fftGeneric.jl:47-54, wrappers ext/...:53-63                */
+    AFB_FOURIER_INV = 3, /* plan_itransform(Fourier(), n): src/Extras/fftGeneric.jl:56-64          */
+    AFB_LAURENT_FWD = 4, /* plan_transform(Laurent(), n): c2c fft /n, order [f0,f-1,f1,f-2,...]
+                            (docs/src/usage/spaces.md:113-125; plan_fft import src/ApproxFun.jl:37) */
+    AFB_LAURENT_INV = 5,
+    AFB_CHEB1_2D_FWD = 6, /* transform!(::TensorSpace{Chebyshev,Chebyshev}, M): UPSTREAM
+                             ApproxFunBase; callers src/Plot/Plot.jl:290-332, src/Extras/sample.jl:196 */
+    AFB_CHEB1_2D_INV = 7
+};
+
+typedef struct afb_plan_s* afb_plan;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int32_t afb_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its status code */
+int32_t afb_last_error(char* buf, size_t len);
+/* Select the CUDA device of this process (one process per GPU).  device < 0 keeps the current one. */
+int32_t afb_init(int32_t device);
+int32_t afb_shutdown(void);
+int32_t afb_device_info(int32_t* sm_count, int64_t* hbm_bytes, char* name, size_t name_len);
+
+/* ---- device / pinned memory helpers (for device-resident use and benchmarking) ---------------- */
+int32_t afb_malloc(void** dptr, size_t bytes);
+int32_t afb_free(void* dptr);
+int32_t afb_host_alloc(void** hptr, size_t bytes); /* page-locked */
+int32_t afb_host_free(void* hptr);
+int32_t afb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int32_t afb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int32_t afb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int32_t afb_stream_sync(void* stream);
+
+/* ---- transform plans ----------------------------------------------------------------------------
+ * Replaces: plan_transform / plan_itransform (import src/ApproxFun.jl:22-23) and the FFTW plan they
+ * wrap (UPSTREAM FFTW.plan_r2r / plan_fft); `plan * v` (NEWS.md:90) = afb_plan_execute_host.
+ *   n      transform length (1D) or number of rows (2D)
+ *   n2     0 for 1D kinds; number of columns for 2D kinds
+ *   batch  number of independent transforms (1D); must be 1 for 2D
+ *   stride elements (double, or complex double for Laurent) between consecutive transforms; >= n
+ * Data type: double for Chebyshev / Fourier, interleaved complex double for Laurent. */
+int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int64_t batch, int64_t stride,
+                        uint32_t flags);
+/* host buffers; in == out allowed.  H2D, kernels and D2H are pipelined over batch chunks. */
+int32_t afb_plan_execute_host(afb_plan plan, const void* in, void* out);
+/* device buffers; in == out allowed; asynchronous on `stream` */
+int32_t afb_plan_execute_device(afb_plan plan, const void* d_in, void* d_out, void* stream);
+int32_t afb_plan_destroy(afb_plan plan);
+/* number of kernels one afb_plan_execute_device call launches (bench.py gpu_launches) */
+int32_t afb_plan_launches(afb_plan plan, int32_t* launches);
+
+/* ---- points ---------------------------------------------------------------------------------------
+ * Replaces points(::Chebyshev, n): UPSTREAM FastTransforms.chebyshevpoints(Float64,n,Val(1)) mapped by
+ * fromcanonical; DESCENDING order (NEWS.md:92).  out[k] = (a+b)/2 + (b-a)*sinpi((n-2k-1)/(2n))/2. */
+int32_t afb_chebpoints(double* out, int64_t n, double a, double b);
+int32_t afb_chebpoints_device(double* d_out, int64_t n, double a, double b, void* stream);
+/* points(::Fourier/Laurent, n): out[j] = a + (b-a) j / n */
+int32_t afb_fourierpoints(double* out, int64_t n, double a, double b);
+
+/* ---- Clenshaw evaluation ----------------------------------------------------------------------------
+ * Replaces clenshaw(::Chebyshev, c, x) and clenshaw(c::Vector, x::Vector, plan::ClenshawPlan) (UPSTREAM
+ * ApproxFunOrthogonalPolynomials; import src/ApproxFun.jl:26; call sites src/Extras/sample.jl:47,56,68).
+ * y[i] = sum_k c[k] T_k(x[i]); x is NOT modified and y never aliases internal scratch. */
+int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y, int64_t P);
+int32_t afb_clenshaw_cheb_device(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P,
+                                 void* stream);
+/* Replaces clenshaw(c::Matrix, x::Vector, plan) (call sites src/Extras/sample.jl:80,94): column j of the
+ * N x P column-major matrix C (leading dimension ld >= N) evaluated at x[j]. */
+int32_t afb_clenshaw_cheb_cols(const double* C, int64_t N, int64_t ld, const double* x, double* y, int64_t P);
+int32_t afb_clenshaw_cheb_cols_device(const double* d_C, int64_t N, int64_t ld, const double* d_x, double* d_y,
+                                      int64_t P, void* stream);
+/* Replaces evaluate.(f.A, ry') (src/Extras/sample.jl:208): each of the M columns of C (N x M column-major)
+ * at each of the P points; Y is M x P column-major, Y[m + M*i] = f_m(x[i]). */
+int32_t afb_clenshaw_cheb_multi(const double* C, int64_t N, int64_t M, const double* x, double* Y, int64_t P);
+int32_t afb_clenshaw_cheb_multi_device(const double* d_C, int64_t N, int64_t M, const double* d_x, double* d_Y,
+                                       int64_t P, void* stream);
+
+/* ---- sampling -----------------------------------------------------------------------------------------
+ * Replaces chebnormalizedcumsum!(f) (src/Extras/sample.jl:170-175 = ultraconversion!, ultraint!,
+ * subtract_zeroatleft!, multiply_oneatright!), in place on ncols columns of length N (leading dimension
+ * ld).  grow != 0: Vector semantics, each column gains one coefficient (needs ld >= N+1);
+ * grow == 0: Matrix semantics, the top term is dropped. */
+int32_t afb_cheb_normcumsum(double* C, int64_t N, int64_t ncols, int64_t ld, int32_t grow);
+int32_t afb_cheb_normcumsum_device(double* d_C, int64_t N, int64_t ncols, int64_t ld, int32_t grow, void* stream);
+/* Replaces chebbisectioninv(c::Vector, u::Vector[, plan]) (src/Extras/sample.jl:55-75): numits (47)
+ * Clenshaw bisections on [-1,1] per entry of u; returns the final midpoint (canonical variable). */
+int32_t afb_cheb_bisect(const double* c, int64_t N, const double* u, double* out, int64_t P, int32_t numits);
+int32_t afb_cheb_bisect_device(const double* d_c, int64_t N, const double* d_u, double* d_out, int64_t P,
+                               int32_t numits, double a, double b, void* stream);
+/* Replaces chebbisectioninv(c::Matrix, u::Vector[, plan]) (src/Extras/sample.jl:79-101). */
+int32_t afb_cheb_bisect_cols(const double* C, int64_t N, int64_t ld, const double* u, double* out, int64_t P,
+                             int32_t numits);
+int32_t afb_cheb_bisect_cols_device(const double* d_C, int64_t N, int64_t ld, const double* d_u, double* d_out,
+                                    int64_t P, int32_t numits, void* stream);
+/* Replaces bisectioninv(cf::Fun{<:Chebyshev,Float64}, u::Vector) (src/Extras/sample.jl:103-109):
+ * fromcanonical.(a..b, chebbisectioninv(cdf_c, u)) with caller-supplied uniforms (`samplecdf`,
+ * src/Extras/sample.jl:184 with rand(n) provided by the caller). */
+int32_t afb_samplecdf_cheb(const double* cdf_c, int64_t N, double a, double b, const double* u, double* out,
+                           int64_t P);
+/* Throughput variant of sample(f, n) (src/Extras/sample.jl:182): uniforms come from an on-device
+ * counter-based generator (Philox4x32-10, stream `seed`, counter offset `offset`); output on device. */
+int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, double b, uint64_t seed,
+                               uint64_t offset, double* d_out, int64_t P, void* stream);
+/* the uniforms afb_sample_cheb_device draws, for parity checks */
+int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
+
+/* ---- multi-GPU 2D transform (one process per GPU) ----------------------------------------------------
+ * The n x n2 matrix is sharded by contiguous column blocks; the plan performs local column transforms,
+ * an all-to-all transpose over NVLink, and local transforms of the other factor.  The caller supplies
+ * an NCCL unique id (128 bytes, broadcast by the host layer) -- see DESIGN.md. */
+int32_t afb_comm_unique_id(void* id128);
+int32_t afb_comm_create(const void* id128, int32_t rank, int32_t world);
+int32_t afb_comm_destroy(void);
+/* kind = AFB_CHEB1_2D_FWD / _INV; n and n2 must be multiples of the world size.
+ * d_in : this rank's column block (column-major n x n2/world)
+ * d_out: this rank's block of rows of the result, as n/world contiguous lines of length n2 */
+int32_t afb_sharded2d_create(void** handle, int32_t kind, int64_t n, int64_t n2);
+int32_t afb_sharded2d_execute_device(void* handle, const double* d_in, double* d_out, void* stream);
+int32_t afb_sharded2d_destroy(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APPROXFUN_B200_H */

@@ -1,0 +1,147 @@
+"""CPU-side unit tests of the CUDA kernel sources through the fiber emulator (tests/emu).
+
+The emulator compiles the very same .cu files with g++ and runs every CUDA thread as a fiber; it is
+a debugging aid for index arithmetic (this container has no GPU) and is not part of the product:
+the shipped library is nvcc-built only and the `-m gpu` tests are the parity tests proper."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import approxfun_oracle as orc
+from oracle import oracle_c as orcc
+from tests.emu_harness import emu_lowlevel
+
+B, ll = emu_lowlevel()
+RNG = np.random.default_rng(1234)
+
+
+def tol(n, scale):
+    return 1e-13 * scale * max(1.0, math.log2(max(n, 2)))
+
+
+REAL_KINDS = [
+    (B.CHEB1_FWD, lambda v: orc.cheb_transform(v, axis=0)),
+    (B.CHEB1_INV, lambda v: orc.cheb_itransform(v, axis=0)),
+    (B.FOURIER_FWD, lambda v: orc.fourier_transform(v, axis=0)),
+    (B.FOURIER_INV, lambda v: orc.fourier_itransform(v, axis=0)),
+]
+CPLX_KINDS = [
+    (B.LAURENT_FWD, lambda v: orc.laurent_transform(v, axis=0)),
+    (B.LAURENT_INV, lambda v: orc.laurent_itransform(v, axis=0)),
+]
+
+# direct (<=32), line (pow2 64..16384), generic Bluestein (odd sizes), generic four-step (2^15)
+SIZES = [1, 2, 3, 4, 5, 7, 8, 16, 17, 31, 32, 33, 50, 64, 100, 127, 128, 256, 500, 512, 1024, 2048, 4096, 8192,
+         16384, 32768]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_real_transforms(n):
+    nb = 3 if n <= 4096 else 1
+    v = RNG.standard_normal((n, nb))
+    for kind, ref in REAL_KINDS:
+        want = ref(v)
+        got = ll.transform(kind, v)
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
+
+
+@pytest.mark.parametrize("n", SIZES[:-2] + [16384])
+def test_complex_transforms(n):
+    nb = 2 if n <= 4096 else 1
+    v = RNG.standard_normal((n, nb)) + 1j * RNG.standard_normal((n, nb))
+    for kind, ref in CPLX_KINDS:
+        want = ref(v)
+        got = ll.transform(kind, v)
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
+
+
+def test_empty_and_vector_shapes():
+    assert ll.transform(B.CHEB1_FWD, np.zeros(0)).shape == (0,)
+    assert ll.transform(B.CHEB1_FWD, np.zeros((8, 0))).shape == (8, 0)
+    v = RNG.standard_normal(64)
+    assert np.allclose(ll.transform(B.CHEB1_FWD, v), orc.cheb_transform(v), atol=1e-14)
+
+
+def test_batch_not_multiple_of_lines_per_cta():
+    v = RNG.standard_normal((64, 7))  # 4 lines per CTA for N=32
+    assert np.allclose(ll.transform(B.CHEB1_FWD, v), orc.cheb_transform(v, axis=0), atol=1e-14)
+    assert np.allclose(ll.transform(B.FOURIER_INV, v), orc.fourier_itransform(v, axis=0), atol=1e-13)
+
+
+def test_strided_plan_and_inplace():
+    n, nb, stride = 128, 5, 160
+    buf = RNG.standard_normal((nb, stride))
+    want = orc.cheb_transform(buf[:, :n].T, axis=0).T
+    h = ll.plan_create(B.CHEB1_FWD, n, 0, nb, stride)
+    work = buf.copy()
+    ll.plan_execute_host(h, work, work)
+    ll.plan_destroy(h)
+    assert np.max(np.abs(work[:, :n] - want)) < 1e-14
+    assert np.array_equal(work[:, n:], buf[:, n:])  # gaps untouched
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (64, 128), (100, 36), (256, 64)])
+def test_tensor2d(shape):
+    V = RNG.standard_normal(shape)
+    got = ll.transform2d(B.CHEB1_2D_FWD, V)
+    want = orc.cheb2_transform(V)
+    assert np.max(np.abs(got - want)) < 1e-13
+    back = ll.transform2d(B.CHEB1_2D_INV, got)
+    assert np.max(np.abs(back - V)) < 1e-12
+
+
+def test_points():
+    for n in (1, 2, 5, 64, 1000):
+        x = ll.chebpoints(n)
+        want = orc.chebpoints_canonical(n)
+        assert np.all(np.diff(x) < 0) or n == 1
+        assert np.max(np.abs(x - want)) <= 2.3e-16
+        assert np.array_equal(ll.chebpoints(n, 0.0, 10.0), orc.fromcanonical(0.0, 10.0, x))
+    assert np.allclose(ll.fourierpoints(8), orc.fourierpoints(8), atol=0)
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 3, 4, 5, 66, 1000, 12288, 12289, 30001])
+def test_clenshaw_bit_exact(N):
+    c = RNG.standard_normal(N) / (1 + np.arange(N)) ** 1.5
+    P = 700 if N < 10000 else 9
+    x = RNG.uniform(-1, 1, P)
+    x[:2] = [-1.0, 1.0]
+    assert np.array_equal(ll.clenshaw(c, x), orcc.clenshaw(c, x))
+
+
+def test_clenshaw_tile_boundaries():
+    c = RNG.standard_normal(9)
+    for P in (0, 1, 511, 512, 2047, 2048, 2049, 5000):
+        x = RNG.uniform(-1, 1, P)
+        assert np.array_equal(ll.clenshaw(c, x), orcc.clenshaw(c, x))
+
+
+def test_clenshaw_cols_and_multi():
+    for N, P in [(0, 5), (1, 5), (7, 130), (300, 3)]:
+        Cm = RNG.standard_normal((N, P))
+        x = RNG.uniform(-1, 1, P)
+        assert np.array_equal(ll.clenshaw_cols(Cm, x), orcc.clenshaw_cols(Cm, x) if N else np.zeros(P))
+    Cm = RNG.standard_normal((9, 4))
+    x = RNG.uniform(-1, 1, 300)
+    assert np.array_equal(ll.clenshaw_multi(Cm, x), orcc.clenshaw_multi(Cm, x))
+    with pytest.raises(B.DimensionMismatch):
+        ll.clenshaw_cols(RNG.standard_normal((4, 6)), np.zeros(5))  # src/Extras/sample.jl:85
+
+
+def test_normcumsum_and_bisection_bit_exact():
+    for N in (1, 2, 3, 4, 9, 66):
+        c = np.abs(RNG.standard_normal(N)) / (1 + np.arange(N)) ** 2
+        c[0] += 2.0
+        cf = ll.cheb_normcumsum(c)
+        assert np.array_equal(cf, orcc.cheb_normcumsum(c))
+        u = RNG.random(600)
+        assert np.array_equal(ll.cheb_bisect(cf, u), orcc.cheb_bisect(cf, u))
+        assert np.array_equal(ll.samplecdf(cf, -5.0, 5.0, u), orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, u)))
+    M = np.abs(RNG.standard_normal((9, 140))) / (1 + np.arange(9))[:, None] ** 2
+    M[0] += 2
+    gm = ll.cheb_normcumsum(M)
+    assert np.array_equal(gm, orcc.cheb_normcumsum(M))
+    u = RNG.random(140)
+    assert np.array_equal(ll.cheb_bisect_cols(gm, u), orcc.cheb_bisect_cols(gm, u))
