@@ -1,0 +1,427 @@
+"""Host-side mirror of the ApproxFun API for the transform / evaluate / sample path.
+
+Same names, argument meaning and error behaviour as the reference (file:line under /root/reference):
+`plan_transform` / `plan_itransform` / `plan*v` (NEWS.md:90, src/ApproxFun.jl:22-23), `transform`,
+`itransform`, `points` (NEWS.md:92), `Fun(f, space, n)`, `coefficients`, `values`
+(docs/src/faq.md:14-17, ext/ApproxFunDualNumbersExt.jl:79-82), `clenshaw`, `ClenshawPlan`
+(src/ApproxFun.jl:26), `bisectioninv`, `chebbisectioninv`, `chebnormalizedcumsum`, `normalizedcumsum`,
+`samplecdf`, `sample` (src/Extras/sample.jl).  All arithmetic on the hot path runs in
+libapproxfun_b200.so on the GPU; this layer only orchestrates (as the Julia layer does upstream).
+
+Julia is not available in this image, so this Python layer is what the parity tests drive; the Julia
+binding a maintainer would add is julia/ApproxFunB200.jl.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+_ll = None
+
+
+def lowlevel() -> L.LowLevel:
+    global _ll
+    if _ll is None:
+        lib = L.load()
+        L.check(lib, lib.afb_init(-1))
+        _ll = L.LowLevel(lib)
+    return _ll
+
+
+# ------------------------------------------------------------------------------------------------------
+# spaces
+# ------------------------------------------------------------------------------------------------------
+class Space:
+    pass
+
+
+class Chebyshev(Space):
+    """`Chebyshev(a..b)`; canonical domain -1..1."""
+
+    def __init__(self, a: float = -1.0, b: float = 1.0):
+        self.a, self.b = float(a), float(b)
+
+    def __repr__(self):
+        return f"Chebyshev({self.a}..{self.b})"
+
+    def fromcanonical(self, x):
+        return (self.a + self.b) / 2.0 + (self.b - self.a) * np.asarray(x, dtype=np.float64) / 2.0
+
+    def tocanonical(self, x):
+        return (2.0 * np.asarray(x, dtype=np.float64) - self.a - self.b) / (self.b - self.a)
+
+    def __pow__(self, k):
+        if k != 2:
+            raise ValueError("only Chebyshev()^2 is supported")
+        return TensorSpace(self, self)
+
+    def __mul__(self, other):
+        return TensorSpace(self, other)
+
+
+class Fourier(Space):
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
+class Laurent(Space):
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
+class TensorSpace(Space):
+    def __init__(self, s1: Chebyshev, s2: Chebyshev):
+        if not (isinstance(s1, Chebyshev) and isinstance(s2, Chebyshev)):
+            raise TypeError("TensorSpace: only Chebyshev (x) Chebyshev has a GPU path")
+        self.factors = (s1, s2)
+
+
+_FWD = {Chebyshev: L.CHEB1_FWD, Fourier: L.FOURIER_FWD, Laurent: L.LAURENT_FWD, TensorSpace: L.CHEB1_2D_FWD}
+_INV = {Chebyshev: L.CHEB1_INV, Fourier: L.FOURIER_INV, Laurent: L.LAURENT_INV, TensorSpace: L.CHEB1_2D_INV}
+
+
+def points(space: Space, n: int, m: int | None = None):
+    """`points(space, n)`; for a TensorSpace `points(sp, N, M)` returns the two 1-D grids."""
+    ll = lowlevel()
+    if isinstance(space, Chebyshev):
+        return ll.chebpoints(n, space.a, space.b)
+    if isinstance(space, (Fourier, Laurent)):
+        return ll.fourierpoints(n, space.a, space.b)
+    if isinstance(space, TensorSpace):
+        return points(space.factors[0], n), points(space.factors[1], n if m is None else m)
+    raise TypeError(space)
+
+
+# ------------------------------------------------------------------------------------------------------
+# plans:  plan = plan_transform(S, v_or_n);  coefficients = plan * v
+# ------------------------------------------------------------------------------------------------------
+class TransformPlan:
+    """`TransformPlan` / `ITransformPlan`: owns a C-ABI plan handle; `plan * v` executes it."""
+
+    inverse = False
+
+    def __init__(self, space: Space, shape):
+        self.space = space
+        self.shape = tuple(int(s) for s in shape)
+        self._ll = lowlevel()
+        table = _INV if self.inverse else _FWD
+        self.kind = table[type(space)]
+        if isinstance(space, TensorSpace):
+            if len(self.shape) != 2:
+                raise L.DimensionMismatch(L.AFB_BAD_SIZE, "TensorSpace plans take an n x m matrix")
+            n, n2 = self.shape
+            self._h = self._ll.plan_create(self.kind, n, n2, 1, n)
+        else:
+            n = self.shape[0]
+            batch = int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
+            self._h = self._ll.plan_create(self.kind, n, 0, batch, n)
+        self.dtype = np.complex128 if isinstance(space, Laurent) else np.float64
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None:
+            try:
+                self._ll.plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __mul__(self, v):
+        v = np.asarray(v)
+        if v.shape != self.shape:
+            raise L.DimensionMismatch(L.AFB_BAD_SIZE, f"plan built for shape {self.shape}, got {v.shape}")
+        if np.iscomplexobj(v) and self.dtype == np.float64:
+            # linear: transform real and imaginary parts separately (what the reference does for Dual/complex)
+            return (self * v.real) + 1j * (self * v.imag)
+        if v.size == 0:
+            return v.astype(self.dtype)
+        a = np.asarray(v, dtype=self.dtype)
+        buf = np.ascontiguousarray(a.T) if a.ndim > 1 else np.ascontiguousarray(a)
+        out = np.empty_like(buf)
+        self._ll.plan_execute_host(self._h, buf, out)
+        return np.ascontiguousarray(out.T) if a.ndim > 1 else out
+
+    @property
+    def launches(self) -> int:
+        return self._ll.plan_launches(self._h)
+
+
+class ITransformPlan(TransformPlan):
+    inverse = True
+
+
+def _shape_of(v_or_n):
+    if isinstance(v_or_n, (int, np.integer)):
+        return (int(v_or_n),)
+    if isinstance(v_or_n, tuple):
+        return v_or_n
+    return np.asarray(v_or_n).shape
+
+
+def plan_transform(space: Space, v_or_n) -> TransformPlan:
+    return TransformPlan(space, _shape_of(v_or_n))
+
+
+def plan_itransform(space: Space, v_or_n) -> ITransformPlan:
+    return ITransformPlan(space, _shape_of(v_or_n))
+
+
+def transform(space: Space, v):
+    """`transform(S, vals) = plan_transform(S, vals) * vals`."""
+    return plan_transform(space, v) * v
+
+
+def itransform(space: Space, c):
+    return plan_itransform(space, c) * c
+
+
+# ------------------------------------------------------------------------------------------------------
+# Clenshaw
+# ------------------------------------------------------------------------------------------------------
+class ClenshawPlan:
+    """`ClenshawPlan(Float64, Chebyshev(), N, n)`: kept for signature parity; the GPU kernel needs no
+    host work vectors, and unlike the reference the result never aliases plan storage."""
+
+    def __init__(self, T=np.float64, space: Space | None = None, N: int = 0, n: int = 0):
+        self.space = space if space is not None else Chebyshev()
+        self.N, self.n = int(N), int(n)
+
+
+def clenshaw(*args):
+    """`clenshaw(sp::Chebyshev, c, x)` (x scalar or vector, canonical variable) or
+    `clenshaw(c, x, plan::ClenshawPlan)` with c a vector (all points) or an N x n matrix (column j at x[j])."""
+    if isinstance(args[0], Space):
+        _, c, x = args
+    else:
+        c, x = args[0], args[1]
+    ll = lowlevel()
+    c = np.asarray(c, dtype=np.float64)
+    scalar = np.ndim(x) == 0
+    xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    if c.ndim == 2:
+        if c.shape[1] != xv.size:
+            raise L.DimensionMismatch(L.AFB_BAD_SIZE, "clenshaw(c::Matrix, x): size(c,2) != length(x)")
+        y = ll.clenshaw_cols(c, xv)
+    else:
+        y = ll.clenshaw(c, xv.ravel()).reshape(xv.shape)
+    return float(y[0]) if scalar else y
+
+
+# ------------------------------------------------------------------------------------------------------
+# Fun
+# ------------------------------------------------------------------------------------------------------
+class Fun:
+    """`Fun(f, space, n)`, `Fun(space, coefficients)`, adaptive `Fun(f, space)`; `f(x)` evaluates."""
+
+    def __init__(self, *args):
+        if len(args) == 2 and isinstance(args[0], Space):
+            self.space, self.coefficients = args[0], np.array(args[1], dtype=np.float64 if not isinstance(args[0], Laurent) else np.complex128)
+        elif len(args) == 3:
+            f, space, n = args
+            self.space = space
+            if isinstance(space, TensorSpace):
+                n1, n2 = (n, n) if isinstance(n, (int, np.integer)) else n
+                x, y = points(space, n1, n2)
+                self.coefficients = transform(space, f(x[:, None], y[None, :]))
+            else:
+                self.coefficients = transform(space, np.asarray(f(points(space, int(n)))))
+        elif len(args) == 2 and callable(args[0]):
+            f, space = args
+            self.space = space
+            self.coefficients = _adaptive(f, space)
+        else:
+            raise TypeError("Fun(f, space, n) | Fun(f, space) | Fun(space, coefficients)")
+
+    def __call__(self, x, y=None):
+        sp = self.space
+        if isinstance(sp, Chebyshev):
+            xa = np.asarray(x, dtype=np.float64)
+            if np.any(xa < min(sp.a, sp.b)) or np.any(xa > max(sp.a, sp.b)):
+                # the reference returns zero outside the domain
+                inside = (xa >= min(sp.a, sp.b)) & (xa <= max(sp.a, sp.b))
+                res = np.zeros_like(xa)
+                if np.any(inside):
+                    res[inside] = clenshaw(sp, self.coefficients, sp.tocanonical(xa[inside]))
+                return res
+            return clenshaw(sp, self.coefficients, sp.tocanonical(x))
+        if isinstance(sp, TensorSpace):
+            s1, s2 = sp.factors
+            Cm = self.coefficients  # C[i, j] T_i(x) T_j(y)
+            # contract y first: columns of C^T are series in y
+            ty = lowlevel().clenshaw_multi(np.ascontiguousarray(Cm.T), np.atleast_1d(s2.tocanonical(y)))  # (n1, P)
+            xs = np.atleast_1d(s1.tocanonical(x))
+            out = lowlevel().clenshaw_cols(ty, xs)
+            return float(out[0]) if np.ndim(x) == 0 else out
+        raise NotImplementedError("evaluation is GPU-accelerated for Chebyshev spaces only")
+
+    def __len__(self):
+        return len(self.coefficients)
+
+
+def coefficients(f: Fun):
+    return f.coefficients
+
+
+def ncoefficients(f: Fun) -> int:
+    return len(f.coefficients)
+
+
+def space(f: Fun) -> Space:
+    return f.space
+
+
+def values(f: Fun):
+    """`values(f) = itransform(space(f), coefficients(f))` (src/Plot/Plot.jl:20, test/ExtrasTest.jl:61)."""
+    return itransform(f.space, f.coefficients)
+
+
+def _adaptive(f, sp: Space):
+    """Adaptive constructor ladder n = 2^4 .. 2^20, then 2^21 (in-tree mirror ext/ApproxFunDualNumbersExt.jl:98-110)."""
+    if not isinstance(sp, Chebyshev):
+        raise NotImplementedError("adaptive construction: Chebyshev only")
+    tol = 20 * np.finfo(np.float64).eps
+    for logn in range(4, 21):
+        c = transform(sp, np.asarray(f(points(sp, 2 ** logn))))
+        mx = float(np.max(np.abs(c)))
+        if mx == 0.0:
+            return np.zeros(1)
+        if float(np.max(np.abs(c[-8:]))) < tol * mx:
+            nz = np.nonzero(np.abs(c) > tol * mx)[0]
+            return c[: nz[-1] + 1].copy()
+    return transform(sp, np.asarray(f(points(sp, 2 ** 21))))
+
+
+# ------------------------------------------------------------------------------------------------------
+# sampling (src/Extras/sample.jl)
+# ------------------------------------------------------------------------------------------------------
+def chebnormalizedcumsum(f, grow=None):
+    """`chebnormalizedcumsum!(f)` (sample.jl:170-175); returns the new array (vectors grow by one)."""
+    return lowlevel().cheb_normcumsum(f, grow)
+
+
+def chebbisectioninv(c, x, plan: ClenshawPlan | None = None, numits: int = 47):
+    """`chebbisectioninv(c, x[, plan])` for vector or matrix `c` (sample.jl:41-101)."""
+    ll = lowlevel()
+    c = np.asarray(c, dtype=np.float64)
+    scalar = np.ndim(x) == 0
+    xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    if c.ndim == 2:
+        if c.shape[1] != xv.size:
+            raise L.DimensionMismatch(L.AFB_BAD_SIZE, "chebbisectioninv: size(c)[2] == length(xl) violated (sample.jl:85)")
+        out = ll.cheb_bisect_cols(c, xv, numits)
+    else:
+        out = ll.cheb_bisect(c, xv, numits)
+    return float(out[0]) if scalar else out
+
+
+def cumsum(f: Fun) -> Fun:
+    """`cumsum(f::Fun{<:Chebyshev})` = integrate(f) - first(integrate(f)) (host: O(N) on a handful of numbers)."""
+    sp = f.space
+    c = np.asarray(f.coefficients, dtype=np.float64)
+    n = c.size
+    v = c.copy()
+    if n == 2:
+        v[1] /= 2
+    elif n > 2:
+        v[0] -= v[2] / 2
+        v[1:n - 2] = (v[1:n - 2] - v[3:n]) / 2
+        v[n - 2] /= 2
+        v[n - 1] /= 2
+    g = np.zeros(n + 1)
+    g[1:] = v / np.arange(1, n + 1)
+    g *= (sp.b - sp.a) / 2.0
+    sgn = np.where(np.arange(n + 1) % 2 == 0, 1.0, -1.0)
+    g[0] -= float(np.sum(sgn * g))
+    return Fun(sp, g)
+
+
+def normalizedcumsum(f: Fun) -> Fun:
+    """sample.jl:114-119: cf = cumsum(f); cf / last(cf)."""
+    cf = cumsum(f)
+    return Fun(cf.space, cf.coefficients / float(np.sum(cf.coefficients)))
+
+
+def bisectioninv(cf: Fun, x, numits: int = 47):
+    """sample.jl:103-109: fromcanonical.(space(cf), chebbisectioninv(coefficients(cf), x))."""
+    sp = cf.space
+    if not isinstance(sp, Chebyshev):
+        raise NotImplementedError("bisectioninv: the GPU path covers Fun{<:Chebyshev,Float64}")
+    scalar = np.ndim(x) == 0
+    xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    if numits == 47:
+        out = lowlevel().samplecdf(cf.coefficients, sp.a, sp.b, xv)
+    else:
+        out = sp.fromcanonical(chebbisectioninv(cf.coefficients, xv, numits=numits))
+    return float(out[0]) if scalar else out
+
+
+def samplecdf(cf: Fun, n: int, rng=None, uniforms=None):
+    """sample.jl:184: bisectioninv(cf, rand(n)).  `uniforms` replaces `rand(n)` for reproducible parity."""
+    if uniforms is None:
+        uniforms = (rng or np.random.default_rng()).random(n)
+    return bisectioninv(cf, np.asarray(uniforms, dtype=np.float64))
+
+
+def sample(f: Fun, n: int | None = None, rng=None, uniforms=None):
+    """sample.jl:182: samplecdf(normalizedcumsum(f), n); `sample(f)` returns one sample."""
+    one = n is None
+    out = samplecdf(normalizedcumsum(f), 1 if one else n, rng, uniforms)
+    return float(out[0]) if one else out
+
+
+# ------------------------------------------------------------------------------------------------------
+# device-resident use (torch tensors or raw pointers): what bench.py times
+# ------------------------------------------------------------------------------------------------------
+class DevicePlan:
+    """Plan executed on device buffers: `execute(in_ptr, out_ptr, stream_ptr)` is asynchronous."""
+
+    def __init__(self, kind: int, n: int, n2: int = 0, batch: int = 1, stride: int | None = None):
+        self._ll = lowlevel()
+        self._h = self._ll.plan_create(kind, n, n2, batch, stride)
+        self.kind, self.n, self.n2, self.batch = kind, n, n2, batch
+
+    def execute(self, in_ptr: int, out_ptr: int, stream: int = 0):
+        lib = self._ll.lib
+        L.check(lib, lib.afb_plan_execute_device(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def execute_host(self, src: np.ndarray, dst: np.ndarray):
+        self._ll.plan_execute_host(self._h, src, dst)
+
+    @property
+    def launches(self) -> int:
+        return self._ll.plan_launches(self._h)
+
+    def close(self):
+        if self._h is not None:
+            self._ll.plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def clenshaw_device(c_ptr: int, N: int, x_ptr: int, y_ptr: int, P: int, stream: int = 0):
+    lib = lowlevel().lib
+    L.check(lib, lib.afb_clenshaw_cheb_device(C.c_void_p(c_ptr), N, C.c_void_p(x_ptr), C.c_void_p(y_ptr), P, C.c_void_p(stream)))
+
+
+def sample_device(cdf_ptr: int, N: int, a: float, b: float, seed: int, offset: int, out_ptr: int, P: int, stream: int = 0):
+    lib = lowlevel().lib
+    L.check(lib, lib.afb_sample_cheb_device(C.c_void_p(cdf_ptr), N, a, b, seed, offset, C.c_void_p(out_ptr), P, C.c_void_p(stream)))
+
+
+def bisect_device(c_ptr: int, N: int, u_ptr: int, out_ptr: int, P: int, a: float = -1.0, b: float = 1.0, numits: int = 47, stream: int = 0):
+    lib = lowlevel().lib
+    L.check(lib, lib.afb_cheb_bisect_device(C.c_void_p(c_ptr), N, C.c_void_p(u_ptr), C.c_void_p(out_ptr), P, numits, a, b, C.c_void_p(stream)))
+
+
+def philox_device(seed: int, offset: int, out_ptr: int, P: int, stream: int = 0):
+    lib = lowlevel().lib
+    L.check(lib, lib.afb_philox_uniform_device(seed, offset, C.c_void_p(out_ptr), P, C.c_void_p(stream)))

@@ -1,0 +1,91 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and fails loudly (AFB_NO_DEVICE) instead of falling back when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+
+    g.build()
+    import approxfun_b200 as af
+
+    return af
+
+
+def test_header_and_library_symbols_agree(built):
+    hdr = open(os.path.join(ROOT, "include", "approxfun_b200.h")).read()
+    declared = sorted(set(re.findall(r"^int32_t\s+(afb_\w+)\s*\(", hdr, flags=re.M)))
+    assert declared == sorted(built._lib.SYMBOLS)
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.afb_version() == 100
+
+
+def test_every_entry_point_cites_the_reference():
+    hdr = open(os.path.join(ROOT, "include", "approxfun_b200.h")).read()
+    for needle in ("src/Extras/sample.jl:55-75", "src/Extras/sample.jl:170-175", "src/Extras/fftGeneric.jl:47-54",
+                   "ext/ApproxFunDualNumbersExt.jl:10-12", "NEWS.md:92", "docs/src/usage/spaces.md:113-125"):
+        assert needle in hdr
+
+
+def test_no_cpu_fallback_without_device(built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = built._lib.load()
+    h = ctypes.c_void_p()
+    st = lib.afb_plan_create(ctypes.byref(h), built._lib.CHEB1_FWD, 64, 0, 1, 64, 0)
+    assert st == built._lib.AFB_NO_DEVICE
+    buf = ctypes.create_string_buffer(256)
+    assert lib.afb_last_error(buf, 256) == built._lib.AFB_NO_DEVICE
+    assert b"no CPU fallback" in buf.value
+    with pytest.raises(built.AfbError):
+        built.transform(built.Chebyshev(), np.zeros(64))
+    with pytest.raises(built.AfbError):
+        built.clenshaw(built.Chebyshev(), np.ones(3), 0.5)
+
+
+def test_argument_validation_needs_no_device(built):
+    lib = built._lib.load()
+    h = ctypes.c_void_p()
+    assert lib.afb_plan_create(None, 0, 8, 0, 1, 8, 0) == built._lib.AFB_BAD_ARG
+    assert lib.afb_plan_create(ctypes.byref(h), 99, 8, 0, 1, 8, 0) == built._lib.AFB_BAD_ARG
+    assert lib.afb_plan_create(ctypes.byref(h), 0, -1, 0, 1, 8, 0) == built._lib.AFB_BAD_SIZE
+    assert lib.afb_clenshaw_cheb(None, -1, None, None, 0) == built._lib.AFB_BAD_SIZE
+    assert lib.afb_cheb_bisect_cols(None, 4, 2, None, None, 3, 47) == built._lib.AFB_BAD_SIZE  # ld < N
+    out = np.empty(4)
+    assert lib.afb_fourierpoints(out.ctypes.data, 4, 0.0, 1.0) == 0
+    assert np.array_equal(out, [0, 0.25, 0.5, 0.75])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "approxfun.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "liboracle" not in txt and "libafb_emu" not in txt, f
+
+
+def test_golden_fixture_matches_oracle():
+    from oracle import approxfun_oracle as orc
+    from oracle import oracle_c as orcc
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    for n in (8, 64, 100, 4096):
+        assert np.max(np.abs(orc.cheb_transform(g[f"v_{n}"]) - g[f"cheb_fwd_{n}"])) < 1e-15
+        assert np.max(np.abs(orc.fourier_itransform(g[f"v_{n}"]) - g[f"fourier_inv_{n}"])) < 1e-13
+    assert np.array_equal(orcc.clenshaw(g["cl_c"], g["cl_x"]), g["cl_y"])
+    assert np.array_equal(orcc.cheb_bisect(g["bis_c"], g["bis_u"]), g["bis_x"])
+    assert np.array_equal(orcc.cheb_normcumsum(g["ncs_in"]), g["ncs_out"])

@@ -1,0 +1,268 @@
+"""Parity tests proper: the CUDA path (through the C ABI, ctypes) against the CPU oracle.  Needs a B200.
+
+Tolerances are BASELINE.json's: coefficients  max-abs <= 1e-13 * ||v||inf * log2(n);
+evaluations <= 1e-13 * ||f||inf (in fact bit-exact against the fma oracle); ordering exact."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import approxfun_oracle as orc  # noqa: E402
+from oracle import oracle_c as orcc  # noqa: E402
+
+EPS = np.finfo(np.float64).eps
+RNG = np.random.default_rng(2024)
+
+
+@pytest.fixture(scope="module")
+def af():
+    import approxfun_b200 as m
+
+    m.api.lowlevel()  # raises if the CUDA library or device is missing: no fallback
+    return m
+
+
+def coef_tol(n, v):
+    return 1e-13 * float(np.max(np.abs(v))) * max(1.0, math.log2(max(n, 2)))
+
+
+SIZES = [1, 2, 3, 5, 8, 16, 31, 32, 33, 64, 100, 128, 256, 500, 512, 1000, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_chebyshev_transform_pair(af, n):
+    nb = 4 if n <= 8192 else 2
+    v = RNG.standard_normal((n, nb))
+    S = af.Chebyshev()
+    c = af.plan_transform(S, v) * v
+    want = orc.cheb_transform(v, axis=0)
+    assert np.max(np.abs(c - want)) <= coef_tol(n, v)
+    vi = af.plan_itransform(S, v) * v
+    wanti = orc.cheb_itransform(v, axis=0)
+    assert np.max(np.abs(vi - wanti)) <= coef_tol(n, wanti)
+    back = af.itransform(S, c)
+    assert np.max(np.abs(back - v)) <= coef_tol(n, v)  # test/ExtrasTest.jl:61 identity
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_fourier_transform_pair(af, n):
+    nb = 3 if n <= 8192 else 1
+    v = RNG.standard_normal((n, nb))
+    S = af.Fourier()
+    c = af.transform(S, v)
+    assert np.max(np.abs(c - orc.fourier_transform(v, axis=0))) <= coef_tol(n, v)
+    if n <= 128:  # in-tree BigFloat twin, restated verbatim (src/Extras/fftGeneric.jl:47-54)
+        assert np.max(np.abs(c[:, 0] - orc.fourier_transform_generic(v[:, 0]))) <= coef_tol(n, v)
+    vi = af.itransform(S, v)
+    wanti = orc.fourier_itransform(v, axis=0)
+    assert np.max(np.abs(vi - wanti)) <= coef_tol(n, wanti)
+
+
+@pytest.mark.parametrize("n", SIZES[:-1])
+def test_laurent_transform_pair(af, n):
+    nb = 2 if n <= 8192 else 1
+    v = RNG.standard_normal((n, nb)) + 1j * RNG.standard_normal((n, nb))
+    S = af.Laurent()
+    c = af.transform(S, v)
+    assert np.max(np.abs(c - orc.laurent_transform(v, axis=0))) <= coef_tol(n, v)
+    vi = af.itransform(S, v)
+    wanti = orc.laurent_itransform(v, axis=0)
+    assert np.max(np.abs(vi - wanti)) <= coef_tol(n, wanti)
+
+
+def test_config1_sin_x2_2pow20(af):
+    # BASELINE.json configs[0]: transform + itransform of sin(x^2) on 0..10 at n = 2^20
+    n = 2 ** 20
+    S = af.Chebyshev(0, 10)
+    x = af.points(S, n)
+    xo = orc.chebpoints(n, 0.0, 10.0)
+    assert np.all(np.diff(x) < 0)                        # descending, NEWS.md:92
+    assert np.max(np.abs(x - xo)) <= 10 * 2.3e-16 * 10   # values to an ulp of the interval scale
+    v = np.sin(xo ** 2)
+    c = af.plan_transform(S, v) * v
+    assert np.max(np.abs(c - orc.cheb_transform(v))) <= 1e-13 * 20
+    back = af.plan_itransform(S, c) * c
+    assert np.max(np.abs(back - v)) <= 1e-13 * 20
+    f = af.Fun(S, c)
+    assert abs(f(0.1) - math.sin(0.01)) < 1000 * EPS      # test/ReadmeTest.jl:19-23
+
+
+def test_golden_fixture(af):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+    for n in (8, 64, 100, 4096):
+        v = g[f"v_{n}"]
+        assert np.max(np.abs(af.transform(af.Chebyshev(), v) - g[f"cheb_fwd_{n}"])) <= coef_tol(n, v)
+        assert np.max(np.abs(af.itransform(af.Chebyshev(), v) - g[f"cheb_inv_{n}"])) <= coef_tol(n, g[f"cheb_inv_{n}"])
+        assert np.max(np.abs(af.transform(af.Fourier(), v) - g[f"fourier_fwd_{n}"])) <= coef_tol(n, v)
+        assert np.max(np.abs(af.itransform(af.Fourier(), v) - g[f"fourier_inv_{n}"])) <= coef_tol(n, g[f"fourier_inv_{n}"])
+    assert np.array_equal(af.clenshaw(af.Chebyshev(), g["cl_c"], g["cl_x"]), g["cl_y"])
+    assert np.array_equal(af.chebbisectioninv(g["bis_c"], g["bis_u"]), g["bis_x"])
+    assert np.array_equal(af.chebnormalizedcumsum(g["ncs_in"]), g["ncs_out"])
+
+
+def test_doctest_orderings(af):
+    # docs/src/usage/spaces.md:94-98 and :121-125
+    th = orc.fourierpoints(5)
+    c = np.array([1.0, 2.0, 3.0, 4.0, 0.0])
+    assert np.allclose(af.itransform(af.Fourier(), c), 1 + 2 * np.sin(th) + 3 * np.cos(th) + 4 * np.sin(2 * th), atol=50 * EPS)
+    cl = np.array([1, 2, 3, 4, 0], dtype=complex)
+    want = 1 + 2 * np.exp(-1j * th) + 3 * np.exp(1j * th) + 4 * np.exp(-2j * th)
+    assert np.allclose(af.itransform(af.Laurent(), cl), want, atol=50 * EPS)
+    th = orc.fourierpoints(20)  # even-n Nyquist rule, fftGeneric.jl:53
+    c = af.transform(af.Fourier(), 5 * np.cos(10 * th))
+    assert abs(c[-1] + 5) < 50 * EPS
+
+
+def test_fun_exp_bessel_and_readme(af):
+    from scipy import special
+    f = af.Fun(np.exp, af.Chebyshev(), 32)
+    assert abs(f.coefficients[0] - special.iv(0, 1.0)) <= 2 * EPS
+    assert abs(f.coefficients[1] - 2 * special.iv(1, 1.0)) <= 4 * EPS
+    g = af.Fun(lambda x: np.sin(x * x), af.Chebyshev(0, 10))       # adaptive ladder
+    assert abs(g(0.1) - math.sin(0.01)) < 1000 * EPS               # test/ReadmeTest.jl:23
+    assert np.max(np.abs(af.transform(g.space, af.values(g)) - g.coefficients)) < 10 * EPS  # ExtrasTest.jl:61
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 3, 66, 1000, 10000, 12289, 40000])
+def test_clenshaw_bit_exact(af, N):
+    c = RNG.standard_normal(N) / (1 + np.arange(N)) ** 1.2
+    x = RNG.uniform(-1, 1, 100003)
+    x[:2] = [-1.0, 1.0]
+    got = af.clenshaw(af.Chebyshev(), c, x)
+    assert np.array_equal(got, orcc.clenshaw(c, x, threads=8))
+    if N == 66:
+        assert af.clenshaw(af.Chebyshev(), c, 0.3) == orcc.clenshaw(c, np.array([0.3]))[0]
+
+
+def test_clenshaw_config3_subsample(af):
+    # config 3 shape: N = 10^4 coefficients of a function that needs them; 10^6-point subsample
+    N = 10000
+    xs = orc.chebpoints_canonical(N)
+    c = orc.cheb_transform(np.sin(3000 * xs ** 2) + np.cos(977 * xs))
+    x = np.random.default_rng(0).uniform(-1, 1, 10 ** 6)
+    got = af.clenshaw(af.Chebyshev(), c, x)
+    want = orcc.clenshaw(c, x, threads=8)
+    assert np.array_equal(got, want)
+    truth = np.sin(3000 * x ** 2) + np.cos(977 * x)
+    assert np.max(np.abs(got - truth)) <= 1e-13 * 2 * 50   # interpolant accuracy, not parity
+
+
+def test_clenshaw_matrix_variants(af):
+    for N, P in [(0, 5), (1, 5), (7, 1000), (150, 257), (3000, 9)]:
+        Cm = RNG.standard_normal((N, P))
+        x = RNG.uniform(-1, 1, P)
+        want = orcc.clenshaw_cols(Cm, x) if N else np.zeros(P)
+        assert np.array_equal(af.clenshaw(Cm, x, af.ClenshawPlan(float, af.Chebyshev(), N, P)), want)
+    Cm = RNG.standard_normal((40, 6))
+    x = RNG.uniform(-1, 1, 5000)
+    assert np.array_equal(af.api.lowlevel().clenshaw_multi(Cm, x), orcc.clenshaw_multi(Cm, x))
+    with pytest.raises(af.DimensionMismatch):
+        af.clenshaw(RNG.standard_normal((4, 6)), np.zeros(5))
+
+
+def test_sampling_golden_and_parity(af):
+    # test/SamplingTest.jl:10-12
+    f = af.Fun(lambda x: np.exp(-x * x / 2), af.Chebyshev(-5, 5))
+    g = af.cumsum(f)
+    assert abs(g(af.bisectioninv(g, 0.5)) - 0.5) < 1e-12
+    # config 5 shape: f = exp(-x^2) on -5..5, caller-supplied uniforms, bit-exact against the oracle
+    f = af.Fun(lambda x: np.exp(-x * x), af.Chebyshev(-5, 5))
+    cf = af.normalizedcumsum(f)
+    assert np.max(np.abs(cf.coefficients - orc.normalizedcumsum(f.coefficients, -5.0, 5.0))) < 1e-15
+    u = np.random.default_rng(5).random(10 ** 6)
+    s = af.sample(f, u.size, uniforms=u)
+    want = orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf.coefficients, u, threads=8))
+    assert np.array_equal(s, want)
+    assert s.min() >= -5 and s.max() <= 5                      # test/PiecewiseSampleTest.jl:5-10 range check
+    from scipy import special
+    assert np.max(np.abs((1 + special.erf(s)) / 2 - u)) < 1e-12
+    assert len(af.sample(af.Fun(np.exp, af.Chebyshev()), 100000)) == 100000   # test/SampleTest.jl:5-7 smoke
+
+
+def test_normcumsum_and_matrix_bisection(af):
+    for N in (1, 2, 3, 4, 9, 66, 300):
+        c = np.abs(RNG.standard_normal(N)) / (1 + np.arange(N)) ** 2
+        c[0] += 2.0
+        assert np.array_equal(af.chebnormalizedcumsum(c), orcc.cheb_normcumsum(c))
+    M = np.abs(RNG.standard_normal((30, 5000))) / (1 + np.arange(30))[:, None] ** 2
+    M[0] += 2
+    gm = af.chebnormalizedcumsum(M)
+    assert np.array_equal(gm, orcc.cheb_normcumsum(M))
+    u = RNG.random(5000)
+    assert np.array_equal(af.chebbisectioninv(gm, u), orcc.cheb_bisect_cols(gm, u))
+    with pytest.raises(af.DimensionMismatch):                       # src/Extras/sample.jl:85
+        af.chebbisectioninv(gm, u[:10])
+
+
+def test_philox_device_sampler_matches_host_uniform_path(af):
+    import torch
+    f = af.Fun(lambda x: np.exp(-x * x), af.Chebyshev(-5, 5))
+    cf = af.normalizedcumsum(f).coefficients
+    P = 200000
+    d_c = torch.tensor(cf, device="cuda")
+    d_u = torch.empty(P, dtype=torch.float64, device="cuda")
+    d_s = torch.empty(P, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    af.api.philox_device(7, 1000, d_u.data_ptr(), P, st)
+    af.api.sample_device(d_c.data_ptr(), cf.size, -5.0, 5.0, 7, 1000, d_s.data_ptr(), P, st)
+    torch.cuda.synchronize()
+    u = d_u.cpu().numpy()
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    assert np.array_equal(d_s.cpu().numpy(), orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, u, threads=8)))
+
+
+def test_tensor_transform_and_sampling_golden(af):
+    # test/SamplingTest.jl:5-9 golden through the GPU 2-D transform + GPU Clenshaw
+    n = 96
+    a, b = -4.0, 4.0
+    S = af.Chebyshev(a, b)
+    x = af.points(S, n)
+    V = (x[:, None] - x[None, :]) ** 2 * np.exp(-x[:, None] ** 2 / 2 - x[None, :] ** 2 / 2)
+    Cm = af.transform(S ** 2, V)
+    assert np.max(np.abs(Cm - orc.cheb2_transform(V))) < 1e-13
+    w = orc.cheb_definite_integrals(n) * (b - a) / 2
+    marg = w @ Cm
+    total = float(marg @ w)
+    assert abs(af.Fun(S, marg)(0.1) / total - 0.2004758624973169) < 4 * EPS
+    V2 = RNG.standard_normal((300, 128))
+    C2 = af.transform(af.Chebyshev() ** 2, V2)
+    assert np.max(np.abs(C2 - orc.cheb2_transform(V2))) < 1e-13 * 4 * 9
+    assert np.max(np.abs(af.itransform(af.Chebyshev() ** 2, C2) - V2)) < 1e-12
+    F2 = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy), af.Chebyshev() ** 2, 32)
+    assert abs(F2(0.1, 0.2) - math.cos(0.5)) < 1e-13
+
+
+def test_config2_full_size_properties(af):
+    # BASELINE.json configs[1] at full size, device resident: round trip + linearity + column subsample vs oracle
+    import torch
+    n, B = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(0)
+    v = torch.randn(B, n, dtype=torch.float64, device="cuda", generator=g)
+    c = torch.empty_like(v)
+    st = torch.cuda.current_stream().cuda_stream
+    fwd = af.api.DevicePlan(af._lib.CHEB1_FWD, n, 0, B, n)
+    inv = af.api.DevicePlan(af._lib.CHEB1_INV, n, 0, B, n)
+    fwd.execute(v.data_ptr(), c.data_ptr(), st)
+    torch.cuda.synchronize()
+    idx = [0, 1, 4095, 32768, 65535]
+    want = orc.cheb_transform(v[idx].cpu().numpy().T, axis=0).T
+    vmax = float(v.abs().max())
+    assert np.max(np.abs(c[idx].cpu().numpy() - want)) <= 1e-13 * vmax * 12
+    # c_0 is the mean of every column: a size-independent checksum
+    assert float((c[:, 0] - v.mean(dim=1)).abs().max()) <= 1e-13 * vmax
+    back = torch.empty_like(v)
+    inv.execute(c.data_ptr(), back.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert float((back - v).abs().max()) <= 1e-13 * vmax * 12
+    # Fourier at full size: round trip
+    ff = af.api.DevicePlan(af._lib.FOURIER_FWD, n, 0, B, n)
+    fi = af.api.DevicePlan(af._lib.FOURIER_INV, n, 0, B, n)
+    ff.execute(v.data_ptr(), c.data_ptr(), st)
+    fi.execute(c.data_ptr(), back.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert float((back - v).abs().max()) <= 1e-13 * vmax * 12
+    wantf = orc.fourier_transform(v[idx].cpu().numpy().T, axis=0).T
+    assert np.max(np.abs(c[idx].cpu().numpy() - wantf)) <= 1e-13 * vmax * 12
