@@ -1,41 +1,54 @@
 // Shared-memory Stockham FFT core (complex FP64, power-of-two length N = 32 .. 8192).
 //
 // One "line" = one length-N complex transform, worked on by T = N / R1 threads that each hold
-// E = N / T complex values (16 for N >= 128) in registers.  A pass of radix R reads E values per
-// thread from the line's shared-memory buffer (stride N/R apart: conflict free), multiplies by the
-// pass twiddles, runs E/R register butterflies and scatters the results (autosort order) back.
-// The buffer is indexed through an XOR swizzle on 16-byte slots so that the first pass' scatter
-// (stride R1 slots between lanes) is conflict free as well.
+// E = R1 complex values (16 for N >= 64) in registers.  A pass of radix R reads E values per thread
+// from the line's shared-memory buffer (stride N/R apart: conflict free), multiplies by the pass
+// twiddles, runs E/R register butterflies and scatters the results (autosort order) back.  The buffer
+// is indexed through an XOR swizzle on 16-byte slots so that the first pass' scatter (stride R1 slots
+// between lanes) is conflict free as well.
 //
-// Twiddles: per pass one table load w = exp(-2 pi i k / (NS R)) per butterfly; the R-1 powers are
-// formed in registers with a depth-<=4 product tree (the FP64 pipe has slack, the L1/shared
-// datapath does not).
+// Two drivers share the butterfly-level primitives:
+//   DIT (forward kinds):  pass 1 from registers, ..., LAST pass leaves its outputs in registers.
+//        The radix lists end in a radix <= E/2, so a thread runs >= 2 butterflies in the last pass;
+//        they are assigned as partner pairs (j, NSL - j), which puts Z[k] and Z[N-k] in the SAME
+//        thread: the real-FFT split / DCT quarter-wave post-processing then runs in registers and
+//        goes straight to global memory (no shared-memory round trip for the post stage).
+//   DIF (inverse kinds):  the exact transpose (passes in reverse order, butterfly then twiddle, load and
+//        store patterns swapped), so the pre-processing of pairs (k, N-k) feeds the first pass from
+//        registers and the last pass leaves z[col + T r] in registers.
+//
+// Twiddles: per butterfly one table load w = exp(-2 pi i k / (NS R)); the R-1 powers are formed in
+// registers with a depth-<=4 product tree (the FP64 pipe has slack, the L1/shared datapath does not).
 #pragma once
 #include "afb_common.cuh"
 
 namespace afb {
 
-// ---- per-length configuration -------------------------------------------------------------------
+// ---- per-length configuration (DIT order) ---------------------------------------------------------
 template <int N> struct FftCfg;
-#define AFB_FFTCFG(N_, R1_, R2_, R3_, R4_)                          \
-    template <> struct FftCfg<N_> {                                   \
-        static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;  \
-        static constexpr int T = N_ / R1_;                            \
-        static constexpr int E = R1_;                                 \
-        static constexpr int SH = (R1_ == 16) ? 4 : 3;                \
+#define AFB_FFTCFG(N_, R1_, R2_, R3_, R4_)                                                       \
+    template <> struct FftCfg<N_> {                                                                \
+        static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;                               \
+        static constexpr int L = (R4_ > 1) ? 4 : (R3_ > 1) ? 3 : 2;                                \
+        static constexpr int T = N_ / R1_;                                                         \
+        static constexpr int E = R1_;                                                              \
+        static constexpr int SH = (R1_ == 16) ? 4 : 3;                                             \
+        static constexpr int RL = (L == 4) ? R4_ : (L == 3) ? R3_ : R2_; /* last radix */          \
+        static constexpr int NSL = N_ / RL;                               /* butterflies in last pass */ \
+        static constexpr int BL = E / RL;                                 /* ... per thread (even) */ \
     }
 AFB_FFTCFG(32, 8, 4, 1, 1);
-AFB_FFTCFG(64, 8, 8, 1, 1);
+AFB_FFTCFG(64, 16, 4, 1, 1);
 AFB_FFTCFG(128, 16, 8, 1, 1);
-AFB_FFTCFG(256, 16, 16, 1, 1);
+AFB_FFTCFG(256, 16, 8, 2, 1);
 AFB_FFTCFG(512, 16, 16, 2, 1);
 AFB_FFTCFG(1024, 16, 16, 4, 1);
 AFB_FFTCFG(2048, 16, 16, 8, 1);
-AFB_FFTCFG(4096, 16, 16, 16, 1);
+AFB_FFTCFG(4096, 16, 16, 8, 2);
 AFB_FFTCFG(8192, 16, 16, 16, 2);
 #undef AFB_FFTCFG
 
-// slots per line in shared memory (one pad slot for short lines packed many per CTA)
+// slots per line in shared memory (pad for short lines packed many per CTA)
 template <int N> struct FftLine {
     static constexpr int STRIDE = (N < 256) ? N + 8 : N;
 };
@@ -113,88 +126,147 @@ template <> struct Dft<16> {
 template <int R> __device__ __forceinline__ void apply_powers(cplx* x, cplx w) {
     if constexpr (R == 2) {
         x[1] = cmul(x[1], w);
-        return;
+    } else {
+        cplx p[R];
+        p[1] = w;
+#pragma unroll
+        for (int r = 2; r < R; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);  // depth <= log2 R
+#pragma unroll
+        for (int r = 1; r < R; ++r) x[r] = cmul(x[r], p[r]);
     }
-    cplx p[R];
-    p[1] = w;
-#pragma unroll
-    for (int r = 2; r < R; ++r) p[r] = cmul(p[r >> 1], p[r - (r >> 1)]);  // depth <= log2 R
-#pragma unroll
-    for (int r = 1; r < R; ++r) x[r] = cmul(x[r], p[r]);
 }
 
-// ---- one Stockham pass on a line -------------------------------------------------------------------
-// x[b*R + r]: butterfly b of this thread, element r.   j_b = t + b*T  in [0, N/R)
-template <int N, int T, int R, int SH>
-__device__ __forceinline__ void pass_load(const cplx* __restrict__ s, int t, cplx* x) {
-    constexpr int B = (N / R) / T;
+// ---- butterfly-level primitives.  Butterfly j of a pass (radix R, NS = product of earlier radices)
+//      reads line elements   j + r N/R        (r < R)         "strided" pattern
+//      writes line elements  (j-k) R + k + q NS, k = j mod NS  "autosort" pattern
+template <int N, int R, int SH>
+__device__ __forceinline__ void ld_strided(const cplx* __restrict__ s, int j, cplx* x) {
 #pragma unroll
-    for (int b = 0; b < B; ++b)
+    for (int r = 0; r < R; ++r) x[r] = s[swz<SH>(j + r * (N / R))];
+}
+template <int N, int R, int SH>
+__device__ __forceinline__ void st_strided(cplx* __restrict__ s, int j, const cplx* x) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[b * R + r] = s[swz<SH>(t + b * T + r * (N / R))];
+    for (int r = 0; r < R; ++r) s[swz<SH>(j + r * (N / R))] = x[r];
+}
+template <int N, int R, int NS, int SH>
+__device__ __forceinline__ void ld_autosort(const cplx* __restrict__ s, int j, cplx* x) {
+    const int k = j & (NS - 1);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; ++q) x[q] = s[swz<SH>(base + q * NS)];
+}
+template <int N, int R, int NS, int SH>
+__device__ __forceinline__ void st_autosort(cplx* __restrict__ s, int j, const cplx* x) {
+    const int k = j & (NS - 1);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; ++q) s[swz<SH>(base + q * NS)] = x[q];
+}
+// DIT butterfly: twiddle then DFT.   DIF (transposed) butterfly: DFT then twiddle.
+template <int N, int R, int NS>
+__device__ __forceinline__ void bfly_dit(int j, cplx* x, const cplx* __restrict__ tw) {
+    if constexpr (NS > 1) apply_powers<R>(x, ldg2(tw + (j & (NS - 1)) * (N / (NS * R))));
+    Dft<R>::run(x);
+}
+template <int N, int R, int NS>
+__device__ __forceinline__ void bfly_dif(int j, cplx* x, const cplx* __restrict__ tw) {
+    Dft<R>::run(x);
+    if constexpr (NS > 1) apply_powers<R>(x, ldg2(tw + (j & (NS - 1)) * (N / (NS * R))));
 }
 
-template <int N, int T, int R, int NS>
-__device__ __forceinline__ void pass_compute(int t, cplx* x, const cplx* __restrict__ tw) {
-    constexpr int B = (N / R) / T;
+// ---- full passes with the default butterfly assignment j = t + b T ----------------------------------
+template <int N, int R, int NS>
+__device__ __forceinline__ void pass_dit(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    constexpr int B = C::E / R;
+#pragma unroll
+    for (int b = 0; b < B; ++b) ld_strided<N, R, C::SH>(s, t + b * C::T, x + b * R);
+    __syncthreads();
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-        if constexpr (NS > 1) {
-            const int k = (t + b * T) & (NS - 1);
-            const cplx w = ldg2(tw + k * (N / (NS * R)));
-            apply_powers<R>(x + b * R, w);
-        }
-        Dft<R>::run(x + b * R);
+        bfly_dit<N, R, NS>(t + b * C::T, x + b * R, tw);
+        st_autosort<N, R, NS, C::SH>(s, t + b * C::T, x + b * R);
     }
+    __syncthreads();
 }
-
-template <int N, int T, int R, int NS, int SH>
-__device__ __forceinline__ void pass_store(cplx* __restrict__ s, int t, const cplx* x) {
-    constexpr int B = (N / R) / T;
+template <int N, int R, int NS>
+__device__ __forceinline__ void pass_dif(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    constexpr int B = C::E / R;
+#pragma unroll
+    for (int b = 0; b < B; ++b) ld_autosort<N, R, NS, C::SH>(s, t + b * C::T, x + b * R);
+    __syncthreads();
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-        const int j = t + b * T;
-        const int k = j & (NS - 1);
-        const int base = (j - k) * R + k;
-#pragma unroll
-        for (int q = 0; q < R; ++q) s[swz<SH>(base + q * NS)] = x[b * R + q];
+        bfly_dif<N, R, NS>(t + b * C::T, x + b * R, tw);
+        st_strided<N, R, C::SH>(s, t + b * C::T, x + b * R);
     }
+    __syncthreads();
 }
 
-// Full transform of one line.  On entry x[] holds this thread's first-pass inputs
-// (x[r] = input[t + T*r]); on exit the natural-order spectrum is in shared memory (swizzled slots)
-// and a __syncthreads() has been executed, so any thread may read any element.
+// ---- DIT driver pieces --------------------------------------------------------------------------------
+// first pass: x[r] = input[col + T r] in registers  ->  shared memory (column `col` is free to choose)
+template <int N>
+__device__ __forceinline__ void dit_first(cplx* __restrict__ s, int col, cplx* x) {
+    typedef FftCfg<N> C;
+    Dft<C::R1>::run(x);
+    st_autosort<N, C::R1, 1, C::SH>(s, col, x);
+    __syncthreads();
+}
+// passes 2 .. L-1
+template <int N>
+__device__ __forceinline__ void dit_middle(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    if constexpr (C::L >= 3) pass_dit<N, C::R2, C::R1>(s, t, x, tw);
+    if constexpr (C::L >= 4) pass_dit<N, C::R3, C::R1 * C::R2>(s, t, x, tw);
+}
+// last pass on butterfly j: outputs x[q] = Z[j + NSL q] stay in registers
+template <int N>
+__device__ __forceinline__ void dit_last_bfly(const cplx* __restrict__ s, int j, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    ld_strided<N, C::RL, C::SH>(s, j, x);
+    bfly_dit<N, C::RL, C::NSL>(j, x, tw);
+}
+// whole transform, result left in shared memory in natural order (generic users: Laurent, plain FFT)
 template <int N>
 __device__ __forceinline__ void fft_line(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
     typedef FftCfg<N> C;
-    constexpr int T = C::T, SH = C::SH;
-    pass_compute<N, T, C::R1, 1>(t, x, tw);
-    pass_store<N, T, C::R1, 1, SH>(s, t, x);
-    __syncthreads();
-    if constexpr (C::R2 > 1) {
-        pass_load<N, T, C::R2, SH>(s, t, x);
-        __syncthreads();
-        pass_compute<N, T, C::R2, C::R1>(t, x, tw);
-        pass_store<N, T, C::R2, C::R1, SH>(s, t, x);
-        __syncthreads();
-    }
-    if constexpr (C::R3 > 1) {
-        pass_load<N, T, C::R3, SH>(s, t, x);
-        __syncthreads();
-        pass_compute<N, T, C::R3, C::R1 * C::R2>(t, x, tw);
-        pass_store<N, T, C::R3, C::R1 * C::R2, SH>(s, t, x);
-        __syncthreads();
-    }
-    if constexpr (C::R4 > 1) {
-        pass_load<N, T, C::R4, SH>(s, t, x);
-        __syncthreads();
-        pass_compute<N, T, C::R4, C::R1 * C::R2 * C::R3>(t, x, tw);
-        pass_store<N, T, C::R4, C::R1 * C::R2 * C::R3, SH>(s, t, x);
-        __syncthreads();
-    }
+    dit_first<N>(s, t, x);
+    dit_middle<N>(s, t, x, tw);
+    pass_dit<N, C::RL, C::NSL>(s, t, x, tw);
 }
 
-// read element i of the finished (or pre-staged) line
+// ---- DIF driver pieces (transpose of the above) -----------------------------------------------------------
+// first executed = transposed last pass on butterfly j: x[q] = input[j + NSL q] from registers
+template <int N>
+__device__ __forceinline__ void dif_first_bfly(cplx* __restrict__ s, int j, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    bfly_dif<N, C::RL, C::NSL>(j, x, tw);
+    st_strided<N, C::RL, C::SH>(s, j, x);
+}
+template <int N>
+__device__ __forceinline__ void dif_middle(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
+    typedef FftCfg<N> C;
+    if constexpr (C::L >= 4) pass_dif<N, C::R3, C::R1 * C::R2>(s, t, x, tw);
+    if constexpr (C::L >= 3) pass_dif<N, C::R2, C::R1>(s, t, x, tw);
+}
+// final = transposed pass 1 on column col: outputs x[r] = result[col + T r] in registers
+template <int N>
+__device__ __forceinline__ void dif_last(const cplx* __restrict__ s, int col, cplx* x) {
+    typedef FftCfg<N> C;
+    ld_autosort<N, C::R1, 1, C::SH>(s, col, x);
+    Dft<C::R1>::run(x);
+}
+
+// partner pairs of the last DIT / first DIF pass: pair index pi in [0, NSL/2):
+//   pi >= 1: butterflies (pi, NSL - pi) ;  pi == 0: the two self-paired butterflies (0, NSL/2)
+template <int N> __device__ __forceinline__ int pair_lo(int pi) { return pi; }
+template <int N> __device__ __forceinline__ int pair_hi(int pi) {
+    return pi == 0 ? FftCfg<N>::NSL / 2 : FftCfg<N>::NSL - pi;
+}
+
+// read / write element i of a natural-order line
 template <int N> __device__ __forceinline__ cplx line_get(const cplx* s, int i) { return s[swz<FftCfg<N>::SH>(i)]; }
 template <int N> __device__ __forceinline__ void line_put(cplx* s, int i, cplx v) { s[swz<FftCfg<N>::SH>(i)] = v; }
 

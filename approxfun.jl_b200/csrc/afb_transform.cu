@@ -43,183 +43,326 @@ template <int N> struct LineGeom {
 };
 
 // =================================================================================================
-// load stages: fill x[r] = z[t + T r] (first-pass inputs).  PRE kinds stage through shared memory.
+// Lane-pair exchange between the permuted DCT layout and first-pass columns.
+//
+// Makhoul's permutation packs a quad of reals v[4q..4q+3] into two complex FFT inputs
+//     z[q] = (v[4q], v[4q+2])      z[N-1-q] = (v[4q+3], v[4q+1])            (q < N/2)
+// Threads (2a, 2a+1) own first-pass columns (a, T-1-a).  For quad q the even lane loads the 16-byte
+// chunk 2q and the odd lane chunk 2q+1 (fully coalesced 128-bit accesses); one 64-bit shuffle each way
+// then gives z[q] to the owner of column q mod T and z[N-1-q] to its partner.
 // =================================================================================================
+template <int N> struct PairMap {
+    typedef FftCfg<N> C;
+    // column owned by thread t of the line
+    static __device__ __forceinline__ int col(int t) { return (t & 1) ? C::T - 1 - (t >> 1) : (t >> 1); }
+};
+
+template <int N>
+__device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v2, bool act, int t, cplx* x) {
+    typedef FftCfg<N> C;
+    constexpr int H = C::R1 / 2;
+    const int role = t & 1, p2 = t >> 1;
+#pragma unroll
+    for (int qq = 0; qq < H; ++qq) {
+        cplx z[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            const int qcol = sg ? C::T - 1 - p2 : p2;
+            const int q = qcol + C::T * qq;
+            const int e = role ^ sg;
+            double2 ch = make_double2(0.0, 0.0);
+            if (act) ch = v2[2 * q + e];
+            const double send = e ? ch.x : ch.y;
+            const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            z[sg] = make_double2(e ? ch.y : ch.x, recv);
+        }
+        x[qq] = role ? z[1] : z[0];
+        x[C::R1 - 1 - qq] = role ? z[0] : z[1];
+    }
+}
+
+// x[r] = r-th FFT output of column col(t); writes v = [Re z, Im z] un-permuted with z = conj(r)
+template <int N>
+__device__ __forceinline__ void cheb_exchange_store(double2* __restrict__ v2, bool act, int t, const cplx* x) {
+    typedef FftCfg<N> C;
+    constexpr int H = C::R1 / 2;
+    const int role = t & 1, p2 = t >> 1;
+#pragma unroll
+    for (int qq = 0; qq < H; ++qq) {
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            const int qcol = sg ? C::T - 1 - p2 : p2;
+            const int q = qcol + C::T * qq;
+            const int e = role ^ sg;
+            const cplx mine = e ? x[C::R1 - 1 - qq] : x[qq];
+            const double recv = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+            // chunk 2q   (e = 0): (Re z[q],      Im z[N-1-q]) = ( a.x, -b.y)
+            // chunk 2q+1 (e = 1): (Im z[q],      Re z[N-1-q]) = (-a.y,  b.x)
+            const double2 out = e ? make_double2(-recv, mine.x) : make_double2(mine.x, -recv);
+            if (act) v2[2 * q + e] = out;
+        }
+    }
+}
+
+// =================================================================================================
+// paired last pass (DIT) / first pass (DIF): visits every unordered pair {k, N-k} exactly once with
+// both members in registers.  F provides  pair(k, A, B) for 1 <= k < N/2 (A <-> index k, B <-> N-k),
+// dc(Z0) and mid(Z_{N/2}).
+// =================================================================================================
+template <int N, class F>
+__device__ __forceinline__ void dit_last_paired(const cplx* __restrict__ s, int t, const cplx* __restrict__ tw, F& f) {
+    typedef FftCfg<N> C;
+    constexpr int RL = C::RL, NSL = C::NSL;
+#pragma unroll
+    for (int i = 0; i < C::BL / 2; ++i) {
+        const int pi = t + C::T * i;
+        cplx lo[RL], hi[RL];
+        dit_last_bfly<N>(s, pair_lo<N>(pi), lo, tw);
+        dit_last_bfly<N>(s, pair_hi<N>(pi), hi, tw);
+        if (pi != 0) {
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q]);
+                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q]);
+            }
+        } else {
+            f.dc(lo[0]);
+            f.mid(lo[RL / 2]);
+#pragma unroll
+            for (int q = 1; q < RL / 2; ++q) f.pair(NSL * q, lo[q], lo[RL - q]);
+#pragma unroll
+            for (int q = 0; q < RL / 2; ++q) f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q]);
+        }
+    }
+}
+
+template <int N, class F>
+__device__ __forceinline__ void dif_first_paired(cplx* __restrict__ s, int t, const cplx* __restrict__ tw, F& f) {
+    typedef FftCfg<N> C;
+    constexpr int RL = C::RL, NSL = C::NSL;
+#pragma unroll
+    for (int i = 0; i < C::BL / 2; ++i) {
+        const int pi = t + C::T * i;
+        cplx lo[RL], hi[RL];
+        if (pi != 0) {
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q]);
+                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q]);
+            }
+        } else {
+            f.dc(lo[0]);
+            f.mid(lo[RL / 2]);
+#pragma unroll
+            for (int q = 1; q < RL / 2; ++q) f.pair(NSL * q, lo[q], lo[RL - q]);
+#pragma unroll
+            for (int q = 0; q < RL / 2; ++q) f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q]);
+        }
+        dif_first_bfly<N>(s, pair_lo<N>(pi), lo, tw);
+        dif_first_bfly<N>(s, pair_hi<N>(pi), hi, tw);
+    }
+    __syncthreads();
+}
+
 template <int N, int KIND> struct LineOp;
 
 // ---- Chebyshev forward (DCT-II) -------------------------------------------------------------------
-template <int N> struct LineOp<N, LK_CHEB_FWD> {
-    typedef FftCfg<N> C;
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        const double* v = reinterpret_cast<const double*>(p.in) + line * p.istride;
-#pragma unroll
-        for (int r = 0; r < C::E; ++r) {
-            const int m = t + C::T * r;
-            double re = 0.0, im = 0.0;
-            if (act) {
-                if (m < N / 2) {
-                    re = v[4 * m];
-                    im = v[4 * m + 2];
-                } else {
-                    const int q = N - 1 - m;
-                    re = v[4 * q + 3];
-                    im = v[4 * q + 1];
-                }
-            }
-            x[r] = make_double2(re, im);
-        }
-    }
-    // aux[2k] = w^k / n, aux[2k+1] = -i w^(5k) / n,  w = exp(-i pi / (2n)),  k = 0..N/2
-    static __device__ __forceinline__ void store(const LineParams& p, int64_t line, bool act, int t, const cplx* s) {
-        if (!act) return;
+// aux[2k] = w^k / n, aux[2k+1] = -i w^(5k) / n,  w = exp(-i pi / (2n)),  k = 0..N/2 ; scale = 1/n
+template <int N> struct ChebFwdPost {
+    double* c;
+    const cplx* aux;
+    double scale;
+    bool act;
+    __device__ __forceinline__ void pair(int k, cplx A, cplx B) {
         constexpr int n = 2 * N;
-        double* c = reinterpret_cast<double*>(p.out) + line * p.ostride;
-        for (int k = 1 + t; k < N / 2; k += C::T) {
-            const cplx A = line_get<N>(s, k), B = line_get<N>(s, N - k);
-            const cplx S = make_double2(A.x + B.x, A.y - B.y);   // A + conj B
-            const cplx D = make_double2(A.x - B.x, A.y + B.y);   // A - conj B
-            const cplx U = cmul(S, ldg2(p.aux + 2 * k));
-            const cplx V = cmul(D, ldg2(p.aux + 2 * k + 1));
-            const cplx P = cadd(U, V), Q = csub(U, V);
+        const cplx S = make_double2(A.x + B.x, A.y - B.y);   // A + conj B
+        const cplx D = make_double2(A.x - B.x, A.y + B.y);   // A - conj B
+        const cplx U = cmul(S, ldg2(aux + 2 * k));
+        const cplx V = cmul(D, ldg2(aux + 2 * k + 1));
+        const cplx P = cadd(U, V), Q = csub(U, V);
+        if (act) {
             c[k] = P.x;
             c[n - k] = -P.y;
             c[N - k] = (Q.x - Q.y) * 0.70710678118654752440;
             c[N + k] = (Q.x + Q.y) * 0.70710678118654752440;
         }
-        if (t == 0) {
-            const cplx A = line_get<N>(s, 0);
-            c[0] = (A.x + A.y) * p.scale;                             // scale = 1/n
-            c[N] = (A.x - A.y) * (p.scale * 1.41421356237309504880);
-            const cplx M = line_get<N>(s, N / 2);
-            const cplx S = make_double2(2.0 * M.x, 0.0);
-            const cplx D = make_double2(0.0, 2.0 * M.y);
-            const cplx P = cadd(cmul(S, ldg2(p.aux + N)), cmul(D, ldg2(p.aux + N + 1)));
+    }
+    __device__ __forceinline__ void dc(cplx A) {
+        if (act) {
+            c[0] = (A.x + A.y) * scale;
+            c[N] = (A.x - A.y) * (scale * 1.41421356237309504880);
+        }
+    }
+    __device__ __forceinline__ void mid(cplx M) {
+        constexpr int n = 2 * N;
+        const cplx S = make_double2(2.0 * M.x, 0.0);
+        const cplx D = make_double2(0.0, 2.0 * M.y);
+        const cplx P = cadd(cmul(S, ldg2(aux + N)), cmul(D, ldg2(aux + N + 1)));
+        if (act) {
             c[N / 2] = P.x;
             c[n - N / 2] = -P.y;
         }
     }
 };
+template <int N> struct LineOp<N, LK_CHEB_FWD> {
+    typedef FftCfg<N> C;
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        const int64_t off = act ? line * p.istride : 0;
+        const double2* v2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + off);
+        cplx x[C::E];
+        cheb_exchange_load<N>(v2, act, t, x);
+        dit_first<N>(s, PairMap<N>::col(t), x);
+        dit_middle<N>(s, t, x, p.tw);
+        ChebFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.aux, p.scale, act};
+        dit_last_paired<N>(s, t, p.tw, f);
+    }
+};
 
 // ---- Chebyshev inverse (DCT-III) ------------------------------------------------------------------
+// aux[2k] = conj(w^k), aux[2k+1] = exp(+2 pi i k / n),  k = 0..N/2
+template <int N> struct ChebInvPre {
+    const double* c;
+    const cplx* aux;
+    bool act;
+    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK) {
+        constexpr int n = 2 * N;
+        const double h = 0.70710678118654752440;
+        double ck = 0, cnk = 0, cNk = 0, cNpk = 0;
+        if (act) { ck = c[k]; cnk = c[n - k]; cNk = c[N - k]; cNpk = c[N + k]; }
+        const cplx wk = ldg2(aux + 2 * k);                       // conj(w^k)
+        const cplx G = cmul(make_double2(ck, -cnk), wk);         // X_k / N
+        const cplx e = make_double2((wk.x + wk.y) * h, (wk.x - wk.y) * h);  // conj(w^(N-k))
+        const cplx H = cmul(make_double2(cNk, -cNpk), e);        // X_{N-k} / N
+        const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
+        const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
+        const cplx Xo = cmul(W, ldg2(aux + 2 * k + 1));
+        ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);            // conj(Z_k)     = conj(Xe) - i conj(Xo)
+        ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);            // conj(Z_{N-k}) = Xe - i Xo
+    }
+    __device__ __forceinline__ void dc(cplx& Z0) {
+        const double h = 0.70710678118654752440;
+        double c0 = 0, cN = 0;
+        if (act) { c0 = c[0]; cN = c[N]; }
+        Z0 = make_double2(c0 + cN * h, -(c0 - cN * h));
+    }
+    __device__ __forceinline__ void mid(cplx& ZM) {
+        cplx dummy;
+        pair(N / 2, ZM, dummy);
+    }
+};
 template <int N> struct LineOp<N, LK_CHEB_INV> {
     typedef FftCfg<N> C;
-    // aux[2k] = conj(w^k), aux[2k+1] = exp(+2 pi i k / n),  k = 0..N/2
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        constexpr int n = 2 * N;
-        const double* c = reinterpret_cast<const double*>(p.in) + line * p.istride;
-        const double h = 0.70710678118654752440;
-        for (int k = 1 + t; k <= N / 2; k += C::T) {
-            double ck = 0, cnk = 0, cNk = 0, cNpk = 0;
-            if (act) { ck = c[k]; cnk = c[n - k]; cNk = c[N - k]; cNpk = c[N + k]; }
-            const cplx wk = ldg2(p.aux + 2 * k);                       // conj(w^k)
-            const cplx G = cmul(make_double2(ck, -cnk), wk);           // X_k / N
-            // conj(w^(N-k)) = e^{i pi/4} w^k = e^{i pi/4} conj(wk)
-            const cplx e = make_double2((wk.x + wk.y) * h, (wk.x - wk.y) * h);
-            const cplx H = cmul(make_double2(cNk, -cNpk), e);          // X_{N-k} / N
-            const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
-            const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
-            const cplx Xo = cmul(W, ldg2(p.aux + 2 * k + 1));
-            // conj(Z_k) = conj(Xe) - i conj(Xo) ;  conj(Z_{N-k}) = Xe - i Xo
-            line_put<N>(s, k, make_double2(Xe.x - Xo.y, -Xe.y - Xo.x));
-            line_put<N>(s, N - k, make_double2(Xe.x + Xo.y, Xe.y - Xo.x));
-        }
-        if (t == 0) {
-            double c0 = 0, cN = 0;
-            if (act) { c0 = c[0]; cN = c[N]; }
-            const double a = c0 + cN * h, b = c0 - cN * h;
-            line_put<N>(s, 0, make_double2(a, -b));
-        }
-        __syncthreads();
-        pass_load<N, C::T, C::R1, C::SH>(s, t, x);
-        __syncthreads();
-    }
-    static __device__ __forceinline__ void store(const LineParams& p, int64_t line, bool act, int t, const cplx* s) {
-        if (!act) return;
-        double2* v2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + line * p.ostride);
-        for (int q = t; q < N / 2; q += C::T) {
-            const cplx zq = line_get<N>(s, q), zr = line_get<N>(s, N - 1 - q);
-            v2[2 * q] = make_double2(zq.x, -zr.y);
-            v2[2 * q + 1] = make_double2(-zq.y, zr.x);
-        }
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        ChebInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), p.aux, act};
+        dif_first_paired<N>(s, t, p.tw, f);
+        cplx x[C::E];
+        dif_middle<N>(s, t, x, p.tw);
+        dif_last<N>(s, PairMap<N>::col(t), x);
+        double2* v2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0));
+        cheb_exchange_store<N>(v2, act, t, x);
     }
 };
 
 // ---- Fourier forward --------------------------------------------------------------------------------
-template <int N> struct LineOp<N, LK_FOURIER_FWD> {
-    typedef FftCfg<N> C;
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        const double2* v2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + line * p.istride);
-#pragma unroll
-        for (int r = 0; r < C::E; ++r) x[r] = act ? v2[t + C::T * r] : make_double2(0.0, 0.0);
-    }
-    // aux[k] = -i exp(-2 pi i k / n) / n,  k = 0..N/2 ;  scale = 1/n
-    static __device__ __forceinline__ void store(const LineParams& p, int64_t line, bool act, int t, const cplx* s) {
-        if (!act) return;
-        constexpr int n = 2 * N;
-        double* c = reinterpret_cast<double*>(p.out) + line * p.ostride;
-        for (int k = 1 + t; k <= N / 2; k += C::T) {
-            const cplx A = line_get<N>(s, k), B = line_get<N>(s, N - k);
-            const cplx S = make_double2((A.x + B.x) * p.scale, (A.y - B.y) * p.scale);
-            const cplx D = make_double2(A.x - B.x, A.y + B.y);
-            const cplx G = cmul(D, ldg2(p.aux + k));
-            // (2/n) F_k = S + G ; (2/n) F_{N-k} = conj(S - G)
+// aux[k] = -i exp(-2 pi i k / n) / n,  k = 0..N/2 ;  scale = 1/n
+template <int N> struct FourierFwdPost {
+    double* c;
+    const cplx* aux;
+    double scale;
+    bool act;
+    __device__ __forceinline__ void pair(int k, cplx A, cplx B) {
+        const cplx S = make_double2((A.x + B.x) * scale, (A.y - B.y) * scale);
+        const cplx D = make_double2(A.x - B.x, A.y + B.y);
+        const cplx G = cmul(D, ldg2(aux + k));
+        if (act) {  // (2/n) F_k = S + G ; (2/n) F_{N-k} = conj(S - G)
             c[2 * k] = S.x + G.x;
             c[2 * k - 1] = -(S.y + G.y);
-            if (k != N / 2) {
-                c[2 * (N - k)] = S.x - G.x;
-                c[2 * (N - k) - 1] = S.y - G.y;
-            }
+            c[2 * (N - k)] = S.x - G.x;
+            c[2 * (N - k) - 1] = S.y - G.y;
         }
-        if (t == 0) {
-            const cplx A = line_get<N>(s, 0);
-            c[0] = (A.x + A.y) * p.scale;
-            c[n - 1] = -(A.x - A.y) * p.scale;
+    }
+    __device__ __forceinline__ void dc(cplx A) {
+        if (act) {
+            c[0] = (A.x + A.y) * scale;
+            c[2 * N - 1] = -(A.x - A.y) * scale;
         }
+    }
+    __device__ __forceinline__ void mid(cplx M) {
+        const cplx S = make_double2(2.0 * M.x * scale, 0.0);
+        const cplx D = make_double2(0.0, 2.0 * M.y);
+        const cplx G = cmul(D, ldg2(aux + N / 2));
+        if (act) {
+            c[N] = S.x + G.x;
+            c[N - 1] = -(S.y + G.y);
+        }
+    }
+};
+template <int N> struct LineOp<N, LK_FOURIER_FWD> {
+    typedef FftCfg<N> C;
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        const double2* v2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0));
+        cplx x[C::E];
+#pragma unroll
+        for (int r = 0; r < C::E; ++r) x[r] = act ? v2[t + C::T * r] : make_double2(0.0, 0.0);
+        dit_first<N>(s, t, x);
+        dit_middle<N>(s, t, x, p.tw);
+        FourierFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.aux, p.scale, act};
+        dit_last_paired<N>(s, t, p.tw, f);
     }
 };
 
 // ---- Fourier inverse --------------------------------------------------------------------------------
+// aux[k] = exp(+2 pi i k / n), k = 0..N/2
+template <int N> struct FourierInvPre {
+    const double* c;
+    const cplx* aux;
+    bool act;
+    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK) {
+        cplx G = make_double2(0, 0), H = make_double2(0, 0);
+        if (act) {
+            G = make_double2(c[2 * k], -c[2 * k - 1]);                // F_k / N
+            H = make_double2(c[2 * (N - k)], -c[2 * (N - k) - 1]);    // F_{N-k} / N
+        }
+        const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
+        const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
+        const cplx Xo = cmul(W, ldg2(aux + k));
+        ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);
+        ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);
+    }
+    __device__ __forceinline__ void dc(cplx& Z0) {
+        double c0 = 0, cl = 0;
+        if (act) { c0 = c[0]; cl = c[2 * N - 1]; }
+        Z0 = make_double2(c0 - cl, -(c0 + cl));  // F_0/N = 2 c0, F_N/N = -2 c_last
+    }
+    __device__ __forceinline__ void mid(cplx& ZM) {
+        cplx dummy;
+        pair(N / 2, ZM, dummy);
+    }
+};
 template <int N> struct LineOp<N, LK_FOURIER_INV> {
     typedef FftCfg<N> C;
-    // aux[k] = exp(+2 pi i k / n), k = 0..N/2
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        constexpr int n = 2 * N;
-        const double* c = reinterpret_cast<const double*>(p.in) + line * p.istride;
-        for (int k = 1 + t; k <= N / 2; k += C::T) {
-            cplx G = make_double2(0, 0), H = make_double2(0, 0);
-            if (act) {
-                G = make_double2(c[2 * k], -c[2 * k - 1]);                // F_k / N
-                H = make_double2(c[2 * (N - k)], -c[2 * (N - k) - 1]);    // F_{N-k} / N
-            }
-            const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
-            const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
-            const cplx Xo = cmul(W, ldg2(p.aux + k));
-            line_put<N>(s, k, make_double2(Xe.x - Xo.y, -Xe.y - Xo.x));
-            line_put<N>(s, N - k, make_double2(Xe.x + Xo.y, Xe.y - Xo.x));
-        }
-        if (t == 0) {
-            double c0 = 0, cl = 0;
-            if (act) { c0 = c[0]; cl = c[n - 1]; }
-            // F_0/N = 2 c0, F_N/N = -2 c_last:  Z_0 = (c0 - cl) + i (c0 + cl)
-            line_put<N>(s, 0, make_double2(c0 - cl, -(c0 + cl)));
-        }
-        __syncthreads();
-        pass_load<N, C::T, C::R1, C::SH>(s, t, x);
-        __syncthreads();
-    }
-    static __device__ __forceinline__ void store(const LineParams& p, int64_t line, bool act, int t, const cplx* s) {
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        FourierInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), p.aux, act};
+        dif_first_paired<N>(s, t, p.tw, f);
+        cplx x[C::E];
+        dif_middle<N>(s, t, x, p.tw);
+        dif_last<N>(s, t, x);
         if (!act) return;
         double2* v2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + line * p.ostride);
-        for (int m = t; m < N; m += C::T) {
-            const cplx z = line_get<N>(s, m);
-            v2[m] = make_double2(z.x, -z.y);
-        }
+#pragma unroll
+        for (int r = 0; r < C::E; ++r) v2[t + C::T * r] = make_double2(x[r].x, -x[r].y);
     }
 };
 
 // ---- Laurent / plain complex ------------------------------------------------------------------------
 template <int N> struct LineOp<N, LK_LAURENT_FWD> {
     typedef FftCfg<N> C;
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        cplx x[C::E];
+        load(p, line, act, t, s, x);
+        fft_line<N>(s, t, x, p.tw);
+        store(p, line, act, t, s);
+    }
     static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
         const cplx* v = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
 #pragma unroll
@@ -236,6 +379,12 @@ template <int N> struct LineOp<N, LK_LAURENT_FWD> {
 };
 template <int N> struct LineOp<N, LK_LAURENT_INV> {
     typedef FftCfg<N> C;
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        cplx x[C::E];
+        load(p, line, act, t, s, x);
+        fft_line<N>(s, t, x, p.tw);
+        store(p, line, act, t, s);
+    }
     static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
         const cplx* c = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
 #pragma unroll
@@ -255,6 +404,12 @@ template <int N> struct LineOp<N, LK_LAURENT_INV> {
 //   out[L*ostride + i*oes] = scale * tw(L,i) * FFT(in[L*istride + j*ies])_i,  optional conj on either side
 template <int N> struct LineOp<N, LK_CFFT> {
     typedef FftCfg<N> C;
+    static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+        cplx x[C::E];
+        load(p, line, act, t, s, x);
+        fft_line<N>(s, t, x, p.tw);
+        store(p, line, act, t, s);
+    }
     static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
         const cplx* v = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
 #pragma unroll
@@ -291,10 +446,7 @@ __global__ void __launch_bounds__(LineGeom<N>::CT) line_kernel(LineParams p) {
     const int64_t line = (int64_t)blockIdx.x * G::LPC + l;
     const bool act = line < p.batch;
     cplx* s = smem + (size_t)l * FftLine<N>::STRIDE;
-    cplx x[FftCfg<N>::E];
-    LineOp<N, KIND>::load(p, line, act, t, s, x);
-    fft_line<N>(s, t, x, p.tw);
-    LineOp<N, KIND>::store(p, line, act, t, s);
+    LineOp<N, KIND>::run(p, line, act, t, s);
 }
 
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
