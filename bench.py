@@ -317,6 +317,34 @@ def main():
         extras["sample_gaussian"] = {"samples_per_s": world * P / (t * 1e-3), "ms_per_step": t, "N": int(cdf.size),
                                      "fp64_frac_of_nominal_peak": 47 * 3.0 * cdf.size * P / (t * 1e-3) / fp64_peak}
         del x, y
+        # config 1: one long transform, n = 2^20 (transform + itransform of sin(x^2) on 0..10); 16 MiB per direction
+        # lives in L2, so rotate over 16 distinct buffers (> 126 MB L2) and report it as a latency-bound number
+        n1 = 1 << 20
+        xs1 = torch.tensor(np.sin(orc.chebpoints(n1, 0.0, 10.0) ** 2), device="cuda")
+        bufs = [xs1.clone() for _ in range(16)]
+        outs = [torch.empty_like(xs1) for _ in range(16)]
+        p1f = af.api.DevicePlan(L.CHEB1_FWD, n1, 0, 1, n1)
+        p1i = af.api.DevicePlan(L.CHEB1_INV, n1, 0, 1, n1)
+        def cfg1():
+            for b_, o_ in zip(bufs, outs):
+                p1f.execute(b_.data_ptr(), o_.data_ptr(), stream)
+                p1i.execute(o_.data_ptr(), o_.data_ptr(), stream)
+        t = time_loop(cfg1, 3, 3) / 16.0
+        rt = float((outs[0] - xs1).abs().max())
+        extras["cheb_2pow20_fwd_plus_inv"] = {"ms_per_pair": t, "coefficients_per_s": 2.0 * n1 / (t * 1e-3),
+                                              "launches_per_pair": p1f.launches + p1i.launches,
+                                              "roundtrip_max_abs_err": rt,
+                                              "note": "latency/L2 bound: 16 rotating buffers, fwd+inv per buffer"}
+        del bufs, outs
+        # config 4: 2-D Chebyshev x Chebyshev 16384 x 16384 on one GPU (columns, transpose, columns, transpose)
+        n2d = 16384
+        V = torch.randn(n2d, n2d, dtype=torch.float64, device="cuda", generator=g)
+        p2 = af.api.DevicePlan(L.CHEB1_2D_FWD, n2d, n2d, 1, n2d)
+        t = time_loop(lambda: p2.execute(V.data_ptr(), V.data_ptr(), stream), 3, 2)
+        extras["cheb2d_16384"] = {"ms_per_step": t, "elements_per_s": float(n2d) * n2d / (t * 1e-3),
+                                  "hbm_frac_of_32B_per_element": 32.0 * n2d * n2d / (t * 1e-3) / 1e9 / peak,
+                                  "launches": p2.launches}
+        del V
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu:
