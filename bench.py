@@ -148,12 +148,30 @@ def run_reference(args):
                                    "(oracle port of FastTransforms.plan_chebyshevtransform; Julia/FFTW absent)"},
         "e2e": {"value": val, "unit": "coefficients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, ...) print to fd 1; keep fd 1 for the ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -366,7 +384,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "max_abs_err_vs_oracle": err, "extras": extras,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
