@@ -115,6 +115,7 @@ struct afb_plan_s {
     int line_kind = 0;
     const cplx* tw = nullptr;
     cplx* aux = nullptr;
+    std::vector<cplx> K;  // MAXJ x MAXRL rotation constants (kernel parameters)
     double scale = 1.0;
     // DIRECT
     cplx* dtab = nullptr;
@@ -158,63 +159,63 @@ static void plan_free(afb_plan_s* p) {
 
 static inline bool kind_is_real(int kind) { return kind <= AFB_FOURIER_INV || kind >= AFB_CHEB1_2D_FWD; }
 
-// fused per-plan tables of the LINE path (see LineOp<> in afb_transform.cu)
+// Per-plan twiddle tables and rotation constants of the LINE path (see dit_last_paired in afb_transform.cu).
+// Every twiddle family is t_j(k) = g_j * exp(-i pi m_j k / (2n)):
+//   aux[J*pi + j] = t_j(pi) for pi = 0..NSL/2, aux[J*(NSL/2+1) + j] = t_j(N/2)
+//   K[j][q] = exp(-i pi m_j NSL q/(2n))                       (2q <  RL: t_j(pi + NSL q)   = t_j(pi) K)
+//           = (g_j/conj g_j) exp(-i pi m_j (N - NSL q)/(2n))  (2q >= RL: t_j(N-pi-NSL q) = conj(t_j(pi)) K)
+struct TwFamily { long double gre, gim; int64_t m; };
+
+static cplx tw_eval(const TwFamily& f, int64_t k, int64_t n, long double sre = 1.0L, long double sim = 0.0L) {
+    const long double PI = 3.141592653589793238462643383279502884L;
+    int64_t e = (int64_t)(((__int128)f.m * k) % (4 * n));
+    if (e < 0) e += 4 * n;
+    const long double a = PI * (long double)e / (2.0L * (long double)n);
+    const long double wr = cosl(a), wi = -sinl(a);
+    const long double gr = sre, gi = sim;  // prefactor
+    return make_double2((double)(gr * wr - gi * wi), (double)(gr * wi + gi * wr));
+}
+
 static int32_t build_line_aux(afb_plan_s* p) {
     const int64_t n = p->n;
     const int64_t N = p->Nc;
-    std::vector<cplx> h;
-    const long double PI = 3.141592653589793238462643383279502884L;
-    auto w = [&](long double k) {  // exp(-i pi k / (2n))
-        const long double a = PI * k / (2.0L * (long double)n);
-        return std::pair<long double, long double>(cosl(a), -sinl(a));
-    };
+    const long double inv_n = 1.0L / (long double)n;
+    TwFamily fam[2];
+    int J = 0;
     switch (p->kind) {
         case AFB_CHEB1_FWD:
-            h.resize((size_t)(N / 2 + 1) * 2);
-            for (int64_t k = 0; k <= N / 2; ++k) {
-                auto a = w((long double)k), b = w((long double)(5 * k));
-                h[2 * k] = make_double2((double)(a.first / n), (double)(a.second / n));
-                // -i (br + i bi) = bi - i br
-                h[2 * k + 1] = make_double2((double)(b.second / n), (double)(-b.first / n));
-            }
-            p->line_kind = ILK_CHEB_FWD;
-            p->scale = 1.0 / (double)n;
-            break;
+            fam[0] = {inv_n, 0.0L, 1}; fam[1] = {0.0L, -inv_n, 5}; J = 2;
+            p->line_kind = ILK_CHEB_FWD; p->scale = 1.0 / (double)n; break;
         case AFB_CHEB1_INV:
-            h.resize((size_t)(N / 2 + 1) * 2);
-            for (int64_t k = 0; k <= N / 2; ++k) {
-                auto a = w((long double)k), b = w((long double)(4 * k));
-                h[2 * k] = make_double2((double)a.first, (double)(-a.second));
-                h[2 * k + 1] = make_double2((double)b.first, (double)(-b.second));
-            }
-            p->line_kind = ILK_CHEB_INV;
-            break;
+            fam[0] = {1.0L, 0.0L, -1}; fam[1] = {1.0L, 0.0L, -4}; J = 2;
+            p->line_kind = ILK_CHEB_INV; break;
         case AFB_FOURIER_FWD:
-            h.resize((size_t)(N / 2 + 1));
-            for (int64_t k = 0; k <= N / 2; ++k) {
-                auto b = w((long double)(4 * k));  // exp(-2 pi i k / n)
-                h[k] = make_double2((double)(b.second / n), (double)(-b.first / n));
-            }
-            p->line_kind = ILK_FOURIER_FWD;
-            p->scale = 1.0 / (double)n;
-            break;
+            fam[0] = {0.0L, -inv_n, 4}; J = 1;
+            p->line_kind = ILK_FOURIER_FWD; p->scale = 1.0 / (double)n; break;
         case AFB_FOURIER_INV:
-            h.resize((size_t)(N / 2 + 1));
-            for (int64_t k = 0; k <= N / 2; ++k) {
-                auto b = w((long double)(4 * k));
-                h[k] = make_double2((double)b.first, (double)(-b.second));
-            }
-            p->line_kind = ILK_FOURIER_INV;
-            break;
+            fam[0] = {1.0L, 0.0L, -4}; J = 1;
+            p->line_kind = ILK_FOURIER_INV; break;
         case AFB_LAURENT_FWD:
-            p->line_kind = ILK_LAURENT_FWD;
-            p->scale = 1.0 / (double)n;
-            return AFB_OK;
+            p->line_kind = ILK_LAURENT_FWD; p->scale = 1.0 / (double)n; return AFB_OK;
         case AFB_LAURENT_INV:
-            p->line_kind = ILK_LAURENT_INV;
-            return AFB_OK;
+            p->line_kind = ILK_LAURENT_INV; return AFB_OK;
         default:
             return fail(AFB_BAD_ARG, "bad kind for line path");
+    }
+    int RL = 0, NSL = 0;
+    AFB_TRY(line_last_pass((int)N, &RL, &NSL));
+    std::vector<cplx> h((size_t)J * (size_t)(NSL / 2 + 2));
+    for (int j = 0; j < J; ++j) {
+        for (int64_t pi = 0; pi <= NSL / 2; ++pi) h[(size_t)(J * pi + j)] = tw_eval(fam[j], pi, n, fam[j].gre, fam[j].gim);
+        h[(size_t)(J * (NSL / 2 + 1) + j)] = tw_eval(fam[j], N / 2, n, fam[j].gre, fam[j].gim);
+    }
+    p->K.assign(2 * 8, make_double2(1.0, 0.0));
+    for (int j = 0; j < J; ++j) {
+        const bool g_imag = fam[j].gim != 0.0L;  // g / conj(g) = -1 for purely imaginary g, +1 for real g
+        for (int q = 0; q < RL; ++q) {
+            if (2 * q < RL) p->K[(size_t)(j * 8 + q)] = tw_eval(fam[j], (int64_t)NSL * q, n);
+            else p->K[(size_t)(j * 8 + q)] = tw_eval(fam[j], N - (int64_t)NSL * q, n, g_imag ? -1.0L : 1.0L, 0.0L);
+        }
     }
     return upload_table(h, &p->aux);
 }
@@ -286,7 +287,7 @@ static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t
 }
 
 static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int64_t batch, int64_t istride,
-                              int64_t ostride, void* stream) {
+                              int64_t ostride, void* stream, int64_t oes = 1) {
     switch (p->path) {
         case PATH_EMPTY: return AFB_OK;
         case PATH_DIRECT: {
@@ -303,11 +304,13 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
                 AFB_CUDA(cudaMemcpyAsync(p->tmp, d_in, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
                 src = p->tmp;
             }
-            return launch_direct(p->kind, (int)p->n, src, d_out, batch, istride, ostride, p->dtab, stream);
+            return launch_direct(p->kind, (int)p->n, src, d_out, batch, istride, ostride, oes, p->dtab, stream);
         }
         case PATH_LINE:
-            return launch_line(p->line_kind, p->Nc, d_in, d_out, batch, istride, ostride, p->tw, p->aux, p->scale, stream);
+            return launch_line(p->line_kind, p->Nc, d_in, d_out, batch, istride, ostride, oes, p->tw, p->aux,
+                               p->K.empty() ? nullptr : p->K.data(), p->scale, stream);
         case PATH_GENERIC: {
+            if (oes != 1) return fail(AFB_UNSUPPORTED, "generic path has no strided output");
             const bool inv = (p->kind & 1) != 0;
             for (int64_t b0 = 0; b0 < batch; b0 += p->gbatch) {
                 const int64_t nb = std::min(p->gbatch, batch - b0);
@@ -332,7 +335,10 @@ static int32_t plan_launch_count(afb_plan_s* p) {
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
         }
-        case PATH_TENSOR2D: return plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan) + 2;
+        case PATH_TENSOR2D: {
+            const bool fused = false;  // see afb_plan_execute_device
+            return plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan) + (fused ? 0 : 2);
+        }
     }
     return 0;
 }
@@ -465,8 +471,18 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(AFB_BAD_ARG, "afb_plan_execute_device: buffers must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(p->mu);
     if (p->path == PATH_TENSOR2D) {
-        // C = T_x V T_y^T on a column-major n x n2 matrix: columns, transpose, columns, transpose back
+        // C = T_x V T_y^T on a column-major n x n2 matrix.
         const int64_t n = p->n, n2 = p->n2;
+        // Scattering 8-byte outputs with a 128 KB element stride (fused transpose) was measured 1.5x SLOWER on a B200 at
+        // 16384^2 (TLB + sector-partial writes: 6.06 ms vs 3.97 ms), so the tiled-transpose route is used.
+        const bool fused = false;
+        if (fused) {
+            // both passes read contiguous lines and scatter their output transposed (element stride = other
+            // dimension), so no separate transpose kernels run: W^T = (T_x V)^T lands in t2buf, then C.
+            AFB_TRY(exec_1d_device(p->col_plan, d_in, p->t2buf, n2, n, 1, stream, n2));
+            AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, d_out, n, n2, 1, stream, n));
+            return AFB_OK;
+        }
         AFB_TRY(exec_1d_device(p->col_plan, d_in, d_out, n2, n, n, stream));
         AFB_TRY(launch_transpose(reinterpret_cast<const double*>(d_out), p->t2buf, n, n2, stream));
         AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, n, n2, n2, stream));

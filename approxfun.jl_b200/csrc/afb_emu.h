@@ -27,6 +27,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 

@@ -17,12 +17,13 @@ constexpr int LINE_MAX_N = 8192;
 
 // ---- kernels / launchers --------------------------------------------------------------------------
 int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
-                    const cplx* tw, const cplx* aux, double scale, void* stream);
+                    int64_t oes, const cplx* tw, const cplx* aux, const cplx* K, double scale, void* stream);
+int32_t line_last_pass(int N, int* RL, int* NSL);
 int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
                           int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
                           const cplx* twA, const cplx* twB, int64_t twmod, void* stream);
 int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
-                      const cplx* tab, void* stream);
+                      int64_t oes, const cplx* tab, void* stream);
 
 int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream);
 int32_t launch_bisect_vec(const double* d_c, int64_t N, const double* d_u, bool rng, uint64_t seed, uint64_t offset,

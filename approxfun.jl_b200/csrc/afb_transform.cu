@@ -6,14 +6,22 @@
 //   FOURIER_*  (R2HC/HC2R + interlace, /root/reference/src/Extras/fftGeneric.jl:47-64)
 //   LAURENT_*  (c2c fft + [f0,f-1,f1,...] ordering, docs/src/usage/spaces.md:113-125)
 //
-// A length-n real transform runs as ONE complex FFT of length N = n/2:
-//   DCT-II : even/odd input permutation (Makhoul) folded into the first-pass register loads, real-FFT
-//            split + quarter-wave twiddle + 1/n scaling folded into the store stage;
-//   DCT-III: the exact mirror image;   Fourier: real-FFT split fused with the interlaced layout.
+// A length-n real transform runs as ONE complex FFT of length N = n/2 with everything else fused:
+//   DCT-II : Makhoul's even/odd permutation is a lane-pair exchange on coalesced 128-bit loads feeding the
+//            first pass from registers; the real-FFT split, the quarter-wave twiddle and the 1/n scaling run
+//            in registers on the outputs of the last pass (partner butterflies (j, NSL-j) share a thread)
+//            and go straight to global memory.  Two shared-memory exchanges per transform.
+//   DCT-III: the transposed (DIF) flow: pair pre-processing in registers -> passes -> lane-pair exchange ->
+//            coalesced 128-bit stores.       Fourier: same with the interlaced [a0,b1,a1,...] layout.
+// Post/pre twiddles: one table load per pair-slot (index pi); the q-dependence k = pi + NSL q is a
+// per-plan constant rotation passed in the kernel parameters (constant bank), so no per-element table traffic.
 // Global traffic is exactly one read and one write of every element (16 B per coefficient).
 #include "afb_fft.cuh"
 
 namespace afb {
+
+constexpr int MAXRL = 8;   // largest last-pass radix
+constexpr int MAXJ = 2;    // twiddle families per kind
 
 struct LineParams {
     const void* in;
@@ -22,14 +30,16 @@ struct LineParams {
     int64_t istride;  // elements between consecutive transforms (double; complex for Laurent / CFFT)
     int64_t ostride;
     const cplx* tw;   // exp(-2 pi i m / N), m < N
-    const cplx* aux;  // kind specific fused table
+    const cplx* aux;  // real kinds: aux[J*pi + j] = t_j(pi), pi = 0..NSL/2, then t_j(N/2)
     double scale;
-    // plain complex FFT (LK_CFFT) extras: element strides, conjugation flags, four-step twiddle
+    // element strides (complex FFT both; Chebyshev kinds: output only, for the fused 2-D transpose)
     int64_t ies, oes;
     int conj_in, conj_out;
-    const cplx* twA;  // w_n^(m >> 12 << 12)
+    const cplx* twA;  // four-step: w_n^(m >> 12 << 12)
     const cplx* twB;  // w_n^(m & 4095);  output (line L, index i) is multiplied by w_n^((L mod twmod) * i)
     int64_t twmod;
+    // t_j(pi + NSL q) = t_j(pi) * K[j][q] (2q < RL);  t_j(N - pi - NSL q) = conj(t_j(pi)) * K[j][q] (2q >= RL)
+    cplx K[MAXJ][MAXRL];
 };
 
 enum LineKind { LK_CHEB_FWD = 0, LK_CHEB_INV = 1, LK_FOURIER_FWD = 2, LK_FOURIER_INV = 3, LK_LAURENT_FWD = 4,
@@ -53,7 +63,6 @@ template <int N> struct LineGeom {
 // =================================================================================================
 template <int N> struct PairMap {
     typedef FftCfg<N> C;
-    // column owned by thread t of the line
     static __device__ __forceinline__ int col(int t) { return (t & 1) ? C::T - 1 - (t >> 1) : (t >> 1); }
 };
 
@@ -62,19 +71,24 @@ __device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v
     typedef FftCfg<N> C;
     constexpr int H = C::R1 / 2;
     const int role = t & 1, p2 = t >> 1;
+    double2 ch[H][2];
+#pragma unroll
+    for (int qq = 0; qq < H; ++qq)
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            const int qcol = sg ? C::T - 1 - p2 : p2;
+            const int q = qcol + C::T * qq;
+            ch[qq][sg] = act ? v2[2 * q + (role ^ sg)] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
     for (int qq = 0; qq < H; ++qq) {
         cplx z[2];
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-            const int qcol = sg ? C::T - 1 - p2 : p2;
-            const int q = qcol + C::T * qq;
             const int e = role ^ sg;
-            double2 ch = make_double2(0.0, 0.0);
-            if (act) ch = v2[2 * q + e];
-            const double send = e ? ch.x : ch.y;
+            const double send = e ? ch[qq][sg].x : ch[qq][sg].y;
             const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            z[sg] = make_double2(e ? ch.y : ch.x, recv);
+            z[sg] = make_double2(e ? ch[qq][sg].y : ch[qq][sg].x, recv);
         }
         x[qq] = role ? z[1] : z[0];
         x[C::R1 - 1 - qq] = role ? z[0] : z[1];
@@ -83,7 +97,7 @@ __device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v
 
 // x[r] = r-th FFT output of column col(t); writes v = [Re z, Im z] un-permuted with z = conj(r)
 template <int N>
-__device__ __forceinline__ void cheb_exchange_store(double2* __restrict__ v2, bool act, int t, const cplx* x) {
+__device__ __forceinline__ void cheb_exchange_store(double* __restrict__ v, int64_t oes, bool act, int t, const cplx* x) {
     typedef FftCfg<N> C;
     constexpr int H = C::R1 / 2;
     const int role = t & 1, p2 = t >> 1;
@@ -96,70 +110,112 @@ __device__ __forceinline__ void cheb_exchange_store(double2* __restrict__ v2, bo
             const int e = role ^ sg;
             const cplx mine = e ? x[C::R1 - 1 - qq] : x[qq];
             const double recv = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-            // chunk 2q   (e = 0): (Re z[q],      Im z[N-1-q]) = ( a.x, -b.y)
-            // chunk 2q+1 (e = 1): (Im z[q],      Re z[N-1-q]) = (-a.y,  b.x)
+            // chunk 2q   (e = 0): (Re z[q], Im z[N-1-q]) = ( a.x, -b.y)
+            // chunk 2q+1 (e = 1): (Im z[q], Re z[N-1-q]) = (-a.y,  b.x)
             const double2 out = e ? make_double2(-recv, mine.x) : make_double2(mine.x, -recv);
-            if (act) v2[2 * q + e] = out;
+            if (act) {
+                if (oes == 1) {
+                    reinterpret_cast<double2*>(v)[2 * q + e] = out;
+                } else {
+                    const int64_t i0 = (int64_t)(4 * q + 2 * e);
+                    v[i0 * oes] = out.x;
+                    v[(i0 + 1) * oes] = out.y;
+                }
+            }
         }
     }
 }
 
 // =================================================================================================
 // paired last pass (DIT) / first pass (DIF): visits every unordered pair {k, N-k} exactly once with
-// both members in registers.  F provides  pair(k, A, B) for 1 <= k < N/2 (A <-> index k, B <-> N-k),
-// dc(Z0) and mid(Z_{N/2}).
+// both members in registers.  F (J twiddle families) provides
+//     pair(k, A, B, t)  for 1 <= k < N/2 (A <-> index k, B <-> index N-k, t[j] = t_j(k)),
+//     dc(Z0) and mid(Z_{N/2}, t) with t[j] = t_j(N/2).
 // =================================================================================================
-template <int N, class F>
-__device__ __forceinline__ void dit_last_paired(const cplx* __restrict__ s, int t, const cplx* __restrict__ tw, F& f) {
+template <int J>
+__device__ __forceinline__ void load_tw(const cplx* __restrict__ aux, int idx, cplx* tb) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) tb[j] = ldg2(aux + J * idx + j);
+}
+// q is a compile-time constant after unrolling, so p.K[j][q] is a constant-bank operand
+template <int N, int J>
+__device__ __forceinline__ void rot_tw(const LineParams& p, const cplx* tb, int q, cplx* tq) {
+    constexpr int RL = FftCfg<N>::RL;
+#pragma unroll
+    for (int j = 0; j < J; ++j) tq[j] = (2 * q < RL) ? cmul(tb[j], p.K[j][q]) : cmul(cconj(tb[j]), p.K[j][q]);
+}
+
+template <int N, int J, class F>
+__device__ __forceinline__ void dit_last_paired(const LineParams& p, const cplx* __restrict__ s, int t, F& f) {
     typedef FftCfg<N> C;
     constexpr int RL = C::RL, NSL = C::NSL;
 #pragma unroll
     for (int i = 0; i < C::BL / 2; ++i) {
         const int pi = t + C::T * i;
-        cplx lo[RL], hi[RL];
-        dit_last_bfly<N>(s, pair_lo<N>(pi), lo, tw);
-        dit_last_bfly<N>(s, pair_hi<N>(pi), hi, tw);
+        cplx lo[RL], hi[RL], tb[J], tq[J];
+        dit_last_bfly<N>(s, pair_lo<N>(pi), lo, p.tw);
+        dit_last_bfly<N>(s, pair_hi<N>(pi), hi, p.tw);
+        load_tw<J>(p.aux, pi, tb);
         if (pi != 0) {
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
-                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q]);
-                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q]);
+                rot_tw<N, J>(p, tb, q, tq);
+                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q], tq);
+                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q], tq);
             }
         } else {
             f.dc(lo[0]);
-            f.mid(lo[RL / 2]);
 #pragma unroll
-            for (int q = 1; q < RL / 2; ++q) f.pair(NSL * q, lo[q], lo[RL - q]);
+            for (int q = 1; q < RL / 2; ++q) {
+                rot_tw<N, J>(p, tb, q, tq);
+                f.pair(NSL * q, lo[q], lo[RL - q], tq);
+            }
+            load_tw<J>(p.aux, NSL / 2 + 1, tq);
+            f.mid(lo[RL / 2], tq);
+            load_tw<J>(p.aux, NSL / 2, tb);
 #pragma unroll
-            for (int q = 0; q < RL / 2; ++q) f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q]);
+            for (int q = 0; q < RL / 2; ++q) {
+                rot_tw<N, J>(p, tb, q, tq);
+                f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q], tq);
+            }
         }
     }
 }
 
-template <int N, class F>
-__device__ __forceinline__ void dif_first_paired(cplx* __restrict__ s, int t, const cplx* __restrict__ tw, F& f) {
+template <int N, int J, class F>
+__device__ __forceinline__ void dif_first_paired(const LineParams& p, cplx* __restrict__ s, int t, F& f) {
     typedef FftCfg<N> C;
     constexpr int RL = C::RL, NSL = C::NSL;
 #pragma unroll
     for (int i = 0; i < C::BL / 2; ++i) {
         const int pi = t + C::T * i;
-        cplx lo[RL], hi[RL];
+        cplx lo[RL], hi[RL], tb[J], tq[J];
+        load_tw<J>(p.aux, pi, tb);
         if (pi != 0) {
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
-                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q]);
-                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q]);
+                rot_tw<N, J>(p, tb, q, tq);
+                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q], tq);
+                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q], tq);
             }
         } else {
             f.dc(lo[0]);
-            f.mid(lo[RL / 2]);
 #pragma unroll
-            for (int q = 1; q < RL / 2; ++q) f.pair(NSL * q, lo[q], lo[RL - q]);
+            for (int q = 1; q < RL / 2; ++q) {
+                rot_tw<N, J>(p, tb, q, tq);
+                f.pair(NSL * q, lo[q], lo[RL - q], tq);
+            }
+            load_tw<J>(p.aux, NSL / 2 + 1, tq);
+            f.mid(lo[RL / 2], tq);
+            load_tw<J>(p.aux, NSL / 2, tb);
 #pragma unroll
-            for (int q = 0; q < RL / 2; ++q) f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q]);
+            for (int q = 0; q < RL / 2; ++q) {
+                rot_tw<N, J>(p, tb, q, tq);
+                f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q], tq);
+            }
         }
-        dif_first_bfly<N>(s, pair_lo<N>(pi), lo, tw);
-        dif_first_bfly<N>(s, pair_hi<N>(pi), hi, tw);
+        dif_first_bfly<N>(s, pair_lo<N>(pi), lo, p.tw);
+        dif_first_bfly<N>(s, pair_hi<N>(pi), hi, p.tw);
     }
     __syncthreads();
 }
@@ -167,40 +223,40 @@ __device__ __forceinline__ void dif_first_paired(cplx* __restrict__ s, int t, co
 template <int N, int KIND> struct LineOp;
 
 // ---- Chebyshev forward (DCT-II) -------------------------------------------------------------------
-// aux[2k] = w^k / n, aux[2k+1] = -i w^(5k) / n,  w = exp(-i pi / (2n)),  k = 0..N/2 ; scale = 1/n
+// t_0(k) = w^k / n, t_1(k) = -i w^(5k) / n,  w = exp(-i pi / (2n)) ; scale = 1/n
 template <int N> struct ChebFwdPost {
     double* c;
-    const cplx* aux;
+    int64_t es;
     double scale;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx A, cplx B) {
+    __device__ __forceinline__ void pair(int k, cplx A, cplx B, const cplx* t) {
         constexpr int n = 2 * N;
         const cplx S = make_double2(A.x + B.x, A.y - B.y);   // A + conj B
         const cplx D = make_double2(A.x - B.x, A.y + B.y);   // A - conj B
-        const cplx U = cmul(S, ldg2(aux + 2 * k));
-        const cplx V = cmul(D, ldg2(aux + 2 * k + 1));
+        const cplx U = cmul(S, t[0]);
+        const cplx V = cmul(D, t[1]);
         const cplx P = cadd(U, V), Q = csub(U, V);
         if (act) {
-            c[k] = P.x;
-            c[n - k] = -P.y;
-            c[N - k] = (Q.x - Q.y) * 0.70710678118654752440;
-            c[N + k] = (Q.x + Q.y) * 0.70710678118654752440;
+            c[(int64_t)k * es] = P.x;
+            c[(int64_t)(n - k) * es] = -P.y;
+            c[(int64_t)(N - k) * es] = (Q.x - Q.y) * 0.70710678118654752440;
+            c[(int64_t)(N + k) * es] = (Q.x + Q.y) * 0.70710678118654752440;
         }
     }
     __device__ __forceinline__ void dc(cplx A) {
         if (act) {
             c[0] = (A.x + A.y) * scale;
-            c[N] = (A.x - A.y) * (scale * 1.41421356237309504880);
+            c[(int64_t)N * es] = (A.x - A.y) * (scale * 1.41421356237309504880);
         }
     }
-    __device__ __forceinline__ void mid(cplx M) {
+    __device__ __forceinline__ void mid(cplx M, const cplx* t) {
         constexpr int n = 2 * N;
         const cplx S = make_double2(2.0 * M.x, 0.0);
         const cplx D = make_double2(0.0, 2.0 * M.y);
-        const cplx P = cadd(cmul(S, ldg2(aux + N)), cmul(D, ldg2(aux + N + 1)));
+        const cplx P = cadd(cmul(S, t[0]), cmul(D, t[1]));
         if (act) {
-            c[N / 2] = P.x;
-            c[n - N / 2] = -P.y;
+            c[(int64_t)(N / 2) * es] = P.x;
+            c[(int64_t)(n - N / 2) * es] = -P.y;
         }
     }
 };
@@ -213,29 +269,28 @@ template <int N> struct LineOp<N, LK_CHEB_FWD> {
         cheb_exchange_load<N>(v2, act, t, x);
         dit_first<N>(s, PairMap<N>::col(t), x);
         dit_middle<N>(s, t, x, p.tw);
-        ChebFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.aux, p.scale, act};
-        dit_last_paired<N>(s, t, p.tw, f);
+        ChebFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.oes, p.scale, act};
+        dit_last_paired<N, 2>(p, s, t, f);
     }
 };
 
 // ---- Chebyshev inverse (DCT-III) ------------------------------------------------------------------
-// aux[2k] = conj(w^k), aux[2k+1] = exp(+2 pi i k / n),  k = 0..N/2
+// t_0(k) = conj(w^k), t_1(k) = exp(+2 pi i k / n)
 template <int N> struct ChebInvPre {
     const double* c;
-    const cplx* aux;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK) {
+    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK, const cplx* t) {
         constexpr int n = 2 * N;
         const double h = 0.70710678118654752440;
         double ck = 0, cnk = 0, cNk = 0, cNpk = 0;
         if (act) { ck = c[k]; cnk = c[n - k]; cNk = c[N - k]; cNpk = c[N + k]; }
-        const cplx wk = ldg2(aux + 2 * k);                       // conj(w^k)
+        const cplx wk = t[0];                                     // conj(w^k)
         const cplx G = cmul(make_double2(ck, -cnk), wk);         // X_k / N
         const cplx e = make_double2((wk.x + wk.y) * h, (wk.x - wk.y) * h);  // conj(w^(N-k))
         const cplx H = cmul(make_double2(cNk, -cNpk), e);        // X_{N-k} / N
         const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
         const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
-        const cplx Xo = cmul(W, ldg2(aux + 2 * k + 1));
+        const cplx Xo = cmul(W, t[1]);
         ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);            // conj(Z_k)     = conj(Xe) - i conj(Xo)
         ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);            // conj(Z_{N-k}) = Xe - i Xo
     }
@@ -245,35 +300,34 @@ template <int N> struct ChebInvPre {
         if (act) { c0 = c[0]; cN = c[N]; }
         Z0 = make_double2(c0 + cN * h, -(c0 - cN * h));
     }
-    __device__ __forceinline__ void mid(cplx& ZM) {
+    __device__ __forceinline__ void mid(cplx& ZM, const cplx* t) {
         cplx dummy;
-        pair(N / 2, ZM, dummy);
+        pair(N / 2, ZM, dummy, t);
     }
 };
 template <int N> struct LineOp<N, LK_CHEB_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        ChebInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), p.aux, act};
-        dif_first_paired<N>(s, t, p.tw, f);
+        ChebInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), act};
+        dif_first_paired<N, 2>(p, s, t, f);
         cplx x[C::E];
         dif_middle<N>(s, t, x, p.tw);
         dif_last<N>(s, PairMap<N>::col(t), x);
-        double2* v2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0));
-        cheb_exchange_store<N>(v2, act, t, x);
+        double* v = reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0);
+        cheb_exchange_store<N>(v, p.oes, act, t, x);
     }
 };
 
 // ---- Fourier forward --------------------------------------------------------------------------------
-// aux[k] = -i exp(-2 pi i k / n) / n,  k = 0..N/2 ;  scale = 1/n
+// t_0(k) = -i exp(-2 pi i k / n) / n ;  scale = 1/n
 template <int N> struct FourierFwdPost {
     double* c;
-    const cplx* aux;
     double scale;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx A, cplx B) {
+    __device__ __forceinline__ void pair(int k, cplx A, cplx B, const cplx* t) {
         const cplx S = make_double2((A.x + B.x) * scale, (A.y - B.y) * scale);
         const cplx D = make_double2(A.x - B.x, A.y + B.y);
-        const cplx G = cmul(D, ldg2(aux + k));
+        const cplx G = cmul(D, t[0]);
         if (act) {  // (2/n) F_k = S + G ; (2/n) F_{N-k} = conj(S - G)
             c[2 * k] = S.x + G.x;
             c[2 * k - 1] = -(S.y + G.y);
@@ -287,10 +341,10 @@ template <int N> struct FourierFwdPost {
             c[2 * N - 1] = -(A.x - A.y) * scale;
         }
     }
-    __device__ __forceinline__ void mid(cplx M) {
+    __device__ __forceinline__ void mid(cplx M, const cplx* t) {
         const cplx S = make_double2(2.0 * M.x * scale, 0.0);
         const cplx D = make_double2(0.0, 2.0 * M.y);
-        const cplx G = cmul(D, ldg2(aux + N / 2));
+        const cplx G = cmul(D, t[0]);
         if (act) {
             c[N] = S.x + G.x;
             c[N - 1] = -(S.y + G.y);
@@ -306,18 +360,17 @@ template <int N> struct LineOp<N, LK_FOURIER_FWD> {
         for (int r = 0; r < C::E; ++r) x[r] = act ? v2[t + C::T * r] : make_double2(0.0, 0.0);
         dit_first<N>(s, t, x);
         dit_middle<N>(s, t, x, p.tw);
-        FourierFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.aux, p.scale, act};
-        dit_last_paired<N>(s, t, p.tw, f);
+        FourierFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.scale, act};
+        dit_last_paired<N, 1>(p, s, t, f);
     }
 };
 
 // ---- Fourier inverse --------------------------------------------------------------------------------
-// aux[k] = exp(+2 pi i k / n), k = 0..N/2
+// t_0(k) = exp(+2 pi i k / n)
 template <int N> struct FourierInvPre {
     const double* c;
-    const cplx* aux;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK) {
+    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK, const cplx* t) {
         cplx G = make_double2(0, 0), H = make_double2(0, 0);
         if (act) {
             G = make_double2(c[2 * k], -c[2 * k - 1]);                // F_k / N
@@ -325,7 +378,7 @@ template <int N> struct FourierInvPre {
         }
         const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
         const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
-        const cplx Xo = cmul(W, ldg2(aux + k));
+        const cplx Xo = cmul(W, t[0]);
         ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);
         ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);
     }
@@ -334,16 +387,16 @@ template <int N> struct FourierInvPre {
         if (act) { c0 = c[0]; cl = c[2 * N - 1]; }
         Z0 = make_double2(c0 - cl, -(c0 + cl));  // F_0/N = 2 c0, F_N/N = -2 c_last
     }
-    __device__ __forceinline__ void mid(cplx& ZM) {
+    __device__ __forceinline__ void mid(cplx& ZM, const cplx* t) {
         cplx dummy;
-        pair(N / 2, ZM, dummy);
+        pair(N / 2, ZM, dummy, t);
     }
 };
 template <int N> struct LineOp<N, LK_FOURIER_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        FourierInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), p.aux, act};
-        dif_first_paired<N>(s, t, p.tw, f);
+        FourierInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), act};
+        dif_first_paired<N, 1>(p, s, t, f);
         cplx x[C::E];
         dif_middle<N>(s, t, x, p.tw);
         dif_last<N>(s, t, x);
@@ -355,16 +408,20 @@ template <int N> struct LineOp<N, LK_FOURIER_INV> {
 };
 
 // ---- Laurent / plain complex ------------------------------------------------------------------------
+template <int N, class Op>
+__device__ __forceinline__ void run_via_smem(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
+    cplx x[FftCfg<N>::E];
+    Op::load(p, line, act, t, x);
+    fft_line<N>(s, t, x, p.tw);
+    Op::store(p, line, act, t, s);
+}
 template <int N> struct LineOp<N, LK_LAURENT_FWD> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        cplx x[C::E];
-        load(p, line, act, t, s, x);
-        fft_line<N>(s, t, x, p.tw);
-        store(p, line, act, t, s);
+        run_via_smem<N, LineOp<N, LK_LAURENT_FWD>>(p, line, act, t, s);
     }
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        const cplx* v = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
+    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* x) {
+        const cplx* v = reinterpret_cast<const cplx*>(p.in) + (act ? line * p.istride : 0);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) x[r] = act ? v[t + C::T * r] : make_double2(0.0, 0.0);
     }
@@ -380,13 +437,10 @@ template <int N> struct LineOp<N, LK_LAURENT_FWD> {
 template <int N> struct LineOp<N, LK_LAURENT_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        cplx x[C::E];
-        load(p, line, act, t, s, x);
-        fft_line<N>(s, t, x, p.tw);
-        store(p, line, act, t, s);
+        run_via_smem<N, LineOp<N, LK_LAURENT_INV>>(p, line, act, t, s);
     }
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        const cplx* c = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
+    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* x) {
+        const cplx* c = reinterpret_cast<const cplx*>(p.in) + (act ? line * p.istride : 0);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
             const int m = t + C::T * r;
@@ -405,13 +459,10 @@ template <int N> struct LineOp<N, LK_LAURENT_INV> {
 template <int N> struct LineOp<N, LK_CFFT> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        cplx x[C::E];
-        load(p, line, act, t, s, x);
-        fft_line<N>(s, t, x, p.tw);
-        store(p, line, act, t, s);
+        run_via_smem<N, LineOp<N, LK_CFFT>>(p, line, act, t, s);
     }
-    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* s, cplx* x) {
-        const cplx* v = reinterpret_cast<const cplx*>(p.in) + line * p.istride;
+    static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* x) {
+        const cplx* v = reinterpret_cast<const cplx*>(p.in) + (act ? line * p.istride : 0);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
             cplx z = act ? v[(int64_t)(t + C::T * r) * p.ies] : make_double2(0.0, 0.0);
@@ -438,7 +489,7 @@ template <int N> struct LineOp<N, LK_CFFT> {
 
 // =================================================================================================
 template <int N, int KIND>
-__global__ void __launch_bounds__(LineGeom<N>::CT) line_kernel(LineParams p) {
+__global__ void __launch_bounds__(LineGeom<N>::CT) line_kernel(const __grid_constant__ LineParams p) {
     typedef LineGeom<N> G;
     AFB_DYN_SMEM(cplx, smem);
     const int tid = threadIdx.x;
@@ -474,11 +525,25 @@ template <int KIND> static int32_t launch_line_k(int N, const LineParams& p, voi
     }
 }
 
-// N = complex FFT length
+// geometry of the last DIT pass for length N (host side: table / constant construction)
+int32_t line_last_pass(int N, int* RL, int* NSL) {
+#define AFB_CASE(N_) case N_: *RL = FftCfg<N_>::RL; *NSL = FftCfg<N_>::NSL; return AFB_OK
+    switch (N) {
+        AFB_CASE(32); AFB_CASE(64); AFB_CASE(128); AFB_CASE(256); AFB_CASE(512); AFB_CASE(1024); AFB_CASE(2048);
+        AFB_CASE(4096); AFB_CASE(8192);
+        default: return fail(AFB_UNSUPPORTED, "line FFT length not instantiated");
+    }
+#undef AFB_CASE
+}
+
+// N = complex FFT length; K = MAXJ x MAXRL rotation constants (may be null for the complex kinds)
 int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
-                    const cplx* tw, const cplx* aux, double scale, void* stream) {
+                    int64_t oes, const cplx* tw, const cplx* aux, const cplx* K, double scale, void* stream) {
     if (batch == 0) return AFB_OK;
-    LineParams p{in, out, batch, istride, ostride, tw, aux, scale, 1, 1, 0, 0, nullptr, nullptr, 1};
+    LineParams p{};
+    p.in = in; p.out = out; p.batch = batch; p.istride = istride; p.ostride = ostride; p.tw = tw; p.aux = aux;
+    p.scale = scale; p.ies = 1; p.oes = oes; p.conj_in = 0; p.conj_out = 0; p.twA = nullptr; p.twB = nullptr; p.twmod = 1;
+    if (K) for (int j = 0; j < MAXJ; ++j) for (int q = 0; q < MAXRL; ++q) p.K[j][q] = K[j * MAXRL + q];
     switch (kind) {
         case LK_CHEB_FWD: return launch_line_k<LK_CHEB_FWD>(N, p, stream);
         case LK_CHEB_INV: return launch_line_k<LK_CHEB_INV>(N, p, stream);
@@ -490,6 +555,18 @@ int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, i
     }
 }
 
+// general strided complex FFT lines (see LineOp<N, LK_CFFT>)
+int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
+                          int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
+                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream) {
+    if (nlines == 0) return AFB_OK;
+    LineParams p{};
+    p.in = in; p.out = out; p.batch = nlines; p.istride = istride; p.ostride = ostride; p.tw = tw; p.aux = nullptr;
+    p.scale = scale; p.ies = ies; p.oes = oes; p.conj_in = conj_in ? 1 : 0; p.conj_out = conj_out ? 1 : 0;
+    p.twA = twA; p.twB = twB; p.twmod = twmod > 0 ? twmod : 1;
+    return launch_line_k<LK_CFFT>(N, p, stream);
+}
+
 // =================================================================================================
 // Direct O(n^2) kernels for tiny n (any n <= DIRECT_MAX): one thread per output element, exact integer
 // argument reduction into a cosine / root table.
@@ -497,22 +574,22 @@ int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, i
 //   tab for Fourier/Laurent: exp(-2 pi i m / n), m = 0..n-1
 // =================================================================================================
 __global__ void direct_kernel(int kind, int n, const void* __restrict__ in, void* __restrict__ out, int64_t batch,
-                              int64_t istride, int64_t ostride, const cplx* __restrict__ tab) {
+                              int64_t istride, int64_t ostride, int64_t oes, const cplx* __restrict__ tab) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= batch * n) return;
     const int64_t line = gid / n;
     const int o = (int)(gid % n);
-    const int l = n, nh = (n + 1) / 2;
+    const int l = n;
     if (kind == AFB_CHEB1_FWD || kind == AFB_CHEB1_INV) {
         const double* v = reinterpret_cast<const double*>(in) + line * istride;
         double* c = reinterpret_cast<double*>(out) + line * ostride;
         double acc = 0.0;
         if (kind == AFB_CHEB1_FWD) {
             for (int j = 0; j < n; ++j) acc += v[j] * tab[(o * (2 * j + 1)) % (4 * n)].x;
-            c[o] = acc * ((o == 0) ? 1.0 / n : 2.0 / n);
+            c[(int64_t)o * oes] = acc * ((o == 0) ? 1.0 / n : 2.0 / n);
         } else {
             for (int k = 0; k < n; ++k) acc += v[k] * tab[(k * (2 * o + 1)) % (4 * n)].x;
-            c[o] = acc;
+            c[(int64_t)o * oes] = acc;
         }
     } else if (kind == AFB_FOURIER_FWD) {
         const double* v = reinterpret_cast<const double*>(in) + line * istride;
@@ -524,7 +601,6 @@ __global__ void direct_kernel(int kind, int n, const void* __restrict__ in, void
         else if ((l % 2 == 0) && o == l - 1) { k = l / 2; nyq = true; }
         else if (o & 1) { k = (o + 1) / 2; sine = true; }
         else k = o / 2;
-        (void)nh;
         double re = 0.0, im = 0.0;
         for (int j = 0; j < n; ++j) {
             const cplx w = tab[(int)(((int64_t)j * k) % n)];
@@ -571,23 +647,13 @@ __global__ void direct_kernel(int kind, int n, const void* __restrict__ in, void
 }
 
 int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
-                      const cplx* tab, void* stream) {
+                      int64_t oes, const cplx* tab, void* stream) {
     if (batch == 0 || n == 0) return AFB_OK;
     const int64_t total = batch * n;
     auto k = direct_kernel;
-    AFB_LAUNCH(k, (unsigned)((total + 127) / 128), 128, 0, stream, kind, n, in, out, batch, istride, ostride, tab);
+    AFB_LAUNCH(k, (unsigned)((total + 127) / 128), 128, 0, stream, kind, n, in, out, batch, istride, ostride, oes, tab);
     AFB_KERNEL_CHECK();
     return AFB_OK;
-}
-
-// general strided complex FFT lines (see LineOp<N, LK_CFFT>)
-int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
-                          int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
-                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream) {
-    if (nlines == 0) return AFB_OK;
-    LineParams p{in, out, nlines, istride, ostride, tw, nullptr, scale, ies, oes, conj_in ? 1 : 0, conj_out ? 1 : 0,
-                 twA, twB, twmod > 0 ? twmod : 1};
-    return launch_line_k<LK_CFFT>(N, p, stream);
 }
 
 }  // namespace afb
