@@ -182,40 +182,70 @@ __device__ __forceinline__ void dit_last_paired(const LineParams& p, const cplx*
     }
 }
 
+// F additionally provides  fetch(k, raw) / fetch_dc(raw) (global loads only) so that every load of the
+// thread is in flight before the first dependent FP64 instruction.
 template <int N, int J, class F>
 __device__ __forceinline__ void dif_first_paired(const LineParams& p, cplx* __restrict__ s, int t, F& f) {
     typedef FftCfg<N> C;
-    constexpr int RL = C::RL, NSL = C::NSL;
+    constexpr int RL = C::RL, NSL = C::NSL, NP = C::BL / 2;
+    typename F::Raw raw[NP][RL + 1];  // +1: the self-paired slot (pi == 0) holds dc, mid and RL-1 pairs
+    // ---- phase A: issue every global load of the thread (twiddles are L1 hits and are fetched in phase B,
+    //      prefetching them as well costs ~40 registers and was measured slower) -------------------------
 #pragma unroll
-    for (int i = 0; i < C::BL / 2; ++i) {
+    for (int i = 0; i < NP; ++i) {
         const int pi = t + C::T * i;
-        cplx lo[RL], hi[RL], tb[J], tq[J];
+        if (pi != 0) {
+#pragma unroll
+            for (int q = 0; q < RL; ++q)
+                f.fetch((2 * q < RL) ? pi + NSL * q : (NSL - pi) + NSL * (RL - 1 - q), raw[i][q]);
+        } else {
+            f.fetch_dc(raw[i][0]);
+#pragma unroll
+            for (int q = 1; q < RL / 2; ++q) f.fetch(NSL * q, raw[i][q]);
+            f.fetch(N / 2, raw[i][RL / 2]);
+#pragma unroll
+            for (int q = 0; q < RL / 2; ++q) f.fetch(NSL / 2 + NSL * q, raw[i][RL / 2 + 1 + q]);  // RL/2 slots: hi
+        }
+    }
+    // ---- phase B: pair pre-processing + transposed last pass ------------------------------------------
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int pi = t + C::T * i;
+        cplx lo[RL], hi[RL], tq[J], tb[J];
         load_tw<J>(p.aux, pi, tb);
+        const cplx wlo = ldg2(p.tw + pair_lo<N>(pi));   // last-pass twiddle base w_N^j of both butterflies
+        const cplx whi = ldg2(p.tw + pair_hi<N>(pi));
         if (pi != 0) {
 #pragma unroll
             for (int q = 0; q < RL; ++q) {
                 rot_tw<N, J>(p, tb, q, tq);
-                if (2 * q < RL) f.pair(pi + NSL * q, lo[q], hi[RL - 1 - q], tq);
-                else f.pair((NSL - pi) + NSL * (RL - 1 - q), hi[RL - 1 - q], lo[q], tq);
+                if (2 * q < RL) f.pair(raw[i][q], lo[q], hi[RL - 1 - q], tq);
+                else f.pair(raw[i][q], hi[RL - 1 - q], lo[q], tq);
             }
         } else {
-            f.dc(lo[0]);
+            f.dc(raw[i][0], lo[0]);
 #pragma unroll
             for (int q = 1; q < RL / 2; ++q) {
                 rot_tw<N, J>(p, tb, q, tq);
-                f.pair(NSL * q, lo[q], lo[RL - q], tq);
+                f.pair(raw[i][q], lo[q], lo[RL - q], tq);
             }
+            cplx dummy;
             load_tw<J>(p.aux, NSL / 2 + 1, tq);
-            f.mid(lo[RL / 2], tq);
+            f.pair(raw[i][RL / 2], lo[RL / 2], dummy, tq);
             load_tw<J>(p.aux, NSL / 2, tb);
 #pragma unroll
             for (int q = 0; q < RL / 2; ++q) {
                 rot_tw<N, J>(p, tb, q, tq);
-                f.pair(NSL / 2 + NSL * q, hi[q], hi[RL - 1 - q], tq);
+                f.pair(raw[i][RL / 2 + 1 + q], hi[q], hi[RL - 1 - q], tq);
             }
         }
-        dif_first_bfly<N>(s, pair_lo<N>(pi), lo, p.tw);
-        dif_first_bfly<N>(s, pair_hi<N>(pi), hi, p.tw);
+        // transposed last pass: DFT then twiddle by w_N^(j r), scatter to the strided positions
+        Dft<RL>::run(lo);
+        apply_powers<RL>(lo, wlo);
+        st_strided<N, RL, C::SH>(s, pair_lo<N>(pi), lo);
+        Dft<RL>::run(hi);
+        apply_powers<RL>(hi, whi);
+        st_strided<N, RL, C::SH>(s, pair_hi<N>(pi), hi);
     }
     __syncthreads();
 }
@@ -277,32 +307,33 @@ template <int N> struct LineOp<N, LK_CHEB_FWD> {
 // ---- Chebyshev inverse (DCT-III) ------------------------------------------------------------------
 // t_0(k) = conj(w^k), t_1(k) = exp(+2 pi i k / n)
 template <int N> struct ChebInvPre {
+    struct Raw { double ck, cnk, cNk, cNpk; };
     const double* c;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK, const cplx* t) {
+    __device__ __forceinline__ void fetch(int k, Raw& r) {
         constexpr int n = 2 * N;
+        r.ck = 0; r.cnk = 0; r.cNk = 0; r.cNpk = 0;
+        if (act) { r.ck = c[k]; r.cnk = c[n - k]; r.cNk = c[N - k]; r.cNpk = c[N + k]; }
+    }
+    __device__ __forceinline__ void fetch_dc(Raw& r) {
+        r.ck = 0; r.cnk = 0; r.cNk = 0; r.cNpk = 0;
+        if (act) { r.ck = c[0]; r.cNk = c[N]; }
+    }
+    __device__ __forceinline__ void pair(const Raw& r, cplx& ZK, cplx& ZNK, const cplx* t) {
         const double h = 0.70710678118654752440;
-        double ck = 0, cnk = 0, cNk = 0, cNpk = 0;
-        if (act) { ck = c[k]; cnk = c[n - k]; cNk = c[N - k]; cNpk = c[N + k]; }
         const cplx wk = t[0];                                     // conj(w^k)
-        const cplx G = cmul(make_double2(ck, -cnk), wk);         // X_k / N
+        const cplx G = cmul(make_double2(r.ck, -r.cnk), wk);     // X_k / N
         const cplx e = make_double2((wk.x + wk.y) * h, (wk.x - wk.y) * h);  // conj(w^(N-k))
-        const cplx H = cmul(make_double2(cNk, -cNpk), e);        // X_{N-k} / N
+        const cplx H = cmul(make_double2(r.cNk, -r.cNpk), e);    // X_{N-k} / N
         const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
         const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
         const cplx Xo = cmul(W, t[1]);
         ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);            // conj(Z_k)     = conj(Xe) - i conj(Xo)
         ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);            // conj(Z_{N-k}) = Xe - i Xo
     }
-    __device__ __forceinline__ void dc(cplx& Z0) {
+    __device__ __forceinline__ void dc(const Raw& r, cplx& Z0) {
         const double h = 0.70710678118654752440;
-        double c0 = 0, cN = 0;
-        if (act) { c0 = c[0]; cN = c[N]; }
-        Z0 = make_double2(c0 + cN * h, -(c0 - cN * h));
-    }
-    __device__ __forceinline__ void mid(cplx& ZM, const cplx* t) {
-        cplx dummy;
-        pair(N / 2, ZM, dummy, t);
+        Z0 = make_double2(r.ck + r.cNk * h, -(r.ck - r.cNk * h));
     }
 };
 template <int N> struct LineOp<N, LK_CHEB_INV> {
@@ -368,28 +399,28 @@ template <int N> struct LineOp<N, LK_FOURIER_FWD> {
 // ---- Fourier inverse --------------------------------------------------------------------------------
 // t_0(k) = exp(+2 pi i k / n)
 template <int N> struct FourierInvPre {
+    struct Raw { double a, b, aN, bN; };
     const double* c;
     bool act;
-    __device__ __forceinline__ void pair(int k, cplx& ZK, cplx& ZNK, const cplx* t) {
-        cplx G = make_double2(0, 0), H = make_double2(0, 0);
-        if (act) {
-            G = make_double2(c[2 * k], -c[2 * k - 1]);                // F_k / N
-            H = make_double2(c[2 * (N - k)], -c[2 * (N - k) - 1]);    // F_{N-k} / N
-        }
+    __device__ __forceinline__ void fetch(int k, Raw& r) {
+        r.a = 0; r.b = 0; r.aN = 0; r.bN = 0;
+        if (act) { r.a = c[2 * k]; r.b = c[2 * k - 1]; r.aN = c[2 * (N - k)]; r.bN = c[2 * (N - k) - 1]; }
+    }
+    __device__ __forceinline__ void fetch_dc(Raw& r) {
+        r.a = 0; r.b = 0; r.aN = 0; r.bN = 0;
+        if (act) { r.a = c[0]; r.b = c[2 * N - 1]; }
+    }
+    __device__ __forceinline__ void pair(const Raw& r, cplx& ZK, cplx& ZNK, const cplx* t) {
+        const cplx G = make_double2(r.a, -r.b);                   // F_k / N
+        const cplx H = make_double2(r.aN, -r.bN);                 // F_{N-k} / N
         const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
         const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
         const cplx Xo = cmul(W, t[0]);
         ZK = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);
         ZNK = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);
     }
-    __device__ __forceinline__ void dc(cplx& Z0) {
-        double c0 = 0, cl = 0;
-        if (act) { c0 = c[0]; cl = c[2 * N - 1]; }
-        Z0 = make_double2(c0 - cl, -(c0 + cl));  // F_0/N = 2 c0, F_N/N = -2 c_last
-    }
-    __device__ __forceinline__ void mid(cplx& ZM, const cplx* t) {
-        cplx dummy;
-        pair(N / 2, ZM, dummy, t);
+    __device__ __forceinline__ void dc(const Raw& r, cplx& Z0) {
+        Z0 = make_double2(r.a - r.b, -(r.a + r.b));  // F_0/N = 2 c0, F_N/N = -2 c_last
     }
 };
 template <int N> struct LineOp<N, LK_FOURIER_INV> {
@@ -489,7 +520,7 @@ template <int N> struct LineOp<N, LK_CFFT> {
 
 // =================================================================================================
 template <int N, int KIND>
-__global__ void __launch_bounds__(LineGeom<N>::CT) line_kernel(const __grid_constant__ LineParams p) {
+__global__ void __launch_bounds__(LineGeom<N>::CT, 512 / LineGeom<N>::CT) line_kernel(const __grid_constant__ LineParams p) {
     typedef LineGeom<N> G;
     AFB_DYN_SMEM(cplx, smem);
     const int tid = threadIdx.x;
@@ -503,7 +534,11 @@ __global__ void __launch_bounds__(LineGeom<N>::CT) line_kernel(const __grid_cons
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
     typedef LineGeom<N> G;
     auto k = line_kernel<N, KIND>;
-    AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    static bool attr_done = false;  // one process drives one device: set the opt-in shared-memory size once
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
     const int64_t grid = (p.batch + G::LPC - 1) / G::LPC;
     AFB_LAUNCH(k, (unsigned)grid, G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();
