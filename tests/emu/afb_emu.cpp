@@ -48,10 +48,20 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
             }
             // round-robin: each sweep runs every live fiber up to its next barrier (or its end).
             // A barrier is complete when every live fiber has yielded once, which one sweep does.
+            // AFB_EMU_ORDER=reverse|shuffle runs the fibers of each sweep in another order: a missing barrier then
+            // shows up as a wrong answer whichever direction the dependency points (poor man's racecheck).
+            static const char* order_env = std::getenv("AFB_EMU_ORDER");
+            const int order = !order_env ? 0 : (order_env[0] == 'r' ? 1 : 2);
+            unsigned lcg = 12345u + bx * 7919u;
             bool live = true;
             while (live) {
                 live = false;
-                for (int t = 0; t < T; ++t) {
+                lcg = lcg * 1664525u + 1013904223u;
+                const int rot = (int)((lcg >> 16) % (unsigned)T);
+                for (int tt = 0; tt < T; ++tt) {
+                    int t = tt;
+                    if (order == 1) t = T - 1 - tt;
+                    else if (order == 2) t = (int)(((long)tt * 37 + rot) % T);  // a permutation: T is a power of two
                     if (blk.done[t]) continue;
                     blk.cur = t;
                     g_tid.x = (unsigned)t; g_tid.y = 0; g_tid.z = 0;

@@ -145,3 +145,44 @@ def test_normcumsum_and_bisection_bit_exact():
     assert np.array_equal(gm, orcc.cheb_normcumsum(M))
     u = RNG.random(140)
     assert np.array_equal(ll.cheb_bisect_cols(gm, u), orcc.cheb_bisect_cols(gm, u))
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle"])
+def test_barrier_placement_under_other_fiber_orders(order):
+    """Poor man's racecheck (compute-sanitizer is closed on the GPU pool): rerun a representative subset with the
+    emulator scheduling the fibers of every barrier interval in reverse / permuted order.  A missing
+    __syncthreads then reads stale or future data and changes the answer."""
+    import subprocess
+    import sys
+    import os
+
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from tests.emu_harness import emu_lowlevel
+from oracle import approxfun_oracle as orc
+B, ll = emu_lowlevel()
+rng = np.random.default_rng(3)
+for n in (64, 256, 1024, 4096, 16384):
+    v = rng.standard_normal((n, 2))
+    assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
+    assert np.max(np.abs(ll.transform(B.CHEB1_INV, v) - orc.cheb_itransform(v, axis=0))) < 1e-11
+    assert np.max(np.abs(ll.transform(B.FOURIER_FWD, v) - orc.fourier_transform(v, axis=0))) < 1e-13
+    assert np.max(np.abs(ll.transform(B.FOURIER_INV, v) - orc.fourier_itransform(v, axis=0))) < 1e-11
+    z = v + 1j * rng.standard_normal((n, 2))
+    if n <= 4096:
+        assert np.max(np.abs(ll.transform(B.LAURENT_FWD, z) - orc.laurent_transform(z, axis=0))) < 1e-13
+v = rng.standard_normal((100, 2))
+assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
+V = rng.standard_normal((64, 128))
+assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V) - orc.cheb2_transform(V))) < 1e-13
+c = rng.standard_normal(13000); x = rng.uniform(-1, 1, 600)
+from oracle import oracle_c as orcc
+assert np.array_equal(ll.clenshaw(c, x), orcc.clenshaw(c, x))
+M = np.abs(rng.standard_normal((9, 140))) + 1
+assert np.array_equal(ll.clenshaw_cols(M, x[:140]), orcc.clenshaw_cols(M, x[:140]))
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AFB_EMU_ORDER=order)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
