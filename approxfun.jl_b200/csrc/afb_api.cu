@@ -102,7 +102,7 @@ using namespace afb;
 // =====================================================================================================
 // plans
 // =====================================================================================================
-enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4 };
+enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4, PATH_LARGE = 5 };
 
 struct afb_plan_s {
     int32_t kind = 0;
@@ -276,6 +276,17 @@ static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t
             p->Nc = (int)Nc;
             st = root_table(Nc, &p->tw);
             if (st == AFB_OK) st = build_line_aux(p);
+        } else if (is_pow2(n) && p->elem == 8 && Nc > LINE_MAX_N) {
+            // large power-of-two real transform: half-length four-step FFT + one pair kernel
+            p->path = PATH_LARGE;
+            p->Nc = (int)Nc;
+            st = cfft_create(&p->cfft, Nc, 1);
+            if (st == AFB_OK) {
+                void* d = nullptr;
+                cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)Nc);
+                if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(large work)", __FILE__, __LINE__);
+                p->gwork = reinterpret_cast<cplx*>(d);
+            }
         } else {
             p->path = PATH_GENERIC;
             st = build_generic(p);
@@ -309,6 +320,22 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
         case PATH_LINE:
             return launch_line(p->line_kind, p->Nc, d_in, d_out, batch, istride, ostride, oes, p->tw, p->aux,
                                p->K.empty() ? nullptr : p->K.data(), p->scale, stream);
+        case PATH_LARGE: {
+            if (oes != 1) return fail(AFB_UNSUPPORTED, "large path has no strided output");
+            const bool cheb = p->kind == AFB_CHEB1_FWD || p->kind == AFB_CHEB1_INV;
+            for (int64_t b = 0; b < batch; ++b) {
+                const double* in = reinterpret_cast<const double*>(d_in) + b * istride;
+                double* out = reinterpret_cast<double*>(d_out) + b * ostride;
+                if ((p->kind & 1) == 0) {
+                    AFB_TRY(cfft_exec_dctorder(p->cfft, in, p->gwork, false, false, 1.0, cheb ? 1 : 0, stream));
+                    AFB_TRY(launch_large_post(p->kind, p->n, p->gwork, out, stream));
+                } else {
+                    AFB_TRY(launch_large_pre(p->kind, p->n, in, p->gwork, stream));
+                    AFB_TRY(cfft_exec_dctorder(p->cfft, p->gwork, out, false, true, 1.0, cheb ? 2 : 0, stream));
+                }
+            }
+            return AFB_OK;
+        }
         case PATH_GENERIC: {
             if (oes != 1) return fail(AFB_UNSUPPORTED, "generic path has no strided output");
             const bool inv = (p->kind & 1) != 0;
@@ -331,6 +358,7 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         case PATH_EMPTY: return 0;
         case PATH_DIRECT: return 1;
         case PATH_LINE: return 1;
+        case PATH_LARGE: return (int32_t)(3 * p->batch);
         case PATH_GENERIC: {
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
@@ -525,7 +553,7 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
         }
         p->pchunk = ch;
     }
-    const bool generic = p->path == PATH_GENERIC;
+    const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE;
     int64_t c = 0;
     for (int64_t b0 = 0; b0 < p->batch; b0 += p->pchunk, ++c) {
         // the generic path shares one work buffer between chunks: keep it on a single stream

@@ -115,6 +115,8 @@ static inline double sinpi(double x) {
     return (std::fmod(k, 2.0) == 0.0) ? s : -s;
 }
 
+static inline void sincospi(double x, double* s, double* c) { *s = sinpi(x); *c = sinpi(x + 0.5); }
+
 // --- runtime API stand-ins (host memory is "device" memory) -------------------------------------
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }

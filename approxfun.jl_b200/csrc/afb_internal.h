@@ -21,7 +21,8 @@ int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, i
 int32_t line_last_pass(int N, int* RL, int* NSL);
 int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
                           int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
-                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream);
+                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream, int io_mode = 0,
+                          int64_t bigN = 0);
 int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
                       int64_t oes, const cplx* tab, void* stream);
 
@@ -42,6 +43,12 @@ void cfft_destroy(CfftPlan* p);
 // out[b*n + k] = scale * sum_j in[b*n + j] exp(-/+ 2 pi i jk/n)   (inverse = +, unnormalised); in == out allowed
 int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale, void* stream);
 int32_t cfft_launches(const CfftPlan* p);
+// four-step only: real DCT-ordered input (io_mode bit 0) / output (bit 1); see LineParams::io_mode
+int32_t cfft_exec_dctorder(CfftPlan* p, const void* in, void* out, bool conj_in, bool conj_out, double scale, int io_mode,
+                           void* stream);
+// large power-of-two real transforms: half-length four-step FFT + one pair kernel (afb_large.cu)
+int32_t launch_large_post(int kind, int64_t n, const cplx* Z, double* out, void* stream);
+int32_t launch_large_pre(int kind, int64_t n, const double* in, cplx* Zc, void* stream);
 
 // pre/post kernels mapping the real transforms onto a length-n complex FFT (afb_large.cu)
 int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,

@@ -312,4 +312,111 @@ int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, in
     return AFB_OK;
 }
 
+// =====================================================================================================
+// Large power-of-two real transforms (n >= 32768; config 1 is n = 2^20): ONE half-length complex four-step FFT
+// (N = n/2 = n1 n2) whose step A gathers straight from the real array in DCT order (or whose step B scatters
+// back to it), plus one pair kernel doing the real-FFT split / quarter-wave twiddle with sincospi twiddles.
+// Three launches and 6 x 8N bytes of (L2-resident) traffic per transform instead of four launches and 14 x 8N.
+// =====================================================================================================
+int32_t cfft_exec_dctorder(CfftPlan* p, const void* in, void* out, bool conj_in, bool conj_out, double scale, int io_mode,
+                           void* stream) {
+    if (p->mode != 1) return fail(AFB_BAD_ARG, "cfft_exec_dctorder needs a four-step plan");
+    const int64_t n = p->n, n1 = p->n1, n2 = p->n2;
+    AFB_TRY(launch_cfft_lines((int)n1, reinterpret_cast<const cplx*>(in), p->tmp, n2, 1, n2, 1, n2, p->tw1, conj_in, false,
+                              1.0, p->twA, p->twB, n2, stream, io_mode & 1, n));
+    AFB_TRY(launch_cfft_lines((int)n2, p->tmp, reinterpret_cast<cplx*>(out), n1, n2, 1, 1, n1, p->tw2, false, conj_out, scale,
+                              nullptr, nullptr, 1, stream, io_mode & 2, n));
+    return AFB_OK;
+}
+
+__device__ __forceinline__ cplx unit_pi(double x) {  // exp(-i pi x)
+    double sn, cs;
+    sincospi(x, &sn, &cs);
+    return make_double2(cs, -sn);
+}
+
+// forward: Z (length N = n/2, natural order) -> coefficients
+__global__ void large_post_kernel(int kind, int64_t N, const cplx* __restrict__ Z, double* __restrict__ c) {
+    const int64_t n = 2 * N;
+    const double inv_n = 1.0 / (double)n, h = 0.70710678118654752440;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= N / 2; k += (int64_t)gridDim.x * blockDim.x) {
+        if (k == 0) {
+            const cplx A = Z[0];
+            c[0] = (A.x + A.y) * inv_n;
+            if (kind == AFB_CHEB1_FWD) c[N] = (A.x - A.y) * (inv_n * 1.41421356237309504880);
+            else c[n - 1] = -(A.x - A.y) * inv_n;
+            continue;
+        }
+        const cplx A = Z[k], B = Z[N - k];
+        const cplx S = make_double2(A.x + B.x, A.y - B.y);
+        const cplx D = make_double2(A.x - B.x, A.y + B.y);
+        if (kind == AFB_CHEB1_FWD) {
+            const cplx w1 = unit_pi((double)k / (double)(2 * n));
+            const cplx w5 = unit_pi((double)(5 * k) / (double)(2 * n));
+            const cplx U = cmul(S, make_double2(w1.x * inv_n, w1.y * inv_n));
+            const cplx V = cmul(D, make_double2(w5.y * inv_n, -w5.x * inv_n));   // -i w^(5k) / n
+            const cplx P = cadd(U, V), Q = csub(U, V);
+            c[k] = P.x;
+            c[n - k] = -P.y;
+            if (2 * k != N) {
+                c[N - k] = (Q.x - Q.y) * h;
+                c[N + k] = (Q.x + Q.y) * h;
+            }
+        } else {  // AFB_FOURIER_FWD
+            const cplx w = unit_pi((double)(2 * k) / (double)n);                     // exp(-2 pi i k / n)
+            const cplx G = cmul(D, make_double2(w.y * inv_n, -w.x * inv_n));        // -i w / n
+            const cplx Sn = make_double2(S.x * inv_n, S.y * inv_n);
+            c[2 * k] = Sn.x + G.x;
+            c[2 * k - 1] = -(Sn.y + G.y);
+            if (2 * k != N) {
+                c[2 * (N - k)] = Sn.x - G.x;
+                c[2 * (N - k) - 1] = Sn.y - G.y;
+            }
+        }
+    }
+}
+
+// inverse: coefficients -> conj(Z') (length N, natural order), 1/N folded in
+__global__ void large_pre_kernel(int kind, int64_t N, const double* __restrict__ c, cplx* __restrict__ Zc) {
+    const int64_t n = 2 * N;
+    const double h = 0.70710678118654752440;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= N / 2; k += (int64_t)gridDim.x * blockDim.x) {
+        if (k == 0) {
+            if (kind == AFB_CHEB1_INV) Zc[0] = make_double2(c[0] + c[N] * h, -(c[0] - c[N] * h));
+            else Zc[0] = make_double2(c[0] - c[n - 1], -(c[0] + c[n - 1]));
+            continue;
+        }
+        cplx G, H;
+        if (kind == AFB_CHEB1_INV) {
+            const cplx w = unit_pi((double)k / (double)(2 * n));
+            const cplx wk = make_double2(w.x, -w.y);                                  // conj(w^k)
+            G = cmul(make_double2(c[k], -c[n - k]), wk);
+            const cplx e = make_double2((wk.x + wk.y) * h, (wk.x - wk.y) * h);       // conj(w^(N-k))
+            H = cmul(make_double2(c[N - k], -c[N + k]), e);
+        } else {
+            G = make_double2(c[2 * k], -c[2 * k - 1]);
+            H = make_double2(c[2 * (N - k)], -c[2 * (N - k) - 1]);
+        }
+        const cplx t = unit_pi(-(double)(2 * k) / (double)n);                        // exp(+2 pi i k / n)
+        const cplx Xe = make_double2(0.5 * (G.x + H.x), 0.5 * (G.y - H.y));
+        const cplx W = make_double2(0.5 * (G.x - H.x), 0.5 * (G.y + H.y));
+        const cplx Xo = cmul(W, t);
+        Zc[k] = make_double2(Xe.x - Xo.y, -Xe.y - Xo.x);
+        Zc[N - k] = make_double2(Xe.x + Xo.y, Xe.y - Xo.x);
+    }
+}
+
+int32_t launch_large_post(int kind, int64_t n, const cplx* Z, double* out, void* stream) {
+    auto k = large_post_kernel;
+    AFB_LAUNCH(k, ew_grid(n / 4 + 1), 256, 0, stream, kind, n / 2, Z, out);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_large_pre(int kind, int64_t n, const double* in, cplx* Zc, void* stream) {
+    auto k = large_pre_kernel;
+    AFB_LAUNCH(k, ew_grid(n / 4 + 1), 256, 0, stream, kind, n / 2, in, Zc);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 }  // namespace afb

@@ -35,6 +35,8 @@ struct LineParams {
     // element strides (complex FFT both; Chebyshev kinds: output only, for the fused 2-D transpose)
     int64_t ies, oes;
     int conj_in, conj_out;
+    int io_mode;      // LK_CFFT: bit 0 = input is a REAL array in Makhoul (DCT) order, bit 1 = output likewise
+    int64_t bigN;     // ... of a length-bigN complex sequence z[m] = (v[4m], v[4m+2]) | (v[4q+3], v[4q+1]), q = bigN-1-m
     const cplx* twA;  // four-step: w_n^(m >> 12 << 12)
     const cplx* twB;  // w_n^(m & 4095);  output (line L, index i) is multiplied by w_n^((L mod twmod) * i)
     int64_t twmod;
@@ -494,9 +496,19 @@ template <int N> struct LineOp<N, LK_CFFT> {
     }
     static __device__ __forceinline__ void load(const LineParams& p, int64_t line, bool act, int t, cplx* x) {
         const cplx* v = reinterpret_cast<const cplx*>(p.in) + (act ? line * p.istride : 0);
+        const double* vr = reinterpret_cast<const double*>(p.in);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
-            cplx z = act ? v[(int64_t)(t + C::T * r) * p.ies] : make_double2(0.0, 0.0);
+            cplx z = make_double2(0.0, 0.0);
+            if (act) {
+                if (p.io_mode & 1) {  // gather from the real array in DCT order
+                    const int64_t m = line * p.istride + (int64_t)(t + C::T * r) * p.ies;
+                    if (2 * m < p.bigN) z = make_double2(vr[4 * m], vr[4 * m + 2]);
+                    else { const int64_t q = p.bigN - 1 - m; z = make_double2(vr[4 * q + 3], vr[4 * q + 1]); }
+                } else {
+                    z = v[(int64_t)(t + C::T * r) * p.ies];
+                }
+            }
             if (p.conj_in) z.y = -z.y;
             x[r] = z;
         }
@@ -513,7 +525,14 @@ template <int N> struct LineOp<N, LK_CFFT> {
             }
             z = cscale(z, p.scale);
             if (p.conj_out) z.y = -z.y;
-            c[(int64_t)i * p.oes] = z;
+            if (p.io_mode & 2) {  // scatter to the real array in DCT order
+                double* vr = reinterpret_cast<double*>(p.out);
+                const int64_t m = line * p.ostride + (int64_t)i * p.oes;
+                if (2 * m < p.bigN) { vr[4 * m] = z.x; vr[4 * m + 2] = z.y; }
+                else { const int64_t q = p.bigN - 1 - m; vr[4 * q + 3] = z.x; vr[4 * q + 1] = z.y; }
+            } else {
+                c[(int64_t)i * p.oes] = z;
+            }
         }
     }
 };
@@ -593,12 +612,13 @@ int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, i
 // general strided complex FFT lines (see LineOp<N, LK_CFFT>)
 int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
                           int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
-                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream) {
+                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream, int io_mode, int64_t bigN) {
     if (nlines == 0) return AFB_OK;
     LineParams p{};
     p.in = in; p.out = out; p.batch = nlines; p.istride = istride; p.ostride = ostride; p.tw = tw; p.aux = nullptr;
     p.scale = scale; p.ies = ies; p.oes = oes; p.conj_in = conj_in ? 1 : 0; p.conj_out = conj_out ? 1 : 0;
     p.twA = twA; p.twB = twB; p.twmod = twmod > 0 ? twmod : 1;
+    p.io_mode = io_mode; p.bigN = bigN;
     return launch_line_k<LK_CFFT>(N, p, stream);
 }
 
