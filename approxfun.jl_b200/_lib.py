@@ -31,6 +31,7 @@ SYMBOLS = [
     "afb_philox_uniform_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
+    "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open",
 ]
 
 
@@ -91,6 +92,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_sharded2d_create": [C.POINTER(vp), i32, i64, i64],
         "afb_sharded2d_execute_device": [vp, vp, vp, vp],
         "afb_sharded2d_destroy": [vp],
+        "afb_sharded2d_ipc_export": [vp, vp],
+        "afb_sharded2d_ipc_open": [vp, vp, i32],
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, args in sig.items():

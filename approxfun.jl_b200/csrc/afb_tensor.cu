@@ -55,6 +55,32 @@ __global__ void a2a_unpack_kernel(const double* __restrict__ R, double* __restri
     }
 }
 
+// Fused transpose + all-to-all over NVLink peer memory: tile (i, j) of this rank's n x nc column block (after the
+// column transforms) is transposed through shared memory and written STRAIGHT into the row-line buffer of the rank
+// that owns row i (local HBM for d == rank, a peer-mapped pointer otherwise): L_d[(i - d nr) * n2 + rank * nc + j].
+// One kernel replaces pack-transpose + NCCL send/recv + unpack; stores are 256-byte contiguous runs per row.
+struct PeerPtrs { double* p[16]; };
+__global__ void __launch_bounds__(256) transpose_to_peers_kernel(const double* __restrict__ in, PeerPtrs peers, int64_t n,
+                                                                 int64_t nc, int64_t nr, int64_t n2, int64_t rank) {
+    AFB_DYN_SMEM(double, tile);  // TR_TILE x (TR_TILE+1)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t i0 = (int64_t)blockIdx.x * TR_TILE, j0 = (int64_t)blockIdx.y * TR_TILE;
+#pragma unroll
+    for (int r = 0; r < TR_TILE; r += 8) {
+        const int64_t i = i0 + tx, j = j0 + ty + r;
+        if (i < n && j < nc) tile[(ty + r) * (TR_TILE + 1) + tx] = in[i + j * n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TR_TILE; r += 8) {
+        const int64_t j = j0 + tx, i = i0 + ty + r;
+        if (i < n && j < nc) {
+            const int64_t d = i / nr;
+            peers.p[d][(i - d * nr) * n2 + rank * nc + j] = tile[tx * (TR_TILE + 1) + ty + r];
+        }
+    }
+}
+
 }  // namespace afb
 
 using namespace afb;
@@ -116,6 +142,11 @@ struct Sharded2D {
     afb_plan col_plan = nullptr;  // length n,  batch n2/G
     afb_plan row_plan = nullptr;  // length n2, batch n/G
     double *tbuf = nullptr, *rbuf = nullptr;
+    // peer-memory (CUDA IPC) mode: lbuf receives every rank's tiles; peer[d] = rank d's lbuf mapped here
+    double* lbuf = nullptr;
+    double* peer[16] = {nullptr};
+    bool p2p = false;
+    double* sync_buf = nullptr;  // 2 x G doubles for the NCCL stream barrier
 };
 
 extern "C" {
@@ -208,6 +239,69 @@ int32_t afb_sharded2d_create(void** out, int32_t kind, int64_t n, int64_t n2) {
 #endif
 }
 
+#ifndef AFB_HOST_EMU
+// stream-ordered barrier over the communicator (one double to and from every peer)
+static int32_t nccl_stream_barrier(Sharded2D& s, void* stream) {
+    AFB_NCCL(g_nccl.GroupStart());
+    for (int64_t d = 0; d < s.G; ++d) {
+        if (d == s.rank) continue;
+        AFB_NCCL(g_nccl.Send(s.sync_buf + d, 1, ncclFloat64, (int)d, g_comm, (cudaStream_t)stream));
+        AFB_NCCL(g_nccl.Recv(s.sync_buf + s.G + d, 1, ncclFloat64, (int)d, g_comm, (cudaStream_t)stream));
+    }
+    AFB_NCCL(g_nccl.GroupEnd());
+    return AFB_OK;
+}
+#endif
+
+// Peer-memory mode (one process per GPU): each rank exports the CUDA IPC handle of its receive buffer
+// (64 bytes), the host layer all-gathers them, and every rank maps its peers' buffers.
+int32_t afb_sharded2d_ipc_export(void* handle, void* handle64) {
+#ifdef AFB_HOST_EMU
+    (void)handle; (void)handle64;
+    return fail(AFB_UNSUPPORTED, "no CUDA IPC in the emulator build");
+#else
+    ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
+    if (!h || h->magic != 0x5348415244324421ull || !handle64) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_export: bad argument");
+    Sharded2D& s = h->s;
+    if (!s.lbuf) {
+        void* d = nullptr;
+        AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)((s.n / s.G) * s.n2)));
+        s.lbuf = reinterpret_cast<double*>(d);
+    }
+    cudaIpcMemHandle_t mh;
+    AFB_CUDA(cudaIpcGetMemHandle(&mh, s.lbuf));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &mh, 64);
+    return AFB_OK;
+#endif
+}
+
+int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world) {
+#ifdef AFB_HOST_EMU
+    (void)handle; (void)handles; (void)world;
+    return fail(AFB_UNSUPPORTED, "no CUDA IPC in the emulator build");
+#else
+    ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
+    if (!h || h->magic != 0x5348415244324421ull || !handles) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_open: bad argument");
+    Sharded2D& s = h->s;
+    if (world != s.G || world > 16 || !s.lbuf) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_open: export first; world <= 16");
+    for (int64_t d = 0; d < s.G; ++d) {
+        if (d == s.rank) { s.peer[d] = s.lbuf; continue; }
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, reinterpret_cast<const char*>(handles) + 64 * d, 64);
+        void* p = nullptr;
+        AFB_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        s.peer[d] = reinterpret_cast<double*>(p);
+    }
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)(2 * s.G)));
+    AFB_CUDA(cudaMemset(d, 0, sizeof(double) * (size_t)(2 * s.G)));
+    s.sync_buf = reinterpret_cast<double*>(d);
+    s.p2p = true;
+    return AFB_OK;
+#endif
+}
+
 // d_in : this rank's column block, column-major n x (n2/G)
 // d_out: this rank's ROW block of the result, stored as n/G contiguous lines of length n2
 //        (= the transposed coefficient matrix sharded by columns); see DESIGN.md "multi-GPU 2-D"
@@ -222,6 +316,20 @@ int32_t afb_sharded2d_execute_device(void* handle, const double* d_in, double* d
     const int64_t n = s.n, G = s.G, nc = s.n2 / G, nr = n / G;
     // 1. local column transforms (in place into rbuf to keep d_in intact)
     AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
+    if (s.p2p) {
+        // every rank must be done reading its lbuf (previous call's row transforms) before anyone overwrites it
+        AFB_TRY(nccl_stream_barrier(s, stream));
+        PeerPtrs pp;
+        for (int d = 0; d < 16; ++d) pp.p[d] = s.peer[d];
+        const int64_t gx = (n + TR_TILE - 1) / TR_TILE, gy = (nc + TR_TILE - 1) / TR_TILE;
+        auto kt = transpose_to_peers_kernel;
+        AFB_LAUNCH(kt, dim3((unsigned)gx, (unsigned)gy), 256, sizeof(double) * TR_TILE * (TR_TILE + 1), stream, s.rbuf, pp, n, nc,
+                   nr, s.n2, s.rank);
+        AFB_KERNEL_CHECK();
+        // all peers' tiles have landed in my lbuf once every rank has passed this barrier
+        AFB_TRY(nccl_stream_barrier(s, stream));
+        return afb_plan_execute_device(s.row_plan, s.lbuf, d_out, stream);
+    }
     // 2. pack = local transpose: T[i*nc + j], rows of destination d are the contiguous range i in [d nr, (d+1) nr)
     AFB_TRY(launch_transpose(s.rbuf, s.tbuf, n, nc, stream));
     // 3. all-to-all over NVLink (grouped send/recv: the installed NCCL header has no ncclAlltoAll)
@@ -249,6 +357,12 @@ int32_t afb_sharded2d_destroy(void* handle) {
     if (h->s.row_plan) afb_plan_destroy(h->s.row_plan);
     if (h->s.tbuf) cudaFree(h->s.tbuf);
     if (h->s.rbuf) cudaFree(h->s.rbuf);
+#ifndef AFB_HOST_EMU
+    for (int64_t d = 0; d < h->s.G; ++d)
+        if (h->s.p2p && d != h->s.rank && h->s.peer[d]) cudaIpcCloseMemHandle(h->s.peer[d]);
+#endif
+    if (h->s.lbuf) cudaFree(h->s.lbuf);
+    if (h->s.sync_buf) cudaFree(h->s.sync_buf);
     h->magic = 0;
     delete h;
     return AFB_OK;

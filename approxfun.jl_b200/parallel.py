@@ -61,7 +61,7 @@ class Sharded2DPlan:
 
     _comm_ready = False
 
-    def __init__(self, kind: int, n: int, n2: int):
+    def __init__(self, kind: int, n: int, n2: int, p2p: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -85,6 +85,18 @@ class Sharded2DPlan:
         L.check(self.lib, self.lib.afb_sharded2d_create(C.byref(h), kind, n, n2))
         self._h = h
         self.n, self.n2, self.world, self.rank = n, n2, world, rank
+        self.p2p = False
+        if p2p and world > 1 and dist.get_backend() == "nccl":
+            # peer-memory mode: all-gather the 64-byte CUDA IPC handles of the receive buffers
+            mine = (C.c_ubyte * 64)()
+            L.check(self.lib, self.lib.afb_sharded2d_ipc_export(self._h, mine))
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allh, t)
+            blob = b"".join(bytes(x.cpu().tolist()) for x in allh)
+            L.check(self.lib, self.lib.afb_sharded2d_ipc_open(self._h, blob, world))
+            self.p2p = True
 
     def execute(self, in_ptr: int, out_ptr: int, stream: int = 0):
         L.check(self.lib, self.lib.afb_sharded2d_execute_device(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_void_p(stream)))

@@ -373,6 +373,23 @@ def main():
                                   "hbm_frac_of_32B_per_element": 32.0 * n2d * n2d / (t * 1e-3) / 1e9 / peak,
                                   "launches": p2.launches}
         del V
+        if world > 1:
+            # config 4 across GPUs (strong scaling: ONE 16384 x 16384 matrix, column slabs -> all-to-all -> row slabs)
+            from approxfun_b200 import parallel as par
+            nc, nr = n2d // world, n2d // world
+            blk = torch.randn(nc, n2d, dtype=torch.float64, device="cuda", generator=g)   # column-major n x nc
+            rows = torch.empty(nr, n2d, dtype=torch.float64, device="cuda")
+            nv_bytes = 8.0 * n2d * nc * (world - 1) / world       # bytes this rank sends over NVLink per transform
+            for mode, p2p in (("nccl_sendrecv", False), ("peer_memory_fused", True)):
+                sp = par.Sharded2DPlan(L.CHEB1_2D_FWD, n2d, n2d, p2p=p2p)
+                t = time_loop(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), stream), 5, 3)
+                extras[f"cheb2d_16384_sharded_{mode}"] = {
+                    "ms_per_step": t, "elements_per_s": float(n2d) * n2d / (t * 1e-3), "scaling": "strong",
+                    "nvlink_bytes_per_rank": nv_bytes,
+                    "nvlink_frac_of_770GBs_if_transfer_alone": nv_bytes / (t * 1e-3) / 1e9 / 770.0}
+                barrier()
+                sp.close()
+            del blk, rows
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu:

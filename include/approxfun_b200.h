@@ -169,6 +169,11 @@ int32_t afb_comm_destroy(void);
 int32_t afb_sharded2d_create(void** handle, int32_t kind, int64_t n, int64_t n2);
 int32_t afb_sharded2d_execute_device(void* handle, const double* d_in, double* d_out, void* stream);
 int32_t afb_sharded2d_destroy(void* handle);
+/* Optional peer-memory mode: replaces pack + NCCL send/recv + unpack by ONE kernel that transposes tiles straight
+ * into the owning rank's buffer over NVLink (CUDA IPC mapped peer memory).  Each rank exports 64 bytes, the host layer
+ * all-gathers them (world x 64 bytes) and passes the array to afb_sharded2d_ipc_open on every rank. */
+int32_t afb_sharded2d_ipc_export(void* handle, void* handle64);
+int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world);
 
 #ifdef __cplusplus
 }

@@ -55,15 +55,20 @@ def _worker(rank, world, port, q):
         af.api.DevicePlan(L.CHEB1_2D_FWD, n1, n2, 1, n1).execute(M.data_ptr(), full.data_ptr(), st)
         nc, nr = n2 // world, n1 // world
         block = M[rank * nc:(rank + 1) * nc].contiguous()
-        out = torch.empty(nr, n2, dtype=torch.float64, device="cuda")
-        plan = par.Sharded2DPlan(L.CHEB1_2D_FWD, n1, n2)
-        plan.execute(block.data_ptr(), out.data_ptr(), st)
-        torch.cuda.synchronize()
         # full is column-major n1 x n2: full[j, i] = C[i, j]; out[i_local, j] = C[rank*nr + i_local, j]
         want = full[:, rank * nr:(rank + 1) * nr].t().contiguous()
-        err = float((out - want).abs().max())
-        plan.close()
-        q.put((rank, ok1, err))
+        errs = []
+        for p2p in (False, True):     # NCCL send/recv all-to-all, then the fused peer-memory transpose kernel
+            out = torch.zeros(nr, n2, dtype=torch.float64, device="cuda")
+            plan = par.Sharded2DPlan(L.CHEB1_2D_FWD, n1, n2, p2p=p2p)
+            assert plan.p2p == p2p
+            for _ in range(3):        # repeated calls exercise the write-after-read barrier
+                plan.execute(block.data_ptr(), out.data_ptr(), st)
+            torch.cuda.synchronize()
+            errs.append(float((out - want).abs().max()))
+            dist.barrier()
+            plan.close()
+        q.put((rank, ok1, max(errs)))
     finally:
         dist.destroy_process_group()
 
