@@ -29,6 +29,7 @@ SYMBOLS = [
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device",
+    "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
     "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open",
@@ -86,6 +87,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_samplecdf_cheb": [vp, i64, dbl, dbl, vp, vp, i64],
         "afb_sample_cheb_device": [vp, i64, dbl, dbl, u64, u64, vp, i64, vp],
         "afb_philox_uniform_device": [u64, u64, vp, i64, vp],
+        "afb_sample2d_cheb_lowrank": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64],
+        "afb_sample2d_cheb_lowrank_device": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64, vp],
+        "afb_dgemm_nn": [vp, vp, vp, i64, i64, i64],
+        "afb_dgemm_nn_device": [vp, vp, vp, i64, i64, i64, vp],
         "afb_comm_unique_id": [vp],
         "afb_comm_create": [vp, i32, i32],
         "afb_comm_destroy": [],
@@ -263,6 +268,32 @@ class LowLevel:
         out = np.empty(u.size)
         check(self.lib, self.lib.afb_cheb_bisect_cols(_ptr(flat), N, N, _ptr(u), _ptr(out), u.size if P == u.size else -1, numits))
         return out
+
+    def sample2d_lowrank(self, A, CB, ya, yb, xa, xb, ry, u) -> np.ndarray:
+        """A: (NA, R), CB: (N, R) coefficient matrices (columns = functions); returns rx."""
+        A = np.asarray(A, dtype=np.float64)
+        CB = np.asarray(CB, dtype=np.float64)
+        ry = np.ascontiguousarray(ry, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if A.shape[1] != CB.shape[1] or ry.size != u.size:
+            raise DimensionMismatch(AFB_BAD_SIZE, "sample2d_lowrank: rank / sample-count mismatch")
+        Af, Cf = np.ascontiguousarray(A.T), np.ascontiguousarray(CB.T)
+        rx = np.empty_like(u)
+        check(self.lib, self.lib.afb_sample2d_cheb_lowrank(_ptr(Af), A.shape[0], _ptr(Cf), CB.shape[0], A.shape[1],
+                                                           ya, yb, xa, xb, _ptr(ry), _ptr(u), _ptr(rx), u.size))
+        return rx
+
+    def dgemm_nn(self, CB, fA) -> np.ndarray:
+        CB = np.asarray(CB, dtype=np.float64)
+        fA = np.asarray(fA, dtype=np.float64)
+        N, R = CB.shape
+        R2, P = fA.shape
+        if R != R2:
+            raise DimensionMismatch(AFB_BAD_SIZE, "dgemm_nn: inner dimensions differ")
+        a, b = np.ascontiguousarray(CB.T), np.ascontiguousarray(fA.T)
+        out = np.empty((P, N))
+        check(self.lib, self.lib.afb_dgemm_nn(_ptr(a), _ptr(b), _ptr(out), N, R, P))
+        return np.ascontiguousarray(out.T)
 
     def samplecdf(self, cdf_c, a: float, b: float, u) -> np.ndarray:
         c = np.ascontiguousarray(cdf_c, dtype=np.float64)

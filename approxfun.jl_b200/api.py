@@ -366,8 +366,113 @@ def samplecdf(cf: Fun, n: int, rng=None, uniforms=None):
     return bisectioninv(cf, np.asarray(uniforms, dtype=np.float64))
 
 
-def sample(f: Fun, n: int | None = None, rng=None, uniforms=None):
-    """sample.jl:182: samplecdf(normalizedcumsum(f), n); `sample(f)` returns one sample."""
+def genmidpoint(a: float, b: float) -> float:
+    """sample.jl:11-21: midpoint that also works for infinite end points."""
+    if math.isinf(a) and math.isinf(b):
+        return 0.0
+    if math.isinf(a):
+        return b - 100
+    if math.isinf(b):
+        return a + 100
+    return (a + b) / 2
+
+
+def bisectioninv_generic(f: Fun, x, numits: int = 47):
+    """sample.jl:23-36: the generic (any-space) bisection -- 47 evaluations of `f` per entry, each evaluation a
+    GPU Clenshaw call over all entries at once."""
+    sp = f.space
+    scalar = np.ndim(x) == 0
+    xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    a = np.full_like(xv, min(sp.a, sp.b))
+    b = np.full_like(xv, max(sp.a, sp.b))
+    for _ in range(numits):
+        m = np.array([genmidpoint(ai, bi) for ai, bi in zip(a, b)]) if (np.isinf(a).any() or np.isinf(b).any()) else (a + b) / 2
+        val = f(m)
+        le = val <= xv
+        a = np.where(le, m, a)
+        b = np.where(le, b, m)
+    out = 0.5 * (a + b)
+    return float(out[0]) if scalar else out
+
+
+class ProductFun:
+    """`ProductFun(f, sp, N, M)`: values on the tensor grid -> coefficient matrix C[i,j] (T_i(x) T_j(y))."""
+
+    def __init__(self, f, sp: "TensorSpace", N: int | None = None, M: int | None = None):
+        if isinstance(f, Fun):
+            self.space, self.coefficients = f.space, np.asarray(f.coefficients)
+        else:
+            g = Fun(f, sp, (N, N if M is None else M))
+            self.space, self.coefficients = g.space, g.coefficients
+
+    def __call__(self, x, y):
+        return Fun(self.space, self.coefficients)(x, y)
+
+
+def coefficientmatrix(funs) -> np.ndarray:
+    """`coefficientmatrix(::Vector{Fun})`: columns = zero-padded coefficient vectors."""
+    n = max(len(f.coefficients) for f in funs)
+    out = np.zeros((n, len(funs)))
+    for r, f in enumerate(funs):
+        out[: len(f.coefficients), r] = f.coefficients
+    return out
+
+
+class LowRankFun:
+    """f(x,y) = sum_r A_r(x) B_r(y).  UPSTREAM ApproxFunBase builds it by adaptive cross approximation; here the
+    factors come from the SVD of the coefficient matrix (same function, same conditional densities)."""
+
+    def __init__(self, f, tol: float = 1e-15):
+        pf = f if isinstance(f, ProductFun) else ProductFun(f, f.space)
+        Cm = np.asarray(pf.coefficients, dtype=np.float64)
+        U, S, Vt = np.linalg.svd(Cm, full_matrices=False)
+        R = max(1, int(np.sum(S > tol * S[0])))
+        s1, s2 = pf.space.factors
+        self.space = pf.space
+        self.A = [Fun(s1, U[:, r] * S[r]) for r in range(R)]
+        self.B = [Fun(s2, Vt[r].copy()) for r in range(R)]
+
+    def __call__(self, x, y):
+        return sum(a(x) * b(y) for a, b in zip(self.A, self.B))
+
+
+def _definite_integral(f: Fun) -> float:
+    c = np.asarray(f.coefficients, dtype=np.float64)
+    k = np.arange(c.size)
+    with np.errstate(divide="ignore"):
+        w = np.where(k % 2 == 0, 2.0 / (1.0 - k.astype(np.float64) ** 2), 0.0)
+    return float(w @ c) * (f.space.b - f.space.a) / 2.0
+
+
+def lowrank_sum(f: LowRankFun, dim: int) -> Fun:
+    """`sum(f::LowRankFun, dim)`: integrate out variable `dim` (1 = x, 2 = y)."""
+    if dim == 1:
+        w = np.array([_definite_integral(a) for a in f.A])
+        return Fun(f.B[0].space, coefficientmatrix(f.B) @ w)
+    w = np.array([_definite_integral(b) for b in f.B])
+    return Fun(f.A[0].space, coefficientmatrix(f.A) @ w)
+
+
+def sample2d(f: LowRankFun, n: int, rng=None, uniforms=None) -> np.ndarray:
+    """`sample(f::LowRankFun{Chebyshev,Chebyshev}, n)` (sample.jl:205-214), line for line; the conditional stage
+    (lines 208-213) is ONE fused GPU kernel that never materialises the N x n matrix AB.  Returns [rx ry]."""
+    if uniforms is None:
+        rng = rng or np.random.default_rng()
+        uniforms = (rng.random(n), rng.random(n))
+    u_y, u_x = (np.asarray(u, dtype=np.float64) for u in uniforms)
+    ry = sample(lowrank_sum(f, 1), n, uniforms=u_y)                 # ry = sample(sum(f,1), n)
+    s1 = f.A[0].space
+    rx = lowlevel().sample2d_lowrank(coefficientmatrix(f.A), coefficientmatrix(f.B), s1.a, s1.b, s1.a, s1.b, ry, u_x)
+    return np.stack([rx, ry], axis=1)
+
+
+def sample(f, n: int | None = None, rng=None, uniforms=None):
+    """sample.jl:182: samplecdf(normalizedcumsum(f), n); `sample(f)` returns one sample.
+    2-D (sample.jl:196,218): Fun on a TensorSpace / ProductFun -> LowRankFun -> `sample2d`."""
+    if isinstance(f, (ProductFun, LowRankFun)) or (isinstance(f, Fun) and isinstance(f.space, TensorSpace)):
+        lr = f if isinstance(f, LowRankFun) else LowRankFun(f)
+        out = sample2d(lr, 1 if n is None else n, rng, uniforms)
+        return out[0] if n is None else out
     one = n is None
     out = samplecdf(normalizedcumsum(f), 1 if one else n, rng, uniforms)
     return float(out[0]) if one else out

@@ -771,4 +771,54 @@ int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out,
     return launch_philox(seed, offset, d_out, P, stream);
 }
 
+
+// ---- 2-D sampling pieces (src/Extras/sample.jl:205-214) ---------------------------------------------------
+int32_t afb_sample2d_cheb_lowrank_device(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R,
+                                         double ya, double yb, double xa, double xb, const double* d_ry,
+                                         const double* d_u, double* d_rx, int64_t P, void* stream) {
+    if (NA < 0 || N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_sample2d_cheb_lowrank: negative size");
+    if (P == 0) return AFB_OK;
+    if ((NA * R && !d_A) || (N * R && !d_CB) || !d_ry || !d_u || !d_rx)
+        return fail(AFB_BAD_ARG, "afb_sample2d_cheb_lowrank: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_sample2d(d_A, NA, d_CB, N, R, ya, yb, xa, xb, d_ry, d_u, d_rx, P, 47, stream);
+}
+int32_t afb_sample2d_cheb_lowrank(const double* A, int64_t NA, const double* CB, int64_t N, int64_t R, double ya,
+                                  double yb, double xa, double xb, const double* ry, const double* u, double* rx,
+                                  int64_t P) {
+    if (NA < 0 || N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_sample2d_cheb_lowrank: negative size");
+    if (P == 0) return AFB_OK;
+    if ((NA * R && !A) || (N * R && !CB) || !ry || !u || !rx) return fail(AFB_BAD_ARG, "afb_sample2d_cheb_lowrank: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dA, dCB, dry, du, drx;
+    AFB_TRY(dA.alloc(8 * (size_t)(NA * R))); AFB_TRY(dCB.alloc(8 * (size_t)(N * R)));
+    AFB_TRY(dry.alloc(8 * (size_t)P)); AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(drx.alloc(8 * (size_t)P));
+    AFB_TRY(dA.put(A, 8 * (size_t)(NA * R))); AFB_TRY(dCB.put(CB, 8 * (size_t)(N * R)));
+    AFB_TRY(dry.put(ry, 8 * (size_t)P)); AFB_TRY(du.put(u, 8 * (size_t)P));
+    AFB_TRY(launch_sample2d(dA.as<double>(), NA, dCB.as<double>(), N, R, ya, yb, xa, xb, dry.as<double>(), du.as<double>(),
+                            drx.as<double>(), P, 47, nullptr));
+    return drx.get(rx, 8 * (size_t)P);
+}
+
+// AB = CB * fA  (N x R times R x P, column-major; the dgemm of src/Extras/sample.jl:210)
+int32_t afb_dgemm_nn_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
+                            void* stream) {
+    if (N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_dgemm_nn: negative size");
+    if (N * P == 0) return AFB_OK;
+    if ((N * R && !d_CB) || (R * P && !d_fA) || !d_AB) return fail(AFB_BAD_ARG, "afb_dgemm_nn: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_gemm_nn(d_CB, d_fA, d_AB, N, R, P, stream);
+}
+int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, int64_t R, int64_t P) {
+    if (N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_dgemm_nn: negative size");
+    if (N * P == 0) return AFB_OK;
+    if ((N * R && !CB) || (R * P && !fA) || !AB) return fail(AFB_BAD_ARG, "afb_dgemm_nn: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf a, b, c;
+    AFB_TRY(a.alloc(8 * (size_t)(N * R))); AFB_TRY(b.alloc(8 * (size_t)(R * P))); AFB_TRY(c.alloc(8 * (size_t)(N * P)));
+    AFB_TRY(a.put(CB, 8 * (size_t)(N * R))); AFB_TRY(b.put(fA, 8 * (size_t)(R * P)));
+    AFB_TRY(launch_gemm_nn(a.as<double>(), b.as<double>(), c.as<double>(), N, R, P, nullptr));
+    return c.get(AB, 8 * (size_t)(N * P));
+}
+
 }  // extern "C"

@@ -430,4 +430,126 @@ int32_t launch_chebpoints(double* d_out, int64_t n, double a, double b, void* st
     return AFB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused conditional sampler of sample(f::LowRankFun{Chebyshev,Chebyshev}, n)  (src/Extras/sample.jl:205-214):
+//     fA = evaluate.(f.A, ry') ; AB = CB*fA ; chebnormalizedcumsum!(AB) ; rx = chebbisectioninv(AB, rand(n))
+// One thread per sample: its column of AB (N coefficients) lives in a padded shared-memory tile and never
+// touches HBM -- the reference materialises the N x n matrix AB (and streams it 47 times).
+//   A  : NA x R column-major (coefficients of the R functions f.A), evaluated at tocanonical(ya..yb, ry)
+//   CB : N  x R column-major (coefficientmatrix(f.B))
+// AB[k] = sum_r CB[k,r] fA[r] is accumulated in r order with fused multiply-adds.
+// ------------------------------------------------------------------------------------------------
+constexpr int S2_W = 128;
+constexpr int S2_LD = S2_W + 1;
+__global__ void __launch_bounds__(S2_W)
+sample2d_kernel(const double* __restrict__ A, int64_t NA, const double* __restrict__ CB, int64_t N, int64_t R,
+                double ya, double yb, double xa, double xb, const double* __restrict__ ry,
+                const double* __restrict__ u, double* __restrict__ rx, int64_t P, int numits) {
+    AFB_DYN_SMEM(double, sm);  // [N][S2_LD]
+    const int tid = threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.x * S2_W + tid;
+    const bool act = j < P;
+    double* col = sm + tid;
+    // tocanonical(d, y) = (2y - a - b) / (b - a); the reference's evaluate returns 0 outside the domain
+    const double y = act ? ry[j] : 0.5 * (ya + yb);
+    const bool inside = (y >= (ya < yb ? ya : yb)) && (y <= (ya < yb ? yb : ya));
+    const double yc = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, y), ya), yb), __dsub_rn(yb, ya));
+    const double y2 = __dmul_rn(2.0, yc);
+    for (int64_t k = 0; k < N; ++k) col[k * S2_LD] = 0.0;
+    for (int64_t r = 0; r < R; ++r) {
+        const double* a = A + r * NA;
+        double fa = 0.0;
+        if (inside) {
+            if (NA == 1) fa = a[0];
+            else if (NA > 1) {
+                double b1 = 0.0, b2 = 0.0;
+                for (int64_t k = NA - 1; k >= 1; --k) {
+                    const double t = __fma_rn(y2, b1, __dsub_rn(__ldg(a + k), b2));
+                    b2 = b1;
+                    b1 = t;
+                }
+                fa = __fma_rn(__dmul_rn(y2, 0.5), b1, __dsub_rn(__ldg(a), b2));
+            }
+        }
+        const double* cb = CB + r * N;
+        for (int64_t k = 0; k < N; ++k) col[k * S2_LD] = __fma_rn(__ldg(cb + k), fa, col[k * S2_LD]);
+    }
+    // chebnormalizedcumsum! (matrix semantics: no growth), same operation order as normcumsum_kernel
+    const int64_t n = N;
+    if (n == 2) {
+        col[S2_LD] = __ddiv_rn(col[S2_LD], 2.0);
+    } else if (n > 2) {
+        col[0] = __dsub_rn(col[0], __ddiv_rn(col[2 * S2_LD], 2.0));
+        for (int64_t q = 1; q <= n - 3; ++q) col[q * S2_LD] = __ddiv_rn(__dsub_rn(col[q * S2_LD], col[(q + 2) * S2_LD]), 2.0);
+        col[(n - 2) * S2_LD] = __ddiv_rn(col[(n - 2) * S2_LD], 2.0);
+        col[(n - 1) * S2_LD] = __ddiv_rn(col[(n - 1) * S2_LD], 2.0);
+    }
+    for (int64_t k = n - 1; k >= 1; --k) col[k * S2_LD] = __ddiv_rn(col[(k - 1) * S2_LD], (double)k);
+    if (n > 0) col[0] = 0.0;
+    for (int64_t k = 2; k <= n; ++k) col[0] = __dadd_rn(col[0], (k & 1) ? -col[(k - 1) * S2_LD] : col[(k - 1) * S2_LD]);
+    double val = 0.0;
+    for (int64_t k = 0; k < n; ++k) val = __dadd_rn(val, col[k * S2_LD]);
+    val = __ddiv_rn(1.0, val);
+    for (int64_t k = 0; k < n; ++k) col[k * S2_LD] = __dmul_rn(col[k * S2_LD], val);
+    // 47 Clenshaw bisections on the thread's own column
+    double lo = -1.0, hi = 1.0;
+    const double uu = act ? u[j] : 0.5;
+    for (int it = 0; it < numits; ++it) {
+        const double m = __dmul_rn(0.5, __dadd_rn(lo, hi));
+        double v;
+        if (n == 0) v = 0.0;
+        else if (n == 1) v = col[0];
+        else {
+            const double x2 = __dmul_rn(2.0, m);
+            double b1 = 0.0, b2 = 0.0;
+            for (int64_t k = n - 1; k >= 1; --k) {
+                const double t = __fma_rn(x2, b1, __dsub_rn(col[k * S2_LD], b2));
+                b2 = b1;
+                b1 = t;
+            }
+            v = __fma_rn(__dmul_rn(x2, 0.5), b1, __dsub_rn(col[0], b2));
+        }
+        if (v <= uu) lo = m; else hi = m;
+    }
+    const double xm = __dmul_rn(0.5, __dadd_rn(lo, hi));
+    const double mid = __dmul_rn(__dadd_rn(xa, xb), 0.5), len = __dsub_rn(xb, xa);
+    if (act) rx[j] = __dadd_rn(mid, __dmul_rn(__dmul_rn(len, xm), 0.5));
+}
+
+// unfused fallback piece for very long B factors (tile does not fit shared memory): AB = CB * fA
+__global__ void gemm_nn_kernel(const double* __restrict__ CB, const double* __restrict__ fA, double* __restrict__ AB,
+                               int64_t N, int64_t R, int64_t P) {
+    const int64_t total = N * P;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = g % N, j = g / N;
+        double acc = 0.0;
+        for (int64_t r = 0; r < R; ++r) acc = __fma_rn(CB[k + N * r], fA[r + R * j], acc);
+        AB[g] = acc;
+    }
+}
+
+int32_t launch_sample2d(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R, double ya, double yb,
+                        double xa, double xb, const double* d_ry, const double* d_u, double* d_rx, int64_t P, int numits,
+                        void* stream) {
+    if (P == 0) return AFB_OK;
+    const size_t smem = sizeof(double) * (size_t)(N > 0 ? N : 1) * S2_LD;
+    if (smem > 200 * 1024) return fail(AFB_UNSUPPORTED, "sample2d: B factors longer than 198 coefficients need the unfused path");
+    auto k = sample2d_kernel;
+    AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AFB_LAUNCH(k, (unsigned)((P + S2_W - 1) / S2_W), S2_W, smem, stream, d_A, NA, d_CB, N, R, ya, yb, xa, xb, d_ry, d_u, d_rx,
+               P, numits);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream) {
+    if (N * P == 0) return AFB_OK;
+    int64_t grid = (N * P + 255) / 256;
+    if (grid > 16 * (int64_t)sm_count()) grid = 16 * (int64_t)sm_count();
+    auto k = gemm_nn_kernel;
+    AFB_LAUNCH(k, (unsigned)grid, 256, 0, stream, d_CB, d_fA, d_AB, N, R, P);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 }  // namespace afb

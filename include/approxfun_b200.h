@@ -156,6 +156,22 @@ int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, doubl
 /* the uniforms afb_sample_cheb_device draws, for parity checks */
 int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
 
+/* ---- 2-D sampling (sample(f::LowRankFun{Chebyshev,Chebyshev}, n), src/Extras/sample.jl:205-214) -------------
+ * Fused replacement of lines 208-213: fA = evaluate.(f.A, ry'); AB = CB*fA; chebnormalizedcumsum!(AB);
+ * rx = chebbisectioninv(AB, u); fromcanonical.(domain(f,1), rx).  A is NA x R and CB is N x R (column-major
+ * coefficient matrices of f.A and f.B), ya..yb the domain f.A is evaluated on, xa..xb = domain(f,1), ry the
+ * samples of the other variable, u the caller's rand(n).  The N x n matrix AB is never materialised (N <= 198). */
+int32_t afb_sample2d_cheb_lowrank(const double* A, int64_t NA, const double* CB, int64_t N, int64_t R, double ya,
+                                  double yb, double xa, double xb, const double* ry, const double* u, double* rx,
+                                  int64_t P);
+int32_t afb_sample2d_cheb_lowrank_device(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R,
+                                         double ya, double yb, double xa, double xb, const double* d_ry,
+                                         const double* d_u, double* d_rx, int64_t P, void* stream);
+/* AB = CB*fA (N x R times R x P, column-major): the dgemm of src/Extras/sample.jl:210 as a stand-alone call. */
+int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, int64_t R, int64_t P);
+int32_t afb_dgemm_nn_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
+                            void* stream);
+
 /* ---- multi-GPU 2D transform (one process per GPU) ----------------------------------------------------
  * The n x n2 matrix is sharded by contiguous column blocks; the plan performs local column transforms,
  * an all-to-all transpose over NVLink, and local transforms of the other factor.  The caller supplies

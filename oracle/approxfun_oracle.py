@@ -549,3 +549,36 @@ def adaptive_fun_coefficients(f, a: float = -1.0, b: float = 1.0):
         if np.max(np.abs(c[-8:])) < tol * mx:
             return chop(c, tol * mx)
     return fun_coefficients(f, 2 ** 21, a, b)
+
+
+# --------------------------------------------------------------------------------------
+# a11 / a15  2-D sampling through a low-rank representation (src/Extras/sample.jl:205-214)
+# --------------------------------------------------------------------------------------
+
+
+def lowrank_factors(Cm: np.ndarray, tol: float = 1e-15):
+    """Low-rank factors of a coefficient matrix C[i,j] (T_i(x) T_j(y)):  f = sum_r A_r(x) B_r(y).
+
+    UPSTREAM ApproxFunBase builds LowRankFun by adaptive cross approximation; any factorisation gives the same
+    conditional densities, so this restatement uses the SVD (A = U*S, B = V) truncated at tol * s_1.
+    Returns (A, B): coefficient matrices (n1, R) and (n2, R)."""
+    U, S, Vt = np.linalg.svd(np.asarray(Cm, dtype=np.float64), full_matrices=False)
+    R = max(1, int(np.sum(S > tol * S[0])))
+    return U[:, :R] * S[:R], Vt[:R].T.copy()
+
+
+def sample2d_lowrank(A, B, dom1, dom2, u_y, u_x) -> np.ndarray:
+    """Literal restatement of sample(f::LowRankFun{Chebyshev,Chebyshev}, n) (sample.jl:205-214) with the two
+    `rand(n)` draws supplied by the caller.  A: (n1, R) coefficients of f.A on dom1, B: (n2, R) of f.B on dom2.
+    Returns the n x 2 matrix [rx ry]."""
+    a1, b1 = dom1
+    a2, b2 = dom2
+    w = cheb_definite_integrals(A.shape[0]) * (b1 - a1) / 2
+    marg = B @ (w @ A)                                   # sum(f,1) = sum_r (int A_r) B_r : a Fun on dom2
+    ry = sample_from_uniforms(marg, a2, b2, u_y)         # ry = sample(sum(f,1), n)
+    inside = (ry >= min(a1, b1)) & (ry <= max(a1, b1))
+    fA = clenshaw_multi(A, tocanonical(a1, b1, ry)) * inside      # fA = evaluate.(f.A, ry')
+    AB = B @ fA                                          # CB = coefficientmatrix(f.B); AB = CB*fA
+    AB = chebnormalizedcumsum(AB, grow=False)
+    rx = chebbisectioninv_cols(AB, u_x)
+    return np.stack([fromcanonical(a1, b1, rx), ry], axis=1)   # [fromcanonical.(domain(f,1), rx) ry]

@@ -36,6 +36,9 @@ def lib():
         L.orc_cheb_bisect_cols.argtypes = [_dp, i64, i64, _dp, _dp, i64, i32, i32]
         L.orc_cheb_bisect_planned.argtypes = [_dp, i64, _dp, _dp, i64, i32, _dp, i32]
         L.orc_cheb_normcumsum.argtypes = [_dp, i64, i64, i64, i32]
+        L.orc_sample2d_lowrank.argtypes = [_dp, i64, _dp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           _dp, _dp, _dp, i64, i32]
+        L.orc_sample2d_lowrank.restype = None
         L.orc_max_threads.restype = i32
         for f in (L.orc_clenshaw, L.orc_clenshaw_planned, L.orc_clenshaw_cols, L.orc_clenshaw_multi,
                   L.orc_cheb_bisect, L.orc_cheb_bisect_cols, L.orc_cheb_bisect_planned,
@@ -133,3 +136,15 @@ def cheb_normcumsum(Cm, grow: bool | None = None):
     lib().orc_cheb_normcumsum(buf.ravel(), N, P, ld, int(g))
     L = N + 1 if g else N
     return np.ascontiguousarray(buf[:, :L].T)
+
+
+def sample2d_lowrank(A, CB, ya, yb, xa, xb, ry, u, threads: int = 1):
+    """A: (NA, R), CB: (N, R) with columns = functions; returns rx (sample.jl:208-213 given ry and u)."""
+    A = np.asarray(A, dtype=np.float64)
+    CB = np.asarray(CB, dtype=np.float64)
+    ry, u = _c(ry), _c(u)
+    rx = np.empty_like(u)
+    Af, Cf = np.ascontiguousarray(A.T).ravel(), np.ascontiguousarray(CB.T).ravel()
+    lib().orc_sample2d_lowrank(Af if Af.size else np.zeros(1), A.shape[0], Cf if Cf.size else np.zeros(1), CB.shape[0],
+                               A.shape[1], ya, yb, xa, xb, ry, u, rx, u.size, threads)
+    return rx

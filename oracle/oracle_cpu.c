@@ -169,6 +169,35 @@ void orc_cheb_normcumsum(double* C, int64_t N, int64_t ncols, int64_t ld, int gr
     for (int64_t j = 0; j < ncols; ++j) normcumsum_col(C + j * ld, N, grow);
 }
 
+/* sample(f::LowRankFun{Chebyshev,Chebyshev}, n), src/Extras/sample.jl:208-213, given ry and the uniforms:
+ *   fA = evaluate.(f.A, ry') ; AB = CB*fA ; chebnormalizedcumsum!(AB) ; rx = chebbisectioninv(AB, u) ; fromcanonical.
+ * BLAS leaves the summation order of CB*fA unspecified; this restatement accumulates over r in order with fma
+ * (the order the GPU kernel uses) so that the two can be compared bit for bit.  A: NA x R, CB: N x R column-major. */
+void orc_sample2d_lowrank(const double* A, int64_t NA, const double* CB, int64_t N, int64_t R, double ya, double yb,
+                          double xa, double xb, const double* ry, const double* u, double* rx, int64_t P, int nthreads) {
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t j = 0; j < P; ++j) {
+        double* col = (double*)malloc(sizeof(double) * (size_t)(N > 0 ? N : 1));
+        const double y = ry[j];
+        const double lo_d = ya < yb ? ya : yb, hi_d = ya < yb ? yb : ya;
+        const int inside = (y >= lo_d) && (y <= hi_d);
+        const double yc = (2.0 * y - ya - yb) / (yb - ya);
+        for (int64_t k = 0; k < N; ++k) col[k] = 0.0;
+        for (int64_t r = 0; r < R; ++r) {
+            const double fa = inside ? clenshaw1(A + r * NA, NA, 1, yc) : 0.0;
+            for (int64_t k = 0; k < N; ++k) col[k] = fma(CB[r * N + k], fa, col[k]);
+        }
+        normcumsum_col(col, N, 0);
+        double a = -1.0, b = 1.0;
+        for (int it = 0; it < 47; ++it) {
+            const double m = 0.5 * (a + b);
+            if (clenshaw1(col, N, 1, m) <= u[j]) a = m; else b = m;
+        }
+        rx[j] = (xa + xb) * 0.5 + ((xb - xa) * (0.5 * (a + b))) * 0.5;
+        free(col);
+    }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

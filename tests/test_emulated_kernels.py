@@ -147,6 +147,25 @@ def test_normcumsum_and_bisection_bit_exact():
     assert np.array_equal(ll.cheb_bisect_cols(gm, u), orcc.cheb_bisect_cols(gm, u))
 
 
+def test_sample2d_fused_kernel_bit_exact():
+    # src/Extras/sample.jl:208-213 as one kernel: evaluate.(f.A, ry'), CB*fA, chebnormalizedcumsum!, chebbisectioninv
+    for NA, N, R, P in [(12, 9, 3, 300), (1, 1, 1, 5), (30, 66, 7, 140), (5, 2, 2, 130)]:
+        A = RNG.standard_normal((NA, R)) / (1 + np.arange(NA))[:, None]
+        CB = np.abs(RNG.standard_normal((N, R))) / (1 + np.arange(N))[:, None] ** 2
+        CB[0] += 3.0
+        A[0] = np.abs(A[0]) + 2.0            # positive weights keep every conditional density positive
+        ry = RNG.uniform(-4, 4, P)
+        ry[0] = 4.5                          # outside the domain: evaluate returns 0 there
+        u = RNG.random(P)
+        got = ll.sample2d_lowrank(A, CB, -4.0, 4.0, -4.0, 4.0, ry, u)
+        want = orcc.sample2d_lowrank(A, CB, -4.0, 4.0, -4.0, 4.0, ry, u)
+        ok = np.isfinite(want)
+        assert np.array_equal(got[ok], want[ok])
+    CB = RNG.standard_normal((7, 4))
+    fA = RNG.standard_normal((4, 50))
+    assert np.max(np.abs(ll.dgemm_nn(CB, fA) - CB @ fA)) < 1e-14
+
+
 @pytest.mark.parametrize("order", ["reverse", "shuffle"])
 def test_barrier_placement_under_other_fiber_orders(order):
     """Poor man's racecheck (compute-sanitizer is closed on the GPU pool): rerun a representative subset with the

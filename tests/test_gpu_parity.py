@@ -235,6 +235,42 @@ def test_tensor_transform_and_sampling_golden(af):
     assert abs(F2(0.1, 0.2) - math.cos(0.5)) < 1e-13
 
 
+def test_sampling_2d_lowrank(af):
+    # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
+    S = af.Chebyshev(-4, 4)
+    f = af.Fun(lambda x, y: (x - y) ** 2 * np.exp(-x ** 2 / 2 - y ** 2 / 2), S ** 2, 96)
+    r = af.sample(f, 5000)
+    assert r.shape == (5000, 2) and np.all(np.abs(r) <= 4)
+    # parity with caller-supplied uniforms, same low-rank factors on both sides
+    lr = af.LowRankFun(f)
+    A, B = af.coefficientmatrix(lr.A), af.coefficientmatrix(lr.B)
+    rng = np.random.default_rng(11)
+    n = 200000
+    u_y, u_x = rng.random(n), rng.random(n)
+    got = af.sample(lr, n, uniforms=(u_y, u_x))
+    marg = af.api.lowrank_sum(lr, 1)
+    cdf = af.normalizedcumsum(marg).coefficients
+    assert np.max(np.abs(cdf - orc.normalizedcumsum(marg.coefficients, -4.0, 4.0))) < 1e-15
+    ry = orc.fromcanonical(-4.0, 4.0, orcc.cheb_bisect(cdf, u_y, threads=8))
+    assert np.array_equal(got[:, 1], ry)                                     # 1-D stage: bit exact
+    rx_c = orcc.sample2d_lowrank(A, B, -4.0, 4.0, -4.0, 4.0, ry, u_x, threads=8)
+    assert np.array_equal(got[:, 0], rx_c)                                    # fused conditional stage: bit exact
+    want = orc.sample2d_lowrank(A, B, (-4.0, 4.0), (-4.0, 4.0), u_y, u_x)    # literal sample.jl:205-214 with a BLAS dgemm
+    d = np.abs(got - want)
+    assert np.mean(d[:, 0] < 1e-9) > 0.999 and np.max(d[:, 1]) < 1e-9         # dgemm summation order may flip rare ties
+    # the samples follow f: compare E[x y] with quadrature of the density
+    x = af.points(S, 96)
+    V = (x[:, None] - x[None, :]) ** 2 * np.exp(-x[:, None] ** 2 / 2 - x[None, :] ** 2 / 2)
+    w = orc.cheb_definite_integrals(96) * 4.0
+    Cm = orc.cheb2_transform(V)
+    Cxy = orc.cheb2_transform(V * x[:, None] * x[None, :])
+    exy = float(w @ Cxy @ w) / float(w @ Cm @ w)
+    assert abs(np.mean(got[:, 0] * got[:, 1]) - exy) < 0.02
+    # stand-alone dgemm entry point (sample.jl:210)
+    fA = rng.standard_normal((B.shape[1], 1000))
+    assert np.max(np.abs(af.api.lowlevel().dgemm_nn(B, fA) - B @ fA)) < 1e-12
+
+
 def test_config2_full_size_properties(af):
     # BASELINE.json configs[1] at full size, device resident: round trip + linearity + column subsample vs oracle
     import torch
