@@ -344,6 +344,25 @@ def main():
         t = time_loop(lambda: af.api.sample_device(dc.data_ptr(), cdf.size, -5.0, 5.0, 42, 0, y.data_ptr(), P, stream), 3, 1)
         extras["sample_gaussian"] = {"samples_per_s": world * P / (t * 1e-3), "ms_per_step": t, "N": int(cdf.size),
                                      "fp64_frac_of_nominal_peak": 47 * 3.0 * cdf.size * P / (t * 1e-3) / fp64_peak}
+        if rank == 0 and not args.no_cpu:
+            # reference-side CPU baselines for configs 3 and 5 (oracle port, reference loop order: whole-vector passes
+            # through the ClenshawPlan work vectors, all host threads), on bounded point sets
+            cores = os.cpu_count() or 1
+            xc = np.random.default_rng(1).uniform(-1, 1, 200000)
+            ccpu = cc.cpu().numpy()
+            t0 = time.perf_counter()
+            orcc.clenshaw_planned(ccpu, xc, threads=cores)
+            tc = time.perf_counter() - t0
+            extras["clenshaw_N1e4"]["cpu_baseline"] = {
+                "value": xc.size / tc, "unit": "evaluations/s", "cores": cores, "kind": "port",
+                "sample": f"{xc.size} points, N=10^4, k-outer/i-inner plan loop order (UPSTREAM AFOP), C + OpenMP"}
+            uc = np.random.default_rng(2).random(2000000)
+            t0 = time.perf_counter()
+            orcc.cheb_bisect_planned(cdf, uc, threads=cores)
+            tc = time.perf_counter() - t0
+            extras["sample_gaussian"]["cpu_baseline"] = {
+                "value": uc.size / tc, "unit": "samples/s", "cores": cores, "kind": "port",
+                "sample": f"{uc.size} samples, 47 whole-vector Clenshaw passes (sample.jl:58-75 loop order), C + OpenMP"}
         del x, y
         # config 1: one long transform, n = 2^20 (transform + itransform of sin(x^2) on 0..10); 16 MiB per direction
         # lives in L2, so rotate over 16 distinct buffers (> 126 MB L2) and report it as a latency-bound number
