@@ -73,6 +73,22 @@ class Laurent(Space):
         self.a, self.b = float(a), float(b)
 
 
+class CosSpace(Space):
+    """`CosSpace()`: f(theta) = sum_k f_k cos(k theta); same coefficients and transform as `Chebyshev`
+    (docs/src/usage/spaces.md:39-49), on theta_j = pi (j + 1/2) / n."""
+
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
+class SinSpace(Space):
+    """`SinSpace()`: f(theta) = sum_k f_k sin((k+1) theta) on theta_j = pi j/(n+1), j = 1..n
+    (plans: src/Extras/fftGeneric.jl:74-81)."""
+
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
 class TensorSpace(Space):
     def __init__(self, s1: Chebyshev, s2: Chebyshev):
         if not (isinstance(s1, Chebyshev) and isinstance(s2, Chebyshev)):
@@ -80,8 +96,10 @@ class TensorSpace(Space):
         self.factors = (s1, s2)
 
 
-_FWD = {Chebyshev: L.CHEB1_FWD, Fourier: L.FOURIER_FWD, Laurent: L.LAURENT_FWD, TensorSpace: L.CHEB1_2D_FWD}
-_INV = {Chebyshev: L.CHEB1_INV, Fourier: L.FOURIER_INV, Laurent: L.LAURENT_INV, TensorSpace: L.CHEB1_2D_INV}
+_FWD = {Chebyshev: L.CHEB1_FWD, Fourier: L.FOURIER_FWD, Laurent: L.LAURENT_FWD, TensorSpace: L.CHEB1_2D_FWD,
+        CosSpace: L.CHEB1_FWD, SinSpace: L.SIN_FWD}
+_INV = {Chebyshev: L.CHEB1_INV, Fourier: L.FOURIER_INV, Laurent: L.LAURENT_INV, TensorSpace: L.CHEB1_2D_INV,
+        CosSpace: L.CHEB1_INV, SinSpace: L.SIN_INV}
 
 
 def points(space: Space, n: int, m: int | None = None):
@@ -93,6 +111,10 @@ def points(space: Space, n: int, m: int | None = None):
         return ll.fourierpoints(n, space.a, space.b)
     if isinstance(space, TensorSpace):
         return points(space.factors[0], n), points(space.factors[1], n if m is None else m)
+    if isinstance(space, CosSpace):
+        return math.pi * (np.arange(n) + 0.5) / n
+    if isinstance(space, SinSpace):
+        return math.pi * np.arange(1, n + 1) / (n + 1)
     raise TypeError(space)
 
 
@@ -168,6 +190,16 @@ def plan_transform(space: Space, v_or_n) -> TransformPlan:
 
 def plan_itransform(space: Space, v_or_n) -> ITransformPlan:
     return ITransformPlan(space, _shape_of(v_or_n))
+
+
+def chebyshevtransform(v, kind: int = 1):
+    """UPSTREAM FastTransforms `chebyshevtransform(v, Val(kind))`: kind 1 = first-kind points (REDFT10),
+    kind 2 = second-kind points cos(pi j/(n-1)) (REDFT00)."""
+    return lowlevel().transform(L.CHEB1_FWD if kind == 1 else L.CHEB2_FWD, v)
+
+
+def ichebyshevtransform(c, kind: int = 1):
+    return lowlevel().transform(L.CHEB1_INV if kind == 1 else L.CHEB2_INV, c)
 
 
 def transform(space: Space, v):

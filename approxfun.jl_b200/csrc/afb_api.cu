@@ -102,7 +102,8 @@ using namespace afb;
 // =====================================================================================================
 // plans
 // =====================================================================================================
-enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4, PATH_LARGE = 5 };
+enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4, PATH_LARGE = 5, PATH_EXT = 6,
+                PATH_IDENTITY = 7 };
 
 struct afb_plan_s {
     int32_t kind = 0;
@@ -124,6 +125,7 @@ struct afb_plan_s {
     cplx* qtab = nullptr;      // exp(-i pi k/(2n)), k = 0..n  (Chebyshev)
     cplx* gwork = nullptr;     // gbatch x n complex
     int64_t gbatch = 0;
+    int64_t cn = 0;            // EXT: complex length of the extension FFT
     // TENSOR2D
     afb_plan_s* col_plan = nullptr;  // length n,  batch n2
     afb_plan_s* row_plan = nullptr;  // length n2, batch n
@@ -266,6 +268,25 @@ static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t
     int32_t st = AFB_OK;
     if (n == 0 || batch == 0) {
         p->path = PATH_EMPTY;
+    } else if (kind >= AFB_CHEB2_FWD) {
+        // extension kinds: REDFT00 through an even extension of length 2(n-1), SinSpace through an odd one of 2n+2
+        const bool cheb2 = kind == AFB_CHEB2_FWD || kind == AFB_CHEB2_INV;
+        if (cheb2 && n == 1) {
+            p->path = PATH_IDENTITY;
+        } else {
+            p->path = PATH_EXT;
+            p->cn = cheb2 ? 2 * (n - 1) : 2 * n + 2;
+            int64_t gb = std::max<int64_t>(1, (int64_t)(256ll << 20) / (16 * p->cn));
+            gb = std::min<int64_t>(gb, batch);
+            p->gbatch = gb;
+            st = cfft_create(&p->cfft, p->cn, gb);
+            if (st == AFB_OK) {
+                void* d = nullptr;
+                cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)(gb * p->cn));
+                if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(ext work)", __FILE__, __LINE__);
+                p->gwork = reinterpret_cast<cplx*>(d);
+            }
+        }
     } else if (n <= DIRECT_MAX) {
         p->path = PATH_DIRECT;
         st = build_direct_tab(p);
@@ -336,6 +357,22 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
             }
             return AFB_OK;
         }
+        case PATH_IDENTITY:
+            AFB_CUDA(cudaMemcpy2DAsync(d_out, 8 * (size_t)ostride, d_in, 8 * (size_t)istride, 8, (size_t)batch,
+                                       cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            return AFB_OK;
+        case PATH_EXT: {
+            if (oes != 1) return fail(AFB_UNSUPPORTED, "extension path has no strided output");
+            for (int64_t b0 = 0; b0 < batch; b0 += p->gbatch) {
+                const int64_t nb = std::min(p->gbatch, batch - b0);
+                const double* in = reinterpret_cast<const double*>(d_in) + b0 * istride;
+                double* out = reinterpret_cast<double*>(d_out) + b0 * ostride;
+                AFB_TRY(launch_ext_pre(p->kind, p->n, p->cn, in, istride, p->gwork, nb, stream));
+                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nb, false, 1.0, stream));
+                AFB_TRY(launch_ext_post(p->kind, p->n, p->cn, p->gwork, out, ostride, nb, stream));
+            }
+            return AFB_OK;
+        }
         case PATH_GENERIC: {
             if (oes != 1) return fail(AFB_UNSUPPORTED, "generic path has no strided output");
             const bool inv = (p->kind & 1) != 0;
@@ -359,6 +396,11 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         case PATH_DIRECT: return 1;
         case PATH_LINE: return 1;
         case PATH_LARGE: return (int32_t)(3 * p->batch);
+        case PATH_IDENTITY: return 0;
+        case PATH_EXT: {
+            const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
+            return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
+        }
         case PATH_GENERIC: {
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
@@ -450,7 +492,7 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
                         uint32_t flags) {
     if (!out) return fail(AFB_BAD_ARG, "afb_plan_create: null out pointer");
     *out = nullptr;
-    if (kind < AFB_CHEB1_FWD || kind > AFB_CHEB1_2D_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
+    if (kind < AFB_CHEB1_FWD || kind > AFB_SIN_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
     if (n < 0 || n2 < 0 || batch < 0) return fail(AFB_BAD_SIZE, "afb_plan_create: negative size");
     AFB_TRY(ensure_device());
     if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV) {
@@ -546,14 +588,14 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
     if (p->pchunk == 0) {
         int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
         ch = std::min(ch, p->batch);
-        if (p->path == PATH_GENERIC) ch = std::min(ch, p->gbatch);
+        if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
         for (int i = 0; i < afb_plan_s::NPIPE; ++i) {
             AFB_CUDA(cudaStreamCreateWithFlags(&p->pstream[i], cudaStreamNonBlocking));
             AFB_CUDA(cudaMalloc(&p->pbuf[i], line_bytes * (size_t)ch));
         }
         p->pchunk = ch;
     }
-    const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE;
+    const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE || p->path == PATH_EXT;
     int64_t c = 0;
     for (int64_t b0 = 0; b0 < p->batch; b0 += p->pchunk, ++c) {
         // the generic path shares one work buffer between chunks: keep it on a single stream

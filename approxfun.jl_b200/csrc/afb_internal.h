@@ -60,6 +60,11 @@ int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride,
 int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, int64_t ostride, int64_t batch,
                             const cplx* qtab, void* stream);
 
+int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_t istride, cplx* work, int64_t batch,
+                       void* stream);
+int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, double* out, int64_t ostride, int64_t batch,
+                        void* stream);
+
 // ---- 2-D (afb_tensor.cu) -----------------------------------------------------------------------------
 int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, void* stream);
 

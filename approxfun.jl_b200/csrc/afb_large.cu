@@ -295,6 +295,70 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
     }
 }
 
+// =====================================================================================================
+// Extension kinds: transforms defined through the FFT of an even / odd extension (complex length cn):
+//   AFB_CHEB2_FWD/INV  second-kind points, FFTW REDFT00 (UPSTREAM FastTransforms plan_(i)chebyshevtransform(x, Val(2)));
+//                      even extension of length cn = 2(n-1):  Y_k = Re FFT([x_0..x_{n-1}, x_{n-2}..x_1])_k
+//                      fwd: c = Y/(n-1), c_0 /= 2, c_{n-1} /= 2 ;  inv: c_0 *= 2, c_{n-1} *= 2, v = Y/2
+//   AFB_SIN_FWD/INV    SinSpace, /root/reference/src/Extras/fftGeneric.jl:74-81, restated verbatim:
+//                      v = imag(fft([0; -x; 0; reverse(x)]))[2:n+1],  fwd: v/(n+1),  inv: v/2     (cn = 2n+2)
+// =====================================================================================================
+__global__ void ext_pre_kernel(int kind, int64_t n, int64_t cn, const double* __restrict__ in, int64_t istride,
+                               cplx* __restrict__ work, int64_t batch) {
+    const int64_t total = batch * cn;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / cn, j = g % cn;
+        const double* x = in + b * istride;
+        double v;
+        if (kind == AFB_CHEB2_FWD || kind == AFB_CHEB2_INV) {
+            const int64_t i = (j < n) ? j : cn - j;
+            v = x[i];
+            if (kind == AFB_CHEB2_INV && (i == 0 || i == n - 1)) v *= 2.0;
+        } else {  // [0; -x; 0; reverse(x)]
+            if (j == 0 || j == n + 1) v = 0.0;
+            else if (j <= n) v = -x[j - 1];
+            else v = x[2 * n + 1 - j];
+        }
+        work[g] = make_double2(v, 0.0);
+    }
+}
+__global__ void ext_post_kernel(int kind, int64_t n, int64_t cn, const cplx* __restrict__ work, double* __restrict__ out,
+                                int64_t ostride, int64_t batch) {
+    const int64_t total = batch * n;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / n, k = g % n;
+        const cplx* W = work + b * cn;
+        double r;
+        if (kind == AFB_CHEB2_FWD) {
+            r = W[k].x / (double)(n - 1);
+            if (k == 0 || k == n - 1) r /= 2.0;
+        } else if (kind == AFB_CHEB2_INV) {
+            r = W[k].x / 2.0;
+        } else if (kind == AFB_SIN_FWD) {
+            r = W[k + 1].y / (double)(n + 1);
+        } else {
+            r = W[k + 1].y / 2.0;
+        }
+        out[b * ostride + k] = r;
+    }
+}
+int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_t istride, cplx* work, int64_t batch,
+                       void* stream) {
+    if (batch == 0) return AFB_OK;
+    auto k = ext_pre_kernel;
+    AFB_LAUNCH(k, ew_grid(batch * cn), 256, 0, stream, kind, n, cn, in, istride, work, batch);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, double* out, int64_t ostride, int64_t batch,
+                        void* stream) {
+    if (batch == 0) return AFB_OK;
+    auto k = ext_post_kernel;
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, cn, work, out, ostride, batch);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
                            const cplx* qtab, void* stream) {
     if (batch == 0) return AFB_OK;

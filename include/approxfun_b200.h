@@ -59,7 +59,15 @@ enum afb_kind {
     AFB_LAURENT_INV = 5,
     AFB_CHEB1_2D_FWD = 6, /* transform!(::TensorSpace{Chebyshev,Chebyshev}, M): UPSTREAM
                              ApproxFunBase; callers src/Plot/Plot.jl:290-332, src/Extras/sample.jl:196 */
-    AFB_CHEB1_2D_INV = 7
+    AFB_CHEB1_2D_INV = 7,
+    /* "next" rows of SURVEY.md section 8f (sibling spaces on the same FFT core; correctness path, not tuned): */
+    AFB_CHEB2_FWD = 8,    /* second-kind points x_j = cos(pi j/(n-1)): UPSTREAM FastTransforms
+                             plan_chebyshevtransform(v, Val(2)) = FFTW REDFT00, /(n-1), ends halved
+                             (Val(kind) boundary: ext/ApproxFunDualNumbersExt.jl:44-45)                      */
+    AFB_CHEB2_INV = 9,    /* plan_ichebyshevtransform(c, Val(2)): ends doubled, REDFT00, /2                 */
+    AFB_SIN_FWD = 10,     /* plan_transform(SinSpace(), n): src/Extras/fftGeneric.jl:74-78 (in-tree spec):
+                             imag(fft([0;-x;0;reverse(x)]))[2:n+1] / (n+1)                                  */
+    AFB_SIN_INV = 11      /* plan_itransform(SinSpace(), n): src/Extras/fftGeneric.jl:80-81: same / 2       */
 };
 
 typedef struct afb_plan_s* afb_plan;

@@ -582,3 +582,59 @@ def sample2d_lowrank(A, B, dom1, dom2, u_y, u_x) -> np.ndarray:
     AB = chebnormalizedcumsum(AB, grow=False)
     rx = chebbisectioninv_cols(AB, u_x)
     return np.stack([fromcanonical(a1, b1, rx), ry], axis=1)   # [fromcanonical.(domain(f,1), rx) ry]
+
+
+# --------------------------------------------------------------------------------------
+# "next" rows: second-kind Chebyshev points and SinSpace
+# --------------------------------------------------------------------------------------
+
+
+def cheb2points_canonical(n: int) -> np.ndarray:
+    """UPSTREAM FastTransforms.chebyshevpoints(Float64, n, Val(2)): x_j = cos(pi j/(n-1)), descending."""
+    if n == 1:
+        return np.zeros(1)
+    j = np.arange(n, dtype=np.float64)
+    return sinpi((n - 2.0 * j - 1.0) / (2.0 * n - 2.0))
+
+
+def chebkind2_transform(v: np.ndarray, axis: int = 0) -> np.ndarray:
+    """UPSTREAM FastTransforms plan_chebyshevtransform(v, Val(2)): FFTW REDFT00, /(n-1), first and last halved
+    (the Val(kind) boundary is visible at ext/ApproxFunDualNumbersExt.jl:44-45).  n == 1: identity."""
+    v = np.asarray(v, dtype=np.float64)
+    n = v.shape[axis]
+    if n <= 1:
+        return v.copy()
+    y = np.moveaxis(_sfft.dct(v, type=1, axis=axis), axis, 0) / (n - 1)
+    y[0] /= 2
+    y[-1] /= 2
+    return np.moveaxis(y, 0, axis)
+
+
+def chebkind2_itransform(c: np.ndarray, axis: int = 0) -> np.ndarray:
+    """plan_ichebyshevtransform(c, Val(2)): ends doubled, REDFT00, /2  =>  v_j = sum_k c_k cos(pi j k/(n-1))."""
+    c = np.moveaxis(np.array(c, dtype=np.float64, copy=True), axis, 0)
+    n = c.shape[0]
+    if n <= 1:
+        return np.moveaxis(c, 0, axis)
+    c[0] *= 2
+    c[-1] *= 2
+    return np.moveaxis(_sfft.dct(c, type=1, axis=0) / 2, 0, axis)
+
+
+def sin_transform_generic(x: np.ndarray) -> np.ndarray:
+    """Verbatim src/Extras/fftGeneric.jl:74-78:  v = imag(fft([0;-x;0;reverse(x)]))[2:length(x)+1]; v/(length(x)+1)."""
+    x = np.asarray(x, dtype=np.float64)
+    s = np.concatenate([[0.0], -x, [0.0], x[::-1]])
+    return np.imag(np.fft.fft(s))[1:x.size + 1] / (x.size + 1)
+
+
+def sin_itransform_generic(x: np.ndarray) -> np.ndarray:
+    """Verbatim src/Extras/fftGeneric.jl:80-81:  imag(fft([0;-x;0;reverse(x)]))[2:length(x)+1]/2."""
+    x = np.asarray(x, dtype=np.float64)
+    s = np.concatenate([[0.0], -x, [0.0], x[::-1]])
+    return np.imag(np.fft.fft(s))[1:x.size + 1] / 2
+
+
+def sinpoints(n: int) -> np.ndarray:
+    """Grid of the SinSpace plans above: theta_j = pi j/(n+1), j = 1..n (f_k <-> sin(k theta), k = 1..n)."""
+    return np.pi * np.arange(1, n + 1) / (n + 1)

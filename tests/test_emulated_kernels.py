@@ -147,6 +147,29 @@ def test_normcumsum_and_bisection_bit_exact():
     assert np.array_equal(ll.cheb_bisect_cols(gm, u), orcc.cheb_bisect_cols(gm, u))
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 17, 33, 64, 65, 100, 129, 1025])
+def test_second_kind_and_sinspace(n):
+    v = RNG.standard_normal((n, 2))
+    got = ll.transform(B.CHEB2_FWD, v)
+    assert np.max(np.abs(got - orc.chebkind2_transform(v, axis=0))) <= tol(n, np.max(np.abs(v)))
+    back = ll.transform(B.CHEB2_INV, got)
+    assert np.max(np.abs(back - v)) <= tol(n, np.max(np.abs(v))) * 4
+    s = ll.transform(B.SIN_FWD, v)
+    for b in range(2):
+        assert np.max(np.abs(s[:, b] - orc.sin_transform_generic(v[:, b]))) <= tol(n, np.max(np.abs(v)))
+    si = ll.transform(B.SIN_INV, v)
+    assert np.max(np.abs(si[:, 0] - orc.sin_itransform_generic(v[:, 0]))) <= tol(n, np.max(np.abs(si)))
+    # definitions: values of sum_k c_k T_k at the second-kind points, and of a sine series on its grid
+    if n >= 2:
+        c = RNG.standard_normal(n)
+        x = orc.cheb2points_canonical(n)
+        assert np.max(np.abs(ll.transform(B.CHEB2_INV, c) - orc.clenshaw(c, x))) < 1e-12 * n
+    th = orc.sinpoints(n)
+    f = RNG.standard_normal(n)
+    vals = sum(f[k] * np.sin((k + 1) * th) for k in range(n))
+    assert np.max(np.abs(ll.transform(B.SIN_FWD, vals) - f)) < 1e-12 * n
+
+
 def test_sample2d_fused_kernel_bit_exact():
     # src/Extras/sample.jl:208-213 as one kernel: evaluate.(f.A, ry'), CB*fA, chebnormalizedcumsum!, chebbisectioninv
     for NA, N, R, P in [(12, 9, 3, 300), (1, 1, 1, 5), (30, 66, 7, 140), (5, 2, 2, 130)]:

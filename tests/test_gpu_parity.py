@@ -235,6 +235,24 @@ def test_tensor_transform_and_sampling_golden(af):
     assert abs(F2(0.1, 0.2) - math.cos(0.5)) < 1e-13
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 64, 65, 100, 1025, 4097])
+def test_sibling_spaces_second_kind_sin_cos(af, n):
+    # Val(2) Chebyshev plans (REDFT00) and SinSpace (in-tree spec src/Extras/fftGeneric.jl:74-81)
+    v = RNG.standard_normal((n, 3))
+    c = af.chebyshevtransform(v, kind=2)
+    assert np.max(np.abs(c - orc.chebkind2_transform(v, axis=0))) <= coef_tol(n, v)
+    assert np.max(np.abs(af.ichebyshevtransform(c, kind=2) - v)) <= 4 * coef_tol(n, v)
+    S = af.SinSpace()
+    s = af.transform(S, v)
+    assert np.max(np.abs(s[:, 0] - orc.sin_transform_generic(v[:, 0]))) <= coef_tol(n, v)
+    si = af.itransform(S, v)
+    assert np.max(np.abs(si[:, 1] - orc.sin_itransform_generic(v[:, 1]))) <= coef_tol(n, si)
+    # docs/src/usage/spaces.md:39-49: CosSpace shares coefficients and transform with Chebyshev
+    assert np.array_equal(af.transform(af.CosSpace(), v), af.transform(af.Chebyshev(), v))
+    th = af.points(af.CosSpace(), n)
+    assert np.allclose(np.cos(th), af.points(af.Chebyshev(), n), atol=4e-16)
+
+
 def test_sampling_2d_lowrank(af):
     # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
     S = af.Chebyshev(-4, 4)
