@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libapproxfun_b200.so")
 AFB_OK, AFB_BAD_ARG, AFB_BAD_SIZE, AFB_NO_DEVICE, AFB_CUDA_ERROR, AFB_NCCL_ERROR, AFB_OOM, AFB_UNSUPPORTED = range(8)
 CHEB1_FWD, CHEB1_INV, FOURIER_FWD, FOURIER_INV, LAURENT_FWD, LAURENT_INV, CHEB1_2D_FWD, CHEB1_2D_INV = range(8)
 CHEB2_FWD, CHEB2_INV, SIN_FWD, SIN_INV = 8, 9, 10, 11
+TAYLOR_FWD, TAYLOR_INV, HARDYM_FWD, HARDYM_INV = 12, 13, 14, 15
 
 # every symbol include/approxfun_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = [
@@ -166,7 +167,7 @@ class LowLevel:
 
     def transform(self, kind: int, v: np.ndarray) -> np.ndarray:
         """v: (n,) or (n, B) array in the reference's column-major sense (each column one transform)."""
-        cplx = kind in (LAURENT_FWD, LAURENT_INV)
+        cplx = kind in (LAURENT_FWD, LAURENT_INV, TAYLOR_FWD, TAYLOR_INV, HARDYM_FWD, HARDYM_INV)
         dt = np.complex128 if cplx else np.float64
         v = np.asarray(v, dtype=dt)
         one = v.ndim == 1

@@ -89,6 +89,20 @@ class SinSpace(Space):
         self.a, self.b = float(a), float(b)
 
 
+class Taylor(Space):
+    """`Taylor()` = `Hardy{true}`: f(t) = sum_k f_k e^{ikt} (docs/src/usage/spaces.md:100-104)."""
+
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
+class Hardy(Space):
+    """`Hardy{false}`: f(t) = sum_k f_k e^{-i(k+1)t} (docs/src/usage/spaces.md:106-110)."""
+
+    def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
+        self.a, self.b = float(a), float(b)
+
+
 class TensorSpace(Space):
     def __init__(self, s1: Chebyshev, s2: Chebyshev):
         if not (isinstance(s1, Chebyshev) and isinstance(s2, Chebyshev)):
@@ -97,9 +111,9 @@ class TensorSpace(Space):
 
 
 _FWD = {Chebyshev: L.CHEB1_FWD, Fourier: L.FOURIER_FWD, Laurent: L.LAURENT_FWD, TensorSpace: L.CHEB1_2D_FWD,
-        CosSpace: L.CHEB1_FWD, SinSpace: L.SIN_FWD}
+        CosSpace: L.CHEB1_FWD, SinSpace: L.SIN_FWD, Taylor: L.TAYLOR_FWD, Hardy: L.HARDYM_FWD}
 _INV = {Chebyshev: L.CHEB1_INV, Fourier: L.FOURIER_INV, Laurent: L.LAURENT_INV, TensorSpace: L.CHEB1_2D_INV,
-        CosSpace: L.CHEB1_INV, SinSpace: L.SIN_INV}
+        CosSpace: L.CHEB1_INV, SinSpace: L.SIN_INV, Taylor: L.TAYLOR_INV, Hardy: L.HARDYM_INV}
 
 
 def points(space: Space, n: int, m: int | None = None):
@@ -107,7 +121,7 @@ def points(space: Space, n: int, m: int | None = None):
     ll = lowlevel()
     if isinstance(space, Chebyshev):
         return ll.chebpoints(n, space.a, space.b)
-    if isinstance(space, (Fourier, Laurent)):
+    if isinstance(space, (Fourier, Laurent, Taylor, Hardy)):
         return ll.fourierpoints(n, space.a, space.b)
     if isinstance(space, TensorSpace):
         return points(space.factors[0], n), points(space.factors[1], n if m is None else m)
@@ -141,7 +155,7 @@ class TransformPlan:
             n = self.shape[0]
             batch = int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
             self._h = self._ll.plan_create(self.kind, n, 0, batch, n)
-        self.dtype = np.complex128 if isinstance(space, Laurent) else np.float64
+        self.dtype = np.complex128 if isinstance(space, (Laurent, Taylor, Hardy)) else np.float64
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -202,13 +216,28 @@ def ichebyshevtransform(c, kind: int = 1):
     return lowlevel().transform(L.CHEB1_INV if kind == 1 else L.CHEB2_INV, c)
 
 
+_plan_cache: dict = {}
+
+
+def _cached_plan(cls, space: Space, shape):
+    """`transform(S, v)` builds a plan per call in the reference (FFTW ESTIMATE plans are cheap); here plans own
+    device tables, so the convenience entry points keep the most recent ones."""
+    key = (cls, type(space), tuple(shape))
+    p = _plan_cache.get(key)
+    if p is None:
+        if len(_plan_cache) >= 64:
+            _plan_cache.pop(next(iter(_plan_cache)))
+        p = _plan_cache[key] = cls(space, shape)
+    return p
+
+
 def transform(space: Space, v):
     """`transform(S, vals) = plan_transform(S, vals) * vals`."""
-    return plan_transform(space, v) * v
+    return _cached_plan(TransformPlan, space, _shape_of(v)) * v
 
 
 def itransform(space: Space, c):
-    return plan_itransform(space, c) * c
+    return _cached_plan(ITransformPlan, space, _shape_of(c)) * c
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -99,6 +99,34 @@ void free_tables() {
 
 using namespace afb;
 
+// process-wide staging pool of afb_plan_execute_host (streams + grow-only device buffers)
+struct HostPipe {
+    static constexpr int NPIPE = 3;
+    std::mutex mu;
+    cudaStream_t stream[NPIPE] = {nullptr, nullptr, nullptr};
+    void* buf[NPIPE] = {nullptr, nullptr, nullptr};
+    size_t cap[NPIPE] = {0, 0, 0};
+    int32_t ensure(int nbuf, size_t bytes) {
+        for (int i = 0; i < nbuf; ++i) {
+            if (!stream[i]) AFB_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+            if (cap[i] < bytes) {
+                if (buf[i]) { AFB_CUDA(cudaStreamSynchronize(stream[i])); cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+                AFB_CUDA(cudaMalloc(&buf[i], bytes));
+                cap[i] = bytes;
+            }
+        }
+        return AFB_OK;
+    }
+    void release() {
+        for (int i = 0; i < NPIPE; ++i) {
+            if (buf[i]) cudaFree(buf[i]);
+            if (stream[i]) cudaStreamDestroy(stream[i]);
+            buf[i] = nullptr; stream[i] = nullptr; cap[i] = 0;
+        }
+    }
+};
+static HostPipe g_pipe;
+
 // =====================================================================================================
 // plans
 // =====================================================================================================
@@ -133,11 +161,6 @@ struct afb_plan_s {
     // scratch for in-place direct execution
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    // host pipeline
-    static constexpr int NPIPE = 3;
-    cudaStream_t pstream[NPIPE] = {nullptr, nullptr, nullptr};
-    void* pbuf[NPIPE] = {nullptr, nullptr, nullptr};
-    int64_t pchunk = 0;  // transforms per chunk
     std::mutex mu;
 };
 
@@ -150,10 +173,6 @@ static void plan_free(afb_plan_s* p) {
     if (p->cfft) cfft_destroy(p->cfft);
     if (p->t2buf) cudaFree(p->t2buf);
     if (p->tmp) cudaFree(p->tmp);
-    for (int i = 0; i < afb_plan_s::NPIPE; ++i) {
-        if (p->pbuf[i]) cudaFree(p->pbuf[i]);
-        if (p->pstream[i]) cudaStreamDestroy(p->pstream[i]);
-    }
     plan_free(p->col_plan);
     plan_free(p->row_plan);
     delete p;
@@ -264,10 +283,13 @@ static int32_t build_generic(afb_plan_s* p) {
 static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t batch, int64_t stride, uint32_t flags) {
     afb_plan_s* p = new afb_plan_s();
     p->kind = kind; p->n = n; p->batch = batch; p->stride = stride; p->flags = flags;
-    p->elem = (kind == AFB_LAURENT_FWD || kind == AFB_LAURENT_INV) ? 16 : 8;
+    p->elem = (kind == AFB_LAURENT_FWD || kind == AFB_LAURENT_INV || kind >= AFB_TAYLOR_FWD) ? 16 : 8;
     int32_t st = AFB_OK;
     if (n == 0 || batch == 0) {
         p->path = PATH_EMPTY;
+    } else if (kind >= AFB_TAYLOR_FWD) {
+        p->path = PATH_GENERIC;   // plain complex FFT with a copy / reversal on either side
+        st = build_generic(p);
     } else if (kind >= AFB_CHEB2_FWD) {
         // extension kinds: REDFT00 through an even extension of length 2(n-1), SinSpace through an odd one of 2n+2
         const bool cheb2 = kind == AFB_CHEB2_FWD || kind == AFB_CHEB2_INV;
@@ -442,6 +464,7 @@ int32_t afb_init(int32_t device) {
 }
 
 int32_t afb_shutdown(void) {
+    { std::lock_guard<std::mutex> lk(g_pipe.mu); g_pipe.release(); }
     free_tables();
     return AFB_OK;
 }
@@ -492,7 +515,7 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
                         uint32_t flags) {
     if (!out) return fail(AFB_BAD_ARG, "afb_plan_create: null out pointer");
     *out = nullptr;
-    if (kind < AFB_CHEB1_FWD || kind > AFB_SIN_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
+    if (kind < AFB_CHEB1_FWD || kind > AFB_HARDYM_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
     if (n < 0 || n2 < 0 || batch < 0) return fail(AFB_BAD_SIZE, "afb_plan_create: negative size");
     AFB_TRY(ensure_device());
     if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV) {
@@ -582,45 +605,46 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
         return st;
     }
     std::lock_guard<std::mutex> lk(p->mu);
-    // chunked three-stage pipeline: H2D | kernels | D2H on NPIPE streams, packed (stride = n) on device
+    // chunked three-stage pipeline: H2D | kernels | D2H on up to NPIPE streams, packed (stride = n) on device.
+    // Streams and staging buffers belong to a process-wide pool (grow-only), so creating / destroying plans stays cheap.
     const int64_t n = p->n;
     const size_t line_bytes = (size_t)p->elem * (size_t)n;
-    if (p->pchunk == 0) {
-        int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
-        ch = std::min(ch, p->batch);
-        if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
-        for (int i = 0; i < afb_plan_s::NPIPE; ++i) {
-            AFB_CUDA(cudaStreamCreateWithFlags(&p->pstream[i], cudaStreamNonBlocking));
-            AFB_CUDA(cudaMalloc(&p->pbuf[i], line_bytes * (size_t)ch));
-        }
-        p->pchunk = ch;
-    }
+    int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
+    ch = std::min(ch, p->batch);
+    if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
     const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE || p->path == PATH_EXT;
+    const int64_t nchunks = (p->batch + ch - 1) / ch;
+    const int nbuf = generic ? 1 : (int)std::min<int64_t>(HostPipe::NPIPE, nchunks);
+    std::lock_guard<std::mutex> pool_lock(g_pipe.mu);
+    AFB_TRY(g_pipe.ensure(nbuf, line_bytes * (size_t)ch));
     int64_t c = 0;
-    for (int64_t b0 = 0; b0 < p->batch; b0 += p->pchunk, ++c) {
-        // the generic path shares one work buffer between chunks: keep it on a single stream
-        const int si = generic ? 0 : (int)(c % afb_plan_s::NPIPE);
-        cudaStream_t s = p->pstream[si];
-        const int64_t nb = std::min(p->pchunk, p->batch - b0);
+    for (int64_t b0 = 0; b0 < p->batch; b0 += ch, ++c) {
+        // the generic paths share one work buffer between chunks: keep them on a single stream
+        const int si = (int)(c % nbuf);
+        cudaStream_t s = g_pipe.stream[si];
+        void* dbuf = g_pipe.buf[si];
+        const int64_t nb = std::min(ch, p->batch - b0);
         const char* src = reinterpret_cast<const char*>(in) + (size_t)p->elem * (size_t)(b0 * p->stride);
         char* dst = reinterpret_cast<char*>(out) + (size_t)p->elem * (size_t)(b0 * p->stride);
 #ifdef AFB_HOST_EMU
         for (int64_t b = 0; b < nb; ++b)
-            std::memcpy((char*)p->pbuf[si] + line_bytes * b, src + (size_t)p->elem * (size_t)(b * p->stride), line_bytes);
+            std::memcpy((char*)dbuf + line_bytes * b, src + (size_t)p->elem * (size_t)(b * p->stride), line_bytes);
 #else
-        AFB_CUDA(cudaMemcpy2DAsync(p->pbuf[si], line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes,
-                                   (size_t)nb, cudaMemcpyHostToDevice, s));
+        if (p->stride == n) AFB_CUDA(cudaMemcpyAsync(dbuf, src, line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s));
+        else AFB_CUDA(cudaMemcpy2DAsync(dbuf, line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes, (size_t)nb,
+                                        cudaMemcpyHostToDevice, s));
 #endif
-        AFB_TRY(exec_1d_device(p, p->pbuf[si], p->pbuf[si], nb, n, n, s));
+        AFB_TRY(exec_1d_device(p, dbuf, dbuf, nb, n, n, s));
 #ifdef AFB_HOST_EMU
         for (int64_t b = 0; b < nb; ++b)
-            std::memcpy(dst + (size_t)p->elem * (size_t)(b * p->stride), (char*)p->pbuf[si] + line_bytes * b, line_bytes);
+            std::memcpy(dst + (size_t)p->elem * (size_t)(b * p->stride), (char*)dbuf + line_bytes * b, line_bytes);
 #else
-        AFB_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, p->pbuf[si], line_bytes, line_bytes,
-                                   (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (p->stride == n) AFB_CUDA(cudaMemcpyAsync(dst, dbuf, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        else AFB_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, dbuf, line_bytes, line_bytes, (size_t)nb,
+                                        cudaMemcpyDeviceToHost, s));
 #endif
     }
-    for (int i = 0; i < afb_plan_s::NPIPE; ++i) AFB_CUDA(cudaStreamSynchronize(p->pstream[i]));
+    for (int i = 0; i < nbuf; ++i) AFB_CUDA(cudaStreamSynchronize(g_pipe.stream[i]));
     return AFB_OK;
 }
 

@@ -251,8 +251,10 @@ __global__ void generic_pre_kernel(int kind, int64_t n, const void* __restrict__
             else if ((n % 2 == 0) && j == n / 2) z.x = -c[n - 1];
             else if (j < nh) z = make_double2(0.5 * c[2 * j], -0.5 * c[2 * j - 1]);
             else { const int64_t k = n - j; z = make_double2(0.5 * c[2 * k], 0.5 * c[2 * k - 1]); }
-        } else if (kind == AFB_LAURENT_FWD) {
+        } else if (kind == AFB_LAURENT_FWD || kind == AFB_TAYLOR_FWD || kind == AFB_HARDYM_FWD || kind == AFB_TAYLOR_INV) {
             z = (reinterpret_cast<const cplx*>(in) + b * istride)[j];
+        } else if (kind == AFB_HARDYM_INV) {  // F[n-1-k] = c[k]
+            z = (reinterpret_cast<const cplx*>(in) + b * istride)[n - 1 - j];
         } else {  // AFB_LAURENT_INV: F[m] = c[imap(m)]
             const cplx* c = reinterpret_cast<const cplx*>(in) + b * istride;
             const int64_t i = (j < nh) ? 2 * j : 2 * (n - j) - 1;
@@ -288,6 +290,10 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
         } else if (kind == AFB_LAURENT_FWD) {
             const int64_t m = (o & 1) ? n - ((o + 1) >> 1) : (o >> 1);
             (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[m], 1.0 / (double)n);
+        } else if (kind == AFB_TAYLOR_FWD) {        // f_k = F_k / n
+            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[o], 1.0 / (double)n);
+        } else if (kind == AFB_HARDYM_FWD) {        // f_k = F_{n-1-k} / n   (mode -(k+1))
+            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[n - 1 - o], 1.0 / (double)n);
         } else {
             (reinterpret_cast<cplx*>(out) + b * ostride)[o] = W[o];
         }

@@ -198,6 +198,24 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_note = None
+    if world > 1:
+        # one process per GPU: run (and first-touch the pinned e2e buffers) on the CPUs NVML reports as local to this
+        # GPU, so that eight ranks do not all stage their PCIe traffic through one socket's memory
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            ncpu = os.cpu_count() or 1
+            masks = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(masks) for b in range(64) if (m >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            pick = sorted(cpus & allowed)
+            if pick:
+                os.sched_setaffinity(0, pick)
+                numa_note = f"rank pinned to {len(pick)} GPU-local CPUs"
+        except Exception as exc:  # affinity is an optimisation only
+            numa_note = f"no CPU affinity ({type(exc).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -304,7 +322,8 @@ def main():
         e2e_err = float(np.max(np.abs(hout[idx] - orc.cheb_transform(hin[idx], axis=1))))
         e2e = {"value": world * coefs_per_step / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
                "d2h_bytes_per_step": int(8 * B * n), "ms_per_step": el * 1e3, "steps": e2e_steps,
-               "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)", "max_abs_err_vs_oracle": e2e_err}
+               "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)", "max_abs_err_vs_oracle": e2e_err,
+               "host_affinity": numa_note}
         hplan.close()
         del hv, hc
 

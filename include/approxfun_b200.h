@@ -67,7 +67,12 @@ enum afb_kind {
     AFB_CHEB2_INV = 9,    /* plan_ichebyshevtransform(c, Val(2)): ends doubled, REDFT00, /2                 */
     AFB_SIN_FWD = 10,     /* plan_transform(SinSpace(), n): src/Extras/fftGeneric.jl:74-78 (in-tree spec):
                              imag(fft([0;-x;0;reverse(x)]))[2:n+1] / (n+1)                                  */
-    AFB_SIN_INV = 11      /* plan_itransform(SinSpace(), n): src/Extras/fftGeneric.jl:80-81: same / 2       */
+    AFB_SIN_INV = 11,     /* plan_itransform(SinSpace(), n): src/Extras/fftGeneric.jl:80-81: same / 2       */
+    AFB_TAYLOR_FWD = 12,  /* Taylor = Hardy{true}: f(t) = sum_k f_k e^{ikt} (docs/src/usage/spaces.md:100-104):
+                             f_k = F_k / n on t_j = 2 pi j / n; complex in/out                              */
+    AFB_TAYLOR_INV = 13,
+    AFB_HARDYM_FWD = 14,  /* Hardy{false}: f(t) = sum_k f_k e^{-i(k+1)t} (spaces.md:106-110): f_k = F_{n-1-k}/n */
+    AFB_HARDYM_INV = 15
 };
 
 typedef struct afb_plan_s* afb_plan;

@@ -170,6 +170,23 @@ def test_second_kind_and_sinspace(n):
     assert np.max(np.abs(ll.transform(B.SIN_FWD, vals) - f)) < 1e-12 * n
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 32, 64, 100, 1024])
+def test_taylor_and_hardy(n):
+    # docs/src/usage/spaces.md:100-110: Taylor f = sum f_k e^{ikt}; Hardy{false} f = sum f_k e^{-i(k+1)t}; t_j = 2 pi j/n
+    v = RNG.standard_normal((n, 2)) + 1j * RNG.standard_normal((n, 2))
+    F = np.fft.fft(v, axis=0) / n
+    assert np.max(np.abs(ll.transform(B.TAYLOR_FWD, v) - F)) <= tol(n, np.max(np.abs(v)))
+    assert np.max(np.abs(ll.transform(B.HARDYM_FWD, v) - F[::-1])) <= tol(n, np.max(np.abs(v)))
+    th = orc.fourierpoints(n)
+    f = RNG.standard_normal(n) + 1j * RNG.standard_normal(n)
+    k = np.arange(n)
+    vt = (f[None, :] * np.exp(1j * np.outer(th, k))).sum(axis=1)
+    vh = (f[None, :] * np.exp(-1j * np.outer(th, k + 1))).sum(axis=1)
+    assert np.max(np.abs(ll.transform(B.TAYLOR_INV, f) - vt)) < 1e-12 * n
+    assert np.max(np.abs(ll.transform(B.HARDYM_INV, f) - vh)) < 1e-12 * n
+    assert np.max(np.abs(ll.transform(B.HARDYM_FWD, vh) - f)) < 1e-12 * n
+
+
 def test_sample2d_fused_kernel_bit_exact():
     # src/Extras/sample.jl:208-213 as one kernel: evaluate.(f.A, ry'), CB*fA, chebnormalizedcumsum!, chebbisectioninv
     for NA, N, R, P in [(12, 9, 3, 300), (1, 1, 1, 5), (30, 66, 7, 140), (5, 2, 2, 130)]:

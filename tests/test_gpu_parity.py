@@ -253,6 +253,17 @@ def test_sibling_spaces_second_kind_sin_cos(af, n):
     assert np.allclose(np.cos(th), af.points(af.Chebyshev(), n), atol=4e-16)
 
 
+@pytest.mark.parametrize("n", [1, 5, 64, 100, 4096])
+def test_taylor_hardy(af, n):
+    # docs/src/usage/spaces.md:100-110
+    v = RNG.standard_normal((n, 2)) + 1j * RNG.standard_normal((n, 2))
+    F = np.fft.fft(v, axis=0) / n
+    assert np.max(np.abs(af.transform(af.Taylor(), v) - F)) <= coef_tol(n, v)
+    assert np.max(np.abs(af.transform(af.Hardy(), v) - F[::-1])) <= coef_tol(n, v)
+    assert np.max(np.abs(af.itransform(af.Taylor(), af.transform(af.Taylor(), v)) - v)) <= 4 * coef_tol(n, v)
+    assert np.max(np.abs(af.itransform(af.Hardy(), af.transform(af.Hardy(), v)) - v)) <= 4 * coef_tol(n, v)
+
+
 def test_sampling_2d_lowrank(af):
     # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
     S = af.Chebyshev(-4, 4)
