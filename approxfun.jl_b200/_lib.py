@@ -31,6 +31,7 @@ SYMBOLS = [
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device",
+    "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device",
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
@@ -89,6 +90,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_samplecdf_cheb": [vp, i64, dbl, dbl, vp, vp, i64],
         "afb_sample_cheb_device": [vp, i64, dbl, dbl, u64, u64, vp, i64, vp],
         "afb_philox_uniform_device": [u64, u64, vp, i64, vp],
+        "afb_clenshaw_cheb2d": [vp, i64, i64, vp, vp, vp, i64],
+        "afb_clenshaw_cheb2d_device": [vp, i64, i64, vp, vp, vp, i64, vp],
         "afb_sample2d_cheb_lowrank": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64],
         "afb_sample2d_cheb_lowrank_device": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64, vp],
         "afb_dgemm_nn": [vp, vp, vp, i64, i64, i64],
@@ -269,6 +272,18 @@ class LowLevel:
         flat = np.ascontiguousarray(Cm.T)
         out = np.empty(u.size)
         check(self.lib, self.lib.afb_cheb_bisect_cols(_ptr(flat), N, N, _ptr(u), _ptr(out), u.size if P == u.size else -1, numits))
+        return out
+
+    def clenshaw2d(self, Cm, x, y) -> np.ndarray:
+        """Cm[i, j] multiplies T_i(x) T_j(y); x, y canonical, same length."""
+        Cm = np.asarray(Cm, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if x.size != y.size:
+            raise DimensionMismatch(AFB_BAD_SIZE, "clenshaw2d: x and y differ in length")
+        flat = np.ascontiguousarray(Cm.T)  # column-major n1 x n2
+        out = np.empty_like(x)
+        check(self.lib, self.lib.afb_clenshaw_cheb2d(_ptr(flat), Cm.shape[0], Cm.shape[1], _ptr(x), _ptr(y), _ptr(out), x.size))
         return out
 
     def sample2d_lowrank(self, A, CB, ya, yb, xa, xb, ry, u) -> np.ndarray:

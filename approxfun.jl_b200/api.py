@@ -311,12 +311,11 @@ class Fun:
             return clenshaw(sp, self.coefficients, sp.tocanonical(x))
         if isinstance(sp, TensorSpace):
             s1, s2 = sp.factors
-            Cm = self.coefficients  # C[i, j] T_i(x) T_j(y)
-            # contract y first: columns of C^T are series in y
-            ty = lowlevel().clenshaw_multi(np.ascontiguousarray(Cm.T), np.atleast_1d(s2.tocanonical(y)))  # (n1, P)
-            xs = np.atleast_1d(s1.tocanonical(x))
-            out = lowlevel().clenshaw_cols(ty, xs)
-            return float(out[0]) if np.ndim(x) == 0 else out
+            xs, ys = np.broadcast_arrays(np.atleast_1d(np.asarray(x, dtype=np.float64)),
+                                         np.atleast_1d(np.asarray(y, dtype=np.float64)))
+            out = lowlevel().clenshaw2d(self.coefficients, s1.tocanonical(xs.ravel()), s2.tocanonical(ys.ravel()))
+            out = out.reshape(xs.shape)
+            return float(out.ravel()[0]) if (np.ndim(x) == 0 and np.ndim(y) == 0) else out
         raise NotImplementedError("evaluation is GPU-accelerated for Chebyshev spaces only")
 
     def __len__(self):

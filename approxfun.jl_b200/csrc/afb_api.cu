@@ -838,6 +838,29 @@ int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out,
 }
 
 
+// ---- bivariate evaluation of a Chebyshev x Chebyshev coefficient matrix --------------------------------------
+int32_t afb_clenshaw_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y,
+                                   double* d_out, int64_t P, void* stream) {
+    if (n1 < 0 || n2 < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb2d: negative size");
+    if (P == 0) return AFB_OK;
+    if ((n1 * n2 && !d_C) || !d_x || !d_y || !d_out) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb2d: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_clenshaw2d(d_C, n1, n2, d_x, d_y, d_out, P, stream);
+}
+int32_t afb_clenshaw_cheb2d(const double* C, int64_t n1, int64_t n2, const double* x, const double* y, double* out,
+                            int64_t P) {
+    if (n1 < 0 || n2 < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb2d: negative size");
+    if (P == 0) return AFB_OK;
+    if ((n1 * n2 && !C) || !x || !y || !out) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb2d: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dx, dy, dout;
+    AFB_TRY(dc.alloc(8 * (size_t)(n1 * n2))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(C, 8 * (size_t)(n1 * n2))); AFB_TRY(dx.put(x, 8 * (size_t)P)); AFB_TRY(dy.put(y, 8 * (size_t)P));
+    AFB_TRY(launch_clenshaw2d(dc.as<double>(), n1, n2, dx.as<double>(), dy.as<double>(), dout.as<double>(), P, nullptr));
+    return dout.get(out, 8 * (size_t)P);
+}
+
 // ---- 2-D sampling pieces (src/Extras/sample.jl:205-214) ---------------------------------------------------
 int32_t afb_sample2d_cheb_lowrank_device(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R,
                                          double ya, double yb, double xa, double xb, const double* d_ry,

@@ -291,6 +291,85 @@ multi_kernel(const double* __restrict__ C, int64_t N, int64_t M, const double* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bivariate Clenshaw: f(x_p, y_p) = sum_{i,j} C[i,j] T_i(x_p) T_j(y_p), C column-major n1 x n2.
+// Evaluation order of a ProductFun (UPSTREAM ApproxFunBase): every column function g_j(x) = sum_i C[i,j] T_i(x)
+// by the 1-D recurrence, then the 1-D recurrence over j in y with the g_j as coefficients -- fused here so that
+// the n2 x P intermediate never exists.  Coefficients in shared memory (broadcast reads), R points per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int C2_THREADS = 256;
+__global__ void __launch_bounds__(C2_THREADS)
+clenshaw2d_kernel(const double* __restrict__ C, int64_t n1, int64_t n2, const double* __restrict__ x,
+                  const double* __restrict__ y, double* __restrict__ out, int64_t P, int64_t ntiles, int use_smem) {
+    AFB_DYN_SMEM(double, sc);
+    const int tid = threadIdx.x;
+    const double* cc = C;
+    if (use_smem) {
+        for (int64_t k = tid; k < n1 * n2; k += C2_THREADS) sc[k] = C[k];
+        __syncthreads();
+        cc = sc;
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * (int64_t)(C2_THREADS * CL_R);
+        double x2[CL_R], y2[CL_R], B1[CL_R], B2[CL_R], res[CL_R];
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * C2_THREADS;
+            x2[r] = __dmul_rn(2.0, (i < P) ? x[i] : 0.0);
+            y2[r] = __dmul_rn(2.0, (i < P) ? y[i] : 0.0);
+            B1[r] = 0.0; B2[r] = 0.0; res[r] = 0.0;
+        }
+        for (int64_t j = n2 - 1; j >= 0; --j) {
+            const double* cj = cc + j * n1;
+            double g[CL_R];
+            if (n1 == 0) {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) g[r] = 0.0;
+            } else if (n1 == 1) {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) g[r] = cj[0];
+            } else {
+                double b1[CL_R], b2[CL_R];
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) { b1[r] = 0.0; b2[r] = 0.0; }
+                clenshaw_span<CL_R>(cj, 1, (int)n1, x2, b1, b2);
+                clenshaw_finish<CL_R>(cj[0], x2, b1, b2, g);
+            }
+            if (j >= 1) {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r) {
+                    const double t = __fma_rn(y2[r], B1[r], __dsub_rn(g[r], B2[r]));
+                    B2[r] = B1[r];
+                    B1[r] = t;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < CL_R; ++r)
+                    res[r] = (n2 == 1) ? g[r] : __fma_rn(__dmul_rn(y2[r], 0.5), B1[r], __dsub_rn(g[r], B2[r]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CL_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * C2_THREADS;
+            if (i < P) out[i] = res[r];
+        }
+    }
+}
+
+int32_t launch_clenshaw2d(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y, double* d_out,
+                          int64_t P, void* stream) {
+    if (P == 0) return AFB_OK;
+    const int64_t ntiles = (P + (int64_t)C2_THREADS * CL_R - 1) / ((int64_t)C2_THREADS * CL_R);
+    const int64_t grid = ntiles < 4 * (int64_t)sm_count() ? ntiles : 4 * (int64_t)sm_count();
+    const size_t need = sizeof(double) * (size_t)(n1 * n2);
+    const int use_smem = (n1 * n2 > 0 && need <= 96 * 1024) ? 1 : 0;
+    auto k = clenshaw2d_kernel;
+    AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    AFB_LAUNCH(k, (unsigned)grid, C2_THREADS, use_smem ? need : 8, stream, d_C, n1, n2, d_x, d_y, d_out, P, ntiles, use_smem);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9: chebnormalizedcumsum! per column (sample.jl:170-175), sequential per column to keep the
 // reference's summation order; one thread per column.
 // ------------------------------------------------------------------------------------------------

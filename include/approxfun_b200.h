@@ -169,6 +169,15 @@ int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, doubl
 /* the uniforms afb_sample_cheb_device draws, for parity checks */
 int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
 
+/* Bivariate evaluation f(x_p, y_p) = sum_{i,j} C[i,j] T_i(x_p) T_j(y_p) of a Chebyshev (x) Chebyshev coefficient matrix
+ * (n1 x n2 column-major; canonical variables), in the order a ProductFun is evaluated upstream (columns in x by the
+ * 1-D recurrence, then the recurrence over columns in y).  Replaces f(x, y) / evaluate for TensorSpace / ProductFun Funs
+ * (callers: examples/PDE_Helmholtz.jl:33-36, src/Plot/Plot.jl:335-338, test/PeriodicXIntervalTest.jl:22-24). */
+int32_t afb_clenshaw_cheb2d(const double* C, int64_t n1, int64_t n2, const double* x, const double* y, double* out,
+                            int64_t P);
+int32_t afb_clenshaw_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y,
+                                   double* d_out, int64_t P, void* stream);
+
 /* ---- 2-D sampling (sample(f::LowRankFun{Chebyshev,Chebyshev}, n), src/Extras/sample.jl:205-214) -------------
  * Fused replacement of lines 208-213: fA = evaluate.(f.A, ry'); AB = CB*fA; chebnormalizedcumsum!(AB);
  * rx = chebbisectioninv(AB, u); fromcanonical.(domain(f,1), rx).  A is NA x R and CB is N x R (column-major

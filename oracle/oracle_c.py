@@ -39,6 +39,8 @@ def lib():
         L.orc_sample2d_lowrank.argtypes = [_dp, i64, _dp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                            _dp, _dp, _dp, i64, i32]
         L.orc_sample2d_lowrank.restype = None
+        L.orc_clenshaw2d.argtypes = [_dp, i64, i64, _dp, _dp, _dp, i64, i32]
+        L.orc_clenshaw2d.restype = None
         L.orc_max_threads.restype = i32
         for f in (L.orc_clenshaw, L.orc_clenshaw_planned, L.orc_clenshaw_cols, L.orc_clenshaw_multi,
                   L.orc_cheb_bisect, L.orc_cheb_bisect_cols, L.orc_cheb_bisect_planned,
@@ -148,3 +150,13 @@ def sample2d_lowrank(A, CB, ya, yb, xa, xb, ry, u, threads: int = 1):
     lib().orc_sample2d_lowrank(Af if Af.size else np.zeros(1), A.shape[0], Cf if Cf.size else np.zeros(1), CB.shape[0],
                                A.shape[1], ya, yb, xa, xb, ry, u, rx, u.size, threads)
     return rx
+
+
+def clenshaw2d(Cm, x, y, threads: int = 1):
+    """Cm[i, j] multiplies T_i(x) T_j(y) (ProductFun evaluation order)."""
+    Cm = np.asarray(Cm, dtype=np.float64)
+    x, y = _c(x), _c(y)
+    out = np.empty_like(x)
+    flat = np.ascontiguousarray(Cm.T).ravel()
+    lib().orc_clenshaw2d(flat if flat.size else np.zeros(1), Cm.shape[0], Cm.shape[1], x, y, out, x.size, threads)
+    return out

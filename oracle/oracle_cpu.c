@@ -198,6 +198,25 @@ void orc_sample2d_lowrank(const double* A, int64_t NA, const double* CB, int64_t
     }
 }
 
+/* bivariate evaluation in ProductFun order: g_j(x) per column, then the recurrence over j in y */
+void orc_clenshaw2d(const double* C, int64_t n1, int64_t n2, const double* x, const double* y, double* out, int64_t P,
+                    int nthreads) {
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t p = 0; p < P; ++p) {
+        if (n2 == 0) { out[p] = 0.0; continue; }
+        const double y2 = 2.0 * y[p];
+        double B1 = 0.0, B2 = 0.0;
+        for (int64_t j = n2 - 1; j >= 1; --j) {
+            const double g = clenshaw1(C + j * n1, n1, 1, x[p]);
+            const double t = fma(y2, B1, g - B2);
+            B2 = B1;
+            B1 = t;
+        }
+        const double g0 = clenshaw1(C, n1, 1, x[p]);
+        out[p] = (n2 == 1) ? g0 : fma(y2 / 2.0, B1, g0 - B2);
+    }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

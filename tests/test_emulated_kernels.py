@@ -187,6 +187,17 @@ def test_taylor_and_hardy(n):
     assert np.max(np.abs(ll.transform(B.HARDYM_FWD, vh) - f)) < 1e-12 * n
 
 
+def test_bivariate_clenshaw_bit_exact():
+    for n1, n2, P in [(1, 1, 5), (5, 1, 40), (1, 6, 40), (9, 7, 1500), (40, 33, 300), (130, 100, 9)]:
+        Cm = RNG.standard_normal((n1, n2)) / (1 + np.arange(n1))[:, None]
+        x = RNG.uniform(-1, 1, P)
+        y = RNG.uniform(-1, 1, P)
+        got = ll.clenshaw2d(Cm, x, y)
+        assert np.array_equal(got, orcc.clenshaw2d(Cm, x, y))
+        want = np.polynomial.chebyshev.chebval2d(x, y, Cm)
+        assert np.max(np.abs(got - want)) < 1e-12 * max(1.0, np.sum(np.abs(Cm)))
+
+
 def test_sample2d_fused_kernel_bit_exact():
     # src/Extras/sample.jl:208-213 as one kernel: evaluate.(f.A, ry'), CB*fA, chebnormalizedcumsum!, chebbisectioninv
     for NA, N, R, P in [(12, 9, 3, 300), (1, 1, 1, 5), (30, 66, 7, 140), (5, 2, 2, 130)]:

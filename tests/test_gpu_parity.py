@@ -264,6 +264,19 @@ def test_taylor_hardy(af, n):
     assert np.max(np.abs(af.itransform(af.Hardy(), af.transform(af.Hardy(), v)) - v)) <= 4 * coef_tol(n, v)
 
 
+def test_bivariate_clenshaw(af):
+    for n1, n2, P in [(1, 1, 5), (9, 7, 100000), (96, 96, 20000), (130, 100, 500)]:
+        Cm = RNG.standard_normal((n1, n2)) / (1 + np.arange(n1))[:, None]
+        x, y = RNG.uniform(-1, 1, P), RNG.uniform(-1, 1, P)
+        assert np.array_equal(af.api.lowlevel().clenshaw2d(Cm, x, y), orcc.clenshaw2d(Cm, x, y, threads=8))
+    # examples/PDE_Helmholtz.jl:33-36 shape: evaluate a 2-D Fun at single points and on a grid
+    F = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy) * np.exp(xx * yy), af.Chebyshev() ** 2, 48)
+    assert abs(F(0.1, 0.2) - math.cos(0.5) * math.exp(0.02)) < 1e-13
+    gx = np.linspace(-1, 1, 50)
+    G = F(gx[:, None], gx[None, :])
+    assert np.max(np.abs(G - np.cos(gx[:, None] + 2 * gx[None, :]) * np.exp(gx[:, None] * gx[None, :]))) < 1e-12
+
+
 def test_sampling_2d_lowrank(af):
     # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
     S = af.Chebyshev(-4, 4)
