@@ -154,7 +154,7 @@ __device__ __forceinline__ void dit_last_paired(const LineParams& p, const cplx*
 #pragma unroll
     for (int i = 0; i < C::BL / 2; ++i) {
         const int pi = t + C::T * i;
-        cplx lo[RL], hi[RL], tb[J], tq[J];
+        cplx lo[RL], hi[RL], tb[J + 1], tq[J + 1];  // +1: J may be 0 (Laurent)
         dit_last_bfly<N>(s, pair_lo<N>(pi), lo, p.tw);
         dit_last_bfly<N>(s, pair_hi<N>(pi), hi, p.tw);
         load_tw<J>(p.aux, pi, tb);
@@ -213,7 +213,7 @@ __device__ __forceinline__ void dif_first_paired(const LineParams& p, cplx* __re
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         const int pi = t + C::T * i;
-        cplx lo[RL], hi[RL], tq[J], tb[J];
+        cplx lo[RL], hi[RL], tq[J + 1], tb[J + 1];
         load_tw<J>(p.aux, pi, tb);
         const cplx wlo = ldg2(p.tw + pair_lo<N>(pi));   // last-pass twiddle base w_N^j of both butterflies
         const cplx whi = ldg2(p.tw + pair_hi<N>(pi));
@@ -448,6 +448,8 @@ __device__ __forceinline__ void run_via_smem(const LineParams& p, int64_t line, 
     fft_line<N>(s, t, x, p.tw);
     Op::store(p, line, act, t, s);
 }
+// (A register-resident variant through the paired last pass -- F_k and F_{N-k} stored as adjacent 16-byte slots -- was
+// measured slower on the B200: 1.05 ms vs 0.84 ms at 32768 x 4096, its half-sector stores defeat coalescing.)
 template <int N> struct LineOp<N, LK_LAURENT_FWD> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
@@ -539,7 +541,7 @@ template <int N> struct LineOp<N, LK_CFFT> {
 
 // =================================================================================================
 template <int N, int KIND>
-__global__ void __launch_bounds__(LineGeom<N>::CT, 512 / LineGeom<N>::CT) line_kernel(const __grid_constant__ LineParams p) {
+__global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (KIND == LK_CHEB_INV || KIND == LK_FOURIER_INV)) ? 5 : 512 / LineGeom<N>::CT)) line_kernel(const __grid_constant__ LineParams p) {
     typedef LineGeom<N> G;
     AFB_DYN_SMEM(cplx, smem);
     const int tid = threadIdx.x;

@@ -136,4 +136,44 @@ function bisectioninv(cf::Fun{<:Chebyshev,Float64}, x::Vector{Float64})
     out
 end
 
+# ---- 2-D: transform!(::TensorSpace{Chebyshev,Chebyshev}, M) and the fused conditional sampler ------------------
+function cheb2d_transform!(M::Matrix{Float64}; inverse::Bool=false)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:afb_plan_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int64, Int64, Int64, Int64, UInt32),
+                h, inverse ? 7 : 6, size(M, 1), size(M, 2), 1, size(M, 1), 0))
+    try
+        GC.@preserve M check(ccall((:afb_plan_execute_host, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], M, M))
+    finally
+        ccall((:afb_plan_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+    end
+    M
+end
+
+# f(x_p, y_p) for a Chebyshev x Chebyshev coefficient matrix (canonical variables)
+function clenshaw2d(C::Matrix{Float64}, x::Vector{Float64}, y::Vector{Float64})
+    length(x) == length(y) || throw(DimensionMismatch("x and y differ in length"))
+    out = similar(x)
+    check(ccall((:afb_clenshaw_cheb2d, LIB), Int32,
+                (Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                C, size(C, 1), size(C, 2), x, y, out, length(x)))
+    out
+end
+
+# lines 208-213 of src/Extras/sample.jl in one call:  fA = evaluate.(f.A, ry'); AB = CB*fA; chebnormalizedcumsum!(AB);
+# rx = chebbisectioninv(AB, u); fromcanonical.(domain(f,1), rx)
+function sample_conditional(A::Matrix{Float64}, CB::Matrix{Float64}, dA, d1, ry::Vector{Float64}, u::Vector{Float64})
+    size(A, 2) == size(CB, 2) || throw(DimensionMismatch("rank mismatch"))
+    rx = similar(u)
+    check(ccall((:afb_sample2d_cheb_lowrank, LIB), Int32,
+                (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Float64, Float64, Float64, Float64,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                A, size(A, 1), CB, size(CB, 1), size(A, 2), ApproxFun.leftendpoint(dA), ApproxFun.rightendpoint(dA),
+                ApproxFun.leftendpoint(d1), ApproxFun.rightendpoint(d1), ry, u, rx, length(u)))
+    rx
+end
+
+# sibling plans on the same engine: kinds 8/9 = FastTransforms Val(2) (REDFT00), 10/11 = SinSpace, 12..15 = Taylor/Hardy
+chebyshevtransform2(v::VecOrMat{Float64}) = B200Plan{Float64}(Cint(8), size(v, 1), size(v, 2)) * v
+ichebyshevtransform2(c::VecOrMat{Float64}) = B200Plan{Float64}(Cint(9), size(c, 1), size(c, 2)) * c
+
 end # module
