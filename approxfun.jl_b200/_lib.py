@@ -30,7 +30,7 @@ SYMBOLS = [
     "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device",
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb_device",
-    "afb_philox_uniform_device",
+    "afb_philox_uniform_device", "afb_fp64_probe_device",
     "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device",
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
@@ -90,6 +90,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_samplecdf_cheb": [vp, i64, dbl, dbl, vp, vp, i64],
         "afb_sample_cheb_device": [vp, i64, dbl, dbl, u64, u64, vp, i64, vp],
         "afb_philox_uniform_device": [u64, u64, vp, i64, vp],
+        "afb_fp64_probe_device": [i32, i32, i32, vp, vp],
         "afb_clenshaw_cheb2d": [vp, i64, i64, vp, vp, vp, i64],
         "afb_clenshaw_cheb2d_device": [vp, i64, i64, vp, vp, vp, i64, vp],
         "afb_sample2d_cheb_lowrank": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64],

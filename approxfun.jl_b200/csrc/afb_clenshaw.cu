@@ -631,4 +631,59 @@ int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int
     return AFB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 issue-rate probe (measurement only, used by bench.py to replace the nominal FP64 peak by a measured one and to
+// test the register-file-port explanation of the Clenshaw ceiling).  Every thread runs 8 independent
+// dependency chains for `iters` steps.
+//   mode 0: DFMA with three distinct register operands          x = fma(a, x, c)        (a, c per-chain registers)
+//   mode 1: DFMA with a repeated register operand                x = fma(x, x, c)
+//   mode 2: the Clenshaw step  t = c - b2 ; b = fma(x2, b1, t)   (DADD + 3-operand DFMA)
+// flops counted by the caller: modes 0/1: 2 per step and chain, mode 2: 3.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, double seed, double* __restrict__ out) {
+    double x[8], a[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = seed * (double)(threadIdx.x + 1 + i);
+        a[i] = 0.999999 + 1e-9 * (double)(i + threadIdx.x);
+        c[i] = 1e-3 * (double)(i + 1) + 1e-12 * (double)threadIdx.x;   // per-thread: keeps it out of the uniform registers
+    }
+    if (mode == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __fma_rn(a[i], x[i], c[i]);
+        }
+    } else if (mode == 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __fma_rn(x[i], x[i], c[i]);
+        }
+    } else {
+        double b2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b2[i] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double t = __fma_rn(a[i], x[i], __dsub_rn(c[i], b2[i]));
+                b2[i] = x[i];
+                x[i] = t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += b2[i];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+int32_t launch_fp64_probe(int mode, int iters, int blocks, double* d_out, void* stream) {
+    auto k = fp64_probe_kernel;
+    AFB_LAUNCH(k, (unsigned)blocks, 256, 0, stream, mode, iters, 1e-7, d_out);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 }  // namespace afb

@@ -363,6 +363,21 @@ def main():
         t = time_loop(lambda: af.api.sample_device(dc.data_ptr(), cdf.size, -5.0, 5.0, 42, 0, y.data_ptr(), P, stream), 3, 1)
         extras["sample_gaussian"] = {"samples_per_s": world * P / (t * 1e-3), "ms_per_step": t, "N": int(cdf.size),
                                      "fp64_frac_of_nominal_peak": 47 * 3.0 * cdf.size * P / (t * 1e-3) / fp64_peak}
+        # measured FP64 issue rates (replaces the nominal peak as the denominator): 8 chains per thread
+        import ctypes as _C
+        blocks, iters = 148 * 8, 20000
+        pbuf = torch.empty(blocks * 256, dtype=torch.float64, device="cuda")
+        probe = {}
+        for mode, name, fl in ((0, "dfma_3_register_operands", 2.0), (1, "dfma_repeated_operand", 2.0),
+                               (2, "clenshaw_step_dadd_dfma", 3.0)):
+            tp = time_loop(lambda: L.check(lib, lib.afb_fp64_probe_device(mode, iters, blocks, _C.c_void_p(pbuf.data_ptr()),
+                                                                        _C.c_void_p(stream))), 3, 2)
+            probe[name] = fl * blocks * 256 * 8 * iters / (tp * 1e-3)
+        extras["fp64_probe_flops"] = probe
+        extras["clenshaw_N1e4"]["frac_of_measured_clenshaw_step_rate"] = extras["clenshaw_N1e4"]["fp64_flops"] / probe["clenshaw_step_dadd_dfma"]
+        extras["clenshaw_N1e4"]["frac_of_measured_dfma_rate"] = extras["clenshaw_N1e4"]["fp64_flops"] / probe["dfma_repeated_operand"]
+        extras["sample_gaussian"]["frac_of_measured_clenshaw_step_rate"] = (
+            47 * 3.0 * cdf.size * P / (extras["sample_gaussian"]["ms_per_step"] * 1e-3) / probe["clenshaw_step_dadd_dfma"])
         if rank == 0 and not args.no_cpu:
             # reference-side CPU baselines for configs 3 and 5 (oracle port, reference loop order: whole-vector passes
             # through the ClenshawPlan work vectors, all host threads), on bounded point sets

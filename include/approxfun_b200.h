@@ -194,6 +194,11 @@ int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, 
 int32_t afb_dgemm_nn_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
                             void* stream);
 
+/* Measurement helper (no reference counterpart): runs `blocks` x 256 threads x 8 chains x `iters` FP64 steps;
+ * mode 0 = DFMA with three distinct register operands, 1 = DFMA with a repeated operand, 2 = the Clenshaw DADD+DFMA step.
+ * d_out needs blocks*256 doubles.  bench.py times it to report a MEASURED FP64 rate next to the nominal peak. */
+int32_t afb_fp64_probe_device(int32_t mode, int32_t iters, int32_t blocks, double* d_out, void* stream);
+
 /* ---- multi-GPU 2D transform (one process per GPU) ----------------------------------------------------
  * The n x n2 matrix is sharded by contiguous column blocks; the plan performs local column transforms,
  * an all-to-all transpose over NVLink, and local transforms of the other factor.  The caller supplies
