@@ -913,7 +913,7 @@ int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, 
 
 // measurement helper for bench.py (not a reference entry point): see fp64_probe_kernel
 int32_t afb_fp64_probe_device(int32_t mode, int32_t iters, int32_t blocks, double* d_out, void* stream) {
-    if (mode < 0 || mode > 2 || iters < 0 || blocks <= 0 || !d_out) return fail(AFB_BAD_ARG, "afb_fp64_probe: bad argument");
+    if (mode < 0 || mode > 3 || iters < 0 || blocks <= 0 || !d_out) return fail(AFB_BAD_ARG, "afb_fp64_probe: bad argument");
     AFB_TRY(ensure_device());
     return launch_fp64_probe(mode, iters, blocks, d_out, stream);
 }

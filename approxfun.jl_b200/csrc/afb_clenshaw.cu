@@ -638,6 +638,7 @@ int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int
 //   mode 0: DFMA with three distinct register operands          x = fma(a, x, c)        (a, c per-chain registers)
 //   mode 1: DFMA with a repeated register operand                x = fma(x, x, c)
 //   mode 2: the Clenshaw step  t = c - b2 ; b = fma(x2, b1, t)   (DADD + 3-operand DFMA)
+//   mode 3: reassociated step  s = fma(x2, b1, c_uniform) ; b = s - b2  (2-register DFMA + DADD; different rounding)
 // flops counted by the caller: modes 0/1: 2 per step and chain, mode 2: 3.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, double seed, double* __restrict__ out) {
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, do
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = __fma_rn(x[i], x[i], c[i]);
         }
-    } else {
+    } else if (mode == 2) {
         double b2[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) b2[i] = 0.0;
@@ -666,6 +667,22 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, do
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const double t = __fma_rn(a[i], x[i], __dsub_rn(c[i], b2[i]));
+                b2[i] = x[i];
+                x[i] = t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += b2[i];
+    } else {
+        // mode 3: reassociated step with a warp-uniform coefficient  s = fma(x2, b1, c_uniform) ; b = s - b2
+        double b2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b2[i] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+            const double cu = seed * (double)(it & 1023);   // uniform across the warp: lives in a uniform register
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double t = __dsub_rn(__fma_rn(a[i], x[i], cu), b2[i]);
                 b2[i] = x[i];
                 x[i] = t;
             }
