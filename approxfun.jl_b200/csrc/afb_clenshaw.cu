@@ -11,8 +11,26 @@
 // shared memory and are read as broadcast 128-bit loads (two coefficients per LDS); every thread
 // carries R independent points so the DFMA dependency chains overlap.
 #include "afb_common.cuh"
+#ifndef AFB_HOST_EMU
+#include <cuda_pipeline.h>
+#endif
 
 namespace afb {
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, many copies in flight per thread
+__device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem_src) {
+#ifdef AFB_HOST_EMU
+    *smem_dst = *gmem_src;
+#else
+    __pipeline_memcpy_async(smem_dst, gmem_src, 8);
+#endif
+}
+__device__ __forceinline__ void async_copy_wait() {
+#ifndef AFB_HOST_EMU
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+#endif
+}
 
 constexpr int CL_THREADS = 512;        // threads per CTA
 constexpr int CL_R = 4;                // points per thread (independent recurrences)
@@ -218,10 +236,18 @@ cols_kernel(const double* __restrict__ C, int64_t N, int64_t ld, const double* _
     const int64_t col0 = (int64_t)blockIdx.x * COLS_W;
     const int64_t j = col0 + tid;
     if (use_smem) {
-        // coalesced: consecutive threads read consecutive k of one column
+        // coalesced: the tile is (nearly) contiguous in global memory; consecutive threads read consecutive k,
+        // and the padded row stride makes the transposed shared-memory writes conflict free
         const int64_t ncol = (P - col0 < COLS_W) ? (P - col0) : COLS_W;
-        for (int64_t cidx = 0; cidx < ncol; ++cidx)
-            for (int64_t k = tid; k < N; k += COLS_W) sm[k * COLS_LD + cidx] = C[(col0 + cidx) * ld + k];
+        const double* src = C + col0 * ld;
+        const int n32 = (int)N, total = (int)ncol * n32;
+        int cidx = tid / n32, k = tid - cidx * n32;          // one division, then incremental (cidx, k) updates
+        for (int e = tid; e < total; e += COLS_W) {
+            async_copy8(sm + k * COLS_LD + cidx, src + (int64_t)cidx * ld + k);
+            k += COLS_W;
+            while (k >= n32) { k -= n32; ++cidx; }
+        }
+        async_copy_wait();
         __syncthreads();
     }
     if (j >= P) return;
@@ -379,12 +405,12 @@ __global__ void normcumsum_kernel(double* __restrict__ C, int64_t N, int64_t nco
     double* v = C + j * ld;
     const int64_t n = N;
     if (n == 2) {
-        v[1] = __ddiv_rn(v[1], 2.0);
+        v[1] = __dmul_rn(v[1], 0.5);
     } else if (n > 2) {
-        v[0] = __dsub_rn(v[0], __ddiv_rn(v[2], 2.0));
-        for (int64_t q = 1; q <= n - 3; ++q) v[q] = __ddiv_rn(__dsub_rn(v[q], v[q + 2]), 2.0);
-        v[n - 2] = __ddiv_rn(v[n - 2], 2.0);
-        v[n - 1] = __ddiv_rn(v[n - 1], 2.0);
+        v[0] = __dsub_rn(v[0], __dmul_rn(v[2], 0.5));
+        for (int64_t q = 1; q <= n - 3; ++q) v[q] = __dmul_rn(__dsub_rn(v[q], v[q + 2]), 0.5);
+        v[n - 2] = __dmul_rn(v[n - 2], 0.5);
+        v[n - 1] = __dmul_rn(v[n - 1], 0.5);
     }
     const int64_t L = grow ? n + 1 : n;
     for (int64_t k = L - 1; k >= 1; --k) v[k] = __ddiv_rn(v[k - 1], (double)k);
@@ -394,6 +420,60 @@ __global__ void normcumsum_kernel(double* __restrict__ C, int64_t N, int64_t nco
     for (int64_t k = 0; k < L; ++k) val = __dadd_rn(val, v[k]);
     val = __ddiv_rn(1.0, val);
     for (int64_t k = 0; k < L; ++k) v[k] = __dmul_rn(v[k], val);
+}
+
+// Tiled variant: a CTA stages 128 columns transposed in shared memory (coalesced both ways) and each thread runs
+// the same sequential column recipe on its shared-memory column.  Same operation order => same bits.
+__global__ void __launch_bounds__(COLS_W)
+normcumsum_tiled_kernel(double* __restrict__ C, int64_t N, int64_t ncols, int64_t ld, int grow) {
+    AFB_DYN_SMEM(double, sm);
+    const int tid = threadIdx.x;
+    const int64_t col0 = (int64_t)blockIdx.x * COLS_W;
+    const int64_t ncol = (ncols - col0 < COLS_W) ? (ncols - col0) : COLS_W;
+    const int64_t n = N, L = grow ? N + 1 : N;
+    {
+        const double* src = C + col0 * ld;
+        const int n32 = (int)n, total = (int)ncol * n32;
+        int cidx = tid / n32, k = tid - cidx * n32;
+        for (int e = tid; e < total; e += COLS_W) {
+            async_copy8(sm + k * COLS_LD + cidx, src + (int64_t)cidx * ld + k);
+            k += COLS_W;
+            while (k >= n32) { k -= n32; ++cidx; }
+        }
+        async_copy_wait();
+    }
+    __syncthreads();
+    if (tid < ncol) {
+        double* v = sm + tid;
+#define V(k) v[(k) * COLS_LD]
+        if (n == 2) {
+            V(1) = __dmul_rn(V(1), 0.5);
+        } else if (n > 2) {
+            V(0) = __dsub_rn(V(0), __dmul_rn(V(2), 0.5));
+            for (int64_t q = 1; q <= n - 3; ++q) V(q) = __dmul_rn(__dsub_rn(V(q), V(q + 2)), 0.5);
+            V(n - 2) = __dmul_rn(V(n - 2), 0.5);
+            V(n - 1) = __dmul_rn(V(n - 1), 0.5);
+        }
+        for (int64_t k = L - 1; k >= 1; --k) V(k) = __ddiv_rn(V(k - 1), (double)k);
+        if (L > 0) V(0) = 0.0;
+        for (int64_t k = 2; k <= L; ++k) V(0) = __dadd_rn(V(0), (k & 1) ? -V(k - 1) : V(k - 1));
+        double val = 0.0;
+        for (int64_t k = 0; k < L; ++k) val = __dadd_rn(val, V(k));
+        val = __ddiv_rn(1.0, val);
+        for (int64_t k = 0; k < L; ++k) V(k) = __dmul_rn(V(k), val);
+#undef V
+    }
+    __syncthreads();
+    {
+        double* dst = C + col0 * ld;
+        const int l32 = (int)L, total = (int)ncol * l32;
+        int cidx = tid / l32, k = tid - cidx * l32;
+        for (int e = tid; e < total; e += COLS_W) {
+            dst[(int64_t)cidx * ld + k] = sm[k * COLS_LD + cidx];
+            k += COLS_W;
+            while (k >= l32) { k -= l32; ++cidx; }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,6 +573,14 @@ int32_t launch_multi(const double* d_C, int64_t N, int64_t M, const double* d_x,
 
 int32_t launch_normcumsum(double* d_C, int64_t N, int64_t ncols, int64_t ld, int grow, void* stream) {
     if (ncols == 0) return AFB_OK;
+    const size_t need = sizeof(double) * (size_t)(N + 1) * COLS_LD;
+    if (ncols >= 64 && need <= 200 * 1024) {
+        auto kt = normcumsum_tiled_kernel;
+        AFB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        AFB_LAUNCH(kt, (unsigned)((ncols + COLS_W - 1) / COLS_W), COLS_W, need, stream, d_C, N, ncols, ld, grow);
+        AFB_KERNEL_CHECK();
+        return AFB_OK;
+    }
     auto k = normcumsum_kernel;
     AFB_LAUNCH(k, (unsigned)((ncols + 127) / 128), 128, 0, stream, d_C, N, ncols, ld, grow);
     AFB_KERNEL_CHECK();
@@ -556,12 +644,12 @@ sample2d_kernel(const double* __restrict__ A, int64_t NA, const double* __restri
     // chebnormalizedcumsum! (matrix semantics: no growth), same operation order as normcumsum_kernel
     const int64_t n = N;
     if (n == 2) {
-        col[S2_LD] = __ddiv_rn(col[S2_LD], 2.0);
+        col[S2_LD] = __dmul_rn(col[S2_LD], 0.5);
     } else if (n > 2) {
-        col[0] = __dsub_rn(col[0], __ddiv_rn(col[2 * S2_LD], 2.0));
-        for (int64_t q = 1; q <= n - 3; ++q) col[q * S2_LD] = __ddiv_rn(__dsub_rn(col[q * S2_LD], col[(q + 2) * S2_LD]), 2.0);
-        col[(n - 2) * S2_LD] = __ddiv_rn(col[(n - 2) * S2_LD], 2.0);
-        col[(n - 1) * S2_LD] = __ddiv_rn(col[(n - 1) * S2_LD], 2.0);
+        col[0] = __dsub_rn(col[0], __dmul_rn(col[2 * S2_LD], 0.5));
+        for (int64_t q = 1; q <= n - 3; ++q) col[q * S2_LD] = __dmul_rn(__dsub_rn(col[q * S2_LD], col[(q + 2) * S2_LD]), 0.5);
+        col[(n - 2) * S2_LD] = __dmul_rn(col[(n - 2) * S2_LD], 0.5);
+        col[(n - 1) * S2_LD] = __dmul_rn(col[(n - 1) * S2_LD], 0.5);
     }
     for (int64_t k = n - 1; k >= 1; --k) col[k * S2_LD] = __ddiv_rn(col[(k - 1) * S2_LD], (double)k);
     if (n > 0) col[0] = 0.0;
