@@ -623,23 +623,37 @@ sample2d_kernel(const double* __restrict__ A, int64_t NA, const double* __restri
     const double yc = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, y), ya), yb), __dsub_rn(yb, ya));
     const double y2 = __dmul_rn(2.0, yc);
     for (int64_t k = 0; k < N; ++k) col[k * S2_LD] = 0.0;
-    for (int64_t r = 0; r < R; ++r) {
-        const double* a = A + r * NA;
-        double fa = 0.0;
-        if (inside) {
-            if (NA == 1) fa = a[0];
-            else if (NA > 1) {
-                double b1 = 0.0, b2 = 0.0;
-                for (int64_t k = NA - 1; k >= 1; --k) {
-                    const double t = __fma_rn(y2, b1, __dsub_rn(__ldg(a + k), b2));
-                    b2 = b1;
-                    b1 = t;
+    // four functions of f.A at a time: four independent Clenshaw chains (ILP), then ONE shared-memory read-modify-write
+    // per coefficient k that applies the four rank-one updates in r order (the same fma sequence as the scalar loop)
+    constexpr int RB = 4;
+    for (int64_t r0 = 0; r0 < R; r0 += RB) {
+        double fa[RB];
+        double b1[RB], b2[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) { fa[i] = 0.0; b1[i] = 0.0; b2[i] = 0.0; }
+        if (inside && NA >= 1) {
+            for (int64_t k = NA - 1; k >= 1; --k) {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    const double ak = (r0 + i < R) ? __ldg(A + (r0 + i) * NA + k) : 0.0;
+                    const double t = __fma_rn(y2, b1[i], __dsub_rn(ak, b2[i]));
+                    b2[i] = b1[i];
+                    b1[i] = t;
                 }
-                fa = __fma_rn(__dmul_rn(y2, 0.5), b1, __dsub_rn(__ldg(a), b2));
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const double a0 = (r0 + i < R) ? __ldg(A + (r0 + i) * NA) : 0.0;
+                fa[i] = (NA == 1) ? a0 : __fma_rn(__dmul_rn(y2, 0.5), b1[i], __dsub_rn(a0, b2[i]));
             }
         }
-        const double* cb = CB + r * N;
-        for (int64_t k = 0; k < N; ++k) col[k * S2_LD] = __fma_rn(__ldg(cb + k), fa, col[k * S2_LD]);
+        for (int64_t k = 0; k < N; ++k) {
+            double acc = col[k * S2_LD];
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+                if (r0 + i < R) acc = __fma_rn(__ldg(CB + (r0 + i) * N + k), fa[i], acc);
+            col[k * S2_LD] = acc;
+        }
     }
     // chebnormalizedcumsum! (matrix semantics: no growth), same operation order as normcumsum_kernel
     const int64_t n = N;
