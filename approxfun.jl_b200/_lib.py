@@ -18,6 +18,7 @@ AFB_OK, AFB_BAD_ARG, AFB_BAD_SIZE, AFB_NO_DEVICE, AFB_CUDA_ERROR, AFB_NCCL_ERROR
 CHEB1_FWD, CHEB1_INV, FOURIER_FWD, FOURIER_INV, LAURENT_FWD, LAURENT_INV, CHEB1_2D_FWD, CHEB1_2D_INV = range(8)
 CHEB2_FWD, CHEB2_INV, SIN_FWD, SIN_INV = 8, 9, 10, 11
 TAYLOR_FWD, TAYLOR_INV, HARDYM_FWD, HARDYM_INV = 12, 13, 14, 15
+PLAN_2D_TRANSPOSE = 1  # afb_plan_create flag: explicit-transpose row pass for 2D kinds
 
 # every symbol include/approxfun_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = [
@@ -190,13 +191,13 @@ class LowLevel:
         res = np.ascontiguousarray(out.T)
         return res[:, 0] if one else res.reshape(v.shape)
 
-    def transform2d(self, kind: int, V: np.ndarray) -> np.ndarray:
+    def transform2d(self, kind: int, V: np.ndarray, flags: int = 0) -> np.ndarray:
         """V[k, j] (n x n2) in the reference's column-major sense."""
         V = np.asarray(V, dtype=np.float64)
         n, n2 = V.shape
         buf = np.ascontiguousarray(V.T)  # memory order of a Julia n x n2 matrix
         out = np.empty_like(buf)
-        h = self.plan_create(kind, n, n2, 1, n)
+        h = self.plan_create(kind, n, n2, 1, n, flags)
         try:
             if n and n2:
                 self.plan_execute_host(h, buf, out)

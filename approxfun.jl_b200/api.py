@@ -544,9 +544,9 @@ def sample(f, n: int | None = None, rng=None, uniforms=None):
 class DevicePlan:
     """Plan executed on device buffers: `execute(in_ptr, out_ptr, stream_ptr)` is asynchronous."""
 
-    def __init__(self, kind: int, n: int, n2: int = 0, batch: int = 1, stride: int | None = None):
+    def __init__(self, kind: int, n: int, n2: int = 0, batch: int = 1, stride: int | None = None, flags: int = 0):
         self._ll = lowlevel()
-        self._h = self._ll.plan_create(kind, n, n2, batch, stride)
+        self._h = self._ll.plan_create(kind, n, n2, batch, stride, flags)
         self.kind, self.n, self.n2, self.batch = kind, n, n2, batch
 
     def execute(self, in_ptr: int, out_ptr: int, stream: int = 0):

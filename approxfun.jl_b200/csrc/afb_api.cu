@@ -89,10 +89,26 @@ int32_t root_table(int64_t N, const cplx** out) {
     return AFB_OK;
 }
 
+static std::map<int64_t, cplx*> g_quarter_tables;
+int32_t quarter_table(int64_t n, const cplx** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_quarter_tables.find(n);
+    if (it != g_quarter_tables.end()) { *out = it->second; return AFB_OK; }
+    std::vector<cplx> h((size_t)n + 1);
+    for (int64_t k = 0; k <= n; ++k) h[(size_t)k] = unit_ld((long double)k, (long double)(4 * n), -1);
+    cplx* d = nullptr;
+    AFB_TRY(upload_table(h, &d));
+    g_quarter_tables[n] = d;
+    *out = d;
+    return AFB_OK;
+}
+
 void free_tables() {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& kv : g_root_tables) cudaFree(kv.second);
     g_root_tables.clear();
+    for (auto& kv : g_quarter_tables) cudaFree(kv.second);
+    g_quarter_tables.clear();
 }
 
 }  // namespace afb
@@ -428,8 +444,8 @@ static int32_t plan_launch_count(afb_plan_s* p) {
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
         }
         case PATH_TENSOR2D: {
-            const bool fused = false;  // see afb_plan_execute_device
-            return plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan) + (fused ? 0 : 2);
+            if (!p->row_plan) return plan_launch_count(p->col_plan) + 2;  // + outer and inner row kernels
+            return plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan) + 2;
         }
     }
     return 0;
@@ -526,10 +542,12 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
         if (p->path == PATH_TENSOR2D) {
             const int32_t k1 = (kind == AFB_CHEB1_2D_FWD) ? AFB_CHEB1_FWD : AFB_CHEB1_INV;
             int32_t st = plan_create_1d(&p->col_plan, k1, n, n2, n, flags);
-            if (st == AFB_OK) st = plan_create_1d(&p->row_plan, k1, n2, n, n2, flags);
+            // row pass: strided four-step on row pairs when the shape allows, else transpose + lines + transpose
+            if (st == AFB_OK && ((flags & AFB_PLAN_2D_TRANSPOSE) || !rows_cheb_supported(n, n2))) st = plan_create_1d(&p->row_plan, k1, n2, n, n2, flags);
             if (st == AFB_OK) {
                 void* d = nullptr;
-                cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)(n * n2));
+                const int64_t tdoubles = p->row_plan ? n * n2 : rows_tmp_doubles(n, n2);
+                cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)tdoubles);
                 if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(2D transpose buffer)", __FILE__, __LINE__);
                 p->t2buf = reinterpret_cast<double*>(d);
             }
@@ -566,17 +584,12 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
     if (p->path == PATH_TENSOR2D) {
         // C = T_x V T_y^T on a column-major n x n2 matrix.
         const int64_t n = p->n, n2 = p->n2;
-        // Scattering 8-byte outputs with a 128 KB element stride (fused transpose) was measured 1.5x SLOWER on a B200 at
-        // 16384^2 (TLB + sector-partial writes: 6.06 ms vs 3.97 ms), so the tiled-transpose route is used.
-        const bool fused = false;
-        if (fused) {
-            // both passes read contiguous lines and scatter their output transposed (element stride = other
-            // dimension), so no separate transpose kernels run: W^T = (T_x V)^T lands in t2buf, then C.
-            AFB_TRY(exec_1d_device(p->col_plan, d_in, p->t2buf, n2, n, 1, stream, n2));
-            AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, d_out, n, n2, 1, stream, n));
-            return AFB_OK;
-        }
+        // Column pass on contiguous lines, then the row pass.  (Fusing the transposes into the line kernels' stores --
+        // 8-byte scatters with a 128 KB stride -- was measured 1.5x SLOWER at 16384^2: 6.06 ms vs 3.97 ms.)
         AFB_TRY(exec_1d_device(p->col_plan, d_in, d_out, n2, n, n, stream));
+        if (!p->row_plan)
+            return launch_rows_cheb(p->kind == AFB_CHEB1_2D_INV, reinterpret_cast<const double*>(d_out), p->t2buf,
+                                    reinterpret_cast<double*>(d_out), n, n2, stream);
         AFB_TRY(launch_transpose(reinterpret_cast<const double*>(d_out), p->t2buf, n, n2, stream));
         AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, n, n2, n2, stream));
         AFB_TRY(launch_transpose(p->t2buf, reinterpret_cast<double*>(d_out), n2, n, stream));

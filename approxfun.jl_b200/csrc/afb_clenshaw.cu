@@ -17,21 +17,6 @@
 
 namespace afb {
 
-// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, many copies in flight per thread
-__device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem_src) {
-#ifdef AFB_HOST_EMU
-    *smem_dst = *gmem_src;
-#else
-    __pipeline_memcpy_async(smem_dst, gmem_src, 8);
-#endif
-}
-__device__ __forceinline__ void async_copy_wait() {
-#ifndef AFB_HOST_EMU
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-#endif
-}
-
 constexpr int CL_THREADS = 512;        // threads per CTA
 constexpr int CL_R = 4;                // points per thread (independent recurrences)
 constexpr int CL_CHUNK = 12288;        // coefficients staged per shared-memory chunk (96 KB)

@@ -6,6 +6,7 @@
 #define AFB_HD
 #else
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #define AFB_HD __host__ __device__
 #define AFB_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -63,6 +64,41 @@ __device__ __forceinline__ cplx ldg2(const cplx* p) {
     return *p;
 #else
     return __ldg(reinterpret_cast<const double2*>(p));
+#endif
+}
+
+// asynchronous global -> shared copies (LDGSTS): no register staging, many copies in flight per thread
+__device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem_src) {
+#ifdef AFB_HOST_EMU
+    *smem_dst = *gmem_src;
+#else
+    __pipeline_memcpy_async(smem_dst, gmem_src, 8);
+#endif
+}
+__device__ __forceinline__ void async_copy16(double* smem_dst, const double* gmem_src) {  // both 16-byte aligned
+#ifdef AFB_HOST_EMU
+    smem_dst[0] = gmem_src[0];
+    smem_dst[1] = gmem_src[1];
+#else
+    __pipeline_memcpy_async(smem_dst, gmem_src, 16);
+#endif
+}
+__device__ __forceinline__ void async_copy_commit() {
+#ifndef AFB_HOST_EMU
+    __pipeline_commit();
+#endif
+}
+__device__ __forceinline__ void async_copy_wait() {
+#ifndef AFB_HOST_EMU
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+#endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* gmem) {
+#ifndef AFB_HOST_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
+#else
+    (void)gmem;
 #endif
 }
 

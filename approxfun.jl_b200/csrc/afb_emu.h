@@ -44,7 +44,7 @@ typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2,
        cudaHostAllocDefault = 0 };
 struct cudaDeviceProp { int multiProcessorCount; int major; int minor; size_t totalGlobalMem; char name[64]; };
 

@@ -71,6 +71,11 @@ int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, doubl
 // ---- 2-D (afb_tensor.cu) -----------------------------------------------------------------------------
 int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, void* stream);
 
+// row pass without transposes (afb_rows.cu): Chebyshev transform along dimension 2 of a column-major n1 x n2 matrix
+bool rows_cheb_supported(int64_t n1, int64_t n2);
+int64_t rows_tmp_doubles(int64_t n1, int64_t n2);  // size of `tmp` below
+int32_t launch_rows_cheb(bool inverse, const double* in, double* tmp, double* out, int64_t n1, int64_t n2, void* stream);
+
 // ---- device table helpers ------------------------------------------------------------------------------
 int32_t upload_table(const std::vector<cplx>& host, cplx** dev);
 

@@ -68,8 +68,10 @@ template <int N> struct PairMap {
     static __device__ __forceinline__ int col(int t) { return (t & 1) ? C::T - 1 - (t >> 1) : (t >> 1); }
 };
 
-template <int N>
-__device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v2, bool act, int t, cplx* x) {
+// HS > 0: the first HS of the R1/2 load groups (2T chunks each) come from the shared-memory stage st2.
+template <int N, int HS = 0>
+__device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v2, bool act, int t, cplx* x,
+                                                   const double2* st2 = nullptr) {
     typedef FftCfg<N> C;
     constexpr int H = C::R1 / 2;
     const int role = t & 1, p2 = t >> 1;
@@ -80,7 +82,8 @@ __device__ __forceinline__ void cheb_exchange_load(const double2* __restrict__ v
         for (int sg = 0; sg < 2; ++sg) {
             const int qcol = sg ? C::T - 1 - p2 : p2;
             const int q = qcol + C::T * qq;
-            ch[qq][sg] = act ? v2[2 * q + (role ^ sg)] : make_double2(0.0, 0.0);
+            if (qq < HS) ch[qq][sg] = st2[2 * q + (role ^ sg)];
+            else ch[qq][sg] = act ? v2[2 * q + (role ^ sg)] : make_double2(0.0, 0.0);
         }
 #pragma unroll
     for (int qq = 0; qq < H; ++qq) {
@@ -338,6 +341,19 @@ template <int N> struct ChebInvPre {
         Z0 = make_double2(r.ck + r.cNk * h, -(r.ck - r.cNk * h));
     }
 };
+// same with c[0 .. 3n/4] read from the shared-memory stage (k < N/2: only c[n-k] is beyond it)
+template <int N> struct ChebInvPreStaged : ChebInvPre<N> {
+    typedef typename ChebInvPre<N>::Raw Raw;
+    const double* st;
+    __device__ __forceinline__ ChebInvPreStaged(const double* c_, const double* st_) : ChebInvPre<N>{c_, true}, st(st_) {}
+    __device__ __forceinline__ void fetch(int k, Raw& r) {
+        constexpr int n = 2 * N;
+        r.ck = st[k]; r.cnk = this->c[n - k]; r.cNk = st[N - k]; r.cNpk = st[N + k];
+    }
+    __device__ __forceinline__ void fetch_dc(Raw& r) {
+        r.ck = st[0]; r.cnk = 0; r.cNk = st[N]; r.cNpk = 0;
+    }
+};
 template <int N> struct LineOp<N, LK_CHEB_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
@@ -552,8 +568,81 @@ __global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (
     LineOp<N, KIND>::run(p, line, act, t, s);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Long lines (N = 8192: one 512-thread CTA fills an SM's register file, so no second CTA can hide the load
+// phase).  Persistent CTAs instead: while line i is transformed, the first 3/4 of the CTA's next line arrives
+// in the spare 96 KB of shared memory through asynchronous copies and the last quarter is pulled into L2.
+// -------------------------------------------------------------------------------------------------
+template <int N> struct StageGeom {
+    typedef FftCfg<N> C;
+    static constexpr int HS = 6;                          // staged load groups (of R1/2 = 8)
+    static constexpr int DOUBLES = 4 * C::T * HS + 16;    // 3n/4, + the slot n*3/4 itself (k = N/2 of the inverse)
+    static constexpr size_t SMEM = sizeof(cplx) * (size_t)N + sizeof(double) * DOUBLES;
+};
+template <int N>
+__device__ __forceinline__ void stage_issue(double* __restrict__ st, const double* __restrict__ src, int t) {
+    typedef StageGeom<N> SG;
+    for (int i = t; i < SG::DOUBLES / 2; i += FftCfg<N>::T) async_copy16(st + 2 * i, src + 2 * i);
+    async_copy_commit();
+    const char* rest = reinterpret_cast<const char*>(src + SG::DOUBLES);
+    for (int b = t * 128; b < (2 * N - SG::DOUBLES) * 8; b += FftCfg<N>::T * 128) prefetch_l2(rest + b);
+}
+template <int N, int KIND>
+__global__ void __launch_bounds__(FftCfg<N>::T, 1) line_kernel_staged(const __grid_constant__ LineParams p) {
+    typedef FftCfg<N> C;
+    typedef StageGeom<N> SG;
+    static_assert(KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV, "staged lines: Chebyshev kinds");
+    AFB_DYN_SMEM(cplx, s);
+    double* st = reinterpret_cast<double*>(s + N);
+    const int t = threadIdx.x;
+    const double* in = reinterpret_cast<const double*>(p.in);
+    double* out = reinterpret_cast<double*>(p.out);
+    int64_t line = blockIdx.x;
+    if (line < p.batch) stage_issue<N>(st, in + line * p.istride, t);
+    for (; line < p.batch; line += gridDim.x) {
+        const int64_t next = line + gridDim.x;
+        async_copy_wait();
+        __syncthreads();  // the stage is complete; every thread is done with the previous line's buffer
+        cplx x[C::E];
+        if constexpr (KIND == LK_CHEB_FWD) {
+            cheb_exchange_load<N, SG::HS>(reinterpret_cast<const double2*>(in + line * p.istride), true, t, x,
+                                          reinterpret_cast<const double2*>(st));
+            dit_first<N>(s, PairMap<N>::col(t), x);   // ends with a barrier: the stage is free again
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t);
+            dit_middle<N>(s, t, x, p.tw);
+            ChebFwdPost<N> f{out + line * p.ostride, p.oes, p.scale, true};
+            dit_last_paired<N, 2>(p, s, t, f);
+        } else {
+            ChebInvPreStaged<N> f(in + line * p.istride, st);
+            dif_first_paired<N, 2>(p, s, t, f);       // ends with a barrier
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t);
+            dif_middle<N>(s, t, x, p.tw);
+            dif_last<N>(s, PairMap<N>::col(t), x);
+            cheb_exchange_store<N>(out + line * p.ostride, p.oes, true, t, x);
+        }
+    }
+}
+template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p, void* stream) {
+    typedef StageGeom<N> SG;
+    auto k = line_kernel_staged<N, KIND>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::SMEM));
+        attr_done = true;
+    }
+    const int64_t grid = p.batch < sm_count() ? p.batch : sm_count();
+    AFB_LAUNCH(k, (unsigned)grid, FftCfg<N>::T, SG::SMEM, stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
     typedef LineGeom<N> G;
+    if constexpr (N == 8192 && (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV)) {
+        // 16-byte aligned lines and more lines than SMs, otherwise there is nothing to overlap
+        if (p.batch > sm_count() && p.istride % 2 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
+            return launch_line_staged<N, KIND>(p, stream);
+    }
     auto k = line_kernel<N, KIND>;
     static bool attr_done = false;  // one process drives one device: set the opt-in shared-memory size once
     if (!attr_done) {

@@ -103,7 +103,11 @@ int32_t afb_stream_sync(void* stream);
  *   n2     0 for 1D kinds; number of columns for 2D kinds
  *   batch  number of independent transforms (1D); must be 1 for 2D
  *   stride elements (double, or complex double for Laurent) between consecutive transforms; >= n
+ *   flags  0, or AFB_PLAN_2D_TRANSPOSE: 2D kinds run the row pass as transpose + contiguous lines + transpose
+ *          (the only route when n is odd or n2 is not a power of two in 2^10..2^18) instead of the strided
+ *          four-step on row pairs; results agree to rounding.
  * Data type: double for Chebyshev / Fourier, interleaved complex double for Laurent. */
+#define AFB_PLAN_2D_TRANSPOSE 1u
 int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int64_t batch, int64_t stride,
                         uint32_t flags);
 /* host buffers; in == out allowed.  H2D, kernels and D2H are pipelined over batch chunks. */

@@ -57,6 +57,18 @@ def test_complex_transforms(n):
         assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
 
 
+def test_long_lines_staged_persistent_kernel():
+    # n = 16384 with more lines than (emulated, 4) SMs: persistent CTAs, next line staged with async copies
+    n, nb = 16384, 11
+    v = RNG.standard_normal((n, nb))
+    got = ll.transform(B.CHEB1_FWD, v)
+    want = orc.cheb_transform(v, axis=0)
+    assert np.max(np.abs(got - want)) <= tol(n, np.max(np.abs(v)))
+    back = ll.transform(B.CHEB1_INV, got)
+    assert np.max(np.abs(back - v)) <= 50 * tol(n, np.max(np.abs(v)))
+    assert np.max(np.abs(ll.transform(B.CHEB1_INV, v) - orc.cheb_itransform(v, axis=0))) <= tol(n, 200 * np.max(np.abs(v)))
+
+
 def test_empty_and_vector_shapes():
     assert ll.transform(B.CHEB1_FWD, np.zeros(0)).shape == (0,)
     assert ll.transform(B.CHEB1_FWD, np.zeros((8, 0))).shape == (8, 0)
@@ -90,6 +102,18 @@ def test_tensor2d(shape):
     assert np.max(np.abs(got - want)) < 1e-13
     back = ll.transform2d(B.CHEB1_2D_INV, got)
     assert np.max(np.abs(back - V)) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(2, 1024), (6, 2048), (34, 1024), (10, 4096), (2, 16384)])
+def test_tensor2d_row_pairs_four_step(shape):
+    # even n, n2 = 2^10..2^18: the row pass runs on row pairs without transposes; flag 1 = transpose route
+    V = RNG.standard_normal(shape)
+    want = orc.cheb2_transform(V)
+    got = ll.transform2d(B.CHEB1_2D_FWD, V)
+    assert np.max(np.abs(got - want)) < 1e-14
+    assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V, B.PLAN_2D_TRANSPOSE) - want)) < 1e-14
+    assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_INV, want) - V)) < 1e-13
+    assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_INV, want, B.PLAN_2D_TRANSPOSE) - V)) < 1e-13
 
 
 def test_points():
@@ -242,10 +266,16 @@ for n in (64, 256, 1024, 4096, 16384):
     z = v + 1j * rng.standard_normal((n, 2))
     if n <= 4096:
         assert np.max(np.abs(ll.transform(B.LAURENT_FWD, z) - orc.laurent_transform(z, axis=0))) < 1e-13
+v = rng.standard_normal((16384, 6))
+assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
+assert np.max(np.abs(ll.transform(B.CHEB1_INV, v) - orc.cheb_itransform(v, axis=0))) < 1e-11
 v = rng.standard_normal((100, 2))
 assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
 V = rng.standard_normal((64, 128))
 assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V) - orc.cheb2_transform(V))) < 1e-13
+V = rng.standard_normal((6, 2048))
+assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V) - orc.cheb2_transform(V))) < 1e-13
+assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_INV, V) - orc.cheb2_itransform(V))) < 1e-11
 c = rng.standard_normal(13000); x = rng.uniform(-1, 1, 600)
 from oracle import oracle_c as orcc
 assert np.array_equal(ll.clenshaw(c, x), orcc.clenshaw(c, x))

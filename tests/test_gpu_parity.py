@@ -235,6 +235,24 @@ def test_tensor_transform_and_sampling_golden(af):
     assert abs(F2(0.1, 0.2) - math.cos(0.5)) < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(2, 1024), (30, 2048), (256, 4096), (130, 8192), (64, 16384), (4, 1 << 16), (2, 1 << 18)])
+def test_tensor_row_pass_without_transposes(af, shape):
+    # n2 = 2^10..2^18, n even: the row pass is the strided four-step on row pairs (afb_rows.cu); flag 1 forces the
+    # transpose route.  Both against the oracle, and against each other.
+    from approxfun_b200 import _lib as L
+    ll = af.api.lowlevel()
+    V = RNG.standard_normal(shape)
+    want = orc.cheb2_transform(V)
+    tol = 1e-13 * np.log2(shape[1]) * np.max(np.abs(V))
+    got = ll.transform2d(L.CHEB1_2D_FWD, V)
+    alt = ll.transform2d(L.CHEB1_2D_FWD, V, L.PLAN_2D_TRANSPOSE)
+    assert np.max(np.abs(got - want)) < tol and np.max(np.abs(alt - want)) < tol
+    back = ll.transform2d(L.CHEB1_2D_INV, want)
+    alt = ll.transform2d(L.CHEB1_2D_INV, want, L.PLAN_2D_TRANSPOSE)
+    vtol = 1e-13 * np.log2(shape[1]) * max(1.0, np.max(np.abs(want))) * np.sqrt(shape[0] * shape[1])
+    assert np.max(np.abs(back - V)) < vtol and np.max(np.abs(alt - V)) < vtol
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 64, 65, 100, 1025, 4097])
 def test_sibling_spaces_second_kind_sin_cos(af, n):
     # Val(2) Chebyshev plans (REDFT00) and SinSpace (in-tree spec src/Extras/fftGeneric.jl:74-81)

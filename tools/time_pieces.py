@@ -53,9 +53,17 @@ t = timeit(lambda: W.copy_(V))
 print(f"torch copy 16384^2: {t:.3f} ms {16.0 * n * n / (t * 1e-3) / 1e9:.0f} GB/s")
 t = timeit(lambda: W.copy_(V.t()))
 print(f"torch transpose-copy 16384^2: {t:.3f} ms {16.0 * n * n / (t * 1e-3) / 1e9:.0f} GB/s")
-p2 = af.api.DevicePlan(L.CHEB1_2D_FWD, n, n, 1, n)
-t = timeit(lambda: p2.execute(V.data_ptr(), W.data_ptr(), st))
-print(f"2D fwd 16384^2: {t:.3f} ms")
+del V, W
+for n in (16384, 8192, 4096, 2048):
+    V = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    W = torch.empty_like(V)
+    for kind, nm in [(L.CHEB1_2D_FWD, "fwd"), (L.CHEB1_2D_INV, "inv")]:
+        for flags, route in [(0, "row pairs four-step"), (L.PLAN_2D_TRANSPOSE, "transposes")]:
+            p2 = af.api.DevicePlan(kind, n, n, 1, n, flags)
+            t = timeit(lambda: p2.execute(V.data_ptr(), W.data_ptr(), st))
+            print(f"2D {nm} {n}^2 [{route}]: {t:.3f} ms  {32.0 * n * n / (t * 1e-3) / 1e9 / peak:.3f} of the 32 B/elem roofline, {p2.launches} launches")
+            p2.close()
+    del V, W
 # single long transforms
 for lg in (15, 17, 20, 22):
     n1 = 1 << lg
