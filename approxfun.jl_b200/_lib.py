@@ -18,6 +18,7 @@ AFB_OK, AFB_BAD_ARG, AFB_BAD_SIZE, AFB_NO_DEVICE, AFB_CUDA_ERROR, AFB_NCCL_ERROR
 CHEB1_FWD, CHEB1_INV, FOURIER_FWD, FOURIER_INV, LAURENT_FWD, LAURENT_INV, CHEB1_2D_FWD, CHEB1_2D_INV = range(8)
 CHEB2_FWD, CHEB2_INV, SIN_FWD, SIN_INV = 8, 9, 10, 11
 TAYLOR_FWD, TAYLOR_INV, HARDYM_FWD, HARDYM_INV = 12, 13, 14, 15
+PADUA_FWD, PADUA_INV = 16, 17
 PLAN_2D_TRANSPOSE = 1  # afb_plan_create flag: explicit-transpose row pass for 2D kinds
 
 # every symbol include/approxfun_b200.h declares (tests check the .so exports each of them)
@@ -26,7 +27,7 @@ SYMBOLS = [
     "afb_malloc", "afb_free", "afb_host_alloc", "afb_host_free", "afb_memcpy_h2d", "afb_memcpy_d2h",
     "afb_memcpy_d2d", "afb_stream_sync",
     "afb_plan_create", "afb_plan_execute_host", "afb_plan_execute_device", "afb_plan_destroy", "afb_plan_launches",
-    "afb_chebpoints", "afb_chebpoints_device", "afb_fourierpoints",
+    "afb_chebpoints", "afb_chebpoints_device", "afb_fourierpoints", "afb_paduapoints",
     "afb_clenshaw_cheb", "afb_clenshaw_cheb_device", "afb_clenshaw_cheb_cols", "afb_clenshaw_cheb_cols_device",
     "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device",
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
@@ -76,6 +77,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_chebpoints": [vp, i64, dbl, dbl],
         "afb_chebpoints_device": [vp, i64, dbl, dbl, vp],
         "afb_fourierpoints": [vp, i64, dbl, dbl],
+        "afb_paduapoints": [vp, i64, dbl, dbl, dbl, dbl, C.POINTER(i64)],
         "afb_clenshaw_cheb": [vp, i64, vp, vp, i64],
         "afb_clenshaw_cheb_device": [vp, i64, vp, vp, i64, vp],
         "afb_clenshaw_cheb_cols": [vp, i64, i64, vp, vp, i64],
@@ -209,6 +211,26 @@ class LowLevel:
     def chebpoints(self, n: int, a: float = -1.0, b: float = 1.0) -> np.ndarray:
         out = np.empty(max(n, 0))
         check(self.lib, self.lib.afb_chebpoints(_ptr(out), n, a, b))
+        return out
+
+    def paduapoints(self, N: int, ax=-1.0, bx=1.0, ay=-1.0, by=1.0) -> np.ndarray:
+        """Np x 2 array [x y] of the Padua points carrying N coefficients (Np = next triangular number >= N)."""
+        npts = C.c_int64()
+        check(self.lib, self.lib.afb_paduapoints(None, N, ax, bx, ay, by, C.byref(npts)))
+        out = np.empty((2, npts.value))  # column-major Np x 2
+        if npts.value:
+            check(self.lib, self.lib.afb_paduapoints(_ptr(out), N, ax, bx, ay, by, C.byref(npts)))
+        return np.ascontiguousarray(out.T)
+
+    def padua(self, kind: int, v: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty_like(v)
+        h = self.plan_create(kind, v.size, 0, 1, v.size)
+        try:
+            if v.size:
+                self.plan_execute_host(h, v, out)
+        finally:
+            self.plan_destroy(h)
         return out
 
     def fourierpoints(self, n: int, a: float = 0.0, b: float = 2 * np.pi) -> np.ndarray:

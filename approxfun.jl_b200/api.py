@@ -117,14 +117,18 @@ _INV = {Chebyshev: L.CHEB1_INV, Fourier: L.FOURIER_INV, Laurent: L.LAURENT_INV, 
 
 
 def points(space: Space, n: int, m: int | None = None):
-    """`points(space, n)`; for a TensorSpace `points(sp, N, M)` returns the two 1-D grids."""
+    """`points(space, n)`.  TensorSpace: `points(sp, N, M)` returns the two 1-D grids of the tensor grid;
+    `points(sp, N)` returns the Padua points carrying N coefficients as an Np x 2 array [x y] (NEWS.md:85)."""
     ll = lowlevel()
     if isinstance(space, Chebyshev):
         return ll.chebpoints(n, space.a, space.b)
     if isinstance(space, (Fourier, Laurent, Taylor, Hardy)):
         return ll.fourierpoints(n, space.a, space.b)
     if isinstance(space, TensorSpace):
-        return points(space.factors[0], n), points(space.factors[1], n if m is None else m)
+        s1, s2 = space.factors
+        if m is None:
+            return ll.paduapoints(int(n), s1.a, s1.b, s2.a, s2.b)
+        return points(s1, n), points(s2, m)
     if isinstance(space, CosSpace):
         return math.pi * (np.arange(n) + 0.5) / n
     if isinstance(space, SinSpace):
@@ -146,9 +150,13 @@ class TransformPlan:
         self._ll = lowlevel()
         table = _INV if self.inverse else _FWD
         self.kind = table[type(space)]
-        if isinstance(space, TensorSpace):
+        if isinstance(space, TensorSpace) and len(self.shape) == 1:
+            # vector of values at the Padua points <-> flat coefficients ordered by total degree
+            self.kind = L.PADUA_INV if self.inverse else L.PADUA_FWD
+            self._h = self._ll.plan_create(self.kind, self.shape[0], 0, 1, self.shape[0])
+        elif isinstance(space, TensorSpace):
             if len(self.shape) != 2:
-                raise L.DimensionMismatch(L.AFB_BAD_SIZE, "TensorSpace plans take an n x m matrix")
+                raise L.DimensionMismatch(L.AFB_BAD_SIZE, "TensorSpace plans take an n x m matrix or a Padua vector")
             n, n2 = self.shape
             self._h = self._ll.plan_create(self.kind, n, n2, 1, n)
         else:
@@ -284,8 +292,12 @@ class Fun:
         elif len(args) == 3:
             f, space, n = args
             self.space = space
-            if isinstance(space, TensorSpace):
-                n1, n2 = (n, n) if isinstance(n, (int, np.integer)) else n
+            if isinstance(space, TensorSpace) and isinstance(n, (int, np.integer)):
+                # Fun(f, Chebyshev()^2, N): values at the Padua points -> flat coefficients by total degree
+                pts = points(space, int(n))
+                self.coefficients = transform(space, np.asarray(f(pts[:, 0], pts[:, 1]), dtype=np.float64))
+            elif isinstance(space, TensorSpace):
+                n1, n2 = n  # tensor grid, coefficient MATRIX (ProductFun layout)
                 x, y = points(space, n1, n2)
                 self.coefficients = transform(space, f(x[:, None], y[None, :]))
             else:
@@ -313,13 +325,41 @@ class Fun:
             s1, s2 = sp.factors
             xs, ys = np.broadcast_arrays(np.atleast_1d(np.asarray(x, dtype=np.float64)),
                                          np.atleast_1d(np.asarray(y, dtype=np.float64)))
-            out = lowlevel().clenshaw2d(self.coefficients, s1.tocanonical(xs.ravel()), s2.tocanonical(ys.ravel()))
+            cm = self.coefficients if self.coefficients.ndim == 2 else totaldegree_to_matrix(self.coefficients)
+            out = lowlevel().clenshaw2d(cm, s1.tocanonical(xs.ravel()), s2.tocanonical(ys.ravel()))
             out = out.reshape(xs.shape)
             return float(out.ravel()[0]) if (np.ndim(x) == 0 and np.ndim(y) == 0) else out
         raise NotImplementedError("evaluation is GPU-accelerated for Chebyshev spaces only")
 
     def __len__(self):
         return len(self.coefficients)
+
+
+def totaldegree_to_matrix(c) -> np.ndarray:
+    """Flat TensorSpace coefficients (T0T0, T0(x)T1(y), T1(x)T0(y), ...: docs/src/usage/constructors.md:98-116) ->
+    coefficient matrix C[i, j] of T_i(x) T_j(y) (`coefficientmatrix(f)`); zero-padded to the next full diagonal."""
+    c = np.asarray(c, dtype=np.float64)
+    d = 0
+    while (d + 1) * (d + 2) // 2 < c.size:
+        d += 1
+    s = np.repeat(np.arange(d + 1), np.arange(1, d + 2))[: c.size]   # diagonal of every entry
+    i = np.arange(c.size) - s * (s + 1) // 2                           # x-degree within the diagonal
+    cm = np.zeros((d + 1, d + 1))
+    cm[i, s - i] = c
+    return cm
+
+
+def matrix_to_totaldegree(cm) -> np.ndarray:
+    """Inverse of `totaldegree_to_matrix` (entries with i + j beyond the last full diagonal must be zero)."""
+    cm = np.asarray(cm, dtype=np.float64)
+    d = cm.shape[0] + cm.shape[1] - 2
+    s = np.repeat(np.arange(d + 1), np.arange(1, d + 2))
+    i = np.arange(s.size) - s * (s + 1) // 2
+    j = s - i
+    ok = (i < cm.shape[0]) & (j < cm.shape[1])
+    out = np.zeros(s.size)
+    out[ok] = cm[i[ok], j[ok]]
+    return out
 
 
 def coefficients(f: Fun):
@@ -460,7 +500,8 @@ class ProductFun:
 
     def __init__(self, f, sp: "TensorSpace", N: int | None = None, M: int | None = None):
         if isinstance(f, Fun):
-            self.space, self.coefficients = f.space, np.asarray(f.coefficients)
+            c = np.asarray(f.coefficients)
+            self.space, self.coefficients = f.space, (c if c.ndim == 2 else totaldegree_to_matrix(c))
         else:
             g = Fun(f, sp, (N, N if M is None else M))
             self.space, self.coefficients = g.space, g.coefficients

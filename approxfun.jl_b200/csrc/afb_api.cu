@@ -147,7 +147,7 @@ static HostPipe g_pipe;
 // plans
 // =====================================================================================================
 enum PlanPath { PATH_EMPTY = 0, PATH_DIRECT = 1, PATH_LINE = 2, PATH_GENERIC = 3, PATH_TENSOR2D = 4, PATH_LARGE = 5, PATH_EXT = 6,
-                PATH_IDENTITY = 7 };
+                PATH_IDENTITY = 7, PATH_PADUA = 8 };
 
 struct afb_plan_s {
     int32_t kind = 0;
@@ -174,6 +174,12 @@ struct afb_plan_s {
     afb_plan_s* col_plan = nullptr;  // length n,  batch n2
     afb_plan_s* row_plan = nullptr;  // length n2, batch n
     double* t2buf = nullptr;
+    // PADUA: degree, index tables (grid position of every point; transposed-grid position of every coefficient),
+    // the (d+2) x (d+1) grid W and its transpose T (= t2buf); col_plan / row_plan are second-kind (REDFT00) plans
+    int64_t pdeg = 0;
+    int32_t* pad_idx = nullptr;
+    int32_t* tri_idx = nullptr;
+    double* wbuf = nullptr;
     // scratch for in-place direct execution
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -188,6 +194,9 @@ static void plan_free(afb_plan_s* p) {
     if (p->gwork) cudaFree(p->gwork);
     if (p->cfft) cfft_destroy(p->cfft);
     if (p->t2buf) cudaFree(p->t2buf);
+    if (p->pad_idx) cudaFree(p->pad_idx);
+    if (p->tri_idx) cudaFree(p->tri_idx);
+    if (p->wbuf) cudaFree(p->wbuf);
     if (p->tmp) cudaFree(p->tmp);
     plan_free(p->col_plan);
     plan_free(p->row_plan);
@@ -435,6 +444,7 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         case PATH_LINE: return 1;
         case PATH_LARGE: return (int32_t)(3 * p->batch);
         case PATH_IDENTITY: return 0;
+        case PATH_PADUA: return 4 + plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan);  // memset, scatter, transpose, gather
         case PATH_EXT: {
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
@@ -449,6 +459,95 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         }
     }
     return 0;
+}
+
+// ---- Padua plans ------------------------------------------------------------------
+// Degree d with (d+1)(d+2)/2 >= N  (upstream: Int(cld(-3 + sqrt(1 + 8N), 2))).
+static int64_t padua_degree(int64_t N) {
+    int64_t d = (int64_t)std::ceil((-3.0 + std::sqrt(1.0 + 8.0 * (double)N)) / 2.0);
+    if (d < 0) d = 0;
+    while ((d + 1) * (d + 2) / 2 < N) ++d;
+    while (d > 0 && d * (d + 1) / 2 >= N) --d;
+    return d;
+}
+// Grid position iy + (d+2) ix of every Padua point, in the emission order of upstream `paduapoints`
+// (k = d..0: x = -cospi(k/d) = cos(ix pi/d), ix = d-k;  j = NN+delta..1: y = cos(iy pi/(d+1)) with
+//  iy = d+2-2j for odd d-k, d+3-2j for even d-k).
+static std::vector<int32_t> padua_grid_index(int64_t d) {
+    std::vector<int32_t> idx;
+    idx.reserve((size_t)((d + 1) * (d + 2) / 2));
+    const int64_t NN = d / 2 + 1;
+    for (int64_t k = d; k >= 0; --k) {
+        const int64_t delta = (d % 2 == 1) ? (k % 2) : 0;
+        for (int64_t j = NN + delta; j >= 1; --j) {
+            const int64_t ix = d - k, iy = ((d - k) % 2 == 1) ? d + 2 - 2 * j : d + 3 - 2 * j;
+            idx.push_back((int32_t)(iy + (d + 2) * ix));
+        }
+    }
+    return idx;
+}
+static int32_t upload_idx(const std::vector<int32_t>& h, int32_t** dev) {
+    void* dptr = nullptr;
+    AFB_CUDA(cudaMalloc(&dptr, sizeof(int32_t) * std::max<size_t>(h.size(), 1)));
+    cudaError_t e = cudaMemcpy(dptr, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dptr); return cuda_fail(e, "cudaMemcpy(index table)", __FILE__, __LINE__); }
+    *dev = reinterpret_cast<int32_t*>(dptr);
+    return AFB_OK;
+}
+static int32_t plan_create_padua(afb_plan_s** out, int32_t kind, int64_t N, uint32_t flags) {
+    const int64_t d = padua_degree(N);
+    if ((d + 1) * (d + 2) / 2 != N)
+        return fail(AFB_BAD_SIZE, "Padua transforms can only be applied to vectors of length (n+1)*(n+2)/2");
+    if ((d + 2) * (d + 1) >= ((int64_t)1 << 31)) return fail(AFB_BAD_SIZE, "Padua transform: degree too large");
+    afb_plan_s* p = new afb_plan_s();
+    p->kind = kind; p->n = N; p->batch = 1; p->stride = N; p->flags = flags; p->pdeg = d;
+    p->path = (N == 0) ? PATH_EMPTY : (d == 0 ? PATH_IDENTITY : PATH_PADUA);
+    int32_t st = AFB_OK;
+    if (p->path == PATH_PADUA) {
+        const int64_t m = d + 2, l = d + 1;  // grid: m y-points (rows, contiguous) x l x-points
+        const int32_t k1 = (kind == AFB_PADUA_FWD) ? AFB_CHEB2_FWD : AFB_CHEB2_INV;
+        st = plan_create_1d(&p->col_plan, k1, m, l, m, flags);               // along y on W (m x l)
+        if (st == AFB_OK) st = plan_create_1d(&p->row_plan, k1, l, m, l, flags);  // along x on T = W^T (l x m)
+        if (st == AFB_OK) st = upload_idx(padua_grid_index(d), &p->pad_idx);
+        if (st == AFB_OK) {
+            // coefficient l of the total-degree order (diagonal s, x-degree i = 0..s, y-degree s - i) sits at T[i + l*j]
+            std::vector<int32_t> tri;
+            tri.reserve((size_t)N);
+            for (int64_t sdeg = 0; sdeg <= d; ++sdeg)
+                for (int64_t i = 0; i <= sdeg; ++i) tri.push_back((int32_t)(i + l * (sdeg - i)));
+            st = upload_idx(tri, &p->tri_idx);
+        }
+        for (double** buf : {&p->wbuf, &p->t2buf}) {
+            if (st != AFB_OK) break;
+            void* dptr = nullptr;
+            cudaError_t e = cudaMalloc(&dptr, sizeof(double) * (size_t)(m * l));
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(Padua grid)", __FILE__, __LINE__);
+            *buf = reinterpret_cast<double*>(dptr);
+        }
+    }
+    if (st != AFB_OK) { plan_free(p); return st; }
+    *out = p;
+    return AFB_OK;
+}
+// forward:  zero grid <- values; REDFT00 along y; transpose; REDFT00 along x; coefficients = 2 * triangle
+// inverse:  zero grid^T <- coefficients; evaluate along x; transpose; evaluate along y; values = grid[points]
+static int32_t exec_padua_device(afb_plan_s* p, const double* d_in, double* d_out, void* stream) {
+    const int64_t d = p->pdeg, m = d + 2, l = d + 1, N = p->n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->kind == AFB_PADUA_FWD) {
+        AFB_CUDA(cudaMemsetAsync(p->wbuf, 0, sizeof(double) * (size_t)(m * l), s));
+        AFB_TRY(launch_scatter_idx(p->wbuf, d_in, p->pad_idx, N, stream));
+        AFB_TRY(exec_1d_device(p->col_plan, p->wbuf, p->wbuf, l, m, m, stream, 1));
+        AFB_TRY(launch_transpose(p->wbuf, p->t2buf, m, l, stream));
+        AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, m, l, l, stream, 1));
+        return launch_gather_idx(d_out, p->t2buf, p->tri_idx, N, 2.0, stream);
+    }
+    AFB_CUDA(cudaMemsetAsync(p->t2buf, 0, sizeof(double) * (size_t)(m * l), s));
+    AFB_TRY(launch_scatter_idx(p->t2buf, d_in, p->tri_idx, N, stream));
+    AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, m, l, l, stream, 1));
+    AFB_TRY(launch_transpose(p->t2buf, p->wbuf, l, m, stream));
+    AFB_TRY(exec_1d_device(p->col_plan, p->wbuf, p->wbuf, l, m, m, stream, 1));
+    return launch_gather_idx(d_out, p->wbuf, p->pad_idx, N, 1.0, stream);
 }
 
 extern "C" {
@@ -531,7 +630,7 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
                         uint32_t flags) {
     if (!out) return fail(AFB_BAD_ARG, "afb_plan_create: null out pointer");
     *out = nullptr;
-    if (kind < AFB_CHEB1_FWD || kind > AFB_HARDYM_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
+    if (kind < AFB_CHEB1_FWD || kind > AFB_PADUA_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
     if (n < 0 || n2 < 0 || batch < 0) return fail(AFB_BAD_SIZE, "afb_plan_create: negative size");
     AFB_TRY(ensure_device());
     if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV) {
@@ -557,6 +656,10 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
         return AFB_OK;
     }
     if (n2 != 0) return fail(AFB_BAD_SIZE, "afb_plan_create: n2 must be 0 for 1D kinds");
+    if (kind == AFB_PADUA_FWD || kind == AFB_PADUA_INV) {
+        if (batch != 1) return fail(AFB_BAD_SIZE, "afb_plan_create: Padua plans take batch == 1");
+        return plan_create_padua(out, kind, n, flags);
+    }
     if (stride < n) return fail(AFB_BAD_SIZE, "afb_plan_create: stride < n");
     if ((kind == AFB_CHEB1_FWD || kind == AFB_CHEB1_INV || kind == AFB_FOURIER_FWD || kind == AFB_FOURIER_INV) &&
         (stride & 1) && batch > 1 && n > DIRECT_MAX && is_pow2(n))
@@ -595,6 +698,8 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
         AFB_TRY(launch_transpose(p->t2buf, reinterpret_cast<double*>(d_out), n2, n, stream));
         return AFB_OK;
     }
+    if (p->path == PATH_PADUA)
+        return exec_padua_device(p, reinterpret_cast<const double*>(d_in), reinterpret_cast<double*>(d_out), stream);
     return exec_1d_device(p, d_in, d_out, p->batch, p->stride, p->stride, stream);
 }
 
@@ -602,8 +707,8 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
     if (!p) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null plan");
     if (p->path == PATH_EMPTY) return AFB_OK;
     if (!in || !out) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null buffer");
-    if (p->path == PATH_TENSOR2D) {
-        const size_t bytes = sizeof(double) * (size_t)(p->n * p->n2);
+    if (p->path == PATH_TENSOR2D || p->path == PATH_PADUA) {
+        const size_t bytes = sizeof(double) * (size_t)(p->path == PATH_PADUA ? p->n : p->n * p->n2);
         void* d = nullptr;
         AFB_CUDA(cudaMalloc(&d, bytes));
         int32_t st = AFB_OK;
@@ -700,6 +805,27 @@ int32_t afb_fourierpoints(double* out, int64_t n, double a, double b) {
     if (n && !out) return fail(AFB_BAD_ARG, "afb_fourierpoints: null buffer");
     for (int64_t j = 0; j < n; ++j) out[j] = a + (b - a) * (double)j / (double)n;  // O(n) host arithmetic, no GPU analogue
     return AFB_OK;
+}
+
+int32_t afb_paduapoints(double* xy, int64_t N, double ax, double bx, double ay, double by, int64_t* np_out) {
+    if (N < 0) return fail(AFB_BAD_SIZE, "afb_paduapoints: N < 0");
+    const int64_t d = padua_degree(N), Np = (N == 0) ? 0 : (d + 1) * (d + 2) / 2;
+    if (np_out) *np_out = Np;
+    if (!xy || Np == 0) return AFB_OK;
+    if (d == 0) {  // upstream evaluates -cospi(0/0) here; the single point is the lower-left corner
+        xy[0] = ax; xy[1] = ay;
+        return AFB_OK;
+    }
+    if ((d + 2) * (d + 1) >= ((int64_t)1 << 31)) return fail(AFB_BAD_SIZE, "afb_paduapoints: degree too large");
+    AFB_TRY(ensure_device());
+    int32_t* idx = nullptr;
+    AFB_TRY(upload_idx(padua_grid_index(d), &idx));
+    DevBuf dev;
+    int32_t st = dev.alloc(sizeof(double) * (size_t)(2 * Np));
+    if (st == AFB_OK) st = launch_paduapoints(dev.as<double>(), idx, Np, d, ax, bx, ay, by, nullptr);
+    if (st == AFB_OK) st = dev.get(xy, sizeof(double) * (size_t)(2 * Np));
+    cudaFree(idx);
+    return st;
 }
 
 // ---- Clenshaw ----------------------------------------------------------------------------------------

@@ -115,6 +115,7 @@ static inline double sinpi(double x) {
     return (std::fmod(k, 2.0) == 0.0) ? s : -s;
 }
 
+static inline double cospi(double x) { return sinpi(0.5 - std::fabs(x)); }
 static inline void sincospi(double x, double* s, double* c) { *s = sinpi(x); *c = sinpi(x + 0.5); }
 
 // --- runtime API stand-ins (host memory is "device" memory) -------------------------------------

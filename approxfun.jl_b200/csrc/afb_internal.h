@@ -22,7 +22,7 @@ int32_t line_last_pass(int N, int* RL, int* NSL);
 int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
                           int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
                           const cplx* twA, const cplx* twB, int64_t twmod, void* stream, int io_mode = 0,
-                          int64_t bigN = 0);
+                          int64_t bigN = 0, int64_t lpb = 0, int64_t ibs = 0, int64_t obs = 0);
 int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,
                       int64_t oes, const cplx* tab, void* stream);
 
@@ -75,6 +75,12 @@ int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t co
 bool rows_cheb_supported(int64_t n1, int64_t n2);
 int64_t rows_tmp_doubles(int64_t n1, int64_t n2);  // size of `tmp` below
 int32_t launch_rows_cheb(bool inverse, const double* in, double* tmp, double* out, int64_t n1, int64_t n2, void* stream);
+
+// Padua helpers (afb_tensor.cu): dst[idx[p]] = src[p] ; dst[p] = scale * src[idx[p]] ; the point coordinates
+int32_t launch_scatter_idx(double* dst, const double* src, const int32_t* idx, int64_t N, void* stream);
+int32_t launch_gather_idx(double* dst, const double* src, const int32_t* idx, int64_t N, double scale, void* stream);
+int32_t launch_paduapoints(double* xy, const int32_t* idx, int64_t N, int64_t d, double ax, double bx, double ay, double by,
+                           void* stream);
 
 // ---- device table helpers ------------------------------------------------------------------------------
 int32_t upload_table(const std::vector<cplx>& host, cplx** dev);

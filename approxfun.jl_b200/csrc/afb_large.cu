@@ -121,7 +121,7 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
         }
         if (st == AFB_OK) {
             void* d = nullptr;
-            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)n);
+            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)(n * p->max_batch));
             if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(four-step tmp)", __FILE__, __LINE__);
             p->tmp = reinterpret_cast<cplx*>(d);
         }
@@ -189,15 +189,17 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
     }
     if (p->mode == 1) {
         const int64_t n1 = p->n1, n2 = p->n2;
-        for (int64_t b = 0; b < batch; ++b) {
-            const cplx* src = in + b * n;
-            cplx* dst = out + b * n;
+        // whole chunks of transforms per launch: line L = (b, column or row) through the lpb / ibs / obs addressing
+        for (int64_t b0 = 0; b0 < batch; b0 += p->max_batch) {
+            const int64_t nb = std::min(p->max_batch, batch - b0);
+            const cplx* src = in + b0 * n;
+            cplx* dst = out + b0 * n;
             // A: for every column b2 (stride-n2 elements): FFT over a, times w_n^(b2 k1), kept in place layout
-            AFB_TRY(launch_cfft_lines((int)n1, src, p->tmp, n2, 1, n2, 1, n2, p->tw1, inverse, false, 1.0, p->twA, p->twB,
-                                      n2, stream));
+            AFB_TRY(launch_cfft_lines((int)n1, src, p->tmp, nb * n2, 1, n2, 1, n2, p->tw1, inverse, false, 1.0, p->twA,
+                                      p->twB, n2, stream, 0, 0, n2, n, n));
             // B: for every row k1 (contiguous n2 elements): FFT over b2, scattered to X[k1 + n1 k2]
-            AFB_TRY(launch_cfft_lines((int)n2, p->tmp, dst, n1, n2, 1, 1, n1, p->tw2, false, inverse, scale, nullptr,
-                                      nullptr, 1, stream));
+            AFB_TRY(launch_cfft_lines((int)n2, p->tmp, dst, nb * n1, n2, 1, 1, n1, p->tw2, false, inverse, scale, nullptr,
+                                      nullptr, 1, stream, 0, 0, n1, n, n));
         }
         return AFB_OK;
     }

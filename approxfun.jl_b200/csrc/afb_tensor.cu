@@ -46,6 +46,51 @@ int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t co
     return AFB_OK;
 }
 
+// ---- Padua transform helpers -----------------------------------------------------------
+__global__ void scatter_idx_kernel(double* __restrict__ dst, const double* __restrict__ src, const int32_t* __restrict__ idx,
+                                   int64_t N) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dst[idx[p]] = src[p];
+}
+__global__ void gather_idx_kernel(double* __restrict__ dst, const double* __restrict__ src, const int32_t* __restrict__ idx,
+                                  int64_t N, double scale) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dst[p] = scale * src[idx[p]];
+}
+// idx[p] = iy + (d+2) ix on the (d+2) x (d+1) Chebyshev-Lobatto grid; x = -cospi(k/d) with k = d - ix
+__global__ void paduapoints_kernel(double* __restrict__ xy, const int32_t* __restrict__ idx, int64_t N, int64_t d, double ax,
+                                   double bx, double ay, double by) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int64_t ix = idx[p] / (d + 2), iy = idx[p] % (d + 2);
+    const double x = -cospi((double)(d - ix) / (double)d);
+    const double y = -cospi((double)(d + 1 - iy) / (double)(d + 1));
+    xy[p] = 0.5 * (ax + bx) + 0.5 * (bx - ax) * x;
+    xy[N + p] = 0.5 * (ay + by) + 0.5 * (by - ay) * y;
+}
+int32_t launch_scatter_idx(double* dst, const double* src, const int32_t* idx, int64_t N, void* stream) {
+    if (N == 0) return AFB_OK;
+    auto k = scatter_idx_kernel;
+    AFB_LAUNCH(k, (unsigned)((N + 255) / 256), 256, 0, stream, dst, src, idx, N);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_gather_idx(double* dst, const double* src, const int32_t* idx, int64_t N, double scale, void* stream) {
+    if (N == 0) return AFB_OK;
+    auto k = gather_idx_kernel;
+    AFB_LAUNCH(k, (unsigned)((N + 255) / 256), 256, 0, stream, dst, src, idx, N, scale);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_paduapoints(double* xy, const int32_t* idx, int64_t N, int64_t d, double ax, double bx, double ay, double by,
+                           void* stream) {
+    if (N == 0) return AFB_OK;
+    auto k = paduapoints_kernel;
+    AFB_LAUNCH(k, (unsigned)((N + 255) / 256), 256, 0, stream, xy, idx, N, d, ax, bx, ay, by);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 // unpack after the all-to-all: R[s][i][jj] (s < G, i < nr, jj < nc) -> L[i][s*nc + jj]
 __global__ void a2a_unpack_kernel(const double* __restrict__ R, double* __restrict__ L, int64_t G, int64_t nr, int64_t nc) {
     const int64_t total = G * nr * nc;

@@ -40,6 +40,8 @@ struct LineParams {
     const cplx* twA;  // four-step: w_n^(m >> 12 << 12)
     const cplx* twB;  // w_n^(m & 4095);  output (line L, index i) is multiplied by w_n^((L mod twmod) * i)
     int64_t twmod;
+    // batched four-step: line L = (b, c) with b = L / lpb; its first element sits at b * ibs + c * istride (lpb = 0: off)
+    int64_t lpb, ibs, obs;
     // t_j(pi + NSL q) = t_j(pi) * K[j][q] (2q < RL);  t_j(N - pi - NSL q) = conj(t_j(pi)) * K[j][q] (2q >= RL)
     cplx K[MAXJ][MAXRL];
 };
@@ -526,7 +528,9 @@ template <int N> struct LineOp<N, LK_CFFT> {
                 x[r] = make_double2(vr[4 * q + (lo ? 0 : 3)], vr[4 * q + (lo ? 2 : 1)]);
             }
         } else {
-            const cplx* v = reinterpret_cast<const cplx*>(p.in) + l0 * p.istride;
+            int64_t off = l0 * p.istride;
+            if (p.lpb) { const int64_t b = l0 / p.lpb; off = b * p.ibs + (l0 - b * p.lpb) * p.istride; }
+            const cplx* v = reinterpret_cast<const cplx*>(p.in) + off;
 #pragma unroll
             for (int r = 0; r < C::E; ++r) x[r] = v[(int64_t)(t + C::T * r) * p.ies];
         }
@@ -537,7 +541,9 @@ template <int N> struct LineOp<N, LK_CFFT> {
     }
     static __device__ __forceinline__ void store(const LineParams& p, int64_t line, bool act, int t, const cplx* s) {
         if (!act) return;
-        cplx* c = reinterpret_cast<cplx*>(p.out) + line * p.ostride;
+        int64_t off = line * p.ostride;
+        if (p.lpb) { const int64_t b = line / p.lpb; off = b * p.obs + (line - b * p.lpb) * p.ostride; }
+        cplx* c = reinterpret_cast<cplx*>(p.out) + off;
         const int64_t lm = p.twA ? (line % p.twmod) : 0;
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
@@ -709,13 +715,14 @@ int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, i
 // general strided complex FFT lines (see LineOp<N, LK_CFFT>)
 int32_t launch_cfft_lines(int N, const cplx* in, cplx* out, int64_t nlines, int64_t istride, int64_t ies,
                           int64_t ostride, int64_t oes, const cplx* tw, bool conj_in, bool conj_out, double scale,
-                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream, int io_mode, int64_t bigN) {
+                          const cplx* twA, const cplx* twB, int64_t twmod, void* stream, int io_mode, int64_t bigN,
+                          int64_t lpb, int64_t ibs, int64_t obs) {
     if (nlines == 0) return AFB_OK;
     LineParams p{};
     p.in = in; p.out = out; p.batch = nlines; p.istride = istride; p.ostride = ostride; p.tw = tw; p.aux = nullptr;
     p.scale = scale; p.ies = ies; p.oes = oes; p.conj_in = conj_in ? 1 : 0; p.conj_out = conj_out ? 1 : 0;
     p.twA = twA; p.twB = twB; p.twmod = twmod > 0 ? twmod : 1;
-    p.io_mode = io_mode; p.bigN = bigN;
+    p.io_mode = io_mode; p.bigN = bigN; p.lpb = lpb; p.ibs = ibs; p.obs = obs;
     return launch_line_k<LK_CFFT>(N, p, stream);
 }
 

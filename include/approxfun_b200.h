@@ -72,7 +72,12 @@ enum afb_kind {
                              f_k = F_k / n on t_j = 2 pi j / n; complex in/out                              */
     AFB_TAYLOR_INV = 13,
     AFB_HARDYM_FWD = 14,  /* Hardy{false}: f(t) = sum_k f_k e^{-i(k+1)t} (spaces.md:106-110): f_k = F_{n-1-k}/n */
-    AFB_HARDYM_INV = 15
+    AFB_HARDYM_INV = 15,
+    AFB_PADUA_FWD = 16,   /* plan_transform(Chebyshev()^2, v::Vector) = FastTransforms.plan_paduatransform!(v, Val{false})
+                             (UPSTREAM; NEWS.md:85): N = (d+1)(d+2)/2 values at afb_paduapoints -> N coefficients in the
+                             order T0T0, T0(x)T1(y), T1(x)T0(y), ... (docs/src/usage/constructors.md:98-116).
+                             afb_plan_create(kind, n = N, 0, 1, N, 0); AFB_BAD_SIZE unless N is triangular.        */
+    AFB_PADUA_INV = 17    /* plan_itransform(Chebyshev()^2, c::Vector) = plan_ipaduatransform!: coefficients -> values */
 };
 
 typedef struct afb_plan_s* afb_plan;
@@ -125,6 +130,10 @@ int32_t afb_chebpoints(double* out, int64_t n, double a, double b);
 int32_t afb_chebpoints_device(double* d_out, int64_t n, double a, double b, void* stream);
 /* points(::Fourier/Laurent, n): out[j] = a + (b-a) j / n */
 int32_t afb_fourierpoints(double* out, int64_t n, double a, double b);
+/* points(Chebyshev(ax..bx) x Chebyshev(ay..by), N): UPSTREAM FastTransforms.paduapoints(d), d = cld(-3+sqrt(1+8N),2),
+ * mapped by fromcanonical.  xy is Np x 2 column-major (x then y), Np = (d+1)(d+2)/2 >= N; *np_out receives Np.
+ * Pass xy == NULL to query Np.  Emission order: k = d..0 (x = -cospi(k/d)), j = NN+delta..1. */
+int32_t afb_paduapoints(double* xy, int64_t N, double ax, double bx, double ay, double by, int64_t* np_out);
 
 /* ---- Clenshaw evaluation ----------------------------------------------------------------------------
  * Replaces clenshaw(::Chebyshev, c, x) and clenshaw(c::Vector, x::Vector, plan::ClenshawPlan) (UPSTREAM

@@ -176,4 +176,19 @@ end
 chebyshevtransform2(v::VecOrMat{Float64}) = B200Plan{Float64}(Cint(8), size(v, 1), size(v, 2)) * v
 ichebyshevtransform2(c::VecOrMat{Float64}) = B200Plan{Float64}(Cint(9), size(c, 1), size(c, 2)) * c
 
+# Padua: points(Chebyshev()^2, N) and the vector transform of Fun(f, Chebyshev()^2, N)  (kinds 16 / 17)
+function paduapoints_b200(N::Integer, dx, dy)
+    np = Ref{Int64}(0)
+    check(ccall((:afb_paduapoints, LIB), Int32, (Ptr{Float64}, Int64, Float64, Float64, Float64, Float64, Ref{Int64}),
+                C_NULL, N, ApproxFun.leftendpoint(dx), ApproxFun.rightendpoint(dx), ApproxFun.leftendpoint(dy),
+                ApproxFun.rightendpoint(dy), np))
+    xy = Matrix{Float64}(undef, np[], 2)
+    check(ccall((:afb_paduapoints, LIB), Int32, (Ptr{Float64}, Int64, Float64, Float64, Float64, Float64, Ref{Int64}),
+                xy, N, ApproxFun.leftendpoint(dx), ApproxFun.rightendpoint(dx), ApproxFun.leftendpoint(dy),
+                ApproxFun.rightendpoint(dy), np))
+    xy
+end
+paduatransform_b200(v::Vector{Float64}) = B200Plan{Float64}(Cint(16), length(v), 1) * v
+ipaduatransform_b200(c::Vector{Float64}) = B200Plan{Float64}(Cint(17), length(c), 1) * c
+
 end # module

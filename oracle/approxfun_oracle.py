@@ -519,6 +519,121 @@ def tensor_interlace(C: np.ndarray) -> np.ndarray:
     return np.array(out)
 
 
+def tensor_deinterlace(c: np.ndarray, n: int | None = None) -> np.ndarray:
+    """Inverse of :func:`tensor_interlace` for a triangular-length vector: (n+1) x (n+1) matrix C[i, j]
+    (x-degree i, y-degree j), zero for i + j > n."""
+    N = len(c)
+    n = padua_degree(N) if n is None else n
+    C = np.zeros((n + 1, n + 1), dtype=np.asarray(c).dtype)
+    l = 0
+    for d in range(n + 1):
+        for i in range(d + 1):
+            if l < N:
+                C[i, d - i] = c[l]
+            l += 1
+    return C
+
+
+# --------------------------------------------------------------------------------------
+# 8(f) rank 1: Padua points / transform  (`Fun(f, Chebyshev()^2, N)`, NEWS.md:85)
+#
+# UPSTREAM FastTransforms `paduapoints`, `plan_paduatransform!`, `plan_ipaduatransform!` (not in
+# /root/reference).  PARITY UNPINNED for the ORDER of the points: it is restated from the published
+# algorithm (Caliari, De Marchi, Vianello 2008; the upstream loop nest k = n:-1:0, j = NN+delta:-1:1)
+# and no in-tree vector fixes it.  What IS pinned in-tree: the coefficient order
+# T0T0, T0(x)T1(y), T1(x)T0(y), ... (docs/src/usage/constructors.md:98-116) and the functional
+# identities (`Fun(f, Chebyshev()^2)(x, y) == f(x, y)`, examples/PDE_Helmholtz.jl:33-36), which any
+# consistent (points, transform) pair with that coefficient order satisfies.
+# --------------------------------------------------------------------------------------
+def padua_degree(N: int) -> int:
+    """n with (n+1)(n+2)/2 >= N: `Int(cld(-3 + sqrt(1 + 8N), 2))`."""
+    n = int(math.ceil((-3.0 + math.sqrt(1.0 + 8.0 * N)) / 2.0 - 1e-12))
+    while (n + 1) * (n + 2) // 2 < N:
+        n += 1
+    while n > 0 and n * (n + 1) // 2 >= N:
+        n -= 1
+    return n
+
+
+def padua_grid_index(n: int):
+    """(ix, iy) of the Padua points in emission order on the tensor Chebyshev-Lobatto grid
+    x = cos(ix pi / n) (ix = 0..n), y = cos(iy pi / (n+1)) (iy = 0..n+1): the points with ix + iy = n+1 mod 2."""
+    ix, iy = [], []
+    NN = n // 2 + 1
+    for k in range(n, -1, -1):
+        delta = (k % 2) if (n % 2 == 1) else 0
+        for j in range(NN + delta, 0, -1):
+            ix.append(n - k)                                   # x = -cospi(k/n) = cos((n-k) pi/n)
+            iy.append(n + 2 - 2 * j if (n - k) % 2 == 1 else n + 3 - 2 * j)
+    return np.array(ix), np.array(iy)
+
+
+def paduapoints(n: int) -> np.ndarray:
+    """N x 2 array [x y] of the (n+1)(n+2)/2 Padua points of degree n on [-1,1]^2."""
+    if n == 0:
+        return np.array([[0.0, 0.0]]) * 0.0 + np.array([[-1.0, -1.0]])  # -cospi(0/0) is undefined upstream; one point
+    ix, iy = padua_grid_index(n)
+    x = -_cospi((n - ix) / n)
+    y = -_cospi((n + 1 - iy) / (n + 1))
+    return np.stack([x, y], axis=1)
+
+
+def _cospi(t):
+    t = np.asarray(t, dtype=np.float64)
+    return np.sin(np.pi * (0.5 - np.abs(((t + 1.0) % 2.0) - 1.0)))  # cos(pi t) through a reduced argument
+
+
+def padua_transform_direct(vals: np.ndarray) -> np.ndarray:
+    """Ground truth: the unique total-degree-n interpolant at the Padua points, by solving the N x N collocation
+    system in the ApproxFun coefficient order (small n only)."""
+    N = len(vals)
+    n = padua_degree(N)
+    P = paduapoints(n)
+    Tx = np.cos(np.outer(np.arccos(np.clip(P[:, 0], -1, 1)), np.arange(n + 1)))
+    Ty = np.cos(np.outer(np.arccos(np.clip(P[:, 1], -1, 1)), np.arange(n + 1)))
+    cols = [Tx[:, i] * Ty[:, d - i] for d in range(n + 1) for i in range(d + 1)]
+    return np.linalg.solve(np.stack(cols, axis=1), np.asarray(vals, dtype=np.float64))
+
+
+def padua_transform(vals: np.ndarray) -> np.ndarray:
+    """`plan_paduatransform!(v, Val{false}) * v`: values at :func:`paduapoints` -> coefficients ordered by total
+    degree.  Zero-filled (n+2) x (n+1) grid -> 2-D REDFT00 -> 2/(n(n+1)), first/last row and column halved ->
+    triangle."""
+    vals = np.asarray(vals, dtype=np.float64)
+    N = len(vals)
+    n = padua_degree(N)
+    if (n + 1) * (n + 2) // 2 != N:
+        raise ValueError("Padua transforms can only be applied to vectors of length (n+1)*(n+2)/2")
+    if n == 0:
+        return vals.copy()
+    ix, iy = padua_grid_index(n)
+    W = np.zeros((n + 2, n + 1))
+    W[iy, ix] = vals
+    C = _sfft.dct(_sfft.dct(W, type=1, axis=0), type=1, axis=1) * (2.0 / (n * (n + 1)))
+    C[0, :] *= 0.5
+    C[-1, :] *= 0.5
+    C[:, 0] *= 0.5
+    C[:, -1] *= 0.5
+    return np.array([C[d - i, i] for d in range(n + 1) for i in range(d + 1)])
+
+
+def padua_itransform(cfs: np.ndarray) -> np.ndarray:
+    """`plan_ipaduatransform!`: coefficients (total-degree order) -> values at the Padua points."""
+    cfs = np.asarray(cfs, dtype=np.float64)
+    N = len(cfs)
+    n = padua_degree(N)
+    if (n + 1) * (n + 2) // 2 != N:
+        raise ValueError("Padua transforms can only be applied to vectors of length (n+1)*(n+2)/2")
+    if n == 0:
+        return cfs.copy()
+    C = tensor_deinterlace(cfs, n)                      # C[i, j]: x-degree i, y-degree j
+    ix, iy = padua_grid_index(n)
+    Tx = np.cos(np.pi * np.outer(np.arange(n + 1), np.arange(n + 1)) / n)            # T_i(x_ix)
+    Ty = np.cos(np.pi * np.outer(np.arange(n + 1), np.arange(n + 2)) / (n + 1))      # T_j(y_iy)
+    V = Tx.T @ C @ Ty                                   # V[ix, iy]
+    return V[ix, iy]
+
+
 # --------------------------------------------------------------------------------------
 # a6  constructors (host orchestration)
 # --------------------------------------------------------------------------------------

@@ -116,6 +116,30 @@ def test_tensor2d_row_pairs_four_step(shape):
     assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_INV, want, B.PLAN_2D_TRANSPOSE) - V)) < 1e-13
 
 
+@pytest.mark.parametrize("d", [0, 1, 2, 5, 8, 31, 63])
+def test_padua(d):
+    N = (d + 1) * (d + 2) // 2
+    P, Po = ll.paduapoints(N), orc.paduapoints(d)
+    assert np.max(np.abs(P - Po)) <= 5e-16
+    assert ll.paduapoints(max(N - 1, 1)).shape[0] == (N if d > 0 and N - 1 > d * (d + 1) // 2 else max(N - 1, 1))
+    v = RNG.standard_normal(N)
+    c = ll.padua(B.PADUA_FWD, v)
+    assert np.max(np.abs(c - orc.padua_transform(v))) < 1e-13
+    assert np.max(np.abs(ll.padua(B.PADUA_INV, c) - v)) < 1e-12
+    with pytest.raises(Exception):
+        ll.padua(B.PADUA_FWD, np.zeros(N + 1))
+
+
+def test_batched_four_step_under_bluestein():
+    # odd lengths above 4096: Bluestein pads to M >= 2^14, whose sub-FFT is the four-step run on whole chunks of lines
+    v = RNG.standard_normal((4500, 3))
+    assert np.max(np.abs(ll.transform(B.CHEB2_FWD, v) - orc.chebkind2_transform(v, axis=0))) < 1e-14
+    v = RNG.standard_normal((9001, 2))
+    assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-14
+    z = RNG.standard_normal((32768, 2)) + 1j * RNG.standard_normal((32768, 2))
+    assert np.max(np.abs(ll.transform(B.LAURENT_FWD, z) - orc.laurent_transform(z, axis=0))) < 1e-14
+
+
 def test_points():
     for n in (1, 2, 5, 64, 1000):
         x = ll.chebpoints(n)

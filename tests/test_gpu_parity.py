@@ -231,7 +231,7 @@ def test_tensor_transform_and_sampling_golden(af):
     C2 = af.transform(af.Chebyshev() ** 2, V2)
     assert np.max(np.abs(C2 - orc.cheb2_transform(V2))) < 1e-13 * 4 * 9
     assert np.max(np.abs(af.itransform(af.Chebyshev() ** 2, C2) - V2)) < 1e-12
-    F2 = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy), af.Chebyshev() ** 2, 32)
+    F2 = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy), af.Chebyshev() ** 2, (32, 32))
     assert abs(F2(0.1, 0.2) - math.cos(0.5)) < 1e-13
 
 
@@ -251,6 +251,37 @@ def test_tensor_row_pass_without_transposes(af, shape):
     alt = ll.transform2d(L.CHEB1_2D_INV, want, L.PLAN_2D_TRANSPOSE)
     vtol = 1e-13 * np.log2(shape[1]) * max(1.0, np.max(np.abs(want))) * np.sqrt(shape[0] * shape[1])
     assert np.max(np.abs(back - V)) < vtol and np.max(np.abs(alt - V)) < vtol
+
+
+@pytest.mark.parametrize("d", [0, 1, 2, 3, 6, 7, 30, 31, 100, 255, 1000])
+def test_padua_points_and_transform(af, d):
+    # Fun(f, Chebyshev()^2, N) = values at the Padua points -> coefficients by total degree (NEWS.md:85).
+    # Oracle: zero-filled grid + scipy REDFT00 (pinned against the N x N collocation solve in test_oracle_goldens.py).
+    from approxfun_b200 import _lib as L
+    ll = af.api.lowlevel()
+    N = (d + 1) * (d + 2) // 2
+    P = ll.paduapoints(N)
+    Po = orc.paduapoints(d)
+    assert P.shape == (N, 2) and np.max(np.abs(P - Po)) <= 5e-16
+    v = np.exp(0.3 * Po[:, 0] - 0.7 * Po[:, 1]) + Po[:, 0] * Po[:, 1] ** 2
+    c = ll.padua(L.PADUA_FWD, v)
+    co = orc.padua_transform(v)
+    tol = 1e-13 * max(1.0, np.log2(d + 2)) * np.max(np.abs(v))
+    assert np.max(np.abs(c - co)) < tol
+    assert np.max(np.abs(ll.padua(L.PADUA_INV, co) - v)) < 10 * tol
+    w = RNG.standard_normal(N)
+    assert np.max(np.abs(ll.padua(L.PADUA_FWD, w) - orc.padua_transform(w))) < 1e-13 * np.log2(d + 2) * 4
+    if d in (7, 100):
+        S2 = af.Chebyshev(-1, 2) * af.Chebyshev(0, 3)
+        f = lambda x, y: np.cos(x + 2 * y) * np.exp(-x * y / 5)  # noqa: E731
+        F = af.Fun(f, S2, N) if d == 100 else af.Fun(lambda x, y: 1 + x + 2 * y + x * y ** 2, S2, N)
+        assert F.coefficients.shape == (N,)
+        xs, ys = RNG.uniform(-1, 2, 50), RNG.uniform(0, 3, 50)
+        want = f(xs, ys) if d == 100 else 1 + xs + 2 * ys + xs * ys ** 2
+        assert np.max(np.abs(F(xs, ys) - want)) < 1e-12
+        assert np.max(np.abs(af.values(F) - F(*af.points(S2, N).T))) < 1e-12
+    with pytest.raises(af.DimensionMismatch):
+        ll.padua(L.PADUA_FWD, np.zeros(N + 1))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 64, 65, 100, 1025, 4097])
@@ -288,8 +319,11 @@ def test_bivariate_clenshaw(af):
         x, y = RNG.uniform(-1, 1, P), RNG.uniform(-1, 1, P)
         assert np.array_equal(af.api.lowlevel().clenshaw2d(Cm, x, y), orcc.clenshaw2d(Cm, x, y, threads=8))
     # examples/PDE_Helmholtz.jl:33-36 shape: evaluate a 2-D Fun at single points and on a grid
-    F = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy) * np.exp(xx * yy), af.Chebyshev() ** 2, 48)
+    F = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy) * np.exp(xx * yy), af.Chebyshev() ** 2, (48, 48))
     assert abs(F(0.1, 0.2) - math.cos(0.5) * math.exp(0.02)) < 1e-13
+    # the same function through the Padua constructor Fun(f, Chebyshev()^2, N): flat coefficients, same values
+    Fp = af.Fun(lambda xx, yy: np.cos(xx + 2 * yy) * np.exp(xx * yy), af.Chebyshev() ** 2, 1326)
+    assert Fp.coefficients.shape == (1326,) and abs(Fp(0.1, 0.2) - F(0.1, 0.2)) < 1e-13
     gx = np.linspace(-1, 1, 50)
     G = F(gx[:, None], gx[None, :])
     assert np.max(np.abs(G - np.cos(gx[:, None] + 2 * gx[None, :]) * np.exp(gx[:, None] * gx[None, :]))) < 1e-12
@@ -298,7 +332,7 @@ def test_bivariate_clenshaw(af):
 def test_sampling_2d_lowrank(af):
     # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
     S = af.Chebyshev(-4, 4)
-    f = af.Fun(lambda x, y: (x - y) ** 2 * np.exp(-x ** 2 / 2 - y ** 2 / 2), S ** 2, 96)
+    f = af.Fun(lambda x, y: (x - y) ** 2 * np.exp(-x ** 2 / 2 - y ** 2 / 2), S ** 2, (96, 96))
     r = af.sample(f, 5000)
     assert r.shape == (5000, 2) and np.all(np.abs(r) <= 4)
     # parity with caller-supplied uniforms, same low-rank factors on both sides

@@ -218,3 +218,26 @@ def test_tensor_interlace_order():
     # docs/src/usage/constructors.md:98-116
     Cm = np.array([[1.0, 2.0], [3.0, 0.0]])
     assert list(orc.tensor_interlace(Cm)[:3]) == [1.0, 2.0, 3.0]
+
+
+def test_padua_oracle_against_collocation_and_documented_order():
+    # SURVEY 8f rank 1.  The DCT-based restatement must reproduce the unique interpolant (N x N collocation solve), and
+    # the flat coefficient order must be the documented one: T0T0, T0(x)T1(y), T1(x)T0(y), ... (constructors.md:98-116).
+    for d in (1, 2, 3, 4, 7, 12):
+        P = orc.paduapoints(d)
+        N = (d + 1) * (d + 2) // 2
+        assert P.shape == (N, 2) and len({(round(a, 12), round(b, 12)) for a, b in P}) == N
+        ix, iy = orc.padua_grid_index(d)
+        assert np.all((ix + iy) % 2 == (d + 1) % 2)            # the checkerboard subset of the Lobatto tensor grid
+        v = np.exp(0.3 * P[:, 0] - 0.7 * P[:, 1]) + P[:, 0] * P[:, 1] ** 2
+        c = orc.padua_transform(v)
+        assert np.max(np.abs(c - orc.padua_transform_direct(v))) < 1e-14
+        assert np.max(np.abs(orc.padua_itransform(c) - v)) < 1e-14
+    P = orc.paduapoints(1)
+    assert np.allclose(orc.padua_itransform(np.array([1.0, 2.0, 3.0])), 1 + 2 * P[:, 1] + 3 * P[:, 0])
+    # published Padua set of degree 2 (Caliari-De Marchi-Vianello): x in {1, 0, -1}, y in {1, 1/2, -1/2, -1}
+    assert np.allclose(sorted(map(tuple, np.round(orc.paduapoints(2), 12))),
+                       sorted([(1, .5), (1, -1), (0, 1), (0, -.5), (-1, .5), (-1, -1)]))
+    assert [orc.padua_degree(N) for N in (1, 2, 3, 4, 6, 7, 10, 32, 36, 37)] == [0, 1, 1, 2, 2, 3, 3, 7, 7, 8]
+    with pytest.raises(ValueError):
+        orc.padua_transform(np.zeros(5))
