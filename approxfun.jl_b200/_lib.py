@@ -29,7 +29,7 @@ SYMBOLS = [
     "afb_plan_create", "afb_plan_execute_host", "afb_plan_execute_device", "afb_plan_destroy", "afb_plan_launches",
     "afb_chebpoints", "afb_chebpoints_device", "afb_fourierpoints", "afb_paduapoints",
     "afb_clenshaw_cheb", "afb_clenshaw_cheb_device", "afb_clenshaw_cheb_cols", "afb_clenshaw_cheb_cols_device",
-    "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device",
+    "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device", "afb_clenshaw_rec", "afb_clenshaw_rec_device",
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device", "afb_fp64_probe_device",
@@ -83,6 +83,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_clenshaw_cheb_cols": [vp, i64, i64, vp, vp, i64],
         "afb_clenshaw_cheb_cols_device": [vp, i64, i64, vp, vp, i64, vp],
         "afb_clenshaw_cheb_multi": [vp, i64, i64, vp, vp, i64],
+        "afb_clenshaw_rec": [vp, i64, vp, vp, vp, vp, vp, i64],
+        "afb_clenshaw_rec_device": [vp, i64, vp, vp, vp, vp, vp, i64, vp],
         "afb_clenshaw_cheb_multi_device": [vp, i64, i64, vp, vp, i64, vp],
         "afb_cheb_normcumsum": [vp, i64, i64, i64, i32],
         "afb_cheb_normcumsum_device": [vp, i64, i64, i64, i32, vp],
@@ -212,6 +214,14 @@ class LowLevel:
         out = np.empty(max(n, 0))
         check(self.lib, self.lib.afb_chebpoints(_ptr(out), n, a, b))
         return out
+
+    def clenshaw_rec(self, c, A, B, Cc, x) -> np.ndarray:
+        c, A, B, Cc, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (c, A, B, Cc, x))
+        if A.size < c.size or B.size < c.size or Cc.size < c.size + 1:
+            raise DimensionMismatch(AFB_BAD_SIZE, "clenshaw_rec: need len(A), len(B) >= N and len(C) >= N + 1")
+        y = np.empty_like(x)
+        check(self.lib, self.lib.afb_clenshaw_rec(_ptr(c), c.size, _ptr(A), _ptr(B), _ptr(Cc), _ptr(x), _ptr(y), x.size))
+        return y
 
     def paduapoints(self, N: int, ax=-1.0, bx=1.0, ay=-1.0, by=1.0) -> np.ndarray:
         """Np x 2 array [x y] of the Padua points carrying N coefficients (Np = next triangular number >= N)."""

@@ -63,6 +63,57 @@ class Chebyshev(Space):
         return TensorSpace(self, other)
 
 
+class PolynomialSpace(Space):
+    """Orthogonal-polynomial spaces evaluated through the general three-term Clenshaw kernel (`afb_clenshaw_rec`):
+    p_{j+1} = (recA(j) x + recB(j)) p_j - recC(j) p_{j-1}  (UPSTREAM ApproxFunOrthogonalPolynomials recA/recB/recC)."""
+
+    def __init__(self, a: float = -1.0, b: float = 1.0):
+        self.a, self.b = float(a), float(b)
+
+    fromcanonical = Chebyshev.fromcanonical
+    tocanonical = Chebyshev.tocanonical
+
+    def rec(self, N: int):
+        """(A[0..N-1], B[0..N-1], C[0..N])"""
+        raise NotImplementedError
+
+
+class Jacobi(PolynomialSpace):
+    """`Jacobi(b, a)`: P_n^{(a,b)} (the reference's argument order), DLMF 18.9.2."""
+
+    def __init__(self, b: float, a: float, lo: float = -1.0, hi: float = 1.0):
+        super().__init__(lo, hi)
+        self.jb, self.ja = float(b), float(a)
+
+    def rec(self, N: int):
+        a, b = self.ja, self.jb
+        n = np.arange(N + 1, dtype=np.float64)
+        s = 2 * n + a + b
+        with np.errstate(divide="ignore", invalid="ignore"):
+            A = (s + 1) * (s + 2) / (2 * (n + 1) * (n + a + b + 1))
+            Bv = (a * a - b * b) * (s + 1) / (2 * (n + 1) * (n + a + b + 1) * s)
+            Cv = (n + a) * (n + b) * (s + 2) / ((n + 1) * (n + a + b + 1) * s)
+        A[0], Bv[0], Cv[0] = (a + b + 2) / 2.0, (a - b) / 2.0, 0.0
+        return A[:N].copy(), Bv[:N].copy(), Cv
+
+
+class Legendre(Jacobi):
+    def __init__(self, lo: float = -1.0, hi: float = 1.0):
+        super().__init__(0.0, 0.0, lo, hi)
+
+
+class Ultraspherical(PolynomialSpace):
+    """`Ultraspherical(lam)`: C_n^{(lam)}; A_n = 2(n+lam)/(n+1), B_n = 0, C_n = (n+2lam-1)/(n+1)."""
+
+    def __init__(self, lam: float, lo: float = -1.0, hi: float = 1.0):
+        super().__init__(lo, hi)
+        self.lam = float(lam)
+
+    def rec(self, N: int):
+        n = np.arange(N + 1, dtype=np.float64)
+        return (2 * (n + self.lam) / (n + 1))[:N].copy(), np.zeros(N), (n + 2 * self.lam - 1) / (n + 1)
+
+
 class Fourier(Space):
     def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
         self.a, self.b = float(a), float(b)
@@ -321,6 +372,11 @@ class Fun:
                     res[inside] = clenshaw(sp, self.coefficients, sp.tocanonical(xa[inside]))
                 return res
             return clenshaw(sp, self.coefficients, sp.tocanonical(x))
+        if isinstance(sp, PolynomialSpace):
+            xa = np.atleast_1d(np.asarray(x, dtype=np.float64))
+            A, Bv, Cv = sp.rec(len(self.coefficients))
+            out = lowlevel().clenshaw_rec(self.coefficients, A, Bv, Cv, sp.tocanonical(xa.ravel())).reshape(xa.shape)
+            return float(out[0]) if np.ndim(x) == 0 else out
         if isinstance(sp, TensorSpace):
             s1, s2 = sp.factors
             xs, ys = np.broadcast_arrays(np.atleast_1d(np.asarray(x, dtype=np.float64)),

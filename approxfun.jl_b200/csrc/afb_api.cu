@@ -848,6 +848,31 @@ int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y
     return dy.get(y, 8 * (size_t)P);
 }
 
+int32_t afb_clenshaw_rec_device(const double* d_c, int64_t N, const double* d_A, const double* d_B, const double* d_C,
+                                const double* d_x, double* d_y, int64_t P, void* stream) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_rec: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && (!d_c || !d_A || !d_B || !d_C)) || !d_x || !d_y) return fail(AFB_BAD_ARG, "afb_clenshaw_rec: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_clenshaw_rec(d_c, N, d_A, d_B, d_C, d_x, d_y, P, stream);
+}
+int32_t afb_clenshaw_rec(const double* c, int64_t N, const double* A, const double* B, const double* C, const double* x,
+                         double* y, int64_t P) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_rec: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && (!c || !A || !B || !C)) || !x || !y) return fail(AFB_BAD_ARG, "afb_clenshaw_rec: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dA, dB, dC, dx, dy;
+    AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dA.alloc(8 * (size_t)N)); AFB_TRY(dB.alloc(8 * (size_t)N));
+    AFB_TRY(dC.alloc(8 * (size_t)(N + 1))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(dA.put(A, 8 * (size_t)N)); AFB_TRY(dB.put(B, 8 * (size_t)N));
+    if (N) AFB_TRY(dC.put(C, 8 * (size_t)(N + 1)));
+    AFB_TRY(dx.put(x, 8 * (size_t)P));
+    AFB_TRY(launch_clenshaw_rec(dc.as<double>(), N, dA.as<double>(), dB.as<double>(), dC.as<double>(), dx.as<double>(),
+                                dy.as<double>(), P, nullptr));
+    return dy.get(y, 8 * (size_t)P);
+}
+
 int32_t afb_clenshaw_cheb_cols_device(const double* d_C, int64_t N, int64_t ld, const double* d_x, double* d_y,
                                       int64_t P, void* stream) {
     if (N < 0 || P < 0 || ld < N) return fail(AFB_BAD_SIZE, "afb_clenshaw_cheb_cols: bad sizes (need ld >= N >= 0)");

@@ -477,6 +477,90 @@ __global__ void chebpoints_kernel(double* __restrict__ out, int64_t n, double da
 // ================================================================================================
 // launchers
 // ================================================================================================
+// ------------------------------------------------------------------------------------------------
+// General three-term Clenshaw (Ultraspherical / Jacobi / Legendre evaluation):
+//   p_{j+1} = (A_j x + B_j) p_j - C_j p_{j-1},  y = sum_j c_j p_j(x)
+//   for j = N-1 .. 0:  bk2, bk1 = bk1, fma(fma(A_j, x, B_j), bk1, fma(-C_{j+1}, bk2, c_j))      y = bk1
+// (the operation order of UPSTREAM `clenshaw(sp::PolynomialSpace, c, x)`; its last step is the same formula at j = 0).
+// Degrees are staged in shared memory four doubles each {c_j, A_j, B_j, -C_{j+1}} (two 128-bit broadcast loads per
+// step); every thread runs four independent points.
+// ------------------------------------------------------------------------------------------------
+constexpr int REC_THREADS = 256;
+constexpr int REC_R = 4;
+constexpr int REC_CHUNK = 3072;  // degrees per chunk: 96 KB
+__global__ void __launch_bounds__(REC_THREADS, 2)
+clenshaw_rec_kernel(const double* __restrict__ c, int64_t N, const double* __restrict__ A, const double* __restrict__ B,
+                    const double* __restrict__ C, const double* __restrict__ x, double* __restrict__ y, int64_t P,
+                    int64_t ntiles) {
+    AFB_DYN_SMEM(double, sc);
+    const int tid = threadIdx.x;
+    const int64_t nchunks = (N + REC_CHUNK - 1) / REC_CHUNK;
+    auto stage = [&](int64_t lo, int64_t hi) {
+        for (int64_t j = lo + tid; j < hi; j += REC_THREADS) {
+            double* q = sc + 4 * (j - lo);
+            q[0] = c[j]; q[1] = A[j]; q[2] = B[j]; q[3] = -C[j + 1];
+        }
+    };
+    if (nchunks == 1) {
+        stage(0, N);
+        __syncthreads();
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * (int64_t)(REC_THREADS * REC_R);
+        double xv[REC_R], b1[REC_R], b2[REC_R];
+#pragma unroll
+        for (int r = 0; r < REC_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * REC_THREADS;
+            xv[r] = (i < P) ? x[i] : 0.0;
+            b1[r] = 0.0;
+            b2[r] = 0.0;
+        }
+        for (int64_t ch = nchunks - 1; ch >= 0; --ch) {
+            const int64_t lo = ch * REC_CHUNK;
+            const int64_t hi = (lo + REC_CHUNK < N) ? lo + REC_CHUNK : N;
+            if (nchunks > 1) {
+                __syncthreads();  // previous chunk fully consumed
+                stage(lo, hi);
+                __syncthreads();
+            }
+            for (int k = (int)(hi - lo) - 1; k >= 0; --k) {
+                const double2 ca = *reinterpret_cast<const double2*>(sc + 4 * k);
+                const double2 bc = *reinterpret_cast<const double2*>(sc + 4 * k + 2);
+#pragma unroll
+                for (int r = 0; r < REC_R; ++r) {
+                    const double t = __fma_rn(__fma_rn(ca.y, xv[r], bc.x), b1[r], __fma_rn(bc.y, b2[r], ca.x));
+                    b2[r] = b1[r];
+                    b1[r] = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < REC_R; ++r) {
+            const int64_t i = base + tid + (int64_t)r * REC_THREADS;
+            if (i < P) y[i] = b1[r];  // N == 0: no step ran, y = 0
+        }
+    }
+}
+
+int32_t launch_clenshaw_rec(const double* d_c, int64_t N, const double* d_A, const double* d_B, const double* d_C,
+                            const double* d_x, double* d_y, int64_t P, void* stream) {
+    if (P == 0) return AFB_OK;
+    const int64_t per = (int64_t)REC_THREADS * REC_R;
+    const int64_t ntiles = (P + per - 1) / per;
+    const int64_t grid = ntiles < 2 * (int64_t)sm_count() ? ntiles : 2 * (int64_t)sm_count();
+    const int64_t staged = N < REC_CHUNK ? (N > 0 ? N : 1) : REC_CHUNK;
+    auto k = clenshaw_rec_kernel;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 4 * REC_CHUNK)));
+        attr_done = true;
+    }
+    AFB_LAUNCH(k, (unsigned)grid, REC_THREADS, sizeof(double) * 4 * (size_t)staged, stream, d_c, N, d_A, d_B, d_C, d_x, d_y, P,
+               ntiles);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 static inline int64_t cl_tiles(int64_t P) { return (P + (int64_t)CL_THREADS * CL_R - 1) / ((int64_t)CL_THREADS * CL_R); }
 
 int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream) {

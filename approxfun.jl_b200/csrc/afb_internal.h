@@ -27,6 +27,8 @@ int32_t launch_direct(int kind, int n, const void* in, void* out, int64_t batch,
                       int64_t oes, const cplx* tab, void* stream);
 
 int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream);
+int32_t launch_clenshaw_rec(const double* d_c, int64_t N, const double* d_A, const double* d_B, const double* d_C,
+                            const double* d_x, double* d_y, int64_t P, void* stream);
 int32_t launch_bisect_vec(const double* d_c, int64_t N, const double* d_u, bool rng, uint64_t seed, uint64_t offset,
                           double* d_out, int64_t P, int numits, double a, double b, void* stream);
 int32_t launch_philox(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);

@@ -321,9 +321,24 @@ def main():
         el = (time.perf_counter() - t0) / e2e_steps
         el = max_over_ranks(el * 1e3) * 1e-3
         chk_e2e = hout[idx].copy()
+        # the bound of this number: the same two pinned buffers copied H2D and D2H concurrently, no kernel
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        dv2 = torch.empty_like(v)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(s_up):
+                dv2.copy_(hv, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hc.copy_(c, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_ms = max_over_ranks((time.perf_counter() - t0) / 2 * 1e3)
+        del dv2
         e2e = {"value": world * coefs_per_step / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
                "d2h_bytes_per_step": int(8 * B * n), "ms_per_step": el * 1e3, "steps": e2e_steps,
                "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)",
+               "pcie_copy_only_ms": copy_ms, "frac_of_pcie_copy_only": copy_ms / (el * 1e3),
                "host_affinity": numa_note}
         hplan.close()
         del hv, hc

@@ -142,6 +142,14 @@ int32_t afb_paduapoints(double* xy, int64_t N, double ax, double bx, double ay, 
 int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y, int64_t P);
 int32_t afb_clenshaw_cheb_device(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P,
                                  void* stream);
+/* General three-term Clenshaw: y[i] = sum_j c[j] p_j(x[i]) with p_0 = 1,
+ * p_{j+1} = (A[j] x + B[j]) p_j - C[j] p_{j-1}  (recA / recB / recC of UPSTREAM ApproxFunOrthogonalPolynomials: Jacobi,
+ * Ultraspherical, Legendre; DLMF 18.9.1).  A, B: N entries, C: N+1 entries (C[0] unused).  Operation order of UPSTREAM
+ * `clenshaw(sp::PolynomialSpace, c, x)`: bk1 <- muladd(muladd(A_j,x,B_j), bk1, muladd(-C_{j+1}, bk2, c_j)), j = N-1..0. */
+int32_t afb_clenshaw_rec(const double* c, int64_t N, const double* A, const double* B, const double* C, const double* x,
+                         double* y, int64_t P);
+int32_t afb_clenshaw_rec_device(const double* d_c, int64_t N, const double* d_A, const double* d_B, const double* d_C,
+                                const double* d_x, double* d_y, int64_t P, void* stream);
 /* Replaces clenshaw(c::Matrix, x::Vector, plan) (call sites src/Extras/sample.jl:80,94): column j of the
  * N x P column-major matrix C (leading dimension ld >= N) evaluated at x[j]. */
 int32_t afb_clenshaw_cheb_cols(const double* C, int64_t N, int64_t ld, const double* x, double* y, int64_t P);

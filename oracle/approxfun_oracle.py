@@ -635,6 +635,51 @@ def padua_itransform(cfs: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# 8(f) rank 4: three-term recurrence tables  p_{j+1} = (A_j x + B_j) p_j - C_j p_{j-1}  (DLMF 18.9.1-2),
+# the `recA / recB / recC` of UPSTREAM ApproxFunOrthogonalPolynomials (Jacobi(b, a) = P^{(a,b)}, Ultraspherical(l) = C^{(l)})
+# --------------------------------------------------------------------------------------
+def jacobi_rec(a: float, b: float, N: int):
+    """A[0..N-1], B[0..N-1], C[0..N] for P_n^{(a,b)}."""
+    n = np.arange(N + 1, dtype=np.float64)
+    s = 2 * n + a + b
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = (s + 1) * (s + 2) / (2 * (n + 1) * (n + a + b + 1))
+        Bv = (a * a - b * b) * (s + 1) / (2 * (n + 1) * (n + a + b + 1) * s)
+        Cv = (n + a) * (n + b) * (s + 2) / ((n + 1) * (n + a + b + 1) * s)
+    A[0] = (a + b + 2) / 2.0                      # n = 0 limits (s may vanish)
+    Bv[0] = (a - b) / 2.0
+    Cv[0] = 0.0
+    return A[:N].copy(), Bv[:N].copy(), Cv
+
+
+def ultraspherical_rec(lam: float, N: int):
+    """A, B, C for C_n^{(lam)}: A_n = 2(n+lam)/(n+1), B_n = 0, C_n = (n+2lam-1)/(n+1)."""
+    n = np.arange(N + 1, dtype=np.float64)
+    return (2 * (n + lam) / (n + 1))[:N].copy(), np.zeros(N), (n + 2 * lam - 1) / (n + 1)
+
+
+def chebyshev_rec(N: int):
+    A = np.full(N, 2.0)
+    if N:
+        A[0] = 1.0
+    return A, np.zeros(N), np.ones(N + 1)
+
+
+def clenshaw_rec(c, A, B, Cc, x):
+    """numpy restatement of the general Clenshaw (no fma; :mod:`oracle_c` has the fused one)."""
+    c = np.asarray(c, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    N = c.size
+    if N == 0:
+        return np.zeros_like(x)
+    bk1 = np.zeros_like(x)
+    bk2 = np.zeros_like(x)
+    for j in range(N - 1, 0, -1):
+        bk2, bk1 = bk1, (A[j] * x + B[j]) * bk1 + (c[j] - Cc[j + 1] * bk2)
+    return (A[0] * x + B[0]) * bk1 + (c[0] - Cc[1] * bk2)
+
+
+# --------------------------------------------------------------------------------------
 # a6  constructors (host orchestration)
 # --------------------------------------------------------------------------------------
 

@@ -41,6 +41,8 @@ def lib():
         L.orc_sample2d_lowrank.restype = None
         L.orc_clenshaw2d.argtypes = [_dp, i64, i64, _dp, _dp, _dp, i64, i32]
         L.orc_clenshaw2d.restype = None
+        L.orc_clenshaw_rec.argtypes = [_dp, i64, _dp, _dp, _dp, _dp, _dp, i64, i32]
+        L.orc_clenshaw_rec.restype = None
         L.orc_max_threads.restype = i32
         for f in (L.orc_clenshaw, L.orc_clenshaw_planned, L.orc_clenshaw_cols, L.orc_clenshaw_multi,
                   L.orc_cheb_bisect, L.orc_cheb_bisect_cols, L.orc_cheb_bisect_planned,
@@ -93,6 +95,15 @@ def clenshaw_multi(Cm, x, threads: int = 1):
     Y = np.empty((M, x.size))
     lib().orc_clenshaw_multi(flat, N, M, x, Y.ravel(), x.size, threads)
     return Y
+
+
+def clenshaw_rec(c, A, B, Cc, x, threads: int = 1):
+    """General three-term Clenshaw with true fma (UPSTREAM `clenshaw(sp::PolynomialSpace, c, x)` operation order)."""
+    c, A, B, Cc, x = _c(c), _c(A), _c(B), _c(Cc), _c(x)
+    assert A.size >= c.size and B.size >= c.size and Cc.size >= c.size + 1
+    y = np.empty_like(x)
+    lib().orc_clenshaw_rec(c, c.size, A, B, Cc, x, y, x.size, threads)
+    return y
 
 
 def cheb_bisect(c, u, numits: int = 47, threads: int = 1):

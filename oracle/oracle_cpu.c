@@ -88,6 +88,26 @@ void orc_clenshaw_multi(const double* C, int64_t N, int64_t M, const double* x, 
         for (int64_t m = 0; m < M; ++m) Y[m * P + i] = clenshaw1(C + m * N, N, 1, x[i]);
 }
 
+/* ---- general three-term Clenshaw (8f rank 4: Ultraspherical / Jacobi evaluation) -------------------------
+ * UPSTREAM ApproxFunOrthogonalPolynomials `clenshaw(sp::PolynomialSpace, c, x)` (call sites of the generic
+ * `clenshaw(sp, c, x)`: src/Extras/sample.jl:47).  p_{j+1} = (A_j x + B_j) p_j - C_j p_{j-1}, p_0 = 1:
+ *   bk1 = bk2 = 0;  for j = N-1 .. 1:  bk2, bk1 = bk1, muladd(muladd(A_j,x,B_j), bk1, muladd(-C_{j+1}, bk2, c_j))
+ *   return muladd(muladd(A_0,x,B_0), bk1, muladd(-C_1, bk2, c_0)).   A, B: N entries; C: N+1 entries (C_0 unused). */
+void orc_clenshaw_rec(const double* c, int64_t N, const double* A, const double* B, const double* C, const double* x,
+                      double* y, int64_t P, int nthreads) {
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t i = 0; i < P; ++i) {
+        if (N == 0) { y[i] = 0.0; continue; }
+        double bk1 = 0.0, bk2 = 0.0;
+        for (int64_t j = N - 1; j >= 1; --j) {
+            const double t = fma(fma(A[j], x[i], B[j]), bk1, fma(-C[j + 1], bk2, c[j]));
+            bk2 = bk1;
+            bk1 = t;
+        }
+        y[i] = fma(fma(A[0], x[i], B[0]), bk1, fma(-C[1], bk2, c[0]));
+    }
+}
+
 /* ---- bisection (a14) ------------------------------------------------------------------------ */
 void orc_cheb_bisect(const double* c, int64_t N, const double* u, double* out, int64_t P, int numits,
                      int nthreads) {

@@ -140,6 +140,15 @@ def test_batched_four_step_under_bluestein():
     assert np.max(np.abs(ll.transform(B.LAURENT_FWD, z) - orc.laurent_transform(z, axis=0))) < 1e-14
 
 
+def test_general_three_term_clenshaw():
+    from oracle import oracle_c as orcc
+    x = RNG.uniform(-1, 1, 1500)
+    for N in (0, 1, 2, 40, 3100):
+        c = RNG.standard_normal(N)
+        for A, Bv, Cv in (orc.jacobi_rec(0.5, 1.5, N), orc.ultraspherical_rec(2.0, N)):
+            assert np.array_equal(ll.clenshaw_rec(c, A, Bv, Cv, x), orcc.clenshaw_rec(c, A, Bv, Cv, x))
+
+
 def test_points():
     for n in (1, 2, 5, 64, 1000):
         x = ll.chebpoints(n)

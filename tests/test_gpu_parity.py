@@ -329,6 +329,29 @@ def test_bivariate_clenshaw(af):
     assert np.max(np.abs(G - np.cos(gx[:, None] + 2 * gx[None, :]) * np.exp(gx[:, None] * gx[None, :]))) < 1e-12
 
 
+def test_general_three_term_clenshaw(af):
+    # Jacobi / Ultraspherical / Legendre evaluation through recA/recB/recC; bit-exact against the
+    # fused C oracle, and against scipy's polynomials for the mathematics
+    import scipy.special as sps
+    ll = af.api.lowlevel()
+    x = RNG.uniform(-1, 1, 20001)
+    for N in (0, 1, 2, 3, 65, 3072, 3073, 10000):
+        c = RNG.standard_normal(N) / (1 + np.arange(N))
+        for A, Bv, Cv in (orc.jacobi_rec(0.5, 1.5, N), orc.ultraspherical_rec(1.0, N), orc.chebyshev_rec(N)):
+            assert np.array_equal(ll.clenshaw_rec(c, A, Bv, Cv, x), orcc.clenshaw_rec(c, A, Bv, Cv, x, threads=8))
+    N = 30
+    c = RNG.standard_normal(N) / (1 + np.arange(N)) ** 2
+    xs = x[:500]
+    f = af.Fun(af.Jacobi(1.5, 0.5), c)   # Jacobi(b, a) = P^{(a,b)} = P^{(0.5, 1.5)}
+    assert np.max(np.abs(f(xs) - sum(c[n] * sps.eval_jacobi(n, 0.5, 1.5, xs) for n in range(N)))) < 1e-12
+    g = af.Fun(af.Ultraspherical(2.0, 0.0, 4.0), c)
+    assert np.max(np.abs(g(2 + 2 * xs) - sum(c[n] * sps.eval_gegenbauer(n, 2.0, xs) for n in range(N)))) < 1e-12
+    h = af.Fun(af.Legendre(), c)
+    assert abs(h(0.3) - sum(c[n] * sps.eval_legendre(n, 0.3) for n in range(N))) < 1e-14
+    with pytest.raises(af.DimensionMismatch):
+        ll.clenshaw_rec(np.ones(5), np.ones(4), np.ones(5), np.ones(6), xs)
+
+
 def test_sampling_2d_lowrank(af):
     # test/SamplingTest.jl:5-8: f = (x-y)^2 exp(-x^2/2-y^2/2) on (-4..4)^2; r = sample(f, 5000)
     S = af.Chebyshev(-4, 4)

@@ -241,3 +241,26 @@ def test_padua_oracle_against_collocation_and_documented_order():
     assert [orc.padua_degree(N) for N in (1, 2, 3, 4, 6, 7, 10, 32, 36, 37)] == [0, 1, 1, 2, 2, 3, 3, 7, 7, 8]
     with pytest.raises(ValueError):
         orc.padua_transform(np.zeros(5))
+
+
+def test_three_term_recurrence_tables_against_scipy():
+    # recA/recB/recC restated from DLMF 18.9.1-2, checked on scipy's Jacobi / Gegenbauer / Legendre
+    import scipy.special as sps
+    from oracle import oracle_c as orcc
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, 300)
+    N = 40
+    c = rng.standard_normal(N) / (1 + np.arange(N))
+    for a, b in [(0.0, 0.0), (0.5, -0.5), (1.5, 2.0), (0.0, 1.0)]:
+        A, B, C = orc.jacobi_rec(a, b, N)
+        want = sum(c[n] * sps.eval_jacobi(n, a, b, x) for n in range(N))
+        tol = 1e-13 * max(1.0, np.max(np.abs(want)))   # evaluations: 1e-13 ||f||_inf (BASELINE.json tolerance)
+        assert np.max(np.abs(orc.clenshaw_rec(c, A, B, C, x) - want)) < tol
+        assert np.max(np.abs(orcc.clenshaw_rec(c, A, B, C, x) - want)) < tol
+    for lam in (0.5, 1.0, 2.0):
+        A, B, C = orc.ultraspherical_rec(lam, N)
+        want = sum(c[n] * sps.eval_gegenbauer(n, lam, x) for n in range(N))
+        assert np.max(np.abs(orcc.clenshaw_rec(c, A, B, C, x) - want)) < 1e-13 * max(1.0, np.max(np.abs(want)))
+    # the Chebyshev table through the general recurrence is the first-kind series of the hot path
+    A, B, C = orc.chebyshev_rec(N)
+    assert np.max(np.abs(orcc.clenshaw_rec(c, A, B, C, x) - orcc.clenshaw(c, x))) < 1e-14
