@@ -391,7 +391,7 @@ def main():
         extras["clenshaw_N1e4"]["frac_of_measured_dfma_rate"] = extras["clenshaw_N1e4"]["fp64_flops"] / probe["dfma_repeated_operand"]
         extras["sample_gaussian"]["frac_of_measured_clenshaw_step_rate"] = (
             47 * 3.0 * cdf.size * P / (extras["sample_gaussian"]["ms_per_step"] * 1e-3) / probe["clenshaw_step_dadd_dfma"])
-        if rank == 0 and not args.no_cpu:
+        if rank == 0 and world == 1 and not args.no_cpu:
             # reference-side CPU baselines for configs 3 and 5 (oracle port, reference loop order: whole-vector passes
             # through the ClenshawPlan work vectors, all host threads), on bounded point sets
             from oracle import oracle_c as orcc
@@ -459,8 +459,11 @@ def main():
                 sp.close()
             del blk, rows
 
-    cpu_baseline = None
-    if rank == 0 and not args.no_cpu:
+    # the CPU legs run at N = 1 only: at N > 1 the other ranks busy-wait in the barrier on the same host cores
+    # (measured: the 32-thread port drops from 8.7e8 to 2.0e8 coefficients/s beside seven waiting ranks)
+    cpu_baseline = None if world == 1 else {"value": None, "unit": "coefficients/s", "cores": 0, "kind": "port",
+                                            "sample": "not timed at N > 1 (rank 0 at N = 1 only); see the N = 1 line"}
+    if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         val, el, reps = cpu_transform_sample(2048, 10.0, cores)
         from oracle import approxfun_oracle as orc
