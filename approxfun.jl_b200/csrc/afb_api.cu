@@ -415,7 +415,7 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
                 const double* in = reinterpret_cast<const double*>(d_in) + b0 * istride;
                 double* out = reinterpret_cast<double*>(d_out) + b0 * ostride;
                 AFB_TRY(launch_ext_pre(p->kind, p->n, p->cn, in, istride, p->gwork, nb, stream));
-                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nb, false, 1.0, stream));
+                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, (nb + 1) / 2, false, 1.0, stream));  // two lines per FFT
                 AFB_TRY(launch_ext_post(p->kind, p->n, p->cn, p->gwork, out, ostride, nb, stream));
             }
             return AFB_OK;

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <vector>
 
+#include "afb_fft.cuh"
 #include "afb_internal.h"
 
 namespace afb {
@@ -68,6 +69,102 @@ __global__ void fill_bfilter_kernel(cplx* __restrict__ b, int64_t n, int64_t M, 
         if (j < n) z = cconj(chirp[j]);
         else if (M - j < n) z = cconj(chirp[M - j]);
         b[j] = z;
+    }
+}
+
+// ---- Bluestein in ONE kernel when the padded length M fits a CTA's shared memory (M <= 8192) ---------------------
+// chirp-multiply and zero-pad in registers -> FFT_M in shared memory -> multiply by bhat -> inverse FFT_M (conj trick)
+// -> chirp-multiply -> store: one read and one write of the line instead of five element-wise / FFT passes over a
+// padded copy.
+struct BlueParams {
+    const cplx* in;
+    cplx* out;
+    int64_t n, batch;
+    const cplx *chirp, *bhat, *tw;
+    int conj_in, conj_out;
+    double scale;  // includes 1/M
+};
+template <int M> struct BlueGeom {
+    static constexpr int T = FftCfg<M>::T;
+    static constexpr int CT = (T < 128) ? 128 : T;
+    static constexpr int LPC = CT / T;
+    static constexpr size_t SMEM = sizeof(cplx) * (size_t)LPC * FftLine<M>::STRIDE;
+};
+template <int M>
+__global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) blue_fused_kernel(const __grid_constant__ BlueParams p) {
+    typedef FftCfg<M> C;
+    typedef BlueGeom<M> G;
+    AFB_DYN_SMEM(cplx, smem);
+    const int l = threadIdx.x / C::T, t = threadIdx.x % C::T;
+    const int64_t line = (int64_t)blockIdx.x * G::LPC + l;
+    const bool act = line < p.batch;
+    cplx* s = smem + (size_t)l * FftLine<M>::STRIDE;
+    const cplx* src = p.in + (act ? line : 0) * p.n;
+    cplx x[C::E];
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {  // unconditional loads on a clamped index, then select
+        const int64_t j = t + C::T * r;
+        const int64_t jc = j < p.n ? j : p.n - 1;
+        cplx z = src[jc];
+        const cplx ch = ldg2(p.chirp + jc);
+        if (p.conj_in) z.y = -z.y;
+        z = cmul(z, ch);
+        x[r] = (j < p.n) ? z : make_double2(0.0, 0.0);
+    }
+    fft_line<M>(s, t, x, p.tw);
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int i = t + C::T * r;
+        const cplx z = cmul(line_get<M>(s, i), ldg2(p.bhat + i));
+        x[r] = make_double2(z.x, -z.y);  // inverse FFT = conj FFT conj
+    }
+    __syncthreads();  // every read of the first result is done before the second transform reuses the buffer
+    // The second transform has the same thread index, buffer and twiddles: hide that from the compiler, which otherwise
+    // keeps the first transform's shared-memory addresses and twiddle powers alive for reuse (~100 registers, spilled).
+    int t2 = t;
+    const cplx* tw2 = p.tw;
+    cplx* s2 = s;
+#ifndef AFB_HOST_EMU
+    asm volatile("" : "+r"(t2), "+l"(tw2), "+l"(s2));
+#endif
+    fft_line<M>(s2, t2, x, tw2);
+    if (!act) return;
+    cplx* dst = p.out + line * p.n;
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int64_t k = t2 + C::T * r;
+        if (k < p.n) {
+            const cplx y = line_get<M>(s2, (int)k);
+            cplx z = cscale(cmul(make_double2(y.x, -y.y), ldg2(p.chirp + k)), p.scale);
+            if (p.conj_out) z.y = -z.y;
+            dst[k] = z;
+        }
+    }
+}
+template <int M> static int32_t launch_blue_fused_m(const BlueParams& p, void* stream) {
+    typedef BlueGeom<M> G;
+    auto k = blue_fused_kernel<M>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    AFB_LAUNCH(k, (unsigned)((p.batch + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+static int32_t launch_blue_fused(int64_t M, const BlueParams& p, void* stream) {
+    switch (M) {
+        case 32: return launch_blue_fused_m<32>(p, stream);
+        case 64: return launch_blue_fused_m<64>(p, stream);
+        case 128: return launch_blue_fused_m<128>(p, stream);
+        case 256: return launch_blue_fused_m<256>(p, stream);
+        case 512: return launch_blue_fused_m<512>(p, stream);
+        case 1024: return launch_blue_fused_m<1024>(p, stream);
+        case 2048: return launch_blue_fused_m<2048>(p, stream);
+        case 4096: return launch_blue_fused_m<4096>(p, stream);
+        case 8192: return launch_blue_fused_m<8192>(p, stream);
+        default: return fail(AFB_UNSUPPORTED, "fused Bluestein: padded length not instantiated");
     }
 }
 
@@ -148,7 +245,8 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
         }
         if (st == AFB_OK) {
             void* d = nullptr;
-            cudaError_t e = cudaMalloc(&d, sizeof(cplx) * (size_t)(M * p->max_batch));
+            // the padded work buffer is only needed by the multi-kernel route (M above one CTA's shared memory)
+            cudaError_t e = (M <= LINE_MAX_N) ? cudaSuccess : cudaMalloc(&d, sizeof(cplx) * (size_t)(M * p->max_batch));
             if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(bluestein pad)", __FILE__, __LINE__);
             p->pad = reinterpret_cast<cplx*>(d);
         }
@@ -176,7 +274,7 @@ int32_t cfft_launches(const CfftPlan* p) {
     switch (p->mode) {
         case 0: return 1;
         case 1: return 2;
-        default: return 3 + 2 * cfft_launches(p->sub);
+        default: return (p->M <= LINE_MAX_N) ? 1 : 3 + 2 * cfft_launches(p->sub);
     }
 }
 
@@ -204,6 +302,11 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
         return AFB_OK;
     }
     // Bluestein: X_k = chirp_k * sum_j (x_j chirp_j) conj(chirp)_{k-j}
+    if (p->M <= LINE_MAX_N) {  // one kernel; in place is safe (a CTA reads its whole lines before it writes them)
+        BlueParams bp{in, out, n, batch, p->chirp, p->bhat, p->sub->tw, inverse ? 1 : 0, inverse ? 1 : 0,
+                      scale / (double)p->M};
+        return launch_blue_fused(p->M, bp, stream);
+    }
     for (int64_t b0 = 0; b0 < batch; b0 += p->max_batch) {
         const int64_t nb = std::min(p->max_batch, batch - b0);
         const int64_t M = p->M;
@@ -311,23 +414,26 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
 //   AFB_SIN_FWD/INV    SinSpace, /root/reference/src/Extras/fftGeneric.jl:74-81, restated verbatim:
 //                      v = imag(fft([0; -x; 0; reverse(x)]))[2:n+1],  fwd: v/(n+1),  inv: v/2     (cn = 2n+2)
 // =====================================================================================================
+// The extensions are real with a real (even) or purely imaginary (odd) spectrum, so TWO lines share one complex FFT:
+// work line q holds ext(line 2q) + i ext(line 2q+1);  FFT = E_{2q} + i E_{2q+1}  (even)  /  -S_{2q+1} + i S_{2q}  (odd, E = iS).
+__device__ __forceinline__ double ext_value(int kind, int64_t n, int64_t cn, const double* __restrict__ x, int64_t j) {
+    if (kind == AFB_CHEB2_FWD || kind == AFB_CHEB2_INV) {
+        const int64_t i = (j < n) ? j : cn - j;
+        const double v = x[i];
+        return (kind == AFB_CHEB2_INV && (i == 0 || i == n - 1)) ? v * 2.0 : v;
+    }
+    // [0; -x; 0; reverse(x)]
+    if (j == 0 || j == n + 1) return 0.0;
+    return (j <= n) ? -x[j - 1] : x[2 * n + 1 - j];
+}
 __global__ void ext_pre_kernel(int kind, int64_t n, int64_t cn, const double* __restrict__ in, int64_t istride,
                                cplx* __restrict__ work, int64_t batch) {
-    const int64_t total = batch * cn;
+    const int64_t total = ((batch + 1) / 2) * cn;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = g / cn, j = g % cn;
-        const double* x = in + b * istride;
-        double v;
-        if (kind == AFB_CHEB2_FWD || kind == AFB_CHEB2_INV) {
-            const int64_t i = (j < n) ? j : cn - j;
-            v = x[i];
-            if (kind == AFB_CHEB2_INV && (i == 0 || i == n - 1)) v *= 2.0;
-        } else {  // [0; -x; 0; reverse(x)]
-            if (j == 0 || j == n + 1) v = 0.0;
-            else if (j <= n) v = -x[j - 1];
-            else v = x[2 * n + 1 - j];
-        }
-        work[g] = make_double2(v, 0.0);
+        const int64_t q = g / cn, j = g % cn;
+        const double re = ext_value(kind, n, cn, in + (2 * q) * istride, j);
+        const double im = (2 * q + 1 < batch) ? ext_value(kind, n, cn, in + (2 * q + 1) * istride, j) : 0.0;
+        work[g] = make_double2(re, im);
     }
 }
 __global__ void ext_post_kernel(int kind, int64_t n, int64_t cn, const cplx* __restrict__ work, double* __restrict__ out,
@@ -335,17 +441,17 @@ __global__ void ext_post_kernel(int kind, int64_t n, int64_t cn, const cplx* __r
     const int64_t total = batch * n;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = g / n, k = g % n;
-        const cplx* W = work + b * cn;
+        const cplx* W = work + (b >> 1) * cn;
+        const bool odd = b & 1;
         double r;
         if (kind == AFB_CHEB2_FWD) {
-            r = W[k].x / (double)(n - 1);
+            r = (odd ? W[k].y : W[k].x) / (double)(n - 1);
             if (k == 0 || k == n - 1) r /= 2.0;
         } else if (kind == AFB_CHEB2_INV) {
-            r = W[k].x / 2.0;
-        } else if (kind == AFB_SIN_FWD) {
-            r = W[k + 1].y / (double)(n + 1);
+            r = (odd ? W[k].y : W[k].x) / 2.0;
         } else {
-            r = W[k + 1].y / 2.0;
+            const double sv = odd ? -W[k + 1].x : W[k + 1].y;
+            r = (kind == AFB_SIN_FWD) ? sv / (double)(n + 1) : sv / 2.0;
         }
         out[b * ostride + k] = r;
     }
@@ -354,7 +460,7 @@ int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_
                        void* stream) {
     if (batch == 0) return AFB_OK;
     auto k = ext_pre_kernel;
-    AFB_LAUNCH(k, ew_grid(batch * cn), 256, 0, stream, kind, n, cn, in, istride, work, batch);
+    AFB_LAUNCH(k, ew_grid(((batch + 1) / 2) * cn), 256, 0, stream, kind, n, cn, in, istride, work, batch);
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }

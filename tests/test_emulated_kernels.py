@@ -206,6 +206,11 @@ def test_normcumsum_and_bisection_bit_exact():
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 17, 33, 64, 65, 100, 129, 1025])
 def test_second_kind_and_sinspace(n):
+    v3 = RNG.standard_normal((n, 3))   # odd batch: two lines share one complex FFT, the last one rides alone
+    assert np.max(np.abs(ll.transform(B.CHEB2_FWD, v3) - orc.chebkind2_transform(v3, axis=0))) <= tol(n, np.max(np.abs(v3)))
+    s3 = ll.transform(B.SIN_INV, v3)
+    for b in range(3):
+        assert np.max(np.abs(s3[:, b] - orc.sin_itransform_generic(v3[:, b]))) <= tol(n, max(1.0, np.max(np.abs(s3))))
     v = RNG.standard_normal((n, 2))
     got = ll.transform(B.CHEB2_FWD, v)
     assert np.max(np.abs(got - orc.chebkind2_transform(v, axis=0))) <= tol(n, np.max(np.abs(v)))
