@@ -428,7 +428,9 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
                 const char* in = reinterpret_cast<const char*>(d_in) + (size_t)p->elem * (size_t)(b0 * istride);
                 char* out = reinterpret_cast<char*>(d_out) + (size_t)p->elem * (size_t)(b0 * ostride);
                 AFB_TRY(launch_generic_pre(p->kind, p->n, in, istride, p->gwork, nb, p->qtab, stream));
-                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nb, inv, 1.0, stream));
+                // the four real kinds ride two lines per complex FFT (see generic_pre_kernel)
+                const int64_t nfft = (p->kind <= AFB_FOURIER_INV) ? (nb + 1) / 2 : nb;
+                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nfft, inv, 1.0, stream));
                 AFB_TRY(launch_generic_post(p->kind, p->n, p->gwork, out, ostride, nb, p->qtab, stream));
             }
             return AFB_OK;

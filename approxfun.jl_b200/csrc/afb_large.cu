@@ -329,69 +329,98 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
 // generic pre / post kernels: real transform <-> length-n complex FFT (one thread per element)
 //   qtab[k] = exp(-i pi k / (2n)), k = 0..n   (Chebyshev kinds only)
 // =====================================================================================================
+// The four REAL kinds transform two lines per complex FFT: work line q = z(line 2q) + i z(line 2q+1).  Inverse kinds
+// produce real sequences, so the two results are the real and imaginary parts; forward kinds recover the spectra of the
+// two real inputs from Z[k] and conj(Z[n-k]).
+__device__ __forceinline__ bool generic_real_kind(int kind) { return kind <= AFB_FOURIER_INV; }
+
+__device__ __forceinline__ cplx generic_pre_value(int kind, int64_t n, int64_t nh, const void* __restrict__ line, int64_t j,
+                                                  const cplx* __restrict__ qtab) {
+    cplx z = make_double2(0.0, 0.0);
+    if (kind == AFB_CHEB1_FWD) {
+        const double* v = reinterpret_cast<const double*>(line);
+        z.x = (j < nh) ? v[2 * j] : v[2 * (n - 1 - j) + 1];
+    } else if (kind == AFB_CHEB1_INV) {
+        // X'_k = conj(w^k) (c'_k - i c'_{n-k}) / 2,  c'_0 = 2 c_0, c'_n = 0
+        const double* c = reinterpret_cast<const double*>(line);
+        if (j == 0) z.x = c[0];
+        else {
+            const cplx w = qtab[j];
+            z = cmul(make_double2(0.5 * c[j], -0.5 * c[n - j]), make_double2(w.x, -w.y));
+        }
+    } else if (kind == AFB_FOURIER_FWD) {
+        z.x = reinterpret_cast<const double*>(line)[j];
+    } else if (kind == AFB_FOURIER_INV) {
+        // F'_0 = c_0 ; F'_k = (a_k - i b_k)/2 (1 <= k < nh) ; F'_{n-k} = conj ; even n: F'_{n/2} = -c_last
+        const double* c = reinterpret_cast<const double*>(line);
+        if (j == 0) z.x = c[0];
+        else if ((n % 2 == 0) && j == n / 2) z.x = -c[n - 1];
+        else if (j < nh) z = make_double2(0.5 * c[2 * j], -0.5 * c[2 * j - 1]);
+        else { const int64_t k = n - j; z = make_double2(0.5 * c[2 * k], 0.5 * c[2 * k - 1]); }
+    } else if (kind == AFB_LAURENT_FWD || kind == AFB_TAYLOR_FWD || kind == AFB_HARDYM_FWD || kind == AFB_TAYLOR_INV) {
+        z = reinterpret_cast<const cplx*>(line)[j];
+    } else if (kind == AFB_HARDYM_INV) {  // F[n-1-k] = c[k]
+        z = reinterpret_cast<const cplx*>(line)[n - 1 - j];
+    } else {  // AFB_LAURENT_INV: F[m] = c[imap(m)]
+        const int64_t i = (j < nh) ? 2 * j : 2 * (n - j) - 1;
+        z = reinterpret_cast<const cplx*>(line)[i];
+    }
+    return z;
+}
+
 __global__ void generic_pre_kernel(int kind, int64_t n, const void* __restrict__ in, int64_t istride,
                                    cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ qtab) {
-    const int64_t total = batch * n;
+    const bool real = generic_real_kind(kind);
+    const int64_t total = (real ? (batch + 1) / 2 : batch) * n;
     const int64_t nh = (n + 1) / 2;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = g / n, j = g % n;
-        cplx z = make_double2(0.0, 0.0);
-        if (kind == AFB_CHEB1_FWD) {
-            const double* v = reinterpret_cast<const double*>(in) + b * istride;
-            z.x = (j < nh) ? v[2 * j] : v[2 * (n - 1 - j) + 1];
-        } else if (kind == AFB_CHEB1_INV) {
-            // X'_k = conj(w^k) (c'_k - i c'_{n-k}) / 2,  c'_0 = 2 c_0, c'_n = 0
-            const double* c = reinterpret_cast<const double*>(in) + b * istride;
-            if (j == 0) z.x = c[0];
-            else {
-                const cplx w = qtab[j];
-                z = cmul(make_double2(0.5 * c[j], -0.5 * c[n - j]), make_double2(w.x, -w.y));
+        const int64_t q = g / n, j = g % n;
+        if (real) {
+            const double* base = reinterpret_cast<const double*>(in);
+            cplx z = generic_pre_value(kind, n, nh, base + (2 * q) * istride, j, qtab);
+            if (2 * q + 1 < batch) {
+                const cplx z2 = generic_pre_value(kind, n, nh, base + (2 * q + 1) * istride, j, qtab);
+                z = make_double2(z.x - z2.y, z.y + z2.x);  // z + i z2
             }
-        } else if (kind == AFB_FOURIER_FWD) {
-            z.x = (reinterpret_cast<const double*>(in) + b * istride)[j];
-        } else if (kind == AFB_FOURIER_INV) {
-            // F'_0 = c_0 ; F'_k = (a_k - i b_k)/2 (1 <= k < nh) ; F'_{n-k} = conj ; even n: F'_{n/2} = -c_last
-            const double* c = reinterpret_cast<const double*>(in) + b * istride;
-            if (j == 0) z.x = c[0];
-            else if ((n % 2 == 0) && j == n / 2) z.x = -c[n - 1];
-            else if (j < nh) z = make_double2(0.5 * c[2 * j], -0.5 * c[2 * j - 1]);
-            else { const int64_t k = n - j; z = make_double2(0.5 * c[2 * k], 0.5 * c[2 * k - 1]); }
-        } else if (kind == AFB_LAURENT_FWD || kind == AFB_TAYLOR_FWD || kind == AFB_HARDYM_FWD || kind == AFB_TAYLOR_INV) {
-            z = (reinterpret_cast<const cplx*>(in) + b * istride)[j];
-        } else if (kind == AFB_HARDYM_INV) {  // F[n-1-k] = c[k]
-            z = (reinterpret_cast<const cplx*>(in) + b * istride)[n - 1 - j];
-        } else {  // AFB_LAURENT_INV: F[m] = c[imap(m)]
-            const cplx* c = reinterpret_cast<const cplx*>(in) + b * istride;
-            const int64_t i = (j < nh) ? 2 * j : 2 * (n - j) - 1;
-            z = c[i];
+            work[g] = z;
+        } else {
+            work[g] = generic_pre_value(kind, n, nh, reinterpret_cast<const cplx*>(in) + q * istride, j, qtab);
         }
-        work[g] = z;
     }
+}
+
+// spectrum of the real input riding in the real (odd = false) or imaginary (odd = true) part of the packed line
+__device__ __forceinline__ cplx pair_spectrum(const cplx* __restrict__ W, int64_t n, int64_t k, bool odd) {
+    const cplx A = W[k], Bc = W[(n - k) % n];
+    return odd ? make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x))   // (A - conj B) / (2i)
+               : make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));   // (A + conj B) / 2
 }
 
 __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict__ work, void* __restrict__ out,
                                     int64_t ostride, int64_t batch, const cplx* __restrict__ qtab) {
     const int64_t total = batch * n;
-    const int64_t nh = (n + 1) / 2;
+    const bool real = generic_real_kind(kind);
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = g / n, o = g % n;
-        const cplx* W = work + b * n;
+        const cplx* W = work + (real ? (b >> 1) : b) * n;
+        const bool odd = b & 1;
         if (kind == AFB_CHEB1_FWD) {
             double* c = reinterpret_cast<double*>(out) + b * ostride;
-            const cplx P = cmul(W[o], qtab[o]);
+            const cplx P = cmul(pair_spectrum(W, n, o, odd), qtab[o]);
             c[o] = (o == 0) ? P.x / (double)n : P.x * (2.0 / (double)n);
         } else if (kind == AFB_CHEB1_INV) {
             double* v = reinterpret_cast<double*>(out) + b * ostride;
-            v[o] = (o & 1) ? W[n - 1 - (o - 1) / 2].x : W[o / 2].x;
+            const cplx z = (o & 1) ? W[n - 1 - (o - 1) / 2] : W[o / 2];
+            v[o] = odd ? z.y : z.x;
         } else if (kind == AFB_FOURIER_FWD) {
             double* c = reinterpret_cast<double*>(out) + b * ostride;
             const double l = (double)n;
-            if (o == 0) c[o] = W[0].x / l;
-            else if ((n % 2 == 0) && o == n - 1) c[o] = -W[n / 2].x / l;
-            else if (o & 1) c[o] = -W[(o + 1) / 2].y * (2.0 / l);
-            else c[o] = W[o / 2].x * (2.0 / l);
+            if (o == 0) c[o] = pair_spectrum(W, n, 0, odd).x / l;
+            else if ((n % 2 == 0) && o == n - 1) c[o] = -pair_spectrum(W, n, n / 2, odd).x / l;
+            else if (o & 1) c[o] = -pair_spectrum(W, n, (o + 1) / 2, odd).y * (2.0 / l);
+            else c[o] = pair_spectrum(W, n, o / 2, odd).x * (2.0 / l);
         } else if (kind == AFB_FOURIER_INV) {
-            (reinterpret_cast<double*>(out) + b * ostride)[o] = W[o].x;
+            (reinterpret_cast<double*>(out) + b * ostride)[o] = odd ? W[o].y : W[o].x;
         } else if (kind == AFB_LAURENT_FWD) {
             const int64_t m = (o & 1) ? n - ((o + 1) >> 1) : (o >> 1);
             (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[m], 1.0 / (double)n);
@@ -402,7 +431,6 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
         } else {
             (reinterpret_cast<cplx*>(out) + b * ostride)[o] = W[o];
         }
-        (void)nh;
     }
 }
 
@@ -477,7 +505,7 @@ int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride,
                            const cplx* qtab, void* stream) {
     if (batch == 0) return AFB_OK;
     auto k = generic_pre_kernel;
-    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, in, istride, work, batch, qtab);
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, in, istride, work, batch, qtab);  // grid-stride: covers the packed count too
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }

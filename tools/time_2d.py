@@ -1,3 +1,4 @@
+"""Times the 2-D Chebyshev transform at 16384^2, forward and inverse (not a benchmark of record)."""
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 import approxfun_b200 as af

@@ -1,3 +1,4 @@
+"""Times the general three-term Clenshaw kernel at N = 10^4 (not a benchmark of record)."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 import approxfun_b200 as af

@@ -1,3 +1,4 @@
+"""Times the arbitrary-length (Bluestein) transforms at a few non-power-of-two lengths (not a benchmark of record)."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 import approxfun_b200 as af

@@ -1,3 +1,4 @@
+"""Times the Padua transform at a few degrees (not a benchmark of record)."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 import approxfun_b200 as af
