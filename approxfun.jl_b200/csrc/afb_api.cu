@@ -423,6 +423,9 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
         case PATH_GENERIC: {
             if (oes != 1) return fail(AFB_UNSUPPORTED, "generic path has no strided output");
             const bool inv = (p->kind & 1) != 0;
+            if (p->kind <= AFB_FOURIER_INV && cfft_real_fused_ok(p->cfft))
+                return launch_blue_real(p->cfft, p->kind, reinterpret_cast<const double*>(d_in), istride,
+                                        reinterpret_cast<double*>(d_out), ostride, batch, p->qtab, stream);
             for (int64_t b0 = 0; b0 < batch; b0 += p->gbatch) {
                 const int64_t nb = std::min(p->gbatch, batch - b0);
                 const char* in = reinterpret_cast<const char*>(d_in) + (size_t)p->elem * (size_t)(b0 * istride);
@@ -452,6 +455,7 @@ static int32_t plan_launch_count(afb_plan_s* p) {
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
         }
         case PATH_GENERIC: {
+            if (p->kind <= AFB_FOURIER_INV && cfft_real_fused_ok(p->cfft)) return 1;
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
         }

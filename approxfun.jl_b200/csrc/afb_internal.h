@@ -52,6 +52,10 @@ void cfft_destroy(CfftPlan* p);
 // out[b*n + k] = scale * sum_j in[b*n + j] exp(-/+ 2 pi i jk/n)   (inverse = +, unnormalised); in == out allowed
 int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale, void* stream);
 int32_t cfft_launches(const CfftPlan* p);
+// arbitrary-length real kinds in one kernel (Bluestein, padded length within one CTA's shared memory)
+bool cfft_real_fused_ok(const CfftPlan* p);
+int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
+                         const cplx* qtab, void* stream);
 // four-step only: real DCT-ordered input (io_mode bit 0) / output (bit 1); see LineParams::io_mode
 int32_t cfft_exec_dctorder(CfftPlan* p, const void* in, void* out, bool conj_in, bool conj_out, double scale, int io_mode,
                            void* stream);

@@ -434,6 +434,142 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
     }
 }
 
+// ---- the four real kinds of arbitrary length in ONE kernel (padded Bluestein length M <= 8192) -------------------
+// pre-processing of two real lines in the load loop, the two shared-memory FFTs of blue_fused_kernel, then the
+// spectrum split and the kind's post-processing straight from shared memory: one read and one write of the data.
+struct BlueRealParams {
+    const double* in;
+    double* out;
+    int64_t n, batch, istride, ostride;  // batch = real lines
+    const cplx *chirp, *bhat, *tw, *qtab;
+    double scale;  // 1/M
+};
+template <int M, int KIND>
+__global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) blue_real_kernel(const __grid_constant__ BlueRealParams p) {
+    typedef FftCfg<M> C;
+    typedef BlueGeom<M> G;
+    constexpr bool INV = (KIND & 1) != 0;
+    AFB_DYN_SMEM(cplx, smem);
+    const int l = threadIdx.x / C::T, t = threadIdx.x % C::T;
+    const int64_t q = (int64_t)blockIdx.x * G::LPC + l;  // pair of lines 2q, 2q+1
+    const bool act = 2 * q < p.batch;
+    const int64_t qc = act ? q : 0;
+    const bool has2 = 2 * qc + 1 < p.batch;
+    const int64_t n = p.n, nh = (n + 1) / 2;
+    cplx* s = smem + (size_t)l * FftLine<M>::STRIDE;
+    const double* l0 = p.in + (2 * qc) * p.istride;
+    const double* l1 = has2 ? l0 + p.istride : l0;
+    cplx x[C::E];
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int64_t j = t + C::T * r;
+        const int64_t jc = j < n ? j : n - 1;
+        const cplx z1 = generic_pre_value(KIND, n, nh, l0, jc, p.qtab);
+        cplx z2 = generic_pre_value(KIND, n, nh, l1, jc, p.qtab);
+        if (!has2) z2 = make_double2(0.0, 0.0);
+        cplx z = make_double2(z1.x - z2.y, z1.y + z2.x);  // z1 + i z2
+        if (INV) z.y = -z.y;
+        z = cmul(z, ldg2(p.chirp + jc));
+        x[r] = (j < n) ? z : make_double2(0.0, 0.0);
+    }
+    fft_line<M>(s, t, x, p.tw);
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int i = t + C::T * r;
+        const cplx z = cmul(line_get<M>(s, i), ldg2(p.bhat + i));
+        x[r] = make_double2(z.x, -z.y);
+    }
+    __syncthreads();
+    int t2 = t;  // see blue_fused_kernel
+    const cplx* tw2 = p.tw;
+    cplx* s2 = s;
+#ifndef AFB_HOST_EMU
+    asm volatile("" : "+r"(t2), "+l"(tw2), "+l"(s2));
+#endif
+    fft_line<M>(s2, t2, x, tw2);
+    if (!act) return;
+    // W(k): element k of the length-n (inverse) DFT of the packed line
+    auto W = [&](int64_t k) -> cplx {
+        const cplx y = line_get<M>(s2, (int)k);
+        cplx z = cscale(cmul(make_double2(y.x, -y.y), ldg2(p.chirp + k)), p.scale);
+        if (INV) z.y = -z.y;
+        return z;
+    };
+    double* o0 = p.out + (2 * q) * p.ostride;
+    double* o1 = o0 + p.ostride;
+    const double dn = (double)n;
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int64_t o = t2 + C::T * r;
+        if (o >= n) continue;
+        double ve, vo;
+        if (KIND == AFB_CHEB1_INV) {
+            const cplx z = W((o & 1) ? n - 1 - (o - 1) / 2 : o / 2);
+            ve = z.x; vo = z.y;
+        } else if (KIND == AFB_FOURIER_INV) {
+            const cplx z = W(o);
+            ve = z.x; vo = z.y;
+        } else {
+            const bool nyq = (KIND == AFB_FOURIER_FWD) && (n % 2 == 0) && o == n - 1;
+            const int64_t k = (KIND == AFB_CHEB1_FWD) ? o : (o == 0 ? 0 : nyq ? n / 2 : (o & 1) ? (o + 1) / 2 : o / 2);
+            const cplx A = W(k), Bc = W((n - k) % n);
+            const cplx Ye = make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));    // (A + conj B) / 2
+            const cplx Yo = make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x));   // (A - conj B) / (2i)
+            if (KIND == AFB_CHEB1_FWD) {
+                const cplx w = ldg2(p.qtab + o);
+                const double sc = (o == 0) ? 1.0 / dn : 2.0 / dn;
+                ve = cmul(Ye, w).x * sc; vo = cmul(Yo, w).x * sc;
+            } else if (o == 0) { ve = Ye.x / dn; vo = Yo.x / dn; }
+            else if (nyq) { ve = -Ye.x / dn; vo = -Yo.x / dn; }
+            else if (o & 1) { ve = -Ye.y * (2.0 / dn); vo = -Yo.y * (2.0 / dn); }
+            else { ve = Ye.x * (2.0 / dn); vo = Yo.x * (2.0 / dn); }
+        }
+        o0[o] = ve;
+        if (has2) o1[o] = vo;
+    }
+}
+template <int M, int KIND> static int32_t launch_blue_real_mk(const BlueRealParams& p, void* stream) {
+    typedef BlueGeom<M> G;
+    auto k = blue_real_kernel<M, KIND>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    const int64_t npairs = (p.batch + 1) / 2;
+    AFB_LAUNCH(k, (unsigned)((npairs + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+template <int KIND> static int32_t launch_blue_real_k(int64_t M, const BlueRealParams& p, void* stream) {
+    switch (M) {
+        case 32: return launch_blue_real_mk<32, KIND>(p, stream);
+        case 64: return launch_blue_real_mk<64, KIND>(p, stream);
+        case 128: return launch_blue_real_mk<128, KIND>(p, stream);
+        case 256: return launch_blue_real_mk<256, KIND>(p, stream);
+        case 512: return launch_blue_real_mk<512, KIND>(p, stream);
+        case 1024: return launch_blue_real_mk<1024, KIND>(p, stream);
+        case 2048: return launch_blue_real_mk<2048, KIND>(p, stream);
+        case 4096: return launch_blue_real_mk<4096, KIND>(p, stream);
+        case 8192: return launch_blue_real_mk<8192, KIND>(p, stream);
+        default: return fail(AFB_UNSUPPORTED, "fused Bluestein: padded length not instantiated");
+    }
+}
+// true when plan p is a Bluestein plan whose padded length fits one CTA: the real kinds then run in a single kernel
+bool cfft_real_fused_ok(const CfftPlan* p) { return p && p->mode == 2 && p->M <= LINE_MAX_N; }
+int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
+                         const cplx* qtab, void* stream) {
+    if (batch == 0) return AFB_OK;
+    BlueRealParams bp{in, out, p->n, batch, istride, ostride, p->chirp, p->bhat, p->sub->tw, qtab, 1.0 / (double)p->M};
+    switch (kind) {
+        case AFB_CHEB1_FWD: return launch_blue_real_k<AFB_CHEB1_FWD>(p->M, bp, stream);
+        case AFB_CHEB1_INV: return launch_blue_real_k<AFB_CHEB1_INV>(p->M, bp, stream);
+        case AFB_FOURIER_FWD: return launch_blue_real_k<AFB_FOURIER_FWD>(p->M, bp, stream);
+        case AFB_FOURIER_INV: return launch_blue_real_k<AFB_FOURIER_INV>(p->M, bp, stream);
+        default: return fail(AFB_BAD_ARG, "fused real Bluestein: not a real kind");
+    }
+}
+
 // =====================================================================================================
 // Extension kinds: transforms defined through the FFT of an even / odd extension (complex length cn):
 //   AFB_CHEB2_FWD/INV  second-kind points, FFTW REDFT00 (UPSTREAM FastTransforms plan_(i)chebyshevtransform(x, Val(2)));
