@@ -419,3 +419,40 @@ def test_config2_full_size_properties(af):
     assert float((back - v).abs().max()) <= 1e-13 * vmax * 12
     wantf = orc.fourier_transform(v[idx].cpu().numpy().T, axis=0).T
     assert np.max(np.abs(c[idx].cpu().numpy() - wantf)) <= 1e-13 * vmax * 12
+
+
+def test_config4_full_size_properties(af):
+    # BASELINE.json configs[3] at full size (16384 x 16384, device resident): a rank-one grid V = a b^T must give
+    # C = T(a) T(b)^T (checked on sampled rows / columns against the 1-D oracle), a random grid must survive the round
+    # trip, and the row-pair route must agree with the explicit-transpose route.
+    import torch
+    n = 16384
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    ca, cb = orc.cheb_transform(a), orc.cheb_transform(b)
+    # column-major n x n2 matrix V[k, j] = a_k b_j  <->  torch (n2, n) row-major with entry [j, k]
+    V = torch.outer(torch.tensor(b, device="cuda"), torch.tensor(a, device="cuda")).contiguous()
+    C = torch.empty_like(V)
+    fwd = af.api.DevicePlan(af._lib.CHEB1_2D_FWD, n, n, 1, n)
+    fwd.execute(V.data_ptr(), C.data_ptr(), st)
+    torch.cuda.synchronize()
+    scale = float(np.max(np.abs(ca)) * np.max(np.abs(cb)))
+    for j in (0, 1, 77, 8191, 8192, 16383):          # coefficient columns C[:, j] = ca * cb[j]
+        assert np.max(np.abs(C[j].cpu().numpy() - ca * cb[j])) <= 1e-13 * 14 * scale
+    for k in (0, 3, 4096, 16382):                     # coefficient rows C[k, :] = ca[k] * cb
+        assert np.max(np.abs(C[:, k].cpu().numpy() - ca[k] * cb)) <= 1e-13 * 14 * scale
+    alt = af.api.DevicePlan(af._lib.CHEB1_2D_FWD, n, n, 1, n, af._lib.PLAN_2D_TRANSPOSE)
+    C2 = torch.empty_like(V)
+    alt.execute(V.data_ptr(), C2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert float((C - C2).abs().max()) <= 1e-13 * 14 * scale
+    del C2, alt
+    g = torch.Generator(device="cuda").manual_seed(1)
+    V.normal_(generator=g)
+    vmax = float(V.abs().max())
+    inv = af.api.DevicePlan(af._lib.CHEB1_2D_INV, n, n, 1, n)
+    fwd.execute(V.data_ptr(), C.data_ptr(), st)
+    inv.execute(C.data_ptr(), C.data_ptr(), st)     # in place
+    torch.cuda.synchronize()
+    assert float((C - V).abs().max()) <= 1e-13 * 28 * vmax
