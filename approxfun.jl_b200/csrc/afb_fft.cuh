@@ -25,18 +25,19 @@
 namespace afb {
 
 // ---- per-length configuration (DIT order) ---------------------------------------------------------
+template <int N_, int R1_, int R2_, int R3_, int R4_> struct FftRadices {
+    static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;
+    static constexpr int L = (R4_ > 1) ? 4 : (R3_ > 1) ? 3 : 2;
+    static constexpr int T = N_ / R1_;
+    static constexpr int E = R1_;
+    static constexpr int SH = (R1_ == 16) ? 4 : 3;
+    static constexpr int RL = (L == 4) ? R4_ : (L == 3) ? R3_ : R2_;  // last radix
+    static constexpr int NSL = N_ / RL;                               // butterflies in the last pass
+    static constexpr int BL = E / RL;                                 // ... per thread
+};
+// Real kinds: the last radix is <= E/2, so every thread runs >= 2 butterflies of the last pass (partner pairs).
 template <int N> struct FftCfg;
-#define AFB_FFTCFG(N_, R1_, R2_, R3_, R4_)                                                       \
-    template <> struct FftCfg<N_> {                                                                \
-        static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, R4 = R4_;                               \
-        static constexpr int L = (R4_ > 1) ? 4 : (R3_ > 1) ? 3 : 2;                                \
-        static constexpr int T = N_ / R1_;                                                         \
-        static constexpr int E = R1_;                                                              \
-        static constexpr int SH = (R1_ == 16) ? 4 : 3;                                             \
-        static constexpr int RL = (L == 4) ? R4_ : (L == 3) ? R3_ : R2_; /* last radix */          \
-        static constexpr int NSL = N_ / RL;                               /* butterflies in last pass */ \
-        static constexpr int BL = E / RL;                                 /* ... per thread (even) */ \
-    }
+#define AFB_FFTCFG(N_, R1_, R2_, R3_, R4_) template <> struct FftCfg<N_> : FftRadices<N_, R1_, R2_, R3_, R4_> {}
 AFB_FFTCFG(32, 8, 4, 1, 1);
 AFB_FFTCFG(64, 16, 4, 1, 1);
 AFB_FFTCFG(128, 16, 8, 1, 1);
@@ -47,6 +48,10 @@ AFB_FFTCFG(2048, 16, 16, 8, 1);
 AFB_FFTCFG(4096, 16, 16, 8, 2);
 AFB_FFTCFG(8192, 16, 16, 16, 2);
 #undef AFB_FFTCFG
+// Complex kinds (whole transform through shared memory, no pairing): fewest passes.  Same R1, so same T and E.
+template <int N> struct FftCfgC : FftCfg<N> {};
+template <> struct FftCfgC<256> : FftRadices<256, 16, 16, 1, 1> {};
+// (4096 as 16.16.16 was measured slower than 16.16.8.2 for Laurent: 0.877 vs 0.847 ms at 32768 x 4096)
 
 // slots per line in shared memory (pad for short lines packed many per CTA)
 template <int N> struct FftLine {
@@ -176,9 +181,8 @@ __device__ __forceinline__ void bfly_dif(int j, cplx* x, const cplx* __restrict_
 }
 
 // ---- full passes with the default butterfly assignment j = t + b T ----------------------------------
-template <int N, int R, int NS>
+template <int N, int R, int NS, class C = FftCfg<N>>
 __device__ __forceinline__ void pass_dit(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
-    typedef FftCfg<N> C;
     constexpr int B = C::E / R;
 #pragma unroll
     for (int b = 0; b < B; ++b) ld_strided<N, R, C::SH>(s, t + b * C::T, x + b * R);
@@ -207,19 +211,17 @@ __device__ __forceinline__ void pass_dif(cplx* __restrict__ s, int t, cplx* x, c
 
 // ---- DIT driver pieces --------------------------------------------------------------------------------
 // first pass: x[r] = input[col + T r] in registers  ->  shared memory (column `col` is free to choose)
-template <int N>
+template <int N, class C = FftCfg<N>>
 __device__ __forceinline__ void dit_first(cplx* __restrict__ s, int col, cplx* x) {
-    typedef FftCfg<N> C;
     Dft<C::R1>::run(x);
     st_autosort<N, C::R1, 1, C::SH>(s, col, x);
     __syncthreads();
 }
 // passes 2 .. L-1
-template <int N>
+template <int N, class C = FftCfg<N>>
 __device__ __forceinline__ void dit_middle(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
-    typedef FftCfg<N> C;
-    if constexpr (C::L >= 3) pass_dit<N, C::R2, C::R1>(s, t, x, tw);
-    if constexpr (C::L >= 4) pass_dit<N, C::R3, C::R1 * C::R2>(s, t, x, tw);
+    if constexpr (C::L >= 3) pass_dit<N, C::R2, C::R1, C>(s, t, x, tw);
+    if constexpr (C::L >= 4) pass_dit<N, C::R3, C::R1 * C::R2, C>(s, t, x, tw);
 }
 // last pass on butterfly j: outputs x[q] = Z[j + NSL q] stay in registers
 template <int N>
@@ -228,13 +230,13 @@ __device__ __forceinline__ void dit_last_bfly(const cplx* __restrict__ s, int j,
     ld_strided<N, C::RL, C::SH>(s, j, x);
     bfly_dit<N, C::RL, C::NSL>(j, x, tw);
 }
-// whole transform, result left in shared memory in natural order (generic users: Laurent, plain FFT)
+// whole transform, result left in shared memory in natural order (complex kinds: Laurent, plain FFT, Bluestein, rows)
 template <int N>
 __device__ __forceinline__ void fft_line(cplx* __restrict__ s, int t, cplx* x, const cplx* __restrict__ tw) {
-    typedef FftCfg<N> C;
-    dit_first<N>(s, t, x);
-    dit_middle<N>(s, t, x, tw);
-    pass_dit<N, C::RL, C::NSL>(s, t, x, tw);
+    typedef FftCfgC<N> C;
+    dit_first<N, C>(s, t, x);
+    dit_middle<N, C>(s, t, x, tw);
+    pass_dit<N, C::RL, C::NSL, C>(s, t, x, tw);
 }
 
 // ---- DIF driver pieces (transpose of the above) -----------------------------------------------------------
