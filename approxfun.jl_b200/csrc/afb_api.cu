@@ -410,6 +410,9 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
             return AFB_OK;
         case PATH_EXT: {
             if (oes != 1) return fail(AFB_UNSUPPORTED, "extension path has no strided output");
+            if (cfft_ext_fused_ok(p->cfft))
+                return launch_ext_fused(p->cfft, p->kind, p->n, reinterpret_cast<const double*>(d_in), istride,
+                                        reinterpret_cast<double*>(d_out), ostride, batch, stream);
             for (int64_t b0 = 0; b0 < batch; b0 += p->gbatch) {
                 const int64_t nb = std::min(p->gbatch, batch - b0);
                 const double* in = reinterpret_cast<const double*>(d_in) + b0 * istride;
@@ -451,6 +454,7 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         case PATH_IDENTITY: return 0;
         case PATH_PADUA: return 4 + plan_launch_count(p->col_plan) + plan_launch_count(p->row_plan);  // memset, scatter, transpose, gather
         case PATH_EXT: {
+            if (cfft_ext_fused_ok(p->cfft)) return 1;
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
             return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
         }

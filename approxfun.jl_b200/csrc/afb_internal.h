@@ -63,6 +63,11 @@ int32_t cfft_exec_dctorder(CfftPlan* p, const void* in, void* out, bool conj_in,
 int32_t launch_large_post(int kind, int64_t n, const cplx* Z, double* out, void* stream);
 int32_t launch_large_pre(int kind, int64_t n, const double* in, cplx* Zc, void* stream);
 
+// extension kinds in one kernel (FFT length a power of two <= 8192, or Bluestein padded length <= 8192)
+bool cfft_ext_fused_ok(const CfftPlan* p);
+int32_t launch_ext_fused(CfftPlan* p, int kind, int64_t n, const double* in, int64_t istride, double* out, int64_t ostride,
+                         int64_t batch, void* stream);
+
 // pre/post kernels mapping the real transforms onto a length-n complex FFT (afb_large.cu)
 int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
                            const cplx* qtab, void* stream);

@@ -620,6 +620,132 @@ __global__ void ext_post_kernel(int kind, int64_t n, int64_t cn, const cplx* __r
         out[b * ostride + k] = r;
     }
 }
+// ---- extension kinds in ONE kernel when the FFT (cn a power of two <= 8192, or Bluestein with M <= 8192) fits a CTA:
+// the extension of two real lines is formed in the load loop, the transform(s) run in shared memory and the wanted
+// real / imaginary parts are scaled and stored straight from there.
+struct ExtParams {
+    const double* in;
+    double* out;
+    int64_t n, cn, batch, istride, ostride;  // batch = real lines
+    const cplx *chirp, *bhat, *tw;
+    double scale;  // 1/M (Bluestein)
+};
+template <int M, int KIND, bool BLUE>
+__global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) ext_fused_kernel(const __grid_constant__ ExtParams p) {
+    typedef FftCfg<M> C;
+    typedef BlueGeom<M> G;
+    AFB_DYN_SMEM(cplx, smem);
+    const int l = threadIdx.x / C::T, t = threadIdx.x % C::T;
+    const int64_t q = (int64_t)blockIdx.x * G::LPC + l;
+    const bool act = 2 * q < p.batch;
+    const int64_t qc = act ? q : 0;
+    const bool has2 = 2 * qc + 1 < p.batch;
+    const int64_t n = p.n, cn = p.cn;
+    cplx* s = smem + (size_t)l * FftLine<M>::STRIDE;
+    const double* l0 = p.in + (2 * qc) * p.istride;
+    const double* l1 = has2 ? l0 + p.istride : l0;
+    cplx x[C::E];
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int64_t j = t + C::T * r;
+        const int64_t jc = j < cn ? j : cn - 1;
+        cplx z = make_double2(ext_value(KIND, n, cn, l0, jc), ext_value(KIND, n, cn, l1, jc));
+        if (!has2) z.y = 0.0;
+        if (BLUE) z = cmul(z, ldg2(p.chirp + jc));
+        x[r] = (j < cn) ? z : make_double2(0.0, 0.0);
+    }
+    fft_line<M>(s, t, x, p.tw);
+    int t2 = t;
+    cplx* s2 = s;
+    if (BLUE) {
+#pragma unroll
+        for (int r = 0; r < C::E; ++r) {
+            const int i = t + C::T * r;
+            const cplx z = cmul(line_get<M>(s, i), ldg2(p.bhat + i));
+            x[r] = make_double2(z.x, -z.y);
+        }
+        __syncthreads();
+        const cplx* tw2 = p.tw;  // see blue_fused_kernel
+#ifndef AFB_HOST_EMU
+        asm volatile("" : "+r"(t2), "+l"(tw2), "+l"(s2));
+#endif
+        fft_line<M>(s2, t2, x, tw2);
+    }
+    if (!act) return;
+    auto W = [&](int64_t k) -> cplx {
+        const cplx y = line_get<M>(s2, (int)k);
+        if (!BLUE) return y;
+        return cscale(cmul(make_double2(y.x, -y.y), ldg2(p.chirp + k)), p.scale);
+    };
+    double* o0 = p.out + (2 * q) * p.ostride;
+    double* o1 = o0 + p.ostride;
+#pragma unroll
+    for (int r = 0; r < C::E; ++r) {
+        const int64_t k = t2 + C::T * r;
+        if (k >= n) continue;
+        double ve, vo;
+        if (KIND == AFB_CHEB2_FWD || KIND == AFB_CHEB2_INV) {
+            const cplx w = W(k);
+            double sc = (KIND == AFB_CHEB2_FWD) ? 1.0 / (double)(n - 1) : 0.5;
+            if (KIND == AFB_CHEB2_FWD && (k == 0 || k == n - 1)) sc *= 0.5;
+            ve = w.x * sc; vo = w.y * sc;
+        } else {
+            const cplx w = W(k + 1);
+            const double sc = (KIND == AFB_SIN_FWD) ? 1.0 / (double)(n + 1) : 0.5;
+            ve = w.y * sc; vo = -w.x * sc;
+        }
+        o0[k] = ve;
+        if (has2) o1[k] = vo;
+    }
+}
+template <int M, int KIND, bool BLUE> static int32_t launch_ext_fused_mk(const ExtParams& p, void* stream) {
+    typedef BlueGeom<M> G;
+    auto k = ext_fused_kernel<M, KIND, BLUE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_done = true;
+    }
+    const int64_t npairs = (p.batch + 1) / 2;
+    AFB_LAUNCH(k, (unsigned)((npairs + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+template <int KIND, bool BLUE> static int32_t launch_ext_fused_k(int64_t M, const ExtParams& p, void* stream) {
+    switch (M) {
+        case 32: return launch_ext_fused_mk<32, KIND, BLUE>(p, stream);
+        case 64: return launch_ext_fused_mk<64, KIND, BLUE>(p, stream);
+        case 128: return launch_ext_fused_mk<128, KIND, BLUE>(p, stream);
+        case 256: return launch_ext_fused_mk<256, KIND, BLUE>(p, stream);
+        case 512: return launch_ext_fused_mk<512, KIND, BLUE>(p, stream);
+        case 1024: return launch_ext_fused_mk<1024, KIND, BLUE>(p, stream);
+        case 2048: return launch_ext_fused_mk<2048, KIND, BLUE>(p, stream);
+        case 4096: return launch_ext_fused_mk<4096, KIND, BLUE>(p, stream);
+        case 8192: return launch_ext_fused_mk<8192, KIND, BLUE>(p, stream);
+        default: return fail(AFB_UNSUPPORTED, "fused extension transform: length not instantiated");
+    }
+}
+bool cfft_ext_fused_ok(const CfftPlan* p) {
+    return p && ((p->mode == 0) || (p->mode == 2 && p->M <= LINE_MAX_N));
+}
+int32_t launch_ext_fused(CfftPlan* p, int kind, int64_t n, const double* in, int64_t istride, double* out, int64_t ostride,
+                         int64_t batch, void* stream) {
+    if (batch == 0) return AFB_OK;
+    const bool blue = p->mode == 2;
+    const int64_t M = blue ? p->M : p->n;
+    ExtParams ep{in, out, n, p->n, batch, istride, ostride, p->chirp, p->bhat, blue ? p->sub->tw : p->tw, 1.0 / (double)M};
+#define AFB_EXT_CASE(K_) \
+    case K_: return blue ? launch_ext_fused_k<K_, true>(M, ep, stream) : launch_ext_fused_k<K_, false>(M, ep, stream)
+    switch (kind) {
+        AFB_EXT_CASE(AFB_CHEB2_FWD);
+        AFB_EXT_CASE(AFB_CHEB2_INV);
+        AFB_EXT_CASE(AFB_SIN_FWD);
+        AFB_EXT_CASE(AFB_SIN_INV);
+        default: return fail(AFB_BAD_ARG, "fused extension transform: not an extension kind");
+    }
+#undef AFB_EXT_CASE
+}
+
 int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_t istride, cplx* work, int64_t batch,
                        void* stream) {
     if (batch == 0) return AFB_OK;
