@@ -311,6 +311,12 @@ v = rng.standard_normal((100, 2))
 assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
 V = rng.standard_normal((64, 128))
 assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V) - orc.cheb2_transform(V))) < 1e-13
+for shape in ((100, 3), (1025, 2)):   # extension kinds in one kernel: Bluestein and power-of-two extension lengths
+    v = rng.standard_normal(shape)
+    assert np.max(np.abs(ll.transform(B.CHEB2_FWD, v) - orc.chebkind2_transform(v, axis=0))) < 1e-13
+    assert np.max(np.abs(ll.transform(B.SIN_FWD, v)[:, 0] - orc.sin_transform_generic(v[:, 0]))) < 1e-13
+z = rng.standard_normal((100, 2)) + 1j * rng.standard_normal((100, 2))
+assert np.max(np.abs(ll.transform(B.LAURENT_FWD, z) - orc.laurent_transform(z, axis=0))) < 1e-13
 V = rng.standard_normal((6, 2048))
 assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_FWD, V) - orc.cheb2_transform(V))) < 1e-13
 assert np.max(np.abs(ll.transform2d(B.CHEB1_2D_INV, V) - orc.cheb2_itransform(V))) < 1e-11
