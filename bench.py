@@ -432,7 +432,7 @@ def main():
                                               "roundtrip_max_abs_err": rt,
                                               "note": "latency/L2 bound: 16 rotating buffers, fwd+inv per buffer"}
         del bufs, outs
-        # config 4: 2-D Chebyshev x Chebyshev 16384 x 16384 on one GPU (columns, transpose, columns, transpose)
+        # config 4: 2-D Chebyshev x Chebyshev 16384 x 16384 on one GPU (contiguous columns, then the row-pair four-step)
         n2d = 16384
         V = torch.randn(n2d, n2d, dtype=torch.float64, device="cuda", generator=g)
         p2 = af.api.DevicePlan(L.CHEB1_2D_FWD, n2d, n2d, 1, n2d)
@@ -441,6 +441,22 @@ def main():
                                   "hbm_frac_of_32B_per_element": 32.0 * n2d * n2d / (t * 1e-3) / 1e9 / peak,
                                   "launches": p2.launches}
         del V
+        # "next" rows, one number each: arbitrary-length transforms (Bluestein in one kernel) and the Padua transform
+        ng, bg = 1000, 65536
+        vg = torch.randn(bg, ng, dtype=torch.float64, device="cuda", generator=g)
+        pg = af.api.DevicePlan(L.CHEB1_FWD, ng, 0, bg, ng)
+        t = time_loop(lambda: pg.execute(vg.data_ptr(), vg.data_ptr(), stream), 5, 3)
+        extras["cheb_n1000_batched"] = {"ms_per_step": t, "coefficients_per_s": float(ng) * bg / (t * 1e-3),
+                                        "hbm_frac": 16.0 * ng * bg / (t * 1e-3) / 1e9 / peak, "launches": pg.launches}
+        del vg
+        dpad = 2047
+        npad = (dpad + 1) * (dpad + 2) // 2
+        vp = torch.randn(npad, dtype=torch.float64, device="cuda", generator=g)
+        pp = af.api.DevicePlan(L.PADUA_FWD, npad, 0, 1, npad)
+        t = time_loop(lambda: pp.execute(vp.data_ptr(), vp.data_ptr(), stream), 5, 3)
+        extras["padua_degree2047"] = {"ms_per_step": t, "coefficients_per_s": float(npad) / (t * 1e-3),
+                                      "launches": pp.launches}
+        del vp
         if world > 1:
             # config 4 across GPUs (strong scaling: ONE 16384 x 16384 matrix, column slabs -> all-to-all -> row slabs)
             from approxfun_b200 import parallel as par
