@@ -190,6 +190,29 @@ def points(space: Space, n: int, m: int | None = None):
 # ------------------------------------------------------------------------------------------------------
 # plans:  plan = plan_transform(S, v_or_n);  coefficients = plan * v
 # ------------------------------------------------------------------------------------------------------
+class DualArray:
+    """Vector of dual numbers value + epsilon*eps (DualNumbers.jl).  Mirrors ext/ApproxFunDualNumbersExt.jl:44-63: a plan
+    for a Dual vector is the plan of its real part, and `P * v = dual.(P*realpart.(v), P*dualpart.(v))`."""
+
+    def __init__(self, value, epsilon):
+        self.value = np.asarray(value, dtype=np.float64)
+        self.epsilon = np.asarray(epsilon, dtype=np.float64)
+        if self.value.shape != self.epsilon.shape:
+            raise L.DimensionMismatch(L.AFB_BAD_SIZE, "DualArray: value and epsilon shapes differ")
+
+    @property
+    def shape(self):
+        return self.value.shape
+
+
+def realpart(d: DualArray):
+    return d.value
+
+
+def dualpart(d: DualArray):
+    return d.epsilon
+
+
 class TransformPlan:
     """`TransformPlan` / `ITransformPlan`: owns a C-ABI plan handle; `plan * v` executes it."""
 
@@ -226,6 +249,8 @@ class TransformPlan:
             self._h = None
 
     def __mul__(self, v):
+        if isinstance(v, DualArray):
+            return DualArray(self * v.value, self * v.epsilon)
         v = np.asarray(v)
         if v.shape != self.shape:
             raise L.DimensionMismatch(L.AFB_BAD_SIZE, f"plan built for shape {self.shape}, got {v.shape}")
@@ -254,6 +279,8 @@ def _shape_of(v_or_n):
         return (int(v_or_n),)
     if isinstance(v_or_n, tuple):
         return v_or_n
+    if isinstance(v_or_n, DualArray):
+        return v_or_n.shape
     return np.asarray(v_or_n).shape
 
 

@@ -302,6 +302,18 @@ def test_sibling_spaces_second_kind_sin_cos(af, n):
     assert np.allclose(np.cos(th), af.points(af.Chebyshev(), n), atol=4e-16)
 
 
+def test_dual_number_plans(af):
+    # ext/ApproxFunDualNumbersExt.jl:44-63: the plan of a Dual vector is the plan of its real part and acts on both parts
+    n = 200
+    d = af.DualArray(RNG.standard_normal(n), RNG.standard_normal(n))
+    for S, fwd in ((af.Chebyshev(), orc.cheb_transform), (af.Fourier(), orc.fourier_transform)):
+        P = af.plan_transform(S, d)
+        c = P * d
+        assert np.max(np.abs(af.realpart(c) - fwd(d.value))) < 1e-14 and np.max(np.abs(af.dualpart(c) - fwd(d.epsilon))) < 1e-14
+        back = af.plan_itransform(S, c) * c
+        assert np.max(np.abs(back.value - d.value)) < 1e-13 and np.max(np.abs(back.epsilon - d.epsilon)) < 1e-13
+
+
 @pytest.mark.parametrize("n", [1, 5, 64, 100, 4096])
 def test_taylor_hardy(af, n):
     # docs/src/usage/spaces.md:100-110
