@@ -16,6 +16,7 @@
 #endif
 
 #include <cstddef>
+#include <cstring>
 #include <cstdint>
 #include <string>
 
@@ -99,6 +100,56 @@ __device__ __forceinline__ void prefetch_l2(const void* gmem) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 #else
     (void)gmem;
+#endif
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+: SASS UBLKCP / SYNCS) ------------------
+// One thread issues; every thread of the CTA waits on the barrier's phase bit.  bytes, dst and src multiples of 16.
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {
+#ifdef AFB_HOST_EMU
+    *bar = 0;
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+#ifdef AFB_HOST_EMU
+    std::memcpy(smem_dst, gmem_src, bytes);
+    (void)bar;
+#else
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    // the buffer was last read through the generic proxy: order those reads before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+#ifndef AFB_HOST_EMU
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+#else
+    (void)gmem_src; (void)bytes;
+#endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+#ifndef AFB_HOST_EMU
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "AFB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra AFB_MBAR_DONE;\n"
+        "bra AFB_MBAR_WAIT;\n"
+        "AFB_MBAR_DONE:\n"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+#else
+    (void)bar; (void)phase;
 #endif
 }
 

@@ -443,6 +443,19 @@ template <int N> struct FourierInvPre {
         Z0 = make_double2(r.a - r.b, -(r.a + r.b));  // F_0/N = 2 c0, F_N/N = -2 c_last
     }
 };
+// same with the first STAGED doubles of the line read from the shared-memory stage
+template <int N, int STAGED> struct FourierInvPreStaged : FourierInvPre<N> {
+    typedef typename FourierInvPre<N>::Raw Raw;
+    const double* st;
+    __device__ __forceinline__ FourierInvPreStaged(const double* c_, const double* st_) : FourierInvPre<N>{c_, true}, st(st_) {}
+    __device__ __forceinline__ double ld(int i) const { return i < STAGED ? st[i] : this->c[i]; }
+    __device__ __forceinline__ void fetch(int k, Raw& r) {
+        r.a = st[2 * k]; r.b = st[2 * k - 1]; r.aN = ld(2 * (N - k)); r.bN = ld(2 * (N - k) - 1);  // k < N/2: 2k is staged
+    }
+    __device__ __forceinline__ void fetch_dc(Raw& r) {
+        r.a = st[0]; r.b = this->c[2 * N - 1]; r.aN = 0; r.bN = 0;
+    }
+};
 template <int N> struct LineOp<N, LK_FOURIER_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
@@ -585,54 +598,82 @@ __global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (
 // -------------------------------------------------------------------------------------------------
 // Long lines (N = 8192: one 512-thread CTA fills an SM's register file, so no second CTA can hide the load
 // phase).  Persistent CTAs instead: while line i is transformed, the first 3/4 of the CTA's next line arrives
-// in the spare 96 KB of shared memory through asynchronous copies and the last quarter is pulled into L2.
+// in the spare 96 KB of shared memory through a TMA bulk copy (cp.async.bulk + mbarrier) and the last quarter is pulled into L2.
 // -------------------------------------------------------------------------------------------------
 template <int N> struct StageGeom {
     typedef FftCfg<N> C;
     static constexpr int HS = 6;                          // staged load groups (of R1/2 = 8)
     static constexpr int DOUBLES = 4 * C::T * HS + 16;    // 3n/4, + the slot n*3/4 itself (k = N/2 of the inverse)
-    static constexpr size_t SMEM = sizeof(cplx) * (size_t)N + sizeof(double) * DOUBLES;
+    static constexpr size_t SMEM = sizeof(cplx) * (size_t)N + sizeof(double) * DOUBLES + 16;  // + the mbarrier
 };
+// One thread hands the 96 KB to the TMA engine (cp.async.bulk, completion counted on an mbarrier) and asks for the rest
+// of the line in L2; no LSU instructions are spent on the copy.
 template <int N>
-__device__ __forceinline__ void stage_issue(double* __restrict__ st, const double* __restrict__ src, int t) {
+__device__ __forceinline__ void stage_issue(double* __restrict__ st, const double* __restrict__ src, int t, uint64_t* bar) {
     typedef StageGeom<N> SG;
-    for (int i = t; i < SG::DOUBLES / 2; i += FftCfg<N>::T) async_copy16(st + 2 * i, src + 2 * i);
-    async_copy_commit();
-    const char* rest = reinterpret_cast<const char*>(src + SG::DOUBLES);
-    for (int b = t * 128; b < (2 * N - SG::DOUBLES) * 8; b += FftCfg<N>::T * 128) prefetch_l2(rest + b);
+    if (t == 0) {
+        bulk_copy_g2s(st, src, (uint32_t)(sizeof(double) * SG::DOUBLES), bar);
+        bulk_prefetch_l2(src + SG::DOUBLES, (uint32_t)(sizeof(double) * (2 * N - SG::DOUBLES)));
+    }
 }
 template <int N, int KIND>
 __global__ void __launch_bounds__(FftCfg<N>::T, 1) line_kernel_staged(const __grid_constant__ LineParams p) {
     typedef FftCfg<N> C;
     typedef StageGeom<N> SG;
-    static_assert(KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV, "staged lines: Chebyshev kinds");
+    static_assert(KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV,
+                  "staged lines: the real kinds");
+    static_assert((sizeof(double) * SG::DOUBLES) % 16 == 0 && (sizeof(double) * (2 * N - SG::DOUBLES)) % 16 == 0, "bulk sizes");
     AFB_DYN_SMEM(cplx, s);
     double* st = reinterpret_cast<double*>(s + N);
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(st + SG::DOUBLES);
     const int t = threadIdx.x;
     const double* in = reinterpret_cast<const double*>(p.in);
     double* out = reinterpret_cast<double*>(p.out);
+    if (t == 0) mbar_init(&bar);
+    __syncthreads();
+    uint32_t phase = 0;
     int64_t line = blockIdx.x;
-    if (line < p.batch) stage_issue<N>(st, in + line * p.istride, t);
+    if (line < p.batch) stage_issue<N>(st, in + line * p.istride, t, &bar);
     for (; line < p.batch; line += gridDim.x) {
         const int64_t next = line + gridDim.x;
-        async_copy_wait();
-        __syncthreads();  // the stage is complete; every thread is done with the previous line's buffer
+        mbar_wait(&bar, phase);  // the stage is complete (and visible: complete_tx)
+        phase ^= 1;
+        __syncthreads();         // every thread is done with the previous line's exchange buffer
         cplx x[C::E];
         if constexpr (KIND == LK_CHEB_FWD) {
             cheb_exchange_load<N, SG::HS>(reinterpret_cast<const double2*>(in + line * p.istride), true, t, x,
                                           reinterpret_cast<const double2*>(st));
             dit_first<N>(s, PairMap<N>::col(t), x);   // ends with a barrier: the stage is free again
-            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t);
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t, &bar);
             dit_middle<N>(s, t, x, p.tw);
             ChebFwdPost<N> f{out + line * p.ostride, p.oes, p.scale, true};
             dit_last_paired<N, 2>(p, s, t, f);
-        } else {
+        } else if constexpr (KIND == LK_CHEB_INV) {
             ChebInvPreStaged<N> f(in + line * p.istride, st);
             dif_first_paired<N, 2>(p, s, t, f);       // ends with a barrier
-            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t);
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t, &bar);
             dif_middle<N>(s, t, x, p.tw);
             dif_last<N>(s, PairMap<N>::col(t), x);
             cheb_exchange_store<N>(out + line * p.ostride, p.oes, true, t, x);
+        } else if constexpr (KIND == LK_FOURIER_FWD) {
+            const double2* v2 = reinterpret_cast<const double2*>(in + line * p.istride);
+            const double2* st2 = reinterpret_cast<const double2*>(st);
+#pragma unroll
+            for (int r = 0; r < C::E; ++r) x[r] = (2 * (C::T * (r + 1)) <= SG::DOUBLES) ? st2[t + C::T * r] : v2[t + C::T * r];
+            dit_first<N>(s, t, x);
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t, &bar);
+            dit_middle<N>(s, t, x, p.tw);
+            FourierFwdPost<N> f{out + line * p.ostride, p.scale, true};
+            dit_last_paired<N, 1>(p, s, t, f);
+        } else {
+            FourierInvPreStaged<N, SG::DOUBLES> f(in + line * p.istride, st);
+            dif_first_paired<N, 1>(p, s, t, f);
+            if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t, &bar);
+            dif_middle<N>(s, t, x, p.tw);
+            dif_last<N>(s, t, x);
+            double2* v2 = reinterpret_cast<double2*>(out + line * p.ostride);
+#pragma unroll
+            for (int r = 0; r < C::E; ++r) v2[t + C::T * r] = make_double2(x[r].x, -x[r].y);
         }
     }
 }
@@ -652,7 +693,7 @@ template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p
 
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
     typedef LineGeom<N> G;
-    if constexpr (N == 8192 && (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV)) {
+    if constexpr (N == 8192 && (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV)) {
         // 16-byte aligned lines and more lines than SMs, otherwise there is nothing to overlap
         if (p.batch > sm_count() && p.istride % 2 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
             return launch_line_staged<N, KIND>(p, stream);

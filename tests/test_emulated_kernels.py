@@ -67,6 +67,10 @@ def test_long_lines_staged_persistent_kernel():
     back = ll.transform(B.CHEB1_INV, got)
     assert np.max(np.abs(back - v)) <= 50 * tol(n, np.max(np.abs(v)))
     assert np.max(np.abs(ll.transform(B.CHEB1_INV, v) - orc.cheb_itransform(v, axis=0))) <= tol(n, 200 * np.max(np.abs(v)))
+    fo = ll.transform(B.FOURIER_FWD, v)
+    assert np.max(np.abs(fo - orc.fourier_transform(v, axis=0))) <= tol(n, np.max(np.abs(v)))
+    assert np.max(np.abs(ll.transform(B.FOURIER_INV, fo) - v)) <= 50 * tol(n, np.max(np.abs(v)))
+    assert np.max(np.abs(ll.transform(B.FOURIER_INV, v) - orc.fourier_itransform(v, axis=0))) <= tol(n, 200 * np.max(np.abs(v)))
 
 
 def test_empty_and_vector_shapes():
@@ -307,6 +311,8 @@ for n in (64, 256, 1024, 4096, 16384):
 v = rng.standard_normal((16384, 6))
 assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
 assert np.max(np.abs(ll.transform(B.CHEB1_INV, v) - orc.cheb_itransform(v, axis=0))) < 1e-11
+assert np.max(np.abs(ll.transform(B.FOURIER_FWD, v) - orc.fourier_transform(v, axis=0))) < 1e-13
+assert np.max(np.abs(ll.transform(B.FOURIER_INV, v) - orc.fourier_itransform(v, axis=0))) < 1e-11
 v = rng.standard_normal((100, 2))
 assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) < 1e-13
 V = rng.standard_normal((64, 128))

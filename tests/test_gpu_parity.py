@@ -60,6 +60,19 @@ def test_fourier_transform_pair(af, n):
     assert np.max(np.abs(vi - wanti)) <= coef_tol(n, wanti)
 
 
+def test_long_lines_persistent_tma_staged(af):
+    # n = 16384 with more lines than SMs: persistent CTAs, next line staged by a TMA bulk copy (line_kernel_staged);
+    # 301 lines = two full rounds of 148 CTAs plus a ragged third
+    from approxfun_b200 import _lib as L
+    ll = af.api.lowlevel()
+    n, nb = 16384, 301
+    v = RNG.standard_normal((n, nb))
+    for kind, ref in ((L.CHEB1_FWD, orc.cheb_transform), (L.CHEB1_INV, orc.cheb_itransform),
+                      (L.FOURIER_FWD, orc.fourier_transform), (L.FOURIER_INV, orc.fourier_itransform)):
+        want = ref(v, axis=0)
+        assert np.max(np.abs(ll.transform(kind, v) - want)) <= coef_tol(n, want), kind
+
+
 @pytest.mark.parametrize("n", SIZES[:-1])
 def test_laurent_transform_pair(af, n):
     nb = 2 if n <= 8192 else 1
