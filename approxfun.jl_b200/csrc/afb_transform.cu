@@ -602,8 +602,14 @@ __global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (
 // -------------------------------------------------------------------------------------------------
 template <int N> struct StageGeom {
     typedef FftCfg<N> C;
-    static constexpr int HS = 6;                          // staged load groups (of R1/2 = 8)
-    static constexpr int DOUBLES = 4 * C::T * HS + 16;    // 3n/4, + the slot n*3/4 itself (k = N/2 of the inverse)
+    // staged load groups (of R1/2 = 8) and resident CTAs per SM: N = 8192 stages 3/4 of the line beside its 128 KB
+    // exchange buffer.  (Other N: whole line, three CTAs per SM -- measured at N = 2048: 0.77 of HBM against 0.905 for
+    // the plain kernel with four CTAs per SM, so only N = 8192 is dispatched here.)
+    static constexpr int HS = (N == 8192) ? 6 : 8;
+    static constexpr int MINB = (N == 8192) ? 1 : 3;
+    static constexpr int FULL = 2 * N;
+    // + the slot n*3/4 itself (k = N/2 of the inverse) when the stage is partial
+    static constexpr int DOUBLES = (4 * C::T * HS + 16 < FULL) ? 4 * C::T * HS + 16 : FULL;
     static constexpr size_t SMEM = sizeof(cplx) * (size_t)N + sizeof(double) * DOUBLES + 16;  // + the mbarrier
 };
 // One thread hands the 96 KB to the TMA engine (cp.async.bulk, completion counted on an mbarrier) and asks for the rest
@@ -613,16 +619,17 @@ __device__ __forceinline__ void stage_issue(double* __restrict__ st, const doubl
     typedef StageGeom<N> SG;
     if (t == 0) {
         bulk_copy_g2s(st, src, (uint32_t)(sizeof(double) * SG::DOUBLES), bar);
-        bulk_prefetch_l2(src + SG::DOUBLES, (uint32_t)(sizeof(double) * (2 * N - SG::DOUBLES)));
+        if constexpr (SG::DOUBLES < SG::FULL)
+            bulk_prefetch_l2(src + SG::DOUBLES, (uint32_t)(sizeof(double) * (SG::FULL - SG::DOUBLES)));
     }
 }
 template <int N, int KIND>
-__global__ void __launch_bounds__(FftCfg<N>::T, 1) line_kernel_staged(const __grid_constant__ LineParams p) {
+__global__ void __launch_bounds__(FftCfg<N>::T, StageGeom<N>::MINB) line_kernel_staged(const __grid_constant__ LineParams p) {
     typedef FftCfg<N> C;
     typedef StageGeom<N> SG;
     static_assert(KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV,
                   "staged lines: the real kinds");
-    static_assert((sizeof(double) * SG::DOUBLES) % 16 == 0 && (sizeof(double) * (2 * N - SG::DOUBLES)) % 16 == 0, "bulk sizes");
+    static_assert((sizeof(double) * SG::DOUBLES) % 16 == 0 && (sizeof(double) * (SG::FULL - SG::DOUBLES)) % 16 == 0, "bulk sizes");
     AFB_DYN_SMEM(cplx, s);
     double* st = reinterpret_cast<double*>(s + N);
     uint64_t& bar = *reinterpret_cast<uint64_t*>(st + SG::DOUBLES);
@@ -685,7 +692,8 @@ template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p
         AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::SMEM));
         attr_done = true;
     }
-    const int64_t grid = p.batch < sm_count() ? p.batch : sm_count();
+    const int64_t cap = (int64_t)SG::MINB * sm_count();
+    const int64_t grid = p.batch < cap ? p.batch : cap;
     AFB_LAUNCH(k, (unsigned)grid, FftCfg<N>::T, SG::SMEM, stream, p);
     AFB_KERNEL_CHECK();
     return AFB_OK;
