@@ -343,14 +343,17 @@ template <int N> struct ChebInvPre {
         Z0 = make_double2(r.ck + r.cNk * h, -(r.ck - r.cNk * h));
     }
 };
-// same with c[0 .. 3n/4] read from the shared-memory stage (k < N/2: only c[n-k] is beyond it)
-template <int N> struct ChebInvPreStaged : ChebInvPre<N> {
+// same with the first STAGED (> n/2) doubles of the line read from the shared-memory stage (k < N/2: c[k] and c[N-k] are
+// always inside it, c[n-k] practically never, c[N+k] depends on STAGED)
+template <int N, int STAGED> struct ChebInvPreStaged : ChebInvPre<N> {
     typedef typename ChebInvPre<N>::Raw Raw;
     const double* st;
     __device__ __forceinline__ ChebInvPreStaged(const double* c_, const double* st_) : ChebInvPre<N>{c_, true}, st(st_) {}
     __device__ __forceinline__ void fetch(int k, Raw& r) {
         constexpr int n = 2 * N;
-        r.ck = st[k]; r.cnk = this->c[n - k]; r.cNk = st[N - k]; r.cNpk = st[N + k];
+        static_assert(STAGED > N, "stage must cover the first half of the line");
+        r.ck = st[k]; r.cnk = this->c[n - k]; r.cNk = st[N - k];
+        r.cNpk = (3 * N / 2 <= STAGED || N + k < STAGED) ? st[N + k] : this->c[N + k];
     }
     __device__ __forceinline__ void fetch_dc(Raw& r) {
         r.ck = st[0]; r.cnk = 0; r.cNk = st[N]; r.cNpk = 0;
@@ -605,8 +608,8 @@ template <int N> struct StageGeom {
     // staged load groups (of R1/2 = 8) and resident CTAs per SM: N = 8192 stages 3/4 of the line beside its 128 KB
     // exchange buffer.  (Other N: whole line, three CTAs per SM -- measured at N = 2048: 0.77 of HBM against 0.905 for
     // the plain kernel with four CTAs per SM, so only N = 8192 is dispatched here.)
-    static constexpr int HS = (N == 8192) ? 6 : 8;
-    static constexpr int MINB = (N == 8192) ? 1 : 3;
+    static constexpr int HS = (N == 8192) ? 6 : (N == 4096) ? 5 : 8;
+    static constexpr int MINB = (N == 8192) ? 1 : (N == 4096) ? 2 : 3;
     static constexpr int FULL = 2 * N;
     // + the slot n*3/4 itself (k = N/2 of the inverse) when the stage is partial
     static constexpr int DOUBLES = (4 * C::T * HS + 16 < FULL) ? 4 * C::T * HS + 16 : FULL;
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(FftCfg<N>::T, StageGeom<N>::MINB) line_kernel_
             ChebFwdPost<N> f{out + line * p.ostride, p.oes, p.scale, true};
             dit_last_paired<N, 2>(p, s, t, f);
         } else if constexpr (KIND == LK_CHEB_INV) {
-            ChebInvPreStaged<N> f(in + line * p.istride, st);
+            ChebInvPreStaged<N, SG::DOUBLES> f(in + line * p.istride, st);
             dif_first_paired<N, 2>(p, s, t, f);       // ends with a barrier
             if (next < p.batch) stage_issue<N>(st, in + next * p.istride, t, &bar);
             dif_middle<N>(s, t, x, p.tw);
@@ -701,9 +704,13 @@ template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p
 
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
     typedef LineGeom<N> G;
-    if constexpr (N == 8192 && (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV)) {
-        // 16-byte aligned lines and more lines than SMs, otherwise there is nothing to overlap
-        if (p.batch > sm_count() && p.istride % 2 == 0 && reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
+    // (N = 4096 with two CTAs per SM and 5/8 of the line staged was measured SLOWER than the plain kernel: Chebyshev
+    //  0.68 vs 0.74, Fourier 0.69 vs 0.75 of HBM -- two resident CTAs already overlap each other's load phase.)
+    if constexpr (N == 8192 &&
+                  (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV)) {
+        // 16-byte aligned contiguous lines and more lines than resident CTAs, otherwise there is nothing to overlap
+        if (p.oes == 1 && p.batch > (int64_t)StageGeom<N>::MINB * sm_count() && p.istride % 2 == 0 &&
+            reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
             return launch_line_staged<N, KIND>(p, stream);
     }
     auto k = line_kernel<N, KIND>;

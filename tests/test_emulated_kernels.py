@@ -57,9 +57,10 @@ def test_complex_transforms(n):
         assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
 
 
-def test_long_lines_staged_persistent_kernel():
-    # n = 16384 with more lines than (emulated, 4) SMs: persistent CTAs, next line staged with async copies
-    n, nb = 16384, 11
+@pytest.mark.parametrize("n,nb", [(16384, 11), (8192, 19)])
+def test_long_lines_staged_persistent_kernel(n, nb):
+    # n = 16384 with more lines than (emulated, 4) SMs: persistent CTAs, next line staged by a bulk copy (3/4 of the line,
+    # the rest read from global memory); n = 8192 takes the plain kernel
     v = RNG.standard_normal((n, nb))
     got = ll.transform(B.CHEB1_FWD, v)
     want = orc.cheb_transform(v, axis=0)

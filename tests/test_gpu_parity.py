@@ -65,12 +65,12 @@ def test_long_lines_persistent_tma_staged(af):
     # 301 lines = two full rounds of 148 CTAs plus a ragged third
     from approxfun_b200 import _lib as L
     ll = af.api.lowlevel()
-    n, nb = 16384, 301
-    v = RNG.standard_normal((n, nb))
-    for kind, ref in ((L.CHEB1_FWD, orc.cheb_transform), (L.CHEB1_INV, orc.cheb_itransform),
-                      (L.FOURIER_FWD, orc.fourier_transform), (L.FOURIER_INV, orc.fourier_itransform)):
-        want = ref(v, axis=0)
-        assert np.max(np.abs(ll.transform(kind, v) - want)) <= coef_tol(n, want), kind
+    for n, nb in ((16384, 301), (8192, 601)):     # 8192: plain kernel, many lines
+        v = RNG.standard_normal((n, nb))
+        for kind, ref in ((L.CHEB1_FWD, orc.cheb_transform), (L.CHEB1_INV, orc.cheb_itransform),
+                          (L.FOURIER_FWD, orc.fourier_transform), (L.FOURIER_INV, orc.fourier_itransform)):
+            want = ref(v, axis=0)
+            assert np.max(np.abs(ll.transform(kind, v) - want)) <= coef_tol(n, want), (kind, n)
 
 
 @pytest.mark.parametrize("n", SIZES[:-1])
