@@ -143,6 +143,47 @@ struct HostPipe {
 };
 static HostPipe g_pipe;
 
+// ---- device block cache for the host-pointer plain functions (grow-only up to a cap, freed by afb_shutdown) ---------
+static std::mutex g_cache_mu;
+static std::multimap<size_t, void*> g_cache;          // capacity -> block
+static size_t g_cache_bytes = 0;
+static const size_t CACHE_MAX_BLOCK = (size_t)64 << 20;    // larger requests go straight to cudaMalloc / cudaFree
+static const size_t CACHE_MAX_TOTAL = (size_t)512 << 20;
+static int32_t block_cache_get(size_t bytes, void** out, size_t* cap) {
+    if (bytes <= CACHE_MAX_BLOCK) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.lower_bound(bytes);
+        if (it != g_cache.end() && it->first <= 4 * bytes + 4096) {
+            *out = it->second; *cap = it->first;
+            g_cache_bytes -= it->first;
+            g_cache.erase(it);
+            return AFB_OK;
+        }
+    }
+    size_t want = bytes;
+    if (bytes <= CACHE_MAX_BLOCK) { want = 4096; while (want < bytes) want <<= 1; }   // size classes: powers of two
+    AFB_CUDA(cudaMalloc(out, want));
+    *cap = want;
+    return AFB_OK;
+}
+static void block_cache_put(void* p, size_t cap) {
+    if (cap <= CACHE_MAX_BLOCK) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cache_bytes + cap <= CACHE_MAX_TOTAL) {
+            g_cache.emplace(cap, p);
+            g_cache_bytes += cap;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+static void block_cache_release() {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& kv : g_cache) cudaFree(kv.second);
+    g_cache.clear();
+    g_cache_bytes = 0;
+}
+
 // =====================================================================================================
 // plans
 // =====================================================================================================
@@ -590,6 +631,7 @@ int32_t afb_init(int32_t device) {
 
 int32_t afb_shutdown(void) {
     { std::lock_guard<std::mutex> lk(g_pipe.mu); g_pipe.release(); }
+    block_cache_release();
     free_tables();
     return AFB_OK;
 }
@@ -787,11 +829,13 @@ int32_t afb_chebpoints_device(double* d_out, int64_t n, double a, double b, void
 
 }  // extern "C"
 
-// generic "copy in, run, copy out" helper for the plain-function entry points
+// generic "copy in, run, copy out" helper for the plain-function entry points.  Small device blocks are recycled through
+// a process-wide cache: cudaMalloc / cudaFree per call cost more than the kernels of a scalar f(x) (69 us -> see DESIGN).
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int32_t alloc(size_t bytes) { AFB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); return AFB_OK; }
+    size_t cap = 0;
+    ~DevBuf() { if (p) block_cache_put(p, cap); }
+    int32_t alloc(size_t bytes) { return block_cache_get(bytes ? bytes : 1, &p, &cap); }
     int32_t put(const void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice)); return AFB_OK; }
     int32_t get(void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost)); return AFB_OK; }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }

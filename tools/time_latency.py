@@ -33,3 +33,13 @@ t0 = time.perf_counter()
 for _ in range(20):
     f(x)
 print(f"f(x) at 1000 points: {(time.perf_counter() - t0) / 20 * 1e6:.0f} us")
+t0 = time.perf_counter()
+for _ in range(50):
+    f(0.1)
+print(f"f(0.1) (scalar): {(time.perf_counter() - t0) / 50 * 1e6:.0f} us")
+g = af.Fun(lambda t: np.exp(-t * t), af.Chebyshev(-5, 5))
+af.sample(g, 1000)
+t0 = time.perf_counter()
+for _ in range(20):
+    af.sample(g, 1000)
+print(f"sample(g, 1000): {(time.perf_counter() - t0) / 20 * 1e6:.0f} us")
