@@ -31,6 +31,7 @@ struct RowsParams {
     const cplx* twL;  // roots of the FFT length of this kernel
     const cplx* wn;   // exp(-2 pi i m / n), m < n
     const cplx* wq;   // exp(-i pi k / (2n)), k <= n
+    const cplx* wqB;  // exp(-i pi k0 / (2 NB)) = wq[NA k0], k0 <= NB: small, L1-resident
 };
 
 template <int NL, int CT_ = 128> struct RowsGeom {
@@ -122,12 +123,15 @@ __global__ void __launch_bounds__(INNER_CT) rows_inner_kernel(const __grid_const
         for (int r = 0; r < C::E; ++r) x[r] = src[p.ldi * ((int64_t)k1 * NB + t + C::T * r)];
         fft_line<NB>(s, t, x, p.twL);
         if (!act || dup) return;
+        // quarter-wave twiddle w^(k1 + NA k0) = w^k1 * (w^NA)^k0: one table entry per thread plus a 2 KB table that stays
+        // in L1, instead of sixteen scattered reads of the (n+1)-entry table
+        const cplx wk1 = ldg2(p.wq + k1);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
             const int k0 = t + C::T * r;
             const int64_t k = k1 + (int64_t)NA * k0;
             const int pk0 = (k1 == 0) ? (NB - k0) % NB : NB - 1 - k0;
-            const cplx w = ldg2(p.wq + k);
+            const cplx w = cmul(wk1, ldg2(p.wqB + k0));
             const cplx z = cadd(cmul(w, line_get<NB>(s, k0)), cmulc(line_get<NB>(sp, pk0), w));
             p.out[ip + p.ldo * k] = cscale(z, (k == 0) ? 0.5 / (double)n : 1.0 / (double)n);
         }
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(INNER_CT) rows_inner_kernel(const __grid_const
             cplx own = x[r], par = line_get<NB>(sp, pk0);
             if (k == 0) { own = cscale(own, 2.0); par = make_double2(0.0, 0.0); }
             const cplx d = make_double2(own.x + par.y, own.y - par.x);  // own - i par
-            const cplx y = cscale(cmulc(d, ldg2(p.wq + k)), 0.5);
+            const cplx y = cscale(cmulc(d, ldg2(p.wq + k)), 0.5);  // (the factored twiddle of the forward kernel gave nothing here)
             x[r] = make_double2(y.x, -y.y);
         }
         __syncthreads();  // every partner read is done before the FFT reuses the buffer
@@ -229,6 +233,7 @@ int32_t launch_rows_cheb(bool inverse, const double* in, double* tmp, double* ou
     AFB_TRY(root_table(NB, &twB));
     AFB_TRY(root_table(n2, &p.wn));
     AFB_TRY(quarter_table(n2, &p.wq));
+    AFB_TRY(quarter_table(NB, &p.wqB));
     const cplx* cin = reinterpret_cast<const cplx*>(in);
     cplx* ctmp = reinterpret_cast<cplx*>(tmp);
     cplx* cout = reinterpret_cast<cplx*>(out);
