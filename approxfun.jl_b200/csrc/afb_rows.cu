@@ -49,7 +49,7 @@ __device__ __forceinline__ int64_t makhoul_col(int64_t m, int64_t n) { return (2
 
 // ---- outer kernel: FFT_NA over m1 for fixed m0 = blockIdx.y ------------------------------------------------
 //   forward: x[m1] = in[., col(m1 NB + m0)]            -> tmp[., k1 NB + m0] = w_n^(k1 m0) FFT(x)[k1]
-//   inverse: x[k1] = conj(w_n^(k1 m0)) tmp[., k1 NB + m0] -> out[., col(m1 NB + m0)] = IFFT(x)[m1]
+//   inverse: x[k1] = tmp[., k1 NB + m0] (already times conj(w_n^(k1 m0)))  -> out[., col(m1 NB + m0)] = IFFT(x)[m1]
 template <int NA, bool INV>
 __global__ void __launch_bounds__(RowsGeom<NA>::CT) rows_outer_kernel(const __grid_constant__ RowsParams p) {
     typedef FftCfg<NA> C;
@@ -69,17 +69,10 @@ __global__ void __launch_bounds__(RowsGeom<NA>::CT) rows_outer_kernel(const __gr
 #pragma unroll
         for (int r = 0; r < C::E; ++r) x[r] = src[p.ldi * makhoul_col((int64_t)(t + C::T * r) * p.NB + m0, n)];
     } else {
-        cplx w[C::E];
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
-            const int k1 = t + C::T * r;
-            x[r] = src[p.ldi * ((int64_t)k1 * p.NB + m0)];
-            w[r] = ldg2(p.wn + (int64_t)k1 * m0);
-        }
-#pragma unroll
-        for (int r = 0; r < C::E; ++r) {
-            const cplx z = cmulc(x[r], w[r]);
-            x[r] = make_double2(z.x, -z.y);  // inverse FFT = conj FFT conj
+            const cplx z = src[p.ldi * ((int64_t)(t + C::T * r) * p.NB + m0)];
+            x[r] = make_double2(z.x, -z.y);  // inverse FFT = conj FFT conj (the twiddle was applied by the inner kernel)
         }
     }
     fft_line<NA>(s, t, x, p.twL);
@@ -99,7 +92,7 @@ __global__ void __launch_bounds__(RowsGeom<NA>::CT) rows_outer_kernel(const __gr
 
 // ---- inner kernel: groups k1 = g and NA - g (g = blockIdx.y <= NA/2) share a CTA, FFT_NB over m0 / k0 -------
 //   forward: Y[k1 + NA k0] = FFT(tmp[., k1 NB + .])[k0], then the combine with Y[n-k] held by the partner line
-//   inverse: Y built from c'[k], c'[n-k] (partner line), inverse FFT over k0 -> tmp[., k1 NB + m0]
+//   inverse: Y built from c'[k], c'[n-k] (partner line), inverse FFT over k0, times conj(w_n^(k1 m0)) -> tmp[., k1 NB + m0]
 template <int NB, bool INV>
 __global__ void __launch_bounds__(INNER_CT) rows_inner_kernel(const __grid_constant__ RowsParams p) {
     typedef FftCfg<NB> C;
@@ -160,7 +153,9 @@ __global__ void __launch_bounds__(INNER_CT) rows_inner_kernel(const __grid_const
 #pragma unroll
         for (int r = 0; r < C::E; ++r) {
             const int m0 = t + C::T * r;
-            const cplx z = line_get<NB>(s, m0);
+            // conj(result) * conj(w_n^(k1 m0)): the four-step twiddle is applied here, where no transform data is held in
+            // registers (applying it in the outer kernel's load loop cost 64 more live registers and a resident CTA)
+            const cplx z = cmul(line_get<NB>(s, m0), ldg2(p.wn + (int64_t)k1 * m0));
             p.out[ip + p.ldo * ((int64_t)k1 * NB + m0)] = make_double2(z.x, -z.y);
         }
     }
