@@ -31,7 +31,7 @@ SYMBOLS = [
     "afb_clenshaw_cheb", "afb_clenshaw_cheb_device", "afb_clenshaw_cheb_cols", "afb_clenshaw_cheb_cols_device",
     "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device", "afb_clenshaw_rec", "afb_clenshaw_rec_device",
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
-    "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb_device",
+    "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device", "afb_fp64_probe_device",
     "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device",
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
@@ -93,6 +93,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_cheb_bisect_cols": [vp, i64, i64, vp, vp, i64, i32],
         "afb_cheb_bisect_cols_device": [vp, i64, i64, vp, vp, i64, i32, vp],
         "afb_samplecdf_cheb": [vp, i64, dbl, dbl, vp, vp, i64],
+        "afb_sample_cheb": [vp, i64, dbl, dbl, u64, vp, i64],
         "afb_sample_cheb_device": [vp, i64, dbl, dbl, u64, u64, vp, i64, vp],
         "afb_philox_uniform_device": [u64, u64, vp, i64, vp],
         "afb_fp64_probe_device": [i32, i32, i32, vp, vp],
@@ -222,6 +223,13 @@ class LowLevel:
         y = np.empty_like(x)
         check(self.lib, self.lib.afb_clenshaw_rec(_ptr(c), c.size, _ptr(A), _ptr(B), _ptr(Cc), _ptr(x), _ptr(y), x.size))
         return y
+
+    def sample_cheb(self, cdf_c, a: float, b: float, seed: int, n: int) -> np.ndarray:
+        """n samples from the normalised cumulative `cdf_c` on a..b, uniforms drawn on the device (Philox, seed)."""
+        cdf_c = np.ascontiguousarray(cdf_c, dtype=np.float64)
+        out = np.empty(n)
+        check(self.lib, self.lib.afb_sample_cheb(_ptr(cdf_c), cdf_c.size, a, b, seed, _ptr(out), n))
+        return out
 
     def paduapoints(self, N: int, ax=-1.0, bx=1.0, ay=-1.0, by=1.0) -> np.ndarray:
         """Np x 2 array [x y] of the Padua points carrying N coefficients (Np = next triangular number >= N)."""

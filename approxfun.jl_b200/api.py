@@ -650,14 +650,20 @@ def sample2d(f: LowRankFun, n: int, rng=None, uniforms=None) -> np.ndarray:
     return np.stack([rx, ry], axis=1)
 
 
-def sample(f, n: int | None = None, rng=None, uniforms=None):
+def sample(f, n: int | None = None, rng=None, uniforms=None, seed: int | None = None):
     """sample.jl:182: samplecdf(normalizedcumsum(f), n); `sample(f)` returns one sample.
-    2-D (sample.jl:196,218): Fun on a TensorSpace / ProductFun -> LowRankFun -> `sample2d`."""
+    2-D (sample.jl:196,218): Fun on a TensorSpace / ProductFun -> LowRankFun -> `sample2d`.
+    `seed` (1-D Chebyshev Funs): draw the uniforms on the device instead of `rand(n)` on the host (Philox4x32-10,
+    reproducible; no host-to-device traffic)."""
     if isinstance(f, (ProductFun, LowRankFun)) or (isinstance(f, Fun) and isinstance(f.space, TensorSpace)):
         lr = f if isinstance(f, LowRankFun) else LowRankFun(f)
         out = sample2d(lr, 1 if n is None else n, rng, uniforms)
         return out[0] if n is None else out
     one = n is None
+    if seed is not None and uniforms is None and isinstance(f.space, Chebyshev):
+        cf = normalizedcumsum(f)
+        out = lowlevel().sample_cheb(cf.coefficients, f.space.a, f.space.b, int(seed), 1 if one else int(n))
+        return float(out[0]) if one else out
     out = samplecdf(normalizedcumsum(f), 1 if one else n, rng, uniforms)
     return float(out[0]) if one else out
 

@@ -1047,6 +1047,30 @@ int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, doubl
     AFB_TRY(ensure_device());
     return launch_bisect_vec(d_cdf_c, N, nullptr, true, seed, offset, d_out, P, 47, a, b, stream);
 }
+// host-pointer sampler with the uniforms drawn on the device (Philox4x32-10, sample i <- counter offset + i): chunks of
+// 2^23 samples ping-pong between two streams so the kernel of chunk i+1 runs under the D2H copy of chunk i
+int32_t afb_sample_cheb(const double* cdf_c, int64_t N, double a, double b, uint64_t seed, double* out, int64_t P) {
+    if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_sample_cheb: negative size");
+    if (P == 0) return AFB_OK;
+    if ((N && !cdf_c) || !out) return fail(AFB_BAD_ARG, "afb_sample_cheb: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc;
+    AFB_TRY(dc.alloc(8 * (size_t)N));
+    AFB_TRY(dc.put(cdf_c, 8 * (size_t)N));
+    const int64_t chunk = std::min<int64_t>(P, (int64_t)1 << 23);
+    std::lock_guard<std::mutex> pool_lock(g_pipe.mu);
+    AFB_TRY(g_pipe.ensure(2, sizeof(double) * (size_t)chunk));
+    int64_t c = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += chunk, ++c) {
+        const int si = (int)(c & 1);
+        const int64_t np = std::min(chunk, P - p0);
+        double* dbuf = reinterpret_cast<double*>(g_pipe.buf[si]);
+        AFB_TRY(launch_bisect_vec(dc.as<double>(), N, nullptr, true, seed, (uint64_t)p0, dbuf, np, 47, a, b, g_pipe.stream[si]));
+        AFB_CUDA(cudaMemcpyAsync(out + p0, dbuf, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, g_pipe.stream[si]));
+    }
+    for (int i = 0; i < 2; ++i) AFB_CUDA(cudaStreamSynchronize(g_pipe.stream[i]));
+    return AFB_OK;
+}
 int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream) {
     if (P < 0) return fail(AFB_BAD_SIZE, "afb_philox_uniform: negative size");
     if (P == 0) return AFB_OK;

@@ -185,6 +185,9 @@ int32_t afb_samplecdf_cheb(const double* cdf_c, int64_t N, double a, double b, c
                            int64_t P);
 /* Throughput variant of sample(f, n) (src/Extras/sample.jl:182): uniforms come from an on-device
  * counter-based generator (Philox4x32-10, stream `seed`, counter offset `offset`); output on device. */
+/* sample(f, n) with the uniforms drawn on the device (host output): sample i uses Philox4x32-10 counter i of `seed`, so the
+ * stream is reproducible and identical to afb_sample_cheb_device(..., seed, 0, ...).  cdf_c = normalizedcumsum coefficients. */
+int32_t afb_sample_cheb(const double* cdf_c, int64_t N, double a, double b, uint64_t seed, double* out, int64_t P);
 int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, double b, uint64_t seed,
                                uint64_t offset, double* d_out, int64_t P, void* stream);
 /* the uniforms afb_sample_cheb_device draws, for parity checks */

@@ -136,6 +136,17 @@ function bisectioninv(cf::Fun{<:Chebyshev,Float64}, x::Vector{Float64})
     out
 end
 
+# sample(f, n) with the uniforms drawn on the device (Philox4x32-10 counter i for sample i): no rand(n), no H2D traffic
+function sample_b200(f::Fun{<:Chebyshev,Float64}, n::Integer; seed::Integer=0)
+    cf = ApproxFun.normalizedcumsum(f)
+    d = domain(f)
+    c = coefficients(cf)
+    out = Vector{Float64}(undef, n)
+    check(ccall((:afb_sample_cheb, LIB), Int32, (Ptr{Float64}, Int64, Float64, Float64, UInt64, Ptr{Float64}, Int64),
+                c, length(c), ApproxFun.leftendpoint(d), ApproxFun.rightendpoint(d), seed, out, n))
+    out
+end
+
 # ---- 2-D: transform!(::TensorSpace{Chebyshev,Chebyshev}, M) and the fused conditional sampler ------------------
 function cheb2d_transform!(M::Matrix{Float64}; inverse::Bool=false)
     h = Ref{Ptr{Cvoid}}(C_NULL)

@@ -225,6 +225,16 @@ def test_philox_device_sampler_matches_host_uniform_path(af):
     u = d_u.cpu().numpy()
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
     assert np.array_equal(d_s.cpu().numpy(), orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, u, threads=8)))
+    # host-pointer sampler with device uniforms (afb_sample_cheb): counter i for sample i, chunked over two streams
+    Ph = (1 << 23) + 12345                                   # more than one chunk
+    d_u2 = torch.empty(Ph, dtype=torch.float64, device="cuda")
+    af.api.philox_device(11, 0, d_u2.data_ptr(), Ph, st)
+    torch.cuda.synchronize()
+    hs = af.api.lowlevel().sample_cheb(cf, -5.0, 5.0, 11, Ph)
+    pick = np.r_[0:1000, (1 << 23) - 500:(1 << 23) + 500, Ph - 1000:Ph]
+    want = orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, d_u2.cpu().numpy()[pick], threads=8))
+    assert np.array_equal(hs[pick], want)
+    assert np.array_equal(af.sample(f, 5000, seed=11), hs[:5000])
 
 
 def test_tensor_transform_and_sampling_golden(af):
