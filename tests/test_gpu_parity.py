@@ -102,6 +102,23 @@ def test_config1_sin_x2_2pow20(af):
     assert abs(f(0.1) - math.sin(0.01)) < 1000 * EPS      # test/ReadmeTest.jl:19-23
 
 
+def test_very_long_single_transform(af):
+    # n = 2^24 (128 MiB): the four-step path far above config 1; coefficients of a known series, round trip, oracle subsample
+    n = 1 << 24
+    S = af.Chebyshev()
+    x = af.points(S, n)
+    v = np.cos(3 * np.arccos(np.clip(x, -1, 1))) * 2.0 + 0.5 + 0.25 * x      # 0.5 T0 + 0.25 T1 + 2 T3
+    c = af.transform(S, v)
+    want = np.zeros(8)
+    want[[0, 1, 3]] = [0.5, 0.25, 2.0]
+    assert np.max(np.abs(c[:8] - want)) < 1e-12 and np.max(np.abs(c[8:])) < 1e-12
+    r = RNG.standard_normal(n)
+    cr = af.transform(S, r)
+    assert abs(cr[0] - r.mean()) < 1e-13
+    assert np.max(np.abs(af.itransform(S, cr) - r)) < coef_tol(n, r)
+    assert np.max(np.abs(cr - orc.cheb_transform(r))) < coef_tol(n, r)
+
+
 def test_golden_fixture(af):
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
