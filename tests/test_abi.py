@@ -89,3 +89,26 @@ def test_golden_fixture_matches_oracle():
     assert np.array_equal(orcc.clenshaw(g["cl_c"], g["cl_x"]), g["cl_y"])
     assert np.array_equal(orcc.cheb_bisect(g["bis_c"], g["bis_u"]), g["bis_x"])
     assert np.array_equal(orcc.cheb_normcumsum(g["ncs_in"]), g["ncs_out"])
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(root, "approxfun.jl_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(root, "tests", "c", "abi_smoke.c"),
+                           "-L" + libdir, "-l:libapproxfun_b200.so", "-lm", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_plain_c_caller_links_and_fails_loudly_without_a_gpu(tmp_path):
+    # a C host (or Julia's ccall) against include/approxfun_b200.h: compiles as C, links, and without a device gets
+    # AFB_NO_DEVICE -- never a CPU result
+    import subprocess
+    import torch
+    exe = _build_c_smoke(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "abi smoke ok" in out.stdout, out.stderr
+    else:
+        assert out.returncode == 3 and "no CUDA device" in out.stderr, (out.returncode, out.stderr)

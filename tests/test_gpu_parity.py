@@ -508,3 +508,11 @@ def test_config4_full_size_properties(af):
     inv.execute(C.data_ptr(), C.data_ptr(), st)     # in place
     torch.cuda.synchronize()
     assert float((C - V).abs().max()) <= 1e-13 * 28 * vmax
+
+
+def test_plain_c_caller(af, tmp_path):
+    # the same C program the CPU suite links: on the GPU it must pass every check through the raw C ABI
+    import subprocess
+    from tests.test_abi import _build_c_smoke
+    out = subprocess.run([_build_c_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "abi smoke ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
