@@ -112,3 +112,25 @@ def test_plain_c_caller_links_and_fails_loudly_without_a_gpu(tmp_path):
         assert out.returncode == 0 and "abi smoke ok" in out.stdout, out.stderr
     else:
         assert out.returncode == 3 and "no CUDA device" in out.stderr, (out.returncode, out.stderr)
+
+
+def test_host_side_index_helpers():
+    # pure host logic of the Python mirror (no device): total-degree interlace <-> coefficient matrix
+    # (docs/src/usage/constructors.md:98-116), DualArray bookkeeping (ext/ApproxFunDualNumbersExt.jl:44-63)
+    import approxfun_b200 as af
+    from oracle import approxfun_oracle as orc
+    rng = np.random.default_rng(0)
+    for d in (0, 1, 2, 5, 9):
+        N = (d + 1) * (d + 2) // 2
+        c = rng.standard_normal(N)
+        cm = af.api.totaldegree_to_matrix(c)
+        assert cm.shape == (d + 1, d + 1)
+        assert np.array_equal(cm, orc.tensor_deinterlace(c, d))
+        assert np.array_equal(af.api.matrix_to_totaldegree(cm)[:N], c)
+        assert np.array_equal(orc.tensor_interlace(cm)[:N], c)
+    # a short vector is zero-padded to the next full diagonal: [1,2,3] = 1 + 2 T1(y) + 3 T1(x)
+    assert np.array_equal(af.api.totaldegree_to_matrix([1.0, 2.0, 3.0]), [[1.0, 2.0], [3.0, 0.0]])
+    dv = af.DualArray([1.0, 2.0], [0.5, 0.25])
+    assert dv.shape == (2,) and np.array_equal(af.realpart(dv), [1.0, 2.0]) and np.array_equal(af.dualpart(dv), [0.5, 0.25])
+    with pytest.raises(af.DimensionMismatch):
+        af.DualArray([1.0, 2.0], [1.0])
