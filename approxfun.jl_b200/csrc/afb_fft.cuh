@@ -41,16 +41,22 @@ template <int N> struct FftCfg;
 AFB_FFTCFG(32, 8, 4, 1, 1);
 AFB_FFTCFG(64, 16, 4, 1, 1);
 AFB_FFTCFG(128, 16, 8, 1, 1);
-AFB_FFTCFG(256, 16, 8, 2, 1);
-AFB_FFTCFG(512, 16, 16, 2, 1);
-AFB_FFTCFG(1024, 16, 16, 4, 1);
+AFB_FFTCFG(256, 16, 4, 4, 1);
+AFB_FFTCFG(512, 16, 8, 4, 1);
+AFB_FFTCFG(1024, 16, 8, 8, 1);
 AFB_FFTCFG(2048, 16, 16, 8, 1);
-AFB_FFTCFG(4096, 16, 16, 8, 2);
+AFB_FFTCFG(4096, 16, 8, 4, 8);
 AFB_FFTCFG(8192, 16, 16, 16, 2);
 #undef AFB_FFTCFG
-// Complex kinds (whole transform through shared memory, no pairing): fewest passes.  Same R1, so same T and E.
+// Complex kinds (whole transform through shared memory, no pairing): fewest passes, largest radices first.  Same R1, so
+// same T and E.  (The real kinds above prefer a LARGE last radix: fewer partner butterflies per thread means fewer twiddle
+// and pair-table loads in the paired pass -- measured n = 1024: 0.83 -> 0.88, n = 2048 inverse 0.83 -> 0.89, n = 8192 inverse
+// 0.60 -> 0.69 of HBM; for the complex kinds the same lists were slower, Laurent n = 4096 0.76 -> 0.66.)
 template <int N> struct FftCfgC : FftCfg<N> {};
 template <> struct FftCfgC<256> : FftRadices<256, 16, 16, 1, 1> {};
+template <> struct FftCfgC<512> : FftRadices<512, 16, 16, 2, 1> {};
+template <> struct FftCfgC<1024> : FftRadices<1024, 16, 16, 4, 1> {};
+template <> struct FftCfgC<4096> : FftRadices<4096, 16, 16, 8, 2> {};
 // (4096 as 16.16.16 was measured slower than 16.16.8.2 for Laurent: 0.877 vs 0.847 ms at 32768 x 4096)
 
 // slots per line in shared memory (pad for short lines packed many per CTA)

@@ -27,7 +27,7 @@ def timeit(fn, reps=5, warm=2):
 
 
 peak = 6459.3
-for n, B in [(16384, 16384), (8192, 32768), (4096, 65536), (2048, 131072), (1024, 262144), (256, 1 << 20), (64, 1 << 22)]:
+for n, B in [(16384, 16384), (8192, 32768), (4096, 65536), (2048, 131072), (1024, 262144), (512, 1 << 19), (256, 1 << 20), (128, 1 << 21), (64, 1 << 22)]:
     v = torch.randn(B, n, dtype=torch.float64, device="cuda")
     c = torch.empty_like(v)
     for kind, nm in [(L.CHEB1_FWD, "cheb_fwd"), (L.CHEB1_INV, "cheb_inv"), (L.FOURIER_FWD, "four_fwd"), (L.FOURIER_INV, "four_inv")]:
