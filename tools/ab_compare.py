@@ -1,3 +1,6 @@
+"""A/B harness: times the four real kinds at a few lengths with the library given on the command line (build variants
+as approxfun.jl_b200/libafb_<name>.so), so that two builds are compared on the SAME box -- boxes of the pool differ by
+several per cent.  usage: python tools/ab_compare.py path/to/lib.so"""
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 from approxfun_b200 import _lib
