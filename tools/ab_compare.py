@@ -17,7 +17,7 @@ def timeit(fn, reps=5, warm=2):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/reps
 out=[]
-for n,B in [(4096,65536),(1024,1<<18),(512,1<<19),(256,1<<20)]:
+for n,B in [(4096,65536),(2048,1<<17),(1024,1<<18),(256,1<<20),(64,1<<22)]:
     v=torch.randn(B,n,dtype=torch.float64,device="cuda"); c=torch.empty_like(v)
     for kind in (L.CHEB1_FWD,L.CHEB1_INV,L.FOURIER_FWD,L.FOURIER_INV):
         pl=af.api.DevicePlan(kind,n,0,B,n)
