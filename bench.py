@@ -354,6 +354,17 @@ def main():
             extras[name] = {"coefficients_per_s": world * coefs_per_step / (t * 1e-3), "ms_per_step": t,
                             "hbm_frac": ALG_BYTES_PER_COEF * coefs_per_step / (t * 1e-3) / 1e9 / peak}
         del c
+        # Laurent (complex): 32 B per coefficient; same batch and length (4 GiB in, 4 GiB out)
+        if B * n * 32 <= (24 << 30):
+            vz = torch.randn(B, n, dtype=torch.complex128, device="cuda", generator=g)
+            cz = torch.empty_like(vz)
+            for name, kind in (("laurent_transform", L.LAURENT_FWD), ("laurent_itransform", L.LAURENT_INV)):
+                pz = af.api.DevicePlan(kind, n, 0, B, n)
+                t = time_loop(lambda: pz.execute(vz.data_ptr(), cz.data_ptr(), stream), 3, 3)
+                extras[name] = {"coefficients_per_s": world * coefs_per_step / (t * 1e-3), "ms_per_step": t,
+                                "hbm_frac": 32.0 * coefs_per_step / (t * 1e-3) / 1e9 / peak}
+                pz.close()
+            del vz, cz
         # config 3: Clenshaw, N = 10^4 coefficients at P = 10^9 points per rank (BASELINE.json configs[2], full size)
         Nc, P = 10000, (10 ** 9 if not args.quick else 1 << 26)
         xs = af.points(af.Chebyshev(), Nc)
