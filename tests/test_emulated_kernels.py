@@ -337,3 +337,20 @@ print("ok")
     env = dict(os.environ, AFB_EMU_ORDER=order)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_host_sampler_with_device_uniforms():
+    # afb_sample_cheb: Philox counter i for sample i, chunked pipeline; in the emulator "device" pointers are host pointers,
+    # so the uniforms the kernel draws can be read back with afb_philox_uniform_device and pushed through the C oracle
+    import ctypes as C
+    from oracle import oracle_c as orcc
+    c = orc.fun_coefficients(lambda x: np.exp(-x * x), 64, -5.0, 5.0)
+    cf = orc.normalizedcumsum(c, -5.0, 5.0)
+    n = 3001
+    s = ll.sample_cheb(cf, -5.0, 5.0, 42, n)
+    u = np.empty(n)
+    assert ll.lib.afb_philox_uniform_device(42, 0, C.c_void_p(u.ctypes.data), n, None) == 0
+    assert 0.0 <= u.min() and u.max() < 1.0
+    assert np.array_equal(s, orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, u)))
+    assert np.array_equal(ll.sample_cheb(cf, -5.0, 5.0, 42, 10), s[:10])      # reproducible prefix
+    assert not np.array_equal(ll.sample_cheb(cf, -5.0, 5.0, 43, 10), s[:10])  # seed matters
