@@ -33,11 +33,11 @@ SYMBOLS = [
     "afb_cheb_normcumsum", "afb_cheb_normcumsum_device", "afb_cheb_bisect", "afb_cheb_bisect_device",
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device", "afb_fp64_probe_device",
-    "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device",
+    "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device", "afb_piecewise_clenshaw", "afb_piecewise_bisect",
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
-    "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open",
+    "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open", "afb_sharded2d_set_chunks",
 ]
 
 
@@ -58,7 +58,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     sig = {
         "afb_version": [],
         "afb_last_error": [C.c_char_p, sz],
-        "afb_init": [i32],
+        "afb_init": [C.POINTER(i32), i32],
         "afb_shutdown": [],
         "afb_device_info": [C.POINTER(i32), C.POINTER(i64), C.c_char_p, sz],
         "afb_malloc": [C.POINTER(vp), sz],
@@ -97,6 +97,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_sample_cheb_device": [vp, i64, dbl, dbl, u64, u64, vp, i64, vp],
         "afb_philox_uniform_device": [u64, u64, vp, i64, vp],
         "afb_fp64_probe_device": [i32, i32, i32, vp, vp],
+        "afb_piecewise_clenshaw": [vp, vp, vp, i64, vp, vp, i64],
+        "afb_piecewise_bisect": [vp, vp, vp, i64, vp, vp, i64, i32],
         "afb_clenshaw_cheb2d": [vp, i64, i64, vp, vp, vp, i64],
         "afb_clenshaw_cheb2d_device": [vp, i64, i64, vp, vp, vp, i64, vp],
         "afb_sample2d_cheb_lowrank": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64],
@@ -111,6 +113,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_sharded2d_destroy": [vp],
         "afb_sharded2d_ipc_export": [vp, vp],
         "afb_sharded2d_ipc_open": [vp, vp, i32],
+        "afb_sharded2d_set_chunks": [vp, i32],
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, args in sig.items():
@@ -135,6 +138,17 @@ def load() -> C.CDLL:
                     "There is no CPU fallback.")
             _lib = bind(C.CDLL(LIB_PATH))
         return _lib
+
+
+def init(lib: C.CDLL, devices=None) -> None:
+    """`afb_init(devices, ndev)`: None keeps the current device; one ordinal selects it (one process per GPU); several
+    ordinals make the host-pointer entry points fan out over those GPUs from this one process."""
+    if devices is None:
+        check(lib, lib.afb_init(None, 0))
+        return
+    devs = [int(devices)] if isinstance(devices, (int, np.integer)) else [int(d) for d in devices]
+    arr = (C.c_int32 * len(devs))(*devs)
+    check(lib, lib.afb_init(arr, len(devs)))
 
 
 def check(lib: C.CDLL, status: int) -> None:
@@ -326,6 +340,21 @@ class LowLevel:
         flat = np.ascontiguousarray(Cm.T)  # column-major n1 x n2
         out = np.empty_like(x)
         check(self.lib, self.lib.afb_clenshaw_cheb2d(_ptr(flat), Cm.shape[0], Cm.shape[1], _ptr(x), _ptr(y), _ptr(out), x.size))
+        return out
+
+    def piecewise(self, pieces, breaks, xu, bisect: bool, numits: int = 47) -> np.ndarray:
+        """pieces: list of coefficient vectors; breaks: len(pieces)+1 increasing break points; evaluation (bisect=False)
+        or the generic bisection of sample.jl:23-36 (bisect=True)."""
+        offs = np.zeros(len(pieces) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(p) for p in pieces])
+        coef = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in pieces])) if offs[-1] else np.zeros(1)
+        brk = np.ascontiguousarray(breaks, dtype=np.float64)
+        xu = np.ascontiguousarray(xu, dtype=np.float64)
+        out = np.empty_like(xu)
+        if bisect:
+            check(self.lib, self.lib.afb_piecewise_bisect(_ptr(coef), _ptr(offs), _ptr(brk), len(pieces), _ptr(xu), _ptr(out), xu.size, numits))
+        else:
+            check(self.lib, self.lib.afb_piecewise_clenshaw(_ptr(coef), _ptr(offs), _ptr(brk), len(pieces), _ptr(xu), _ptr(out), xu.size))
         return out
 
     def sample2d_lowrank(self, A, CB, ya, yb, xa, xb, ry, u) -> np.ndarray:

@@ -27,9 +27,15 @@ def lowlevel() -> L.LowLevel:
     global _ll
     if _ll is None:
         lib = L.load()
-        L.check(lib, lib.afb_init(-1))
+        L.init(lib, None)
         _ll = L.LowLevel(lib)
     return _ll
+
+
+def use_devices(devices=None) -> None:
+    """Select the GPUs of this process (`afb_init`): an int, a list of ordinals (single-process multi-GPU: host-array calls
+    fan out over them), or None for the current device."""
+    L.init(lowlevel().lib, devices)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -522,14 +528,20 @@ def cumsum(f: Fun) -> Fun:
     return Fun(sp, g)
 
 
-def normalizedcumsum(f: Fun) -> Fun:
+def normalizedcumsum(f):
     """sample.jl:114-119: cf = cumsum(f); cf / last(cf)."""
+    if isinstance(f, PiecewiseFun):
+        cf = _piecewise_cumsum(f)
+        last = float(np.sum(cf.pieces[-1].coefficients))
+        return PiecewiseFun([Fun(p.space, p.coefficients / last) for p in cf.pieces])
     cf = cumsum(f)
     return Fun(cf.space, cf.coefficients / float(np.sum(cf.coefficients)))
 
 
 def bisectioninv(cf: Fun, x, numits: int = 47):
     """sample.jl:103-109: fromcanonical.(space(cf), chebbisectioninv(coefficients(cf), x))."""
+    if isinstance(cf, PiecewiseFun):   # no Chebyshev dispatch: the generic method (sample.jl:8, 23-36)
+        return bisectioninv_generic(cf, x, numits)
     sp = cf.space
     if not isinstance(sp, Chebyshev):
         raise NotImplementedError("bisectioninv: the GPU path covers Fun{<:Chebyshev,Float64}")
@@ -560,22 +572,82 @@ def genmidpoint(a: float, b: float) -> float:
     return (a + b) / 2
 
 
-def bisectioninv_generic(f: Fun, x, numits: int = 47):
-    """sample.jl:23-36: the generic (any-space) bisection -- 47 evaluations of `f` per entry, each evaluation a
-    GPU Clenshaw call over all entries at once."""
-    sp = f.space
+def bisectioninv_generic(f, x, numits: int = 47):
+    """sample.jl:8, 23-36: the generic (any-space) `bisectioninv(f::Fun, x; numits=47)` -- bisection in the DOMAIN variable
+    between minimum(d) and maximum(d) with `genmidpoint`; one fused GPU kernel (`afb_piecewise_bisect`) for Chebyshev and
+    piecewise-Chebyshev Funs."""
     scalar = np.ndim(x) == 0
     xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
-    a = np.full_like(xv, min(sp.a, sp.b))
-    b = np.full_like(xv, max(sp.a, sp.b))
-    for _ in range(numits):
-        m = np.array([genmidpoint(ai, bi) for ai, bi in zip(a, b)]) if (np.isinf(a).any() or np.isinf(b).any()) else (a + b) / 2
-        val = f(m)
-        le = val <= xv
-        a = np.where(le, m, a)
-        b = np.where(le, b, m)
-    out = 0.5 * (a + b)
+    if isinstance(f, PiecewiseFun):
+        pieces, breaks = [p.coefficients for p in f.pieces], f.breaks
+    elif isinstance(f.space, Chebyshev):
+        if not f.space.a < f.space.b:
+            raise NotImplementedError("bisectioninv: reversed segments")
+        pieces, breaks = [f.coefficients], [f.space.a, f.space.b]
+    else:
+        raise NotImplementedError("bisectioninv: the GPU path covers Chebyshev and piecewise-Chebyshev Funs")
+    out = lowlevel().piecewise(pieces, breaks, xv.ravel(), True, numits).reshape(xv.shape)
     return float(out[0]) if scalar else out
+
+
+class PiecewiseFun:
+    """A Fun on a `PiecewiseSpace` of Chebyshev segments (what `abs(Fun(sin, -5..5))` returns, test/PiecewiseSampleTest.jl:5):
+    `pieces[k]` is a Fun on Chebyshev(breaks[k]..breaks[k+1]).  Evaluation picks the first piece whose closed interval
+    contains x (zero outside the domain) and runs on the GPU (`afb_piecewise_clenshaw`)."""
+
+    def __init__(self, pieces):
+        self.pieces = list(pieces)
+        self.breaks = [self.pieces[0].space.a] + [p.space.b for p in self.pieces]
+        for p, q in zip(self.pieces[:-1], self.pieces[1:]):
+            if p.space.b != q.space.a:
+                raise ValueError("PiecewiseFun: pieces must share break points")
+
+    def __call__(self, x):
+        xa = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        out = lowlevel().piecewise([p.coefficients for p in self.pieces], self.breaks, xa.ravel(), False).reshape(xa.shape)
+        return float(out[0]) if np.ndim(x) == 0 else out
+
+
+def roots(f: Fun) -> np.ndarray:
+    """Real roots of a Chebyshev Fun inside its domain (host: colleague-matrix eigenvalues, as upstream; O(N^3) on a
+    handful of numbers -- not part of the data-parallel path)."""
+    c = np.trim_zeros(np.asarray(f.coefficients, dtype=np.float64), "b")
+    if c.size < 2:
+        return np.zeros(0)
+    r = np.polynomial.chebyshev.chebroots(c)
+    r = np.sort(r[np.abs(r.imag) < 1e-10].real)
+    r = r[(r > -1 - 1e-12) & (r < 1 + 1e-12)]
+    return f.space.fromcanonical(np.clip(r, -1, 1))
+
+
+def abs_fun(f: Fun) -> PiecewiseFun:
+    """`abs(f::Fun)`: split the domain at the roots of f and take |f| on every piece (each piece built by the adaptive
+    constructor through the GPU transform).  Device-resident variant: `DeviceFun.abs`."""
+    sp = f.space
+    rts = [r for r in roots(f) if sp.a < r < sp.b]
+    brk = [sp.a] + rts + [sp.b]
+    pieces = []
+    for lo, hi in zip(brk[:-1], brk[1:]):
+        sgn = 1.0 if float(f(0.5 * (lo + hi))) >= 0 else -1.0
+        pieces.append(Fun(lambda t, s=sgn: s * f(t), Chebyshev(lo, hi)))
+    return PiecewiseFun(pieces)
+
+
+def _piecewise_cumsum(f: PiecewiseFun) -> PiecewiseFun:
+    """cumsum on a PiecewiseSpace: every piece is integrated and shifted by the total of the pieces to its left."""
+    acc, out = 0.0, []
+    for p in f.pieces:
+        g = cumsum(p)
+        c = g.coefficients.copy()
+        c[0] += acc
+        acc = float(np.sum(c))   # value at the right end point: sum of Chebyshev coefficients
+        out.append(Fun(p.space, c))
+    return PiecewiseFun(out)
+
+
+def integrate(f):
+    """`integrate(f)` with the reference's normalisation F(left end) = 0 (= cumsum)."""
+    return _piecewise_cumsum(f) if isinstance(f, PiecewiseFun) else cumsum(f)
 
 
 class ProductFun:
@@ -660,7 +732,7 @@ def sample(f, n: int | None = None, rng=None, uniforms=None, seed: int | None = 
         out = sample2d(lr, 1 if n is None else n, rng, uniforms)
         return out[0] if n is None else out
     one = n is None
-    if seed is not None and uniforms is None and isinstance(f.space, Chebyshev):
+    if seed is not None and uniforms is None and isinstance(f, Fun) and isinstance(f.space, Chebyshev):
         cf = normalizedcumsum(f)
         out = lowlevel().sample_cheb(cf.coefficients, f.space.a, f.space.b, int(seed), 1 if one else int(n))
         return float(out[0]) if one else out

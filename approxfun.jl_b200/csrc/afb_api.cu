@@ -1,11 +1,13 @@
 // extern "C" boundary of libapproxfun_b200.so: status plumbing, twiddle tables, plans, host wrappers.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "afb_internal.h"
@@ -31,35 +33,54 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return fail(e == cudaErrorMemoryAllocation ? AFB_OOM : AFB_CUDA_ERROR, buf);
 }
 
-// ---- device ---------------------------------------------------------------------------------------
-static std::mutex g_mu;
-static int g_sm_count = 0;
-static bool g_dev_ok = false;
+// ---- devices ----------------------------------------------------------------------------------------
+// The library follows the calling thread's current CUDA device (as cuFFT does): tables, staging pools and the block cache
+// are kept per device, a plan belongs to the device that was current when it was created, and afb_init(devices, ndev)
+// names the set of devices over which the host-pointer entry points fan out (one host thread and one stream set each).
+struct DeviceState {
+    std::atomic<bool> ok{false};
+    int sms = 0;
+    std::mutex mu;                                   // tables
+    std::map<int64_t, cplx*> root_tables, quarter_tables;
+};
+static DeviceState g_dev[MAX_DEVICES];
+static std::mutex g_mu;                              // device list, first-touch of a device
+static std::vector<int> g_devlist;                   // afb_init's device set (empty: the current device only)
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
 
 int32_t ensure_device() {
-    if (g_dev_ok) return AFB_OK;
+    int n = 0, dev = 0;
+    // fast path: the current device has been seen before
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEVICES && g_dev[dev].ok.load(std::memory_order_acquire))
+        return AFB_OK;
+    cudaGetLastError();
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev_ok) return AFB_OK;
-    int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return fail(AFB_NO_DEVICE, "no CUDA device visible: libapproxfun_b200 has no CPU fallback");
     }
-    int dev = 0;
     AFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(AFB_UNSUPPORTED, "device ordinal beyond MAX_DEVICES (16)");
+    if (g_dev[dev].ok.load(std::memory_order_acquire)) return AFB_OK;
     cudaDeviceProp prop;
     AFB_CUDA(cudaGetDeviceProperties(&prop, dev));
-    g_sm_count = prop.multiProcessorCount;
-    g_dev_ok = true;
+    g_dev[dev].sms = prop.multiProcessorCount;
+    g_dev[dev].ok.store(true, std::memory_order_release);
     return AFB_OK;
 }
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+int sm_count() {
+    const int s = g_dev[current_device()].sms;
+    return s > 0 ? s : 148;
+}
+const std::vector<int>& device_list() { return g_devlist; }
 
-// ---- tables -----------------------------------------------------------------------------------------
-static std::map<int64_t, cplx*> g_root_tables;
-static std::vector<void*> g_owned;
-
+// ---- tables (per device) -------------------------------------------------------------------------------
 int32_t upload_table(const std::vector<cplx>& host, cplx** dev) {
     void* d = nullptr;
     AFB_CUDA(cudaMalloc(&d, sizeof(cplx) * std::max<size_t>(host.size(), 1)));
@@ -77,48 +98,46 @@ static inline cplx unit_ld(long double turns_num, long double turns_den, int sig
 }
 
 int32_t root_table(int64_t N, const cplx** out) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_root_tables.find(N);
-    if (it != g_root_tables.end()) { *out = it->second; return AFB_OK; }
+    DeviceState& ds = g_dev[current_device()];
+    std::lock_guard<std::mutex> lk(ds.mu);
+    auto it = ds.root_tables.find(N);
+    if (it != ds.root_tables.end()) { *out = it->second; return AFB_OK; }
     std::vector<cplx> h((size_t)N);
     for (int64_t m = 0; m < N; ++m) h[(size_t)m] = unit_ld((long double)m, (long double)N, -1);
     cplx* d = nullptr;
     AFB_TRY(upload_table(h, &d));
-    g_root_tables[N] = d;
+    ds.root_tables[N] = d;
     *out = d;
     return AFB_OK;
 }
 
-static std::map<int64_t, cplx*> g_quarter_tables;
 int32_t quarter_table(int64_t n, const cplx** out) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_quarter_tables.find(n);
-    if (it != g_quarter_tables.end()) { *out = it->second; return AFB_OK; }
+    DeviceState& ds = g_dev[current_device()];
+    std::lock_guard<std::mutex> lk(ds.mu);
+    auto it = ds.quarter_tables.find(n);
+    if (it != ds.quarter_tables.end()) { *out = it->second; return AFB_OK; }
     std::vector<cplx> h((size_t)n + 1);
     for (int64_t k = 0; k <= n; ++k) h[(size_t)k] = unit_ld((long double)k, (long double)(4 * n), -1);
     cplx* d = nullptr;
     AFB_TRY(upload_table(h, &d));
-    g_quarter_tables[n] = d;
+    ds.quarter_tables[n] = d;
     *out = d;
     return AFB_OK;
 }
 
-void free_tables() {
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (auto& kv : g_root_tables) cudaFree(kv.second);
-    g_root_tables.clear();
-    for (auto& kv : g_quarter_tables) cudaFree(kv.second);
-    g_quarter_tables.clear();
-}
+// Tables live as long as the process: plans (and the Python layer's plan cache) keep raw pointers into them, so
+// afb_shutdown does NOT free them (a few MB per length); it only drops the staging pools and the block cache.
+void free_tables() {}
 
 }  // namespace afb
 
 using namespace afb;
 
-// process-wide staging pool of afb_plan_execute_host (streams + grow-only device buffers)
+// Staging pipes of the host-pointer entry points: NPIPE streams with grow-only device buffers.  Every device keeps a
+// free list of pipes; a call leases one (or makes a new one), so calls on different plans -- and on different devices --
+// never wait for each other (include/approxfun_b200.h "Threading").
 struct HostPipe {
     static constexpr int NPIPE = 3;
-    std::mutex mu;
     cudaStream_t stream[NPIPE] = {nullptr, nullptr, nullptr};
     void* buf[NPIPE] = {nullptr, nullptr, nullptr};
     size_t cap[NPIPE] = {0, 0, 0};
@@ -141,22 +160,61 @@ struct HostPipe {
         }
     }
 };
-static HostPipe g_pipe;
+struct PipePool {
+    std::mutex mu;
+    std::vector<HostPipe*> idle;
+};
+static PipePool g_pipes[MAX_DEVICES];
+static constexpr size_t PIPES_KEPT = 4;  // idle pipes kept per device (each up to 3 x 64 MiB)
+struct PipeLease {
+    int dev;
+    HostPipe* pipe = nullptr;
+    PipeLease() : dev(current_device()) {
+        std::lock_guard<std::mutex> lk(g_pipes[dev].mu);
+        if (!g_pipes[dev].idle.empty()) { pipe = g_pipes[dev].idle.back(); g_pipes[dev].idle.pop_back(); }
+        else pipe = new HostPipe();
+    }
+    ~PipeLease() {
+        std::unique_lock<std::mutex> lk(g_pipes[dev].mu);
+        if (g_pipes[dev].idle.size() < PIPES_KEPT) { g_pipes[dev].idle.push_back(pipe); return; }
+        lk.unlock();
+        pipe->release();
+        delete pipe;
+    }
+    HostPipe* operator->() { return pipe; }
+};
+static void pipes_release_all() {
+    int keep = 0;
+    const bool have = cudaGetDevice(&keep) == cudaSuccess;
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        std::lock_guard<std::mutex> lk(g_pipes[d].mu);
+        if (g_pipes[d].idle.empty()) continue;
+        cudaSetDevice(d);
+        for (HostPipe* hp : g_pipes[d].idle) { hp->release(); delete hp; }
+        g_pipes[d].idle.clear();
+    }
+    if (have) cudaSetDevice(keep);
+    cudaGetLastError();
+}
 
-// ---- device block cache for the host-pointer plain functions (grow-only up to a cap, freed by afb_shutdown) ---------
-static std::mutex g_cache_mu;
-static std::multimap<size_t, void*> g_cache;          // capacity -> block
-static size_t g_cache_bytes = 0;
+// ---- device block cache for the host-pointer plain functions (per device, grow-only up to a cap, freed by afb_shutdown) --
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> blocks;  // capacity -> block
+    size_t bytes = 0;
+};
+static BlockCache g_cache[MAX_DEVICES];
 static const size_t CACHE_MAX_BLOCK = (size_t)64 << 20;    // larger requests go straight to cudaMalloc / cudaFree
 static const size_t CACHE_MAX_TOTAL = (size_t)512 << 20;
 static int32_t block_cache_get(size_t bytes, void** out, size_t* cap) {
     if (bytes <= CACHE_MAX_BLOCK) {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
-        auto it = g_cache.lower_bound(bytes);
-        if (it != g_cache.end() && it->first <= 4 * bytes + 4096) {
+        BlockCache& bc = g_cache[current_device()];
+        std::lock_guard<std::mutex> lk(bc.mu);
+        auto it = bc.blocks.lower_bound(bytes);
+        if (it != bc.blocks.end() && it->first <= 4 * bytes + 4096) {
             *out = it->second; *cap = it->first;
-            g_cache_bytes -= it->first;
-            g_cache.erase(it);
+            bc.bytes -= it->first;
+            bc.blocks.erase(it);
             return AFB_OK;
         }
     }
@@ -166,22 +224,53 @@ static int32_t block_cache_get(size_t bytes, void** out, size_t* cap) {
     *cap = want;
     return AFB_OK;
 }
-static void block_cache_put(void* p, size_t cap) {
+static void block_cache_put(void* p, size_t cap, int dev) {
     if (cap <= CACHE_MAX_BLOCK) {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
-        if (g_cache_bytes + cap <= CACHE_MAX_TOTAL) {
-            g_cache.emplace(cap, p);
-            g_cache_bytes += cap;
+        BlockCache& bc = g_cache[dev];
+        std::lock_guard<std::mutex> lk(bc.mu);
+        if (bc.bytes + cap <= CACHE_MAX_TOTAL) {
+            bc.blocks.emplace(cap, p);
+            bc.bytes += cap;
             return;
         }
     }
     cudaFree(p);
 }
 static void block_cache_release() {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto& kv : g_cache) cudaFree(kv.second);
-    g_cache.clear();
-    g_cache_bytes = 0;
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        std::lock_guard<std::mutex> lk(g_cache[d].mu);
+        for (auto& kv : g_cache[d].blocks) cudaFree(kv.second);   // cudaFree works across devices of one process
+        g_cache[d].blocks.clear();
+        g_cache[d].bytes = 0;
+    }
+}
+
+// ---- fan-out over afb_init's device set -----------------------------------------------------------------
+// Splits [0, total) into contiguous shares, one per device, and runs fn(share_index, lo, hi) on one host thread per device
+// with that device current.  The first non-OK status (and its message) is returned to the caller's thread.
+template <class Fn> static int32_t fanout(const std::vector<int>& devs, int64_t total, Fn fn) {
+    const int G = (int)devs.size();
+    std::vector<int32_t> st((size_t)G, AFB_OK);
+    std::vector<std::string> msg((size_t)G);
+    std::vector<std::thread> th;
+    int keep = 0;
+    AFB_CUDA(cudaGetDevice(&keep));
+    for (int g = 0; g < G; ++g) {
+        const int64_t q = total / G, r = total % G;
+        const int64_t lo = g * q + std::min<int64_t>(g, r), hi = lo + q + (g < r ? 1 : 0);
+        th.emplace_back([&, g, lo, hi]() {
+            cudaError_t e = cudaSetDevice(devs[(size_t)g]);
+            int32_t s = (e == cudaSuccess) ? ensure_device() : cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+            if (s == AFB_OK && hi > lo) s = fn(g, lo, hi);
+            st[(size_t)g] = s;
+            if (s != AFB_OK) { char buf[512]; afb_last_error(buf, sizeof buf); msg[(size_t)g] = buf; }
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(keep);
+    for (int g = 0; g < G; ++g)
+        if (st[(size_t)g] != AFB_OK) return fail(st[(size_t)g], msg[(size_t)g]);
+    return AFB_OK;
 }
 
 // =====================================================================================================
@@ -225,10 +314,28 @@ struct afb_plan_s {
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
     std::mutex mu;
+    int dev = afb::current_device();          // the device the plan's tables and work buffers live on
+    // host-pointer execution over several devices: one replica plan per device of afb_init's set (made on first use)
+    std::vector<afb_plan_s*> replicas;
+    std::vector<int> replica_devs;
+    void* mdev2d = nullptr;                   // in-process multi-device 2-D state (afb_tensor.cu)
+};
+
+// makes the plan's device current for the scope (a plan may be executed from any thread)
+struct DeviceGuard {
+    int keep = -1;
+    explicit DeviceGuard(int dev) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) { keep = cur; cudaSetDevice(dev); }
+    }
+    ~DeviceGuard() { if (keep >= 0) cudaSetDevice(keep); }
 };
 
 static void plan_free(afb_plan_s* p) {
     if (!p) return;
+    for (afb_plan_s* r : p->replicas) plan_free(r);
+    if (p->mdev2d) mdev2d_destroy(p->mdev2d);
+    DeviceGuard guard(p->dev);
     if (p->aux) cudaFree(p->aux);
     if (p->dtab) cudaFree(p->dtab);
     if (p->qtab) cudaFree(p->qtab);
@@ -601,6 +708,14 @@ static int32_t exec_padua_device(afb_plan_s* p, const double* d_in, double* d_ou
     return launch_gather_idx(d_out, p->wbuf, p->pad_idx, N, 1.0, stream);
 }
 
+namespace afb {
+int32_t slab_col_chunk(afb_plan p, const double* d_in, double* d_out, int64_t batch, void* stream) {
+    if (!p || batch < 0 || batch > p->batch) return fail(AFB_BAD_ARG, "slab_col_chunk: bad argument");
+    DeviceGuard guard(p->dev);
+    return exec_1d_device(p, d_in, d_out, batch, p->stride, p->stride, stream);
+}
+}  // namespace afb
+
 extern "C" {
 
 int32_t afb_version(void) { return AFB_VERSION; }
@@ -613,26 +728,52 @@ int32_t afb_last_error(char* buf, size_t len) {
     return g_err_code;
 }
 
-int32_t afb_init(int32_t device) {
+int32_t afb_init(const int32_t* devices, int32_t ndev) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return fail(AFB_NO_DEVICE, "no CUDA device visible: libapproxfun_b200 has no CPU fallback");
     }
-    if (device >= 0) {
-        if (device >= n) return fail(AFB_BAD_ARG, "device index out of range");
-        AFB_CUDA(cudaSetDevice(device));
+    if (ndev < 0 || (ndev > 0 && !devices)) return fail(AFB_BAD_ARG, "afb_init: bad device list");
+    if (ndev > MAX_DEVICES) return fail(AFB_UNSUPPORTED, "afb_init: at most 16 devices");
+    std::vector<int> list;
+    for (int32_t i = 0; i < ndev; ++i) {
+        if (devices[i] < 0 || devices[i] >= n || devices[i] >= MAX_DEVICES) return fail(AFB_BAD_ARG, "afb_init: device index out of range");
+        for (int d : list) if (d == devices[i]) return fail(AFB_BAD_ARG, "afb_init: device listed twice");
+        list.push_back(devices[i]);
+    }
+    if (!list.empty()) {
+#ifndef AFB_HOST_EMU
+        // every pair of the set talks over NVLink peer memory (the 2-D exchange writes straight into the peers' buffers)
+        for (int a : list) {
+            AFB_CUDA(cudaSetDevice(a));
+            AFB_TRY(ensure_device());
+            for (int b : list) {
+                if (a == b) continue;
+                int can = 0;
+                AFB_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
+                if (!can) continue;
+                cudaError_t pe = cudaDeviceEnablePeerAccess(b, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(pe, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                cudaGetLastError();
+            }
+        }
+#endif
+        AFB_CUDA(cudaSetDevice(list[0]));
+    }
+    {
         std::lock_guard<std::mutex> lk(g_mu);
-        g_dev_ok = false;
+        g_devlist = list.size() > 1 ? list : std::vector<int>();
     }
     return ensure_device();
 }
 
+// Drops the staging pipes and the block cache of every device.  Plans stay valid (the twiddle tables they point into live
+// as long as the process); the device set of afb_init is kept.
 int32_t afb_shutdown(void) {
-    { std::lock_guard<std::mutex> lk(g_pipe.mu); g_pipe.release(); }
+    pipes_release_all();
     block_cache_release();
-    free_tables();
     return AFB_OK;
 }
 
@@ -736,6 +877,7 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
     if (!d_in || !d_out) return fail(AFB_BAD_ARG, "afb_plan_execute_device: null buffer");
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(AFB_BAD_ARG, "afb_plan_execute_device: buffers must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(p->mu);
+    DeviceGuard guard(p->dev);
     if (p->path == PATH_TENSOR2D) {
         // C = T_x V T_y^T on a column-major n x n2 matrix.
         const int64_t n = p->n, n2 = p->n2;
@@ -755,11 +897,85 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
     return exec_1d_device(p, d_in, d_out, p->batch, p->stride, p->stride, stream);
 }
 
+}  // extern "C"
+
+// One device: chunked three-stage pipeline H2D | kernels | D2H on up to NPIPE streams of a leased pipe, packed
+// (stride = n) on the device.  `batch` lines starting at in / out (the plan's stride apart).
+static int32_t host_pipeline_1d(afb_plan_s* p, const void* in, void* out, int64_t batch) {
+    const int64_t n = p->n;
+    const size_t line_bytes = (size_t)p->elem * (size_t)n;
+    int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
+    ch = std::min(ch, batch);
+    if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
+    // the generic paths share one work buffer between chunks: keep them on a single stream
+    const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE || p->path == PATH_EXT;
+    // the O(n^2) kernel is not in-place safe: its chunks get separate input and output halves of the staging buffer
+    const bool direct = p->path == PATH_DIRECT;
+    const int64_t nchunks = (batch + ch - 1) / ch;
+    const int nbuf = generic ? 1 : (int)std::min<int64_t>(HostPipe::NPIPE, nchunks);
+    const size_t chunk_bytes = line_bytes * (size_t)ch;
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(nbuf, chunk_bytes * (direct ? 2 : 1)));
+    int64_t c = 0;
+    int32_t st = AFB_OK;
+    for (int64_t b0 = 0; b0 < batch && st == AFB_OK; b0 += ch, ++c) {
+        const int si = (int)(c % nbuf);
+        cudaStream_t s = pipe->stream[si];
+        void* dbuf = pipe->buf[si];
+        void* dout = direct ? (void*)((char*)dbuf + chunk_bytes) : dbuf;
+        const int64_t nb = std::min(ch, batch - b0);
+        const char* src = reinterpret_cast<const char*>(in) + (size_t)p->elem * (size_t)(b0 * p->stride);
+        char* dst = reinterpret_cast<char*>(out) + (size_t)p->elem * (size_t)(b0 * p->stride);
+        cudaError_t e;
+        if (p->stride == n) e = cudaMemcpyAsync(dbuf, src, line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s);
+        else e = cudaMemcpy2DAsync(dbuf, line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes, (size_t)nb,
+                                   cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { st = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
+        st = exec_1d_device(p, dbuf, dout, nb, n, n, s);
+        if (st != AFB_OK) break;
+        if (p->stride == n) e = cudaMemcpyAsync(dst, dout, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s);
+        else e = cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, dout, line_bytes, line_bytes, (size_t)nb,
+                                   cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+    }
+    // the pipe goes back to the pool only when its streams are idle (also on the error path)
+    for (int i = 0; i < nbuf; ++i) {
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
+        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    return st;
+}
+
+static int32_t plan_create_1d(afb_plan_s** out, int32_t kind, int64_t n, int64_t batch, int64_t stride, uint32_t flags);
+
+// the replica of a 1-D plan on device `dev` (current), able to run `batch` lines
+static int32_t plan_replica(afb_plan_s* p, int dev, int64_t batch, afb_plan_s** out) {
+    if (dev == p->dev) { *out = p; return AFB_OK; }
+    for (size_t i = 0; i < p->replicas.size(); ++i)
+        if (p->replica_devs[i] == dev && p->replicas[i]->batch >= batch) { *out = p->replicas[i]; return AFB_OK; }
+    afb_plan_s* r = nullptr;
+    AFB_TRY(plan_create_1d(&r, p->kind, p->n, batch, p->stride, p->flags));
+    p->replicas.push_back(r);
+    p->replica_devs.push_back(dev);
+    *out = r;
+    return AFB_OK;
+}
+
+extern "C" {
+
 int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
     if (!p) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null plan");
     if (p->path == PATH_EMPTY) return AFB_OK;
     if (!in || !out) return fail(AFB_BAD_ARG, "afb_plan_execute_host: null buffer");
+    std::vector<int> devs;
+    { std::lock_guard<std::mutex> lk(g_mu); devs = g_devlist; }
     if (p->path == PATH_TENSOR2D || p->path == PATH_PADUA) {
+        if (p->path == PATH_TENSOR2D && devs.size() > 1 && mdev2d_supported(p->kind, p->n, p->n2, (int)devs.size(), p->flags)) {
+            std::lock_guard<std::mutex> lk(p->mu);
+            if (!p->mdev2d) AFB_TRY(mdev2d_create(&p->mdev2d, p->kind, p->n, p->n2, devs));
+            return mdev2d_execute_host(p->mdev2d, reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out));
+        }
+        DeviceGuard guard(p->dev);
         const size_t bytes = sizeof(double) * (size_t)(p->path == PATH_PADUA ? p->n : p->n * p->n2);
         void* d = nullptr;
         AFB_CUDA(cudaMalloc(&d, bytes));
@@ -775,47 +991,23 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
         return st;
     }
     std::lock_guard<std::mutex> lk(p->mu);
-    // chunked three-stage pipeline: H2D | kernels | D2H on up to NPIPE streams, packed (stride = n) on device.
-    // Streams and staging buffers belong to a process-wide pool (grow-only), so creating / destroying plans stays cheap.
-    const int64_t n = p->n;
-    const size_t line_bytes = (size_t)p->elem * (size_t)n;
-    int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
-    ch = std::min(ch, p->batch);
-    if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
-    const bool generic = p->path == PATH_GENERIC || p->path == PATH_LARGE || p->path == PATH_EXT;
-    const int64_t nchunks = (p->batch + ch - 1) / ch;
-    const int nbuf = generic ? 1 : (int)std::min<int64_t>(HostPipe::NPIPE, nchunks);
-    std::lock_guard<std::mutex> pool_lock(g_pipe.mu);
-    AFB_TRY(g_pipe.ensure(nbuf, line_bytes * (size_t)ch));
-    int64_t c = 0;
-    for (int64_t b0 = 0; b0 < p->batch; b0 += ch, ++c) {
-        // the generic paths share one work buffer between chunks: keep them on a single stream
-        const int si = (int)(c % nbuf);
-        cudaStream_t s = g_pipe.stream[si];
-        void* dbuf = g_pipe.buf[si];
-        const int64_t nb = std::min(ch, p->batch - b0);
-        const char* src = reinterpret_cast<const char*>(in) + (size_t)p->elem * (size_t)(b0 * p->stride);
-        char* dst = reinterpret_cast<char*>(out) + (size_t)p->elem * (size_t)(b0 * p->stride);
-#ifdef AFB_HOST_EMU
-        for (int64_t b = 0; b < nb; ++b)
-            std::memcpy((char*)dbuf + line_bytes * b, src + (size_t)p->elem * (size_t)(b * p->stride), line_bytes);
-#else
-        if (p->stride == n) AFB_CUDA(cudaMemcpyAsync(dbuf, src, line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s));
-        else AFB_CUDA(cudaMemcpy2DAsync(dbuf, line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes, (size_t)nb,
-                                        cudaMemcpyHostToDevice, s));
-#endif
-        AFB_TRY(exec_1d_device(p, dbuf, dbuf, nb, n, n, s));
-#ifdef AFB_HOST_EMU
-        for (int64_t b = 0; b < nb; ++b)
-            std::memcpy(dst + (size_t)p->elem * (size_t)(b * p->stride), (char*)dbuf + line_bytes * b, line_bytes);
-#else
-        if (p->stride == n) AFB_CUDA(cudaMemcpyAsync(dst, dbuf, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s));
-        else AFB_CUDA(cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, dbuf, line_bytes, line_bytes, (size_t)nb,
-                                        cudaMemcpyDeviceToHost, s));
-#endif
+    // several devices: contiguous shares of the batch, one host thread + one pipe per device (no collective)
+    const int64_t total_bytes = (int64_t)p->elem * p->n * p->batch;
+    if (devs.size() > 1 && p->batch >= (int64_t)devs.size() && total_bytes >= ((int64_t)8 << 20)) {
+        const int64_t share = (p->batch + (int64_t)devs.size() - 1) / (int64_t)devs.size();
+        return fanout(devs, p->batch, [&](int g, int64_t lo, int64_t hi) -> int32_t {
+            afb_plan_s* r = nullptr;
+            {
+                static std::mutex rep_mu;
+                std::lock_guard<std::mutex> rl(rep_mu);
+                AFB_TRY(plan_replica(p, devs[(size_t)g], share, &r));
+            }
+            const size_t off = (size_t)p->elem * (size_t)(lo * p->stride);
+            return host_pipeline_1d(r, reinterpret_cast<const char*>(in) + off, reinterpret_cast<char*>(out) + off, hi - lo);
+        });
     }
-    for (int i = 0; i < nbuf; ++i) AFB_CUDA(cudaStreamSynchronize(g_pipe.stream[i]));
-    return AFB_OK;
+    DeviceGuard guard(p->dev);
+    return host_pipeline_1d(p, in, out, p->batch);
 }
 
 // ---- points -------------------------------------------------------------------------------------------
@@ -834,12 +1026,19 @@ int32_t afb_chebpoints_device(double* d_out, int64_t n, double a, double b, void
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-    ~DevBuf() { if (p) block_cache_put(p, cap); }
-    int32_t alloc(size_t bytes) { return block_cache_get(bytes ? bytes : 1, &p, &cap); }
+    int dev = 0;
+    ~DevBuf() { if (p) block_cache_put(p, cap, dev); }
+    int32_t alloc(size_t bytes) { dev = current_device(); return block_cache_get(bytes ? bytes : 1, &p, &cap); }
     int32_t put(const void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice)); return AFB_OK; }
     int32_t get(void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost)); return AFB_OK; }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
+
+// point sets / sample sets shard over afb_init's devices when there is enough work to pay for the host threads
+static bool fan_points(int64_t P, int64_t work_per_point, std::vector<int>* devs) {
+    { std::lock_guard<std::mutex> lk(g_mu); *devs = device_list(); }
+    return devs->size() > 1 && P >= ((int64_t)1 << 20) && (double)P * (double)std::max<int64_t>(work_per_point, 1) >= 1e9;
+}
 
 extern "C" {
 
@@ -895,6 +1094,9 @@ int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y
     if (P == 0) return AFB_OK;
     if ((N && !c) || !x || !y) return fail(AFB_BAD_ARG, "afb_clenshaw_cheb: null buffer");
     AFB_TRY(ensure_device());
+    std::vector<int> devs;
+    if (fan_points(P, N, &devs))
+        return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return afb_clenshaw_cheb(c, N, x + lo, y + lo, hi - lo); });
     DevBuf dc, dx, dy;
     AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
     AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(dx.put(x, 8 * (size_t)P));
@@ -916,6 +1118,9 @@ int32_t afb_clenshaw_rec(const double* c, int64_t N, const double* A, const doub
     if (P == 0) return AFB_OK;
     if ((N && (!c || !A || !B || !C)) || !x || !y) return fail(AFB_BAD_ARG, "afb_clenshaw_rec: null buffer");
     AFB_TRY(ensure_device());
+    std::vector<int> devs;
+    if (fan_points(P, N, &devs))
+        return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return afb_clenshaw_rec(c, N, A, B, C, x + lo, y + lo, hi - lo); });
     DevBuf dc, dA, dB, dC, dx, dy;
     AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dA.alloc(8 * (size_t)N)); AFB_TRY(dB.alloc(8 * (size_t)N));
     AFB_TRY(dC.alloc(8 * (size_t)(N + 1))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
@@ -1004,6 +1209,9 @@ static int32_t bisect_host(const double* c, int64_t N, const double* u, double* 
     if (P == 0) return AFB_OK;
     if ((N && !c) || !u || !out) return fail(AFB_BAD_ARG, "afb_cheb_bisect: null buffer");
     AFB_TRY(ensure_device());
+    std::vector<int> devs;
+    if (fan_points(P, (int64_t)numits * N, &devs))
+        return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return bisect_host(c, N, u + lo, out + lo, hi - lo, numits, a, b); });
     DevBuf dc, du, dout;
     AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
     AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(du.put(u, 8 * (size_t)P));
@@ -1049,27 +1257,40 @@ int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, doubl
 }
 // host-pointer sampler with the uniforms drawn on the device (Philox4x32-10, sample i <- counter offset + i): chunks of
 // 2^23 samples ping-pong between two streams so the kernel of chunk i+1 runs under the D2H copy of chunk i
+static int32_t sample_host_one(const double* cdf_c, int64_t N, double a, double b, uint64_t seed, uint64_t offset, double* out,
+                               int64_t P) {
+    DevBuf dc;
+    AFB_TRY(dc.alloc(8 * (size_t)N));
+    AFB_TRY(dc.put(cdf_c, 8 * (size_t)N));
+    const int64_t chunk = std::min<int64_t>(P, (int64_t)1 << 23);
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(2, sizeof(double) * (size_t)chunk));
+    int64_t c = 0;
+    int32_t st = AFB_OK;
+    for (int64_t p0 = 0; p0 < P && st == AFB_OK; p0 += chunk, ++c) {
+        const int si = (int)(c & 1);
+        const int64_t np = std::min(chunk, P - p0);
+        double* dbuf = reinterpret_cast<double*>(pipe->buf[si]);
+        st = launch_bisect_vec(dc.as<double>(), N, nullptr, true, seed, offset + (uint64_t)p0, dbuf, np, 47, a, b, pipe->stream[si]);
+        if (st != AFB_OK) break;
+        cudaError_t e = cudaMemcpyAsync(out + p0, dbuf, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, pipe->stream[si]);
+        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
+        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    return st;
+}
 int32_t afb_sample_cheb(const double* cdf_c, int64_t N, double a, double b, uint64_t seed, double* out, int64_t P) {
     if (N < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_sample_cheb: negative size");
     if (P == 0) return AFB_OK;
     if ((N && !cdf_c) || !out) return fail(AFB_BAD_ARG, "afb_sample_cheb: null buffer");
     AFB_TRY(ensure_device());
-    DevBuf dc;
-    AFB_TRY(dc.alloc(8 * (size_t)N));
-    AFB_TRY(dc.put(cdf_c, 8 * (size_t)N));
-    const int64_t chunk = std::min<int64_t>(P, (int64_t)1 << 23);
-    std::lock_guard<std::mutex> pool_lock(g_pipe.mu);
-    AFB_TRY(g_pipe.ensure(2, sizeof(double) * (size_t)chunk));
-    int64_t c = 0;
-    for (int64_t p0 = 0; p0 < P; p0 += chunk, ++c) {
-        const int si = (int)(c & 1);
-        const int64_t np = std::min(chunk, P - p0);
-        double* dbuf = reinterpret_cast<double*>(g_pipe.buf[si]);
-        AFB_TRY(launch_bisect_vec(dc.as<double>(), N, nullptr, true, seed, (uint64_t)p0, dbuf, np, 47, a, b, g_pipe.stream[si]));
-        AFB_CUDA(cudaMemcpyAsync(out + p0, dbuf, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, g_pipe.stream[si]));
-    }
-    for (int i = 0; i < 2; ++i) AFB_CUDA(cudaStreamSynchronize(g_pipe.stream[i]));
-    return AFB_OK;
+    std::vector<int> devs;
+    if (fan_points(P, 47 * N, &devs))   // sample i always uses Philox counter i: the stream does not depend on the device count
+        return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return sample_host_one(cdf_c, N, a, b, seed, (uint64_t)lo, out + lo, hi - lo); });
+    return sample_host_one(cdf_c, N, a, b, seed, 0, out, P);
 }
 int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream) {
     if (P < 0) return fail(AFB_BAD_SIZE, "afb_philox_uniform: negative size");
@@ -1079,6 +1300,41 @@ int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out,
     return launch_philox(seed, offset, d_out, P, stream);
 }
 
+
+// ---- piecewise Chebyshev Funs: evaluation and the generic bisection of sample.jl:8-36 -----------------------------
+static int32_t piecewise_host(const double* coef, const int64_t* offsets, const double* breaks, int64_t np, const double* xu,
+                              double* out, int64_t P, bool bisect, int32_t numits) {
+    if (np < 1 || P < 0 || numits < 0) return fail(AFB_BAD_SIZE, "afb_piecewise: need npieces >= 1, P >= 0, numits >= 0");
+    if (P == 0) return AFB_OK;
+    if (!offsets || !breaks || !xu || !out) return fail(AFB_BAD_ARG, "afb_piecewise: null buffer");
+    if (offsets[0] != 0) return fail(AFB_BAD_SIZE, "afb_piecewise: offsets[0] must be 0");
+    for (int64_t k = 0; k < np; ++k) {
+        if (offsets[k + 1] < offsets[k]) return fail(AFB_BAD_SIZE, "afb_piecewise: offsets must be non-decreasing");
+        if (!(breaks[k] < breaks[k + 1])) return fail(AFB_BAD_SIZE, "afb_piecewise: break points must be increasing");
+    }
+    const int64_t total = offsets[np];
+    if (total >= ((int64_t)1 << 31)) return fail(AFB_BAD_SIZE, "afb_piecewise: too many coefficients");
+    if (total && !coef) return fail(AFB_BAD_ARG, "afb_piecewise: null coefficients");
+    AFB_TRY(ensure_device());
+    std::vector<int32_t> off32((size_t)np + 1);
+    for (int64_t k = 0; k <= np; ++k) off32[(size_t)k] = (int32_t)offsets[k];
+    DevBuf dc, doff, dbrk, dxu, dout;
+    AFB_TRY(dc.alloc(8 * (size_t)total)); AFB_TRY(doff.alloc(4 * (size_t)(np + 1))); AFB_TRY(dbrk.alloc(8 * (size_t)(np + 1)));
+    AFB_TRY(dxu.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(coef, 8 * (size_t)total)); AFB_TRY(doff.put(off32.data(), 4 * (size_t)(np + 1)));
+    AFB_TRY(dbrk.put(breaks, 8 * (size_t)(np + 1))); AFB_TRY(dxu.put(xu, 8 * (size_t)P));
+    AFB_TRY(launch_piecewise(dc.as<double>(), doff.as<int32_t>(), dbrk.as<double>(), np, total, dxu.as<double>(), dout.as<double>(),
+                             P, bisect, numits, nullptr));
+    return dout.get(out, 8 * (size_t)P);
+}
+int32_t afb_piecewise_clenshaw(const double* coef, const int64_t* offsets, const double* breaks, int64_t npieces, const double* x,
+                               double* y, int64_t P) {
+    return piecewise_host(coef, offsets, breaks, npieces, x, y, P, false, 0);
+}
+int32_t afb_piecewise_bisect(const double* coef, const int64_t* offsets, const double* breaks, int64_t npieces, const double* u,
+                             double* out, int64_t P, int32_t numits) {
+    return piecewise_host(coef, offsets, breaks, npieces, u, out, P, true, numits);
+}
 
 // ---- bivariate evaluation of a Chebyshev x Chebyshev coefficient matrix --------------------------------------
 int32_t afb_clenshaw_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y,

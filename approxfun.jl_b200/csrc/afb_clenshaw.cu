@@ -10,7 +10,9 @@
 // issue slots), so the structural ceiling is 75 % of the 2-flop/slot FMA peak.  Coefficients live in
 // shared memory and are read as broadcast 128-bit loads (two coefficients per LDS); every thread
 // carries R independent points so the DFMA dependency chains overlap.
-#include "afb_common.cuh"
+#include <algorithm>
+
+#include "afb_internal.h"
 #ifndef AFB_HOST_EMU
 #include <cuda_pipeline.h>
 #endif
@@ -550,13 +552,76 @@ int32_t launch_clenshaw_rec(const double* d_c, int64_t N, const double* d_A, con
     const int64_t grid = ntiles < 2 * (int64_t)sm_count() ? ntiles : 2 * (int64_t)sm_count();
     const int64_t staged = N < REC_CHUNK ? (N > 0 ? N : 1) : REC_CHUNK;
     auto k = clenshaw_rec_kernel;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 4 * REC_CHUNK)));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, (sizeof(double) * 4 * REC_CHUNK));
     AFB_LAUNCH(k, (unsigned)grid, REC_THREADS, sizeof(double) * 4 * (size_t)staged, stream, d_c, N, d_A, d_B, d_C, d_x, d_y, P,
                ntiles);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Piecewise Chebyshev Funs (PiecewiseSpace of Chebyshev segments): evaluation and the GENERIC bisection
+// of src/Extras/sample.jl:8-36 (the path `sample(abs(Fun(sin, -5..5)), n)` takes, test/PiecewiseSampleTest.jl:5-10):
+//     a = minimum(d); b = maximum(d); numits x { m = genmidpoint(a,b); v = f(m); (v <= u) ? a = m : b = m }; .5(a+b)
+// f(m) = the FIRST piece whose closed interval contains m, evaluated by the Chebyshev recurrence at
+// tocanonical(piece, m) = (2m - lo - hi)/(hi - lo); zero outside the domain.
+// Coefficients of all pieces (concatenated, offs[k]..offs[k+1]) and the np+1 break points live in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double genmidpoint_dev(double a, double b) {  // sample.jl:11-21
+    const bool ia = isinf(a), ib = isinf(b);
+    if (ia && ib) return 0.0;
+    if (ia) return __dsub_rn(b, 100.0);
+    if (ib) return __dadd_rn(a, 100.0);
+    return __dmul_rn(__dadd_rn(a, b), 0.5);
+}
+__device__ __forceinline__ double piecewise_eval(const double* sc, const int32_t* soff, const double* sbrk, int np, double m) {
+    if (!(m >= sbrk[0] && m <= sbrk[np])) return 0.0;
+    int lo = 0, hi = np - 1;  // smallest k with m <= brk[k+1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (m <= sbrk[mid + 1]) hi = mid; else lo = mid + 1;
+    }
+    const double l = sbrk[lo], h = sbrk[lo + 1];
+    const int o = soff[lo], N = soff[lo + 1] - o;
+    if (N == 0) return 0.0;
+    if (N == 1) return sc[o];
+    const double x = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, m), l), h), __dsub_rn(h, l));
+    double x2[1] = {__dmul_rn(2.0, x)}, b1[1] = {0.0}, b2[1] = {0.0}, y[1];
+    clenshaw_span<1>(sc + o, 1, N, x2, b1, b2);
+    clenshaw_finish<1>(sc[o], x2, b1, b2, y);
+    return y[0];
+}
+__global__ void __launch_bounds__(256)
+piecewise_kernel(const double* __restrict__ coef, const int32_t* __restrict__ offs, const double* __restrict__ brk, int np,
+                 const double* __restrict__ xu, double* __restrict__ out, int64_t P, int bisect, int numits) {
+    AFB_DYN_SMEM(double, sc);
+    const int total = offs[np];
+    double* sbrk = sc + total;
+    int32_t* soff = reinterpret_cast<int32_t*>(sbrk + np + 1);
+    for (int k = threadIdx.x; k < total; k += blockDim.x) sc[k] = coef[k];
+    for (int k = threadIdx.x; k <= np; k += blockDim.x) { sbrk[k] = brk[k]; soff[k] = offs[k]; }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = xu[i];
+        if (!bisect) { out[i] = piecewise_eval(sc, soff, sbrk, np, v); continue; }
+        double a = sbrk[0], b = sbrk[np];
+        for (int it = 0; it < numits; ++it) {
+            const double m = genmidpoint_dev(a, b);
+            if (piecewise_eval(sc, soff, sbrk, np, m) <= v) a = m; else b = m;
+        }
+        out[i] = __dmul_rn(0.5, __dadd_rn(a, b));
+    }
+}
+int32_t launch_piecewise(const double* d_coef, const int32_t* d_offs, const double* d_brk, int64_t np, int64_t total,
+                         const double* d_xu, double* d_out, int64_t P, bool bisect, int numits, void* stream) {
+    if (P == 0) return AFB_OK;
+    const size_t smem = sizeof(double) * (size_t)(total + np + 1) + sizeof(int32_t) * (size_t)(np + 1) + 16;
+    if (smem > 200 * 1024) return fail(AFB_UNSUPPORTED, "piecewise Fun: more than 200 KB of coefficients and break points");
+    int64_t grid = (P + 255) / 256;
+    if (grid > 8 * (int64_t)sm_count()) grid = 8 * (int64_t)sm_count();
+    auto k = piecewise_kernel;
+    AFB_SMEM_OPTIN(k, 200 * 1024);
+    AFB_LAUNCH(k, (unsigned)grid, 256, smem, stream, d_coef, d_offs, d_brk, (int)np, d_xu, d_out, P, bisect ? 1 : 0, numits);
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
@@ -778,12 +843,70 @@ __global__ void gemm_nn_kernel(const double* __restrict__ CB, const double* __re
     }
 }
 
+// ---- unfused route of the 2-D conditional sampler (any N): the reference's own sequence of src/Extras/sample.jl:208-213 as
+// separate kernels over chunks of samples -- evaluate.(f.A, ry') -> CB*fA -> chebnormalizedcumsum! -> chebbisectioninv ->
+// fromcanonical -- with the operation order of the fused kernel, so both routes give the same bits.
+__global__ void s2_tocanonical_kernel(const double* __restrict__ ry, double* __restrict__ yc, int64_t P, double ya, double yb) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x)
+        yc[j] = __ddiv_rn(__dsub_rn(__dsub_rn(__dmul_rn(2.0, ry[j]), ya), yb), __dsub_rn(yb, ya));
+}
+// evaluate returns zero outside the domain
+__global__ void s2_mask_outside_kernel(const double* __restrict__ ry, double* __restrict__ fA, int64_t R, int64_t P, double lo, double hi) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < R * P; g += (int64_t)gridDim.x * blockDim.x) {
+        const double y = ry[g / R];
+        if (!(y >= lo && y <= hi)) fA[g] = 0.0;
+    }
+}
+__global__ void s2_fromcanonical_kernel(double* __restrict__ rx, int64_t P, double xa, double xb) {
+    const double mid = __dmul_rn(__dadd_rn(xa, xb), 0.5), len = __dsub_rn(xb, xa);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x)
+        rx[j] = __dadd_rn(mid, __dmul_rn(__dmul_rn(len, rx[j]), 0.5));
+}
+static int32_t sample2d_unfused(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R, double ya, double yb,
+                                double xa, double xb, const double* d_ry, const double* d_u, double* d_rx, int64_t P, int numits,
+                                void* stream) {
+    const int64_t per = 8 * (N + R + 1);
+    int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / per);
+    if (chunk > P) chunk = P;
+    double *yc = nullptr, *fA = nullptr, *AB = nullptr;
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)(chunk * (N + R + 1))));
+    yc = reinterpret_cast<double*>(d); fA = yc + chunk; AB = fA + chunk * R;
+    int32_t st = AFB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t p0 = 0; p0 < P && st == AFB_OK; p0 += chunk) {
+        const int64_t np = std::min(chunk, P - p0);
+        int64_t grid = std::min<int64_t>((np + 255) / 256, 8 * (int64_t)sm_count());
+        auto k1 = s2_tocanonical_kernel;
+        AFB_LAUNCH(k1, (unsigned)grid, 256, 0, s, d_ry + p0, yc, np, ya, yb);
+        st = launch_multi(d_A, NA, R, yc, fA, np, stream);
+        if (st != AFB_OK) break;
+        auto k2 = s2_mask_outside_kernel;
+        grid = std::min<int64_t>((np * R + 255) / 256, 8 * (int64_t)sm_count());
+        if (R > 0) AFB_LAUNCH(k2, (unsigned)grid, 256, 0, s, d_ry + p0, fA, R, np, ya < yb ? ya : yb, ya < yb ? yb : ya);
+        if (R > 0) st = launch_gemm_nn(d_CB, fA, AB, N, R, np, stream);
+        else if (N * np > 0) { cudaError_t e = cudaMemsetAsync(AB, 0, sizeof(double) * (size_t)(N * np), s); if (e != cudaSuccess) st = cuda_fail(e, "memset", __FILE__, __LINE__); }
+        if (st == AFB_OK) st = launch_normcumsum(AB, N, np, N, 0, stream);
+        if (st == AFB_OK) st = launch_cols(true, AB, N, N, d_u + p0, d_rx + p0, np, numits, stream);
+        if (st != AFB_OK) break;
+        auto k3 = s2_fromcanonical_kernel;
+        grid = std::min<int64_t>((np + 255) / 256, 8 * (int64_t)sm_count());
+        AFB_LAUNCH(k3, (unsigned)grid, 256, 0, s, d_rx + p0, np, xa, xb);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    cudaFree(d);
+    if (st == AFB_OK) { e = cudaGetLastError(); if (e != cudaSuccess) st = cuda_fail(e, "sample2d_unfused", __FILE__, __LINE__); }
+    return st;
+}
+
 int32_t launch_sample2d(const double* d_A, int64_t NA, const double* d_CB, int64_t N, int64_t R, double ya, double yb,
                         double xa, double xb, const double* d_ry, const double* d_u, double* d_rx, int64_t P, int numits,
                         void* stream) {
     if (P == 0) return AFB_OK;
     const size_t smem = sizeof(double) * (size_t)(N > 0 ? N : 1) * S2_LD;
-    if (smem > 200 * 1024) return fail(AFB_UNSUPPORTED, "sample2d: B factors longer than 198 coefficients need the unfused path");
+    if (smem > 200 * 1024)   // B factors longer than 198 coefficients: the column tile no longer fits shared memory
+        return sample2d_unfused(d_A, NA, d_CB, N, R, ya, yb, xa, xb, d_ry, d_u, d_rx, P, numits, stream);
     auto k = sample2d_kernel;
     AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AFB_LAUNCH(k, (unsigned)((P + S2_W - 1) / S2_W), S2_W, smem, stream, d_A, NA, d_CB, N, R, ya, yb, xa, xb, d_ry, d_u, d_rx,

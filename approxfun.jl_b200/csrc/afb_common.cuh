@@ -41,8 +41,25 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 #define AFB_KERNEL_CHECK() AFB_CUDA(cudaGetLastError())
 
+constexpr int MAX_DEVICES = 16;  // device ordinals 0..15 (one node); also the limit of the peer-pointer tables
 int32_t ensure_device();  // AFB_NO_DEVICE unless a CUDA device is usable (no CPU fallback)
-int sm_count();
+int current_device();     // the calling thread's current CUDA device ordinal
+int sm_count();           // ... and its SM count
+
+// Opt-in dynamic shared memory: the attribute belongs to the (kernel, device) pair, so it is set once per device.
+#ifndef AFB_HOST_EMU
+#define AFB_SMEM_OPTIN(kernel, bytes)                                                                          \
+    do {                                                                                                       \
+        static unsigned afb_done_mask_ = 0;  /* benign race: the attribute call is idempotent */                \
+        const unsigned afb_bit_ = 1u << afb::current_device();                                                 \
+        if (!(__atomic_load_n(&afb_done_mask_, __ATOMIC_ACQUIRE) & afb_bit_)) {                                 \
+            AFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            __atomic_fetch_or(&afb_done_mask_, afb_bit_, __ATOMIC_RELEASE);                                    \
+        }                                                                                                      \
+    } while (0)
+#else
+#define AFB_SMEM_OPTIN(kernel, bytes) do { (void)(bytes); } while (0)
+#endif
 
 // ---- complex helpers ----------------------------------------------------------------------------
 typedef double2 cplx;

@@ -115,6 +115,7 @@ static inline double sinpi(double x) {
     return (std::fmod(k, 2.0) == 0.0) ? s : -s;
 }
 
+using std::isinf;
 static inline double cospi(double x) { return sinpi(0.5 - std::fabs(x)); }
 static inline void sincospi(double x, double* s, double* c) { *s = sinpi(x); *c = sinpi(x + 0.5); }
 
@@ -132,6 +133,7 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
     return 0;
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }

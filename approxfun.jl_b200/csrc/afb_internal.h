@@ -31,6 +31,8 @@ int32_t launch_clenshaw_rec(const double* d_c, int64_t N, const double* d_A, con
                             const double* d_x, double* d_y, int64_t P, void* stream);
 int32_t launch_bisect_vec(const double* d_c, int64_t N, const double* d_u, bool rng, uint64_t seed, uint64_t offset,
                           double* d_out, int64_t P, int numits, double a, double b, void* stream);
+int32_t launch_piecewise(const double* d_coef, const int32_t* d_offs, const double* d_brk, int64_t np, int64_t total,
+                         const double* d_xu, double* d_out, int64_t P, bool bisect, int numits, void* stream);
 int32_t launch_philox(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
 int32_t launch_cols(bool bisect, const double* d_C, int64_t N, int64_t ld, const double* d_xu, double* d_out,
                     int64_t P, int numits, void* stream);
@@ -92,6 +94,15 @@ int32_t launch_scatter_idx(double* dst, const double* src, const int32_t* idx, i
 int32_t launch_gather_idx(double* dst, const double* src, const int32_t* idx, int64_t N, double scale, void* stream);
 int32_t launch_paduapoints(double* xy, const int32_t* idx, int64_t N, int64_t d, double ax, double bx, double ay, double by,
                            void* stream);
+
+// in-process multi-device 2-D plan (afb_tensor.cu), reached through afb_plan_execute_host
+bool mdev2d_supported(int32_t kind, int64_t n, int64_t n2, int ndev, uint32_t flags);
+int32_t mdev2d_create(void** out, int32_t kind, int64_t n, int64_t n2, const std::vector<int>& devs);
+int32_t mdev2d_execute_host(void* handle, const double* in, double* out);
+void mdev2d_destroy(void* handle);
+// `batch` lines of a 1-D plan (batch <= the plan's batch), on the plan's device; used by the chunked column pass
+int32_t slab_col_chunk(afb_plan plan, const double* d_in, double* d_out, int64_t batch, void* stream);
+const std::vector<int>& device_list();
 
 // ---- device table helpers ------------------------------------------------------------------------------
 int32_t upload_table(const std::vector<cplx>& host, cplx** dev);

@@ -144,11 +144,7 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) blue_f
 template <int M> static int32_t launch_blue_fused_m(const BlueParams& p, void* stream) {
     typedef BlueGeom<M> G;
     auto k = blue_fused_kernel<M>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     AFB_LAUNCH(k, (unsigned)((p.batch + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();
     return AFB_OK;
@@ -531,11 +527,7 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) blue_r
 template <int M, int KIND> static int32_t launch_blue_real_mk(const BlueRealParams& p, void* stream) {
     typedef BlueGeom<M> G;
     auto k = blue_real_kernel<M, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     const int64_t npairs = (p.batch + 1) / 2;
     AFB_LAUNCH(k, (unsigned)((npairs + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();
@@ -701,11 +693,7 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, 512 / BlueGeom<M>::CT) ext_fu
 template <int M, int KIND, bool BLUE> static int32_t launch_ext_fused_mk(const ExtParams& p, void* stream) {
     typedef BlueGeom<M> G;
     auto k = ext_fused_kernel<M, KIND, BLUE>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     const int64_t npairs = (p.batch + 1) / 2;
     AFB_LAUNCH(k, (unsigned)((npairs + G::LPC - 1) / G::LPC), G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();

@@ -164,11 +164,7 @@ __global__ void __launch_bounds__(INNER_CT) rows_inner_kernel(const __grid_const
 template <int NL, bool INV> static int32_t launch_outer(const RowsParams& p, void* stream) {
     typedef RowsGeom<NL> G;
     auto k = rows_outer_kernel<NL, INV>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     const int64_t gx = (p.half + G::LINES - 1) / G::LINES;
     AFB_LAUNCH(k, dim3((unsigned)gx, (unsigned)p.NB), G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();
@@ -177,11 +173,7 @@ template <int NL, bool INV> static int32_t launch_outer(const RowsParams& p, voi
 template <int NL, bool INV> static int32_t launch_inner(const RowsParams& p, void* stream) {
     typedef RowsGeom<NL, INNER_CT> G;
     auto k = rows_inner_kernel<NL, INV>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     const int64_t gx = (p.half + G::LINES / 2 - 1) / (G::LINES / 2);
     AFB_LAUNCH(k, dim3((unsigned)gx, (unsigned)(p.NA / 2 + 1)), G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();

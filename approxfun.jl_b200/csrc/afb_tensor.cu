@@ -11,6 +11,9 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "afb_internal.h"
 
@@ -100,30 +103,112 @@ __global__ void a2a_unpack_kernel(const double* __restrict__ R, double* __restri
     }
 }
 
-// Fused transpose + all-to-all over NVLink peer memory: tile (i, j) of this rank's n x nc column block (after the
-// column transforms) is transposed through shared memory and written STRAIGHT into the row-line buffer of the rank
-// that owns row i (local HBM for d == rank, a peer-mapped pointer otherwise): L_d[(i - d nr) * n2 + rank * nc + j].
-// One kernel replaces pack-transpose + NCCL send/recv + unpack; stores are 256-byte contiguous runs per row.
-struct PeerPtrs { double* p[16]; };
-__global__ void __launch_bounds__(256) transpose_to_peers_kernel(const double* __restrict__ in, PeerPtrs peers, int64_t n,
-                                                                 int64_t nc, int64_t nr, int64_t n2, int64_t rank) {
-    AFB_DYN_SMEM(double, tile);  // TR_TILE x (TR_TILE+1)
+// Fused transpose + all-to-all over NVLink peer memory.  A 32 (rows i) x 64 (columns j) tile of this rank's n x nc column
+// block (after the column transforms) is transposed through shared memory and written STRAIGHT into the receive buffer of the
+// rank that owns row i (local HBM for d == rank, a peer-mapped pointer otherwise): R_d[(i - d nr) * n2 + rank * nc + j], as
+// 128-bit stores (a warp writes two 256-byte runs).  One kernel replaces pack-transpose + NCCL send/recv + unpack.
+//   * Tiles are visited destination by destination, starting at rank + 1: at any moment the G ranks write to G different
+//     destinations (no incast on one NVSwitch egress port).
+//   * Completion is signalled on the device: every CTA fences its stores at system scope and counts itself on a local
+//     counter; the last one stores the call's epoch into flags[rank] of EVERY destination (st.release.sys).  The row pass of
+//     a destination is launched behind xchg_wait_kernel, which spins (ld.acquire.sys) until all G senders have reported the
+//     epoch.  No host synchronisation and no NCCL on the data path.
+//   * Receive buffers are double-buffered by epoch parity, so no "everyone is done reading" barrier is needed before the
+//     writes: a sender reaches epoch e+2 only after the receiver's flag of epoch e+1, which the receiver stores after its
+//     row pass of epoch e (stream order) -- see DESIGN.md section 6.
+constexpr int XT_I = 32, XT_J = 64;
+struct XchgPeers {
+    double* recv[MAX_DEVICES];       // receive buffer of this epoch's parity on every rank
+    uint64_t* flags[MAX_DEVICES];    // flags[d][s] = last epoch for which sender s's tiles have landed on rank d
+};
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+#ifndef AFB_HOST_EMU
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+#ifndef AFB_HOST_EMU
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+// in: column-major n x nc (this rank's columns j0g..j0g+nc of the global matrix); rows [r0, r1) of every destination's
+// nr-row share are sent (r0 = 0, r1 = nr: everything).  signal != 0: the last CTA publishes `epoch`.
+__global__ void __launch_bounds__(256) xchg_transpose_kernel(const double* __restrict__ in, XchgPeers peers, int64_t n, int64_t nc,
+                                                             int64_t nr, int64_t n2, int G, int rank, int64_t c0, int64_t c1,
+                                                             int vec, unsigned* ctr, uint64_t epoch, int signal) {
+    AFB_DYN_SMEM(double, tile);  // XT_J x (XT_I + 1)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const int64_t i0 = (int64_t)blockIdx.x * TR_TILE, j0 = (int64_t)blockIdx.y * TR_TILE;
+    const int64_t ti_per = (nr + XT_I - 1) / XT_I, tj_cnt = (c1 - c0 + XT_J - 1) / XT_J;
+    const int64_t per_dest = ti_per * tj_cnt;
+    for (int64_t b = blockIdx.x; b < per_dest * G; b += gridDim.x) {
+        const int k = (int)(b / per_dest);
+        const int d = (rank + 1 + k) % G;             // rotated destination order; the local share goes last
+        const int64_t w = b - (int64_t)k * per_dest;
+        const int64_t il0 = (w % ti_per) * XT_I, j0 = c0 + (w / ti_per) * XT_J;
+        const int64_t i0 = (int64_t)d * nr + il0;
 #pragma unroll
-    for (int r = 0; r < TR_TILE; r += 8) {
-        const int64_t i = i0 + tx, j = j0 + ty + r;
-        if (i < n && j < nc) tile[(ty + r) * (TR_TILE + 1) + tx] = in[i + j * n];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < TR_TILE; r += 8) {
-        const int64_t j = j0 + tx, i = i0 + ty + r;
-        if (i < n && j < nc) {
-            const int64_t d = i / nr;
-            peers.p[d][(i - d * nr) * n2 + rank * nc + j] = tile[tx * (TR_TILE + 1) + ty + r];
+        for (int r = 0; r < XT_J; r += 8) {
+            const int64_t il = il0 + tx, j = j0 + ty + r;
+            if (il < nr && j < c1) tile[(ty + r) * (XT_I + 1) + tx] = in[i0 + tx + j * n];
         }
+        __syncthreads();
+        double* dst = peers.recv[d] + (int64_t)rank * nc;
+        // lanes 0-15: row ii, column pairs 0..15 ; lanes 16-31: row ii + 1
+        const int half = tx >> 4, jp = tx & 15;
+#pragma unroll
+        for (int r = 0; r < XT_I; r += 16) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // column pairs jp and jp + 16... covers 64 columns in two halves
+                const int ii = r + 2 * ty + half;
+                const int jj = 2 * (jp + 16 * h);
+                const int64_t il = il0 + ii, j = j0 + jj;
+                if (il < nr && j < c1) {
+                    const double a = tile[jj * (XT_I + 1) + ii];
+                    if (vec && j + 1 < c1) {
+                        const double bb = tile[(jj + 1) * (XT_I + 1) + ii];
+                        *reinterpret_cast<double2*>(dst + il * n2 + j) = make_double2(a, bb);
+                    } else {
+                        dst[il * n2 + j] = a;
+                        if (j + 1 < c1) dst[il * n2 + j + 1] = tile[(jj + 1) * (XT_I + 1) + ii];
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
+    if (!signal) return;
+    // completion: fence this CTA's stores at system scope, count it; the last CTA publishes the epoch to every destination
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#ifndef AFB_HOST_EMU
+        __threadfence_system();
+        const unsigned prev = atomicAdd(ctr, 1u);
+        if (prev == gridDim.x - 1) {
+            *ctr = 0;                 // the next launch on this stream starts from zero
+            __threadfence_system();
+            for (int d = 0; d < G; ++d) st_release_sys(peers.flags[d] + rank, epoch);
+        }
+#endif
+    }
+}
+// One warp: lane s < G waits until sender s has published `epoch` (or a later one).  A peer that never arrives would hang
+// the stream; after ~10 s the kernel traps instead, which surfaces as a CUDA error at the caller's next synchronisation.
+__global__ void xchg_wait_kernel(const uint64_t* __restrict__ flags, int G, uint64_t epoch) {
+#ifndef AFB_HOST_EMU
+    const int s = threadIdx.x;
+    if (s >= G) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + s) < epoch) {
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll) __trap();
+    }
+#endif
 }
 
 }  // namespace afb
@@ -181,18 +266,125 @@ static int32_t nccl_load() {
     } while (0)
 #endif
 
+// One rank's share of the slab-decomposed 2-D transform (used by the one-process-per-GPU entry points afb_sharded2d_* and by
+// the in-process multi-device plan behind afb_plan_execute_host).
 struct Sharded2D {
-    int32_t kind;
-    int64_t n, n2, G, rank;
+    int32_t kind = 0;
+    int64_t n = 0, n2 = 0, G = 1, rank = 0;
+    int dev = 0;
     afb_plan col_plan = nullptr;  // length n,  batch n2/G
     afb_plan row_plan = nullptr;  // length n2, batch n/G
     double *tbuf = nullptr, *rbuf = nullptr;
-    // peer-memory (CUDA IPC) mode: lbuf receives every rank's tiles; peer[d] = rank d's lbuf mapped here
-    double* lbuf = nullptr;
-    double* peer[16] = {nullptr};
-    bool p2p = false;
-    double* sync_buf = nullptr;  // 2 x G doubles for the NCCL stream barrier
+    // peer-memory mode: ONE allocation [recv 0 | recv 1 | flags | counter] (one CUDA IPC handle in the multi-process case)
+    char* xblock = nullptr;
+    double* peer_recv[2][MAX_DEVICES] = {{nullptr}};
+    uint64_t* peer_flags[MAX_DEVICES] = {nullptr};
+    void* peer_base[MAX_DEVICES] = {nullptr};  // IPC mappings to close
+    bool p2p = false, ipc = false;
+    uint64_t epoch = 0;
+    int chunks = 1;               // column-pass / exchange pipeline depth (see slab_execute)
+    cudaStream_t side = nullptr;  // the exchange runs here while the next column chunk is transformed
+    cudaEvent_t ev_col[8] = {nullptr}, ev_x = nullptr;
+    size_t recv_bytes() const { return sizeof(double) * (size_t)((n / G) * n2); }
+    size_t xblock_bytes() const { return 2 * recv_bytes() + 4096; }
+    double* recv(int parity) const { return reinterpret_cast<double*>(xblock + (size_t)parity * recv_bytes()); }
+    uint64_t* flags() const { return reinterpret_cast<uint64_t*>(xblock + 2 * recv_bytes()); }
+    unsigned* ctr() const { return reinterpret_cast<unsigned*>(xblock + 2 * recv_bytes() + 2048); }
 };
+
+static int32_t slab_alloc_xblock(Sharded2D& s) {
+    if (s.xblock) return AFB_OK;
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, s.xblock_bytes()));
+    s.xblock = reinterpret_cast<char*>(d);
+    AFB_CUDA(cudaMemset(s.xblock + 2 * s.recv_bytes(), 0, 4096));
+    return AFB_OK;
+}
+static void slab_wire_peer(Sharded2D& s, int d, char* base) {
+    s.peer_recv[0][d] = reinterpret_cast<double*>(base);
+    s.peer_recv[1][d] = reinterpret_cast<double*>(base + s.recv_bytes());
+    s.peer_flags[d] = reinterpret_cast<uint64_t*>(base + 2 * s.recv_bytes());
+}
+static int32_t slab_create(Sharded2D& s, int32_t kind, int64_t n, int64_t n2, int64_t G, int64_t rank) {
+    s.kind = kind; s.n = n; s.n2 = n2; s.G = G; s.rank = rank; s.dev = current_device();
+    const int32_t k1 = (kind == AFB_CHEB1_2D_FWD) ? AFB_CHEB1_FWD : AFB_CHEB1_INV;
+    AFB_TRY(afb_plan_create(&s.col_plan, k1, n, 0, n2 / G, n, 0));
+    AFB_TRY(afb_plan_create(&s.row_plan, k1, n2, 0, n / G, n2, 0));
+    void* d = nullptr;
+    AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)(n * (n2 / G))));
+    s.rbuf = reinterpret_cast<double*>(d);
+    return AFB_OK;
+}
+static void slab_free(Sharded2D& s) {
+    if (s.col_plan) afb_plan_destroy(s.col_plan);
+    if (s.row_plan) afb_plan_destroy(s.row_plan);
+    if (s.tbuf) cudaFree(s.tbuf);
+    if (s.rbuf) cudaFree(s.rbuf);
+#ifndef AFB_HOST_EMU
+    if (s.ipc)
+        for (int64_t d = 0; d < s.G; ++d)
+            if (d != s.rank && s.peer_base[d]) cudaIpcCloseMemHandle(s.peer_base[d]);
+    for (auto& e : s.ev_col) if (e) cudaEventDestroy(e);
+    if (s.ev_x) cudaEventDestroy(s.ev_x);
+    if (s.side) cudaStreamDestroy(s.side);
+#endif
+    if (s.xblock) cudaFree(s.xblock);
+    s = Sharded2D();
+}
+
+// Peer-memory execution of one rank: column transforms -> fused transpose straight into the owners' receive buffers ->
+// wait for every sender's epoch flag -> row transforms.  With chunks > 1 the column pass runs in `chunks` pieces on the
+// caller's stream and each finished piece is sent on a side stream while the next is transformed.
+static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out, void* stream) {
+#ifdef AFB_HOST_EMU
+    (void)s; (void)d_in; (void)d_out; (void)stream;
+    return fail(AFB_UNSUPPORTED, "no peer memory in the emulator build");
+#else
+    const int64_t n = s.n, G = s.G, nc = s.n2 / G, nr = n / G;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t epoch = ++s.epoch;
+    const int par = (int)(epoch & 1);
+    XchgPeers pp;
+    for (int d = 0; d < MAX_DEVICES; ++d) { pp.recv[d] = s.peer_recv[par][d]; pp.flags[d] = s.peer_flags[d]; }
+    auto kt = xchg_transpose_kernel;
+    const size_t smem = sizeof(double) * XT_J * (XT_I + 1);
+    // chunk boundaries on multiples of 64 columns (vector stores stay aligned)
+    int K = s.chunks;
+    while (K > 1 && (nc / K) % XT_J) --K;
+    if (K > 8) K = 8;
+    if (K == 1) {
+        AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
+        const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
+        const int64_t grid = std::min<int64_t>(tiles, 8 * (int64_t)sm_count());
+        const int vec = (nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+        AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
+                   s.ctr(), epoch, 1);
+        AFB_KERNEL_CHECK();
+    } else {
+        if (!s.side) AFB_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        if (!s.ev_x) AFB_CUDA(cudaEventCreateWithFlags(&s.ev_x, cudaEventDisableTiming));
+        const int64_t cw = nc / K;
+        for (int c = 0; c < K; ++c) {
+            if (!s.ev_col[c]) AFB_CUDA(cudaEventCreateWithFlags(&s.ev_col[c], cudaEventDisableTiming));
+            AFB_TRY(slab_col_chunk(s.col_plan, d_in + c * cw * n, s.rbuf + c * cw * n, cw, stream));
+            AFB_CUDA(cudaEventRecord(s.ev_col[c], st));
+            AFB_CUDA(cudaStreamWaitEvent(s.side, s.ev_col[c], 0));
+            const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * (cw / XT_J);
+            // a few CTAs per chunk: the exchange is NVLink-bound and must leave the SMs to the next column chunk
+            const int64_t grid = std::min<int64_t>(tiles, c + 1 < K ? 2 * (int64_t)sm_count() : 8 * (int64_t)sm_count());
+            AFB_LAUNCH(kt, (unsigned)grid, 256, smem, s.side, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, c * cw, (c + 1) * cw, 1,
+                       s.ctr(), epoch, c + 1 == K ? 1 : 0);
+            AFB_KERNEL_CHECK();
+        }
+        AFB_CUDA(cudaEventRecord(s.ev_x, s.side));
+        AFB_CUDA(cudaStreamWaitEvent(st, s.ev_x, 0));
+    }
+    auto kw = xchg_wait_kernel;
+    AFB_LAUNCH(kw, 1, 32, 0, st, s.flags(), (int)G, epoch);
+    AFB_KERNEL_CHECK();
+    return afb_plan_execute_device(s.row_plan, s.recv(par), d_out, stream);
+#endif
+}
 
 extern "C" {
 
@@ -242,8 +434,7 @@ int32_t afb_comm_destroy(void) {
 
 }  // extern "C"
 
-// The sharded plan is an ordinary afb_plan whose handle wraps Sharded2D; to keep afb_plan_s private to
-// afb_api.cu the sharded entry points live here and use their own handle type behind the same typedef.
+// The sharded entry points use their own handle type (afb_plan_s stays private to afb_api.cu).
 namespace {
 struct ShardHandle {
     uint64_t magic = 0x5348415244324421ull;  // "SHARD2D!"
@@ -264,42 +455,21 @@ int32_t afb_sharded2d_create(void** out, int32_t kind, int64_t n, int64_t n2) {
     const int64_t G = g_world;
     if (n <= 0 || n2 <= 0 || n % G || n2 % G) return fail(AFB_BAD_SIZE, "afb_sharded2d_create: n and n2 must be multiples of the world size");
     ShardHandle* h = new ShardHandle();
-    h->s.kind = kind; h->s.n = n; h->s.n2 = n2; h->s.G = G; h->s.rank = g_rank;
-    const int32_t k1 = (kind == AFB_CHEB1_2D_FWD) ? AFB_CHEB1_FWD : AFB_CHEB1_INV;
-    int32_t st = afb_plan_create(&h->s.col_plan, k1, n, 0, n2 / G, n, 0);
-    if (st == AFB_OK) st = afb_plan_create(&h->s.row_plan, k1, n2, 0, n / G, n2, 0);
-    const size_t bytes = sizeof(double) * (size_t)(n * (n2 / G));
-    if (st == AFB_OK) { void* d = nullptr; cudaError_t e = cudaMalloc(&d, bytes); if (e) st = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); h->s.tbuf = (double*)d; }
-    if (st == AFB_OK) { void* d = nullptr; cudaError_t e = cudaMalloc(&d, bytes); if (e) st = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); h->s.rbuf = (double*)d; }
-    if (st != AFB_OK) {
-        if (h->s.col_plan) afb_plan_destroy(h->s.col_plan);
-        if (h->s.row_plan) afb_plan_destroy(h->s.row_plan);
-        if (h->s.tbuf) cudaFree(h->s.tbuf);
-        if (h->s.rbuf) cudaFree(h->s.rbuf);
-        delete h;
-        return st;
+    int32_t st = slab_create(h->s, kind, n, n2, G, g_rank);
+    if (st == AFB_OK) {  // pack buffer of the NCCL baseline route
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)(n * (n2 / G)));
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+        h->s.tbuf = reinterpret_cast<double*>(d);
     }
+    if (st != AFB_OK) { slab_free(h->s); delete h; return st; }
     *out = h;
     return AFB_OK;
 #endif
 }
 
-#ifndef AFB_HOST_EMU
-// stream-ordered barrier over the communicator (one double to and from every peer)
-static int32_t nccl_stream_barrier(Sharded2D& s, void* stream) {
-    AFB_NCCL(g_nccl.GroupStart());
-    for (int64_t d = 0; d < s.G; ++d) {
-        if (d == s.rank) continue;
-        AFB_NCCL(g_nccl.Send(s.sync_buf + d, 1, ncclFloat64, (int)d, g_comm, (cudaStream_t)stream));
-        AFB_NCCL(g_nccl.Recv(s.sync_buf + s.G + d, 1, ncclFloat64, (int)d, g_comm, (cudaStream_t)stream));
-    }
-    AFB_NCCL(g_nccl.GroupEnd());
-    return AFB_OK;
-}
-#endif
-
-// Peer-memory mode (one process per GPU): each rank exports the CUDA IPC handle of its receive buffer
-// (64 bytes), the host layer all-gathers them, and every rank maps its peers' buffers.
+// Peer-memory mode (one process per GPU): each rank exports the CUDA IPC handle of its receive block
+// (64 bytes), the host layer all-gathers them, and every rank maps its peers' blocks.
 int32_t afb_sharded2d_ipc_export(void* handle, void* handle64) {
 #ifdef AFB_HOST_EMU
     (void)handle; (void)handle64;
@@ -308,13 +478,9 @@ int32_t afb_sharded2d_ipc_export(void* handle, void* handle64) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h || h->magic != 0x5348415244324421ull || !handle64) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_export: bad argument");
     Sharded2D& s = h->s;
-    if (!s.lbuf) {
-        void* d = nullptr;
-        AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)((s.n / s.G) * s.n2)));
-        s.lbuf = reinterpret_cast<double*>(d);
-    }
+    AFB_TRY(slab_alloc_xblock(s));
     cudaIpcMemHandle_t mh;
-    AFB_CUDA(cudaIpcGetMemHandle(&mh, s.lbuf));
+    AFB_CUDA(cudaIpcGetMemHandle(&mh, s.xblock));
     static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
     std::memcpy(handle64, &mh, 64);
     return AFB_OK;
@@ -329,22 +495,27 @@ int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world)
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h || h->magic != 0x5348415244324421ull || !handles) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_open: bad argument");
     Sharded2D& s = h->s;
-    if (world != s.G || world > 16 || !s.lbuf) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_open: export first; world <= 16");
+    if (world != s.G || world > MAX_DEVICES || !s.xblock) return fail(AFB_BAD_ARG, "afb_sharded2d_ipc_open: export first; world <= 16");
     for (int64_t d = 0; d < s.G; ++d) {
-        if (d == s.rank) { s.peer[d] = s.lbuf; continue; }
+        if (d == s.rank) { slab_wire_peer(s, (int)d, s.xblock); continue; }
         cudaIpcMemHandle_t mh;
         std::memcpy(&mh, reinterpret_cast<const char*>(handles) + 64 * d, 64);
         void* p = nullptr;
         AFB_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
-        s.peer[d] = reinterpret_cast<double*>(p);
+        s.peer_base[d] = p;
+        slab_wire_peer(s, (int)d, reinterpret_cast<char*>(p));
     }
-    void* d = nullptr;
-    AFB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)(2 * s.G)));
-    AFB_CUDA(cudaMemset(d, 0, sizeof(double) * (size_t)(2 * s.G)));
-    s.sync_buf = reinterpret_cast<double*>(d);
     s.p2p = true;
+    s.ipc = true;
     return AFB_OK;
 #endif
+}
+
+int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks) {
+    ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
+    if (!h || h->magic != 0x5348415244324421ull || chunks < 1 || chunks > 8) return fail(AFB_BAD_ARG, "afb_sharded2d_set_chunks: bad argument");
+    h->s.chunks = chunks;
+    return AFB_OK;
 }
 
 // d_in : this rank's column block, column-major n x (n2/G)
@@ -358,23 +529,10 @@ int32_t afb_sharded2d_execute_device(void* handle, const double* d_in, double* d
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h || h->magic != 0x5348415244324421ull) return fail(AFB_BAD_ARG, "afb_sharded2d_execute_device: bad handle");
     Sharded2D& s = h->s;
+    if (s.p2p) return slab_execute_p2p(s, d_in, d_out, stream);
     const int64_t n = s.n, G = s.G, nc = s.n2 / G, nr = n / G;
-    // 1. local column transforms (in place into rbuf to keep d_in intact)
+    // NCCL baseline route.  1. local column transforms (into rbuf to keep d_in intact)
     AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
-    if (s.p2p) {
-        // every rank must be done reading its lbuf (previous call's row transforms) before anyone overwrites it
-        AFB_TRY(nccl_stream_barrier(s, stream));
-        PeerPtrs pp;
-        for (int d = 0; d < 16; ++d) pp.p[d] = s.peer[d];
-        const int64_t gx = (n + TR_TILE - 1) / TR_TILE, gy = (nc + TR_TILE - 1) / TR_TILE;
-        auto kt = transpose_to_peers_kernel;
-        AFB_LAUNCH(kt, dim3((unsigned)gx, (unsigned)gy), 256, sizeof(double) * TR_TILE * (TR_TILE + 1), stream, s.rbuf, pp, n, nc,
-                   nr, s.n2, s.rank);
-        AFB_KERNEL_CHECK();
-        // all peers' tiles have landed in my lbuf once every rank has passed this barrier
-        AFB_TRY(nccl_stream_barrier(s, stream));
-        return afb_plan_execute_device(s.row_plan, s.lbuf, d_out, stream);
-    }
     // 2. pack = local transpose: T[i*nc + j], rows of destination d are the contiguous range i in [d nr, (d+1) nr)
     AFB_TRY(launch_transpose(s.rbuf, s.tbuf, n, nc, stream));
     // 3. all-to-all over NVLink (grouped send/recv: the installed NCCL header has no ncclAlltoAll)
@@ -398,19 +556,139 @@ int32_t afb_sharded2d_destroy(void* handle) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h) return AFB_OK;
     if (h->magic != 0x5348415244324421ull) return fail(AFB_BAD_ARG, "afb_sharded2d_destroy: bad handle");
-    if (h->s.col_plan) afb_plan_destroy(h->s.col_plan);
-    if (h->s.row_plan) afb_plan_destroy(h->s.row_plan);
-    if (h->s.tbuf) cudaFree(h->s.tbuf);
-    if (h->s.rbuf) cudaFree(h->s.rbuf);
-#ifndef AFB_HOST_EMU
-    for (int64_t d = 0; d < h->s.G; ++d)
-        if (h->s.p2p && d != h->s.rank && h->s.peer[d]) cudaIpcCloseMemHandle(h->s.peer[d]);
-#endif
-    if (h->s.lbuf) cudaFree(h->s.lbuf);
-    if (h->s.sync_buf) cudaFree(h->s.sync_buf);
+    slab_free(h->s);
     h->magic = 0;
     delete h;
     return AFB_OK;
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// In-process multi-device 2-D plan (afb_init(devices, ndev) with ndev > 1; reached through afb_plan_execute_host): the same
+// slab decomposition with every device driven by one host thread of THIS process.  Peer buffers are plain pointers
+// (cudaDeviceEnablePeerAccess in afb_init): no IPC, no NCCL, no torch.
+// =====================================================================================================================
+namespace afb {
+
+struct MultiDev2D {
+    std::vector<int> devs;
+    std::vector<Sharded2D> slab;
+    std::vector<double*> din, dout, tout;   // per device: column block, row lines, row block transposed back to column-major
+    std::vector<cudaStream_t> stream;
+    int64_t n = 0, n2 = 0;
+};
+
+bool mdev2d_supported(int32_t kind, int64_t n, int64_t n2, int ndev, uint32_t flags) {
+    (void)flags;
+    if (kind != AFB_CHEB1_2D_FWD && kind != AFB_CHEB1_2D_INV) return false;
+    return ndev > 1 && ndev <= MAX_DEVICES && n > 0 && n2 > 0 && n % ndev == 0 && n2 % ndev == 0 && n * n2 >= ((int64_t)1 << 21);
+}
+
+void mdev2d_destroy(void* handle) {
+    MultiDev2D* m = reinterpret_cast<MultiDev2D*>(handle);
+    if (!m) return;
+    int keep = 0;
+    cudaGetDevice(&keep);
+    for (size_t g = 0; g < m->slab.size(); ++g) {
+        cudaSetDevice(m->devs[g]);
+        slab_free(m->slab[g]);
+        if (g < m->din.size() && m->din[g]) cudaFree(m->din[g]);
+        if (g < m->dout.size() && m->dout[g]) cudaFree(m->dout[g]);
+        if (g < m->tout.size() && m->tout[g]) cudaFree(m->tout[g]);
+        if (g < m->stream.size() && m->stream[g]) cudaStreamDestroy(m->stream[g]);
+    }
+    cudaSetDevice(keep);
+    delete m;
+}
+
+int32_t mdev2d_create(void** out, int32_t kind, int64_t n, int64_t n2, const std::vector<int>& devs) {
+#ifdef AFB_HOST_EMU
+    (void)out; (void)kind; (void)n; (void)n2; (void)devs;
+    return fail(AFB_UNSUPPORTED, "no peer memory in the emulator build");
+#else
+    const int G = (int)devs.size();
+    MultiDev2D* m = new MultiDev2D();
+    m->devs = devs; m->n = n; m->n2 = n2;
+    m->slab.resize((size_t)G);
+    m->din.assign((size_t)G, nullptr); m->dout.assign((size_t)G, nullptr); m->tout.assign((size_t)G, nullptr);
+    m->stream.assign((size_t)G, nullptr);
+    int keep = 0;
+    cudaGetDevice(&keep);
+    int32_t st = AFB_OK;
+    const size_t blk = sizeof(double) * (size_t)(n * (n2 / G));
+    for (int g = 0; g < G && st == AFB_OK; ++g) {
+        cudaError_t e = cudaSetDevice(devs[(size_t)g]);
+        if (e != cudaSuccess) { st = cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); break; }
+        st = ensure_device();
+        if (st == AFB_OK) st = slab_create(m->slab[(size_t)g], kind, n, n2, G, g);
+        if (st == AFB_OK) st = slab_alloc_xblock(m->slab[(size_t)g]);
+        for (double** b : {&m->din[(size_t)g], &m->dout[(size_t)g], &m->tout[(size_t)g]}) {
+            if (st != AFB_OK) break;
+            void* d = nullptr;
+            e = cudaMalloc(&d, blk);
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(2-D slab)", __FILE__, __LINE__);
+            *b = reinterpret_cast<double*>(d);
+        }
+        if (st == AFB_OK) {
+            e = cudaStreamCreateWithFlags(&m->stream[(size_t)g], cudaStreamNonBlocking);
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+        }
+    }
+    if (st == AFB_OK) {
+        for (int g = 0; g < G; ++g) {
+            for (int d = 0; d < G; ++d) slab_wire_peer(m->slab[(size_t)g], d, m->slab[(size_t)d].xblock);
+            m->slab[(size_t)g].p2p = true;
+        }
+    }
+    cudaSetDevice(keep);
+    if (st != AFB_OK) { mdev2d_destroy(m); return st; }
+    *out = m;
+    return AFB_OK;
+#endif
+}
+
+// in / out: the whole column-major n x n2 matrix on the host.  Device g takes columns [g nc, (g+1) nc) (one contiguous
+// block), and after the exchange owns rows [g nr, (g+1) nr) as lines; they are transposed back on the device and land in
+// `out` through a strided (pitch n) device-to-host copy.
+int32_t mdev2d_execute_host(void* handle, const double* in, double* out) {
+#ifdef AFB_HOST_EMU
+    (void)handle; (void)in; (void)out;
+    return fail(AFB_UNSUPPORTED, "no peer memory in the emulator build");
+#else
+    MultiDev2D* m = reinterpret_cast<MultiDev2D*>(handle);
+    const int G = (int)m->devs.size();
+    const int64_t n = m->n, n2 = m->n2, nc = n2 / G, nr = n / G;
+    std::vector<int32_t> st((size_t)G, AFB_OK);
+    std::vector<std::string> msg((size_t)G);
+    std::vector<std::thread> th;
+    int keep = 0;
+    AFB_CUDA(cudaGetDevice(&keep));
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g]() {
+            auto run = [&]() -> int32_t {
+                AFB_CUDA(cudaSetDevice(m->devs[(size_t)g]));
+                cudaStream_t s = m->stream[(size_t)g];
+                AFB_CUDA(cudaMemcpyAsync(m->din[(size_t)g], in + (size_t)g * nc * n, sizeof(double) * (size_t)(n * nc),
+                                         cudaMemcpyHostToDevice, s));
+                AFB_TRY(slab_execute_p2p(m->slab[(size_t)g], m->din[(size_t)g], m->dout[(size_t)g], s));
+                AFB_TRY(launch_transpose(m->dout[(size_t)g], m->tout[(size_t)g], n2, nr, s));
+                AFB_CUDA(cudaMemcpy2DAsync(out + (size_t)g * nr, sizeof(double) * (size_t)n, m->tout[(size_t)g],
+                                           sizeof(double) * (size_t)nr, sizeof(double) * (size_t)nr, (size_t)n2,
+                                           cudaMemcpyDeviceToHost, s));
+                AFB_CUDA(cudaStreamSynchronize(s));
+                return AFB_OK;
+            };
+            st[(size_t)g] = run();
+            if (st[(size_t)g] != AFB_OK) { char buf[512]; afb_last_error(buf, sizeof buf); msg[(size_t)g] = buf; }
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(keep);
+    for (int g = 0; g < G; ++g)
+        if (st[(size_t)g] != AFB_OK) return fail(st[(size_t)g], msg[(size_t)g]);
+    return AFB_OK;
+#endif
+}
+
+}  // namespace afb

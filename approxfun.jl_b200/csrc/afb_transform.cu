@@ -690,11 +690,7 @@ __global__ void __launch_bounds__(FftCfg<N>::T, StageGeom<N>::MINB) line_kernel_
 template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p, void* stream) {
     typedef StageGeom<N> SG;
     auto k = line_kernel_staged<N, KIND>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, SG::SMEM);
     const int64_t cap = (int64_t)SG::MINB * sm_count();
     const int64_t grid = p.batch < cap ? p.batch : cap;
     AFB_LAUNCH(k, (unsigned)grid, FftCfg<N>::T, SG::SMEM, stream, p);
@@ -714,11 +710,7 @@ template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, vo
             return launch_line_staged<N, KIND>(p, stream);
     }
     auto k = line_kernel<N, KIND>;
-    static bool attr_done = false;  // one process drives one device: set the opt-in shared-memory size once
-    if (!attr_done) {
-        AFB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-        attr_done = true;
-    }
+    AFB_SMEM_OPTIN(k, G::SMEM);
     const int64_t grid = (p.batch + G::LPC - 1) / G::LPC;
     AFB_LAUNCH(k, (unsigned)grid, G::CT, G::SMEM, stream, p);
     AFB_KERNEL_CHECK();

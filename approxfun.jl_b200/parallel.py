@@ -98,6 +98,10 @@ class Sharded2DPlan:
             L.check(self.lib, self.lib.afb_sharded2d_ipc_open(self._h, blob, world))
             self.p2p = True
 
+    def set_chunks(self, chunks: int):
+        """Peer-memory mode: column pass in `chunks` pieces, each sent on a side stream while the next is transformed."""
+        L.check(self.lib, self.lib.afb_sharded2d_set_chunks(self._h, int(chunks)))
+
     def execute(self, in_ptr: int, out_ptr: int, stream: int = 0):
         L.check(self.lib, self.lib.afb_sharded2d_execute_device(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_void_p(stream)))
 

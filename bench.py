@@ -99,53 +99,84 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_transform_sample(sample_batch: int, min_seconds: float, workers: int):
-    """Reference-side CPU path: DCT-II (pocketfft) + /n, c0/2 -- the oracle port, all host threads."""
-    import numpy as np
-    from oracle import approxfun_oracle as orc
+def workload_config(B: int, n: int) -> dict:
+    """The `config` object, identical in both arms (ours and `--impl reference`)."""
+    return {"workload": f"batched Chebyshev transform: {B} functions x n={n} Float64 per GPU "
+                        "(BASELINE.json configs[1]), plan_transform(Chebyshev(), n) forward",
+            "batch_per_gpu": B, "n": n, "sharding": "by function batch, no collective",
+            "l2": "inputs (2 GiB per step) are larger than the 126 MB L2; no flush needed"}
 
-    rng = np.random.default_rng(0)
-    v = rng.standard_normal((sample_batch, N_LEN))
-    orc.cheb_transform(v[:64], axis=1, workers=workers)  # warm
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        orc.cheb_transform(v, axis=1, workers=workers)
-        reps += 1
-        el = time.perf_counter() - t0
-        if el >= min_seconds or reps >= 200:
-            break
-    return reps * sample_batch * N_LEN / el, el, reps
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class CpuChebTransform:
+    """Reference-side CPU path: DCT-II (pocketfft) + /n, c0/2 -- the oracle port -- on ALL host threads.
+
+    The batch is cut into contiguous blocks of functions and every block goes to one thread of a pool that this class owns
+    (pocketfft releases the GIL), so the worker count is explicit and does not depend on OMP_NUM_THREADS (torchrun exports
+    OMP_NUM_THREADS=1 to every rank when nproc > 1) or on scipy's internal pool."""
+
+    def __init__(self, threads: int):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import approxfun_oracle as orc
+        self.orc = orc
+        self.threads = threads
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+
+    def __call__(self, v, out):
+        B = v.shape[0]
+        nblk = min(B, self.threads * 4)
+        edges = [B * i // nblk for i in range(nblk + 1)]
+
+        def work(i):
+            out[edges[i]:edges[i + 1]] = self.orc.cheb_transform(v[edges[i]:edges[i + 1]], axis=1, workers=1)
+
+        list(self.pool.map(work, range(nblk)))
+        return out
+
+    def timed(self, v, out, steps: int):
+        """(seconds per step, effective busy threads = process CPU time / wall time)"""
+        c0, t0 = time.process_time(), time.perf_counter()
+        for _ in range(steps):
+            self(v, out)
+        wall = time.perf_counter() - t0
+        return wall / steps, (time.process_time() - c0) / wall
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path on the host cores (oracle port)."""
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores (oracle port: Julia and FFTW
+    are absent from this image), on the SAME workload as our arm: the full batch of args.batch functions per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
-    from oracle import approxfun_oracle as orc
 
-    cores = os.cpu_count() or 1
-    sample_batch = 2048  # 2048 x 4096 doubles = 64 MiB per step
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())   # torchrun sets 1 for nproc > 1; nothing here relies on OpenMP
+    cores = host_threads()
+    B = args.batch
     rng = np.random.default_rng(0)
-    v = rng.standard_normal((sample_batch, N_LEN))
+    v = rng.standard_normal((B, N_LEN))
+    out = np.empty_like(v)
+    cpu = CpuChebTransform(cores)
     for _ in range(max(args.warmup, 1)):
-        orc.cheb_transform(v, axis=1, workers=cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.cheb_transform(v, axis=1, workers=cores)
-    el = time.perf_counter() - t0
-    val = args.steps * sample_batch * N_LEN / el
+        cpu(v, out)
+    sec, busy = cpu.timed(v, out, args.steps)
+    val = B * N_LEN / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "coefficients/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batched Chebyshev transform n={N_LEN}, Float64 (BASELINE.json configs[1]); "
-                               f"each step a bounded sample of {sample_batch} of the {BATCH} functions"},
+        "config": workload_config(B, N_LEN),
         "cpu_baseline": {"value": val, "unit": "coefficients/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_batch} x {N_LEN} f64 per step, scipy.fft.dct(type=2, workers={cores}) + /n, c0/2 "
-                                   "(oracle port of FastTransforms.plan_chebyshevtransform; Julia/FFTW absent)"},
+                         "threads_requested": cores, "threads_effective": round(busy, 2),
+                         "sample": f"the full {B} x {N_LEN} f64 batch per step (2 GiB in, 2 GiB out, host memory): "
+                                   f"scipy.fft.dct(type=2) + /n, c0/2 on {cores} pool threads, one contiguous block of "
+                                   "functions per task (oracle port of FastTransforms.plan_chebyshevtransform; Julia/FFTW absent)"},
         "e2e": {"value": val, "unit": "coefficients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -216,14 +247,19 @@ def main():
                 numa_note = f"rank pinned to {len(pick)} GPU-local CPUs"
         except Exception as exc:  # affinity is an optimisation only
             numa_note = f"no CPU affinity ({type(exc).__name__})"
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:
+            cpu_group = dist.new_group(backend="gloo")     # CPU-side waits (no spinning NCCL kernel on an idle GPU)
+        except Exception:
+            cpu_group = None
 
     import approxfun_b200 as af
     from approxfun_b200 import _lib as L
 
     lib = L.load()
-    L.check(lib, lib.afb_init(local))
+    L.init(lib, local)
     n, B = N_LEN, args.batch
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -335,11 +371,27 @@ def main():
         torch.cuda.synchronize()
         copy_ms = max_over_ranks((time.perf_counter() - t0) / 2 * 1e3)
         del dv2
+        # the same call on PAGEABLE host arrays (what a Julia Vector{Float64} / a NumPy array is): the driver stages them
+        # through its own pinned bounce buffers
+        pv, pc = np.empty((B, n)), np.empty((B, n))
+        pv[:] = hin
+        hplan.execute_host(pv, pc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            hplan.execute_host(pv, pc)
+        torch.cuda.synchronize()
+        el_pg = max_over_ranks((time.perf_counter() - t0) / 2 * 1e3) * 1e-3
+        pageable_ok = bool(np.array_equal(pc[idx], chk_e2e))
+        del pv, pc
+        e2e_pageable = {"value": world * coefs_per_step / el_pg, "unit": "coefficients/s", "ms_per_step": el_pg * 1e3,
+                        "same_bits_as_pinned": pageable_ok,
+                        "note": "afb_plan_execute_host on plain (pageable) NumPy arrays, as a Julia Array would be passed"}
         e2e = {"value": world * coefs_per_step / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
                "d2h_bytes_per_step": int(8 * B * n), "ms_per_step": el * 1e3, "steps": e2e_steps,
                "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)",
                "pcie_copy_only_ms": copy_ms, "frac_of_pcie_copy_only": copy_ms / (el * 1e3),
-               "host_affinity": numa_note}
+               "host_affinity": numa_note, "pageable": e2e_pageable}
         hplan.close()
         del hv, hc
 
@@ -468,35 +520,178 @@ def main():
         extras["padua_degree2047"] = {"ms_per_step": t, "coefficients_per_s": float(npad) / (t * 1e-3),
                                       "launches": pp.launches}
         del vp
+        # ---- strong scaling (total work fixed, shared by the ranks) with parity checks on the record ------------------
+        from approxfun_b200 import parallel as par
+        strong = {}
+        ok_all = lambda flag: bool(max_over_ranks(0.0 if flag else 1.0) == 0.0)   # true on every rank
+        # config 2: 65536 x 4096 in total, 65536 / N functions per rank, bit-identical to the 1-GPU slices
+        gs = torch.Generator(device="cuda").manual_seed(777)                      # the SAME global batch on every rank
+        Vg = torch.randn(B, n, dtype=torch.float64, device="cuda", generator=gs)
+        lo, hi = par.shard_range(B, rank, world)
         if world > 1:
-            # config 4 across GPUs (strong scaling: ONE 16384 x 16384 matrix, column slabs -> all-to-all -> row slabs)
-            from approxfun_b200 import parallel as par
+            Cg = torch.empty_like(Vg)
+            fwd.execute(Vg.data_ptr(), Cg.data_ptr(), stream)                     # the 1-GPU result of the whole batch
+            Cs = torch.empty(hi - lo, n, dtype=torch.float64, device="cuda")
+            ps = af.api.DevicePlan(L.CHEB1_FWD, n, 0, hi - lo, n)
+            t = time_loop(lambda: ps.execute(Vg[lo:hi].data_ptr(), Cs.data_ptr(), stream), 10, 3)
+            same = ok_all(bool(torch.equal(Cs, Cg[lo:hi])))
+            ps.close()
+            del Cg, Cs
+        else:
+            t, same = ms, True
+        strong["cheb_65536x4096"] = {"ms_per_step": t, "coefficients_per_s": float(B) * n / (t * 1e-3), "functions_per_rank": hi - lo,
+                                     "bit_identical_to_1gpu_slices": same, "scaling": "strong"}
+        del Vg
+        # configs 3 and 5: 10^9 points / samples in total, 10^9 / N per rank (Philox counters = GLOBAL indices, so the union
+        # of the ranks' outputs is the 1-GPU stream); a 4096-point piece is recomputed by a separate call and, on rank 0,
+        # checked against the oracle (checker use only)
+        Pg = 10 ** 9 if not args.quick else 1 << 26
+        plo, phi = par.shard_range(Pg, rank, world)
+        Ps = phi - plo
+        xs_ = torch.empty(Ps, dtype=torch.float64, device="cuda")
+        ys_ = torch.empty(Ps, dtype=torch.float64, device="cuda")
+        af.api.philox_device(7, plo, xs_.data_ptr(), Ps, stream)
+        xs_.mul_(2.0).sub_(1.0)
+        t = time_loop(lambda: af.api.clenshaw_device(cc.data_ptr(), Nc, xs_.data_ptr(), ys_.data_ptr(), Ps, stream), 2, 1)
+        piece = torch.empty(4096, dtype=torch.float64, device="cuda")
+        af.api.clenshaw_device(cc.data_ptr(), Nc, xs_[Ps - 4096:].data_ptr(), piece.data_ptr(), 4096, stream)
+        torch.cuda.synchronize()
+        same = ok_all(bool(torch.equal(piece, ys_[Ps - 4096:])))
+        strong["clenshaw_N1e4_1e9_points"] = {"ms_per_step": t, "evals_per_s": float(Pg) / (t * 1e-3), "points_per_rank": Ps,
+                                              "piece_recomputed_bit_identical": same, "scaling": "strong"}
+        st_x, st_y = xs_[:4096].cpu().numpy(), ys_[:4096].cpu().numpy()
+        t = time_loop(lambda: af.api.sample_device(dc.data_ptr(), cdf.size, -5.0, 5.0, 42, plo, ys_.data_ptr(), Ps, stream), 2, 1)
+        af.api.sample_device(dc.data_ptr(), cdf.size, -5.0, 5.0, 42, plo + Ps - 4096, piece.data_ptr(), 4096, stream)
+        torch.cuda.synchronize()
+        same = ok_all(bool(torch.equal(piece, ys_[Ps - 4096:])))
+        strong["sample_gaussian_1e9"] = {"ms_per_step": t, "samples_per_s": float(Pg) / (t * 1e-3), "samples_per_rank": Ps,
+                                         "piece_recomputed_bit_identical": same, "scaling": "strong"}
+        af.api.philox_device(42, plo, piece.data_ptr(), 4096, stream)
+        st_u, st_s = piece.cpu().numpy(), ys_[:4096].cpu().numpy()
+        if rank == 0 and not args.no_cpu:
+            from oracle import approxfun_oracle as orc
+            from oracle import oracle_c as orcc
+            strong["clenshaw_N1e4_1e9_points"]["bit_exact_vs_oracle_4096"] = bool(np.array_equal(st_y, orcc.clenshaw(cc.cpu().numpy(), st_x)))
+            strong["sample_gaussian_1e9"]["bit_exact_vs_oracle_4096"] = bool(
+                np.array_equal(st_s, orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cdf, st_u))))
+        del xs_, ys_, piece
+        # config 4: ONE 16384 x 16384 matrix, column slabs -> all-to-all -> row slabs; every rank compares its WHOLE row
+        # block with the 1-GPU plan applied to the same matrix
+        if world > 1:
             nc, nr = n2d // world, n2d // world
-            blk = torch.randn(nc, n2d, dtype=torch.float64, device="cuda", generator=g)   # column-major n x nc
+            gs2 = torch.Generator(device="cuda").manual_seed(4242)
+            Vfull = torch.randn(n2d, n2d, dtype=torch.float64, device="cuda", generator=gs2)   # same on every rank
+            blk = Vfull[rank * nc:(rank + 1) * nc].contiguous()                               # column-major n x nc
+            p2.execute(Vfull.data_ptr(), Vfull.data_ptr(), stream)                            # 1-GPU result, in place
+            want_rows = Vfull[:, rank * nr:(rank + 1) * nr].t().contiguous()                  # out[il, j] = C[rank nr + il, j]
+            vmax = 6.0
+            del Vfull
             rows = torch.empty(nr, n2d, dtype=torch.float64, device="cuda")
             nv_bytes = 8.0 * n2d * nc * (world - 1) / world       # bytes this rank sends over NVLink per transform
-            for mode, p2p in (("nccl_sendrecv", False), ("peer_memory_fused", True)):
+            tol2d = 1e-13 * vmax * 14
+            for mode, p2p, chunks in (("nccl_sendrecv", False, 1), ("peer_memory_fused", True, 1),
+                                      ("peer_memory_fused_chunked4", True, 4)):
                 sp = par.Sharded2DPlan(L.CHEB1_2D_FWD, n2d, n2d, p2p=p2p)
-                t = time_loop(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), stream), 5, 3)
+                if chunks > 1:
+                    sp.set_chunks(chunks)
+                rows.zero_()
+                t = time_loop(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), stream), 8, 3)
+                err = max_over_ranks(float((rows - want_rows).abs().max()))
                 extras[f"cheb2d_16384_sharded_{mode}"] = {
                     "ms_per_step": t, "elements_per_s": float(n2d) * n2d / (t * 1e-3), "scaling": "strong",
+                    "max_abs_err_vs_1gpu_plan": err, "tolerance": tol2d, "pass": bool(err <= tol2d),
+                    "rows_checked": "every row of every rank's block (16384 x 16384 elements in total)",
                     "nvlink_bytes_per_rank": nv_bytes,
-                    "nvlink_frac_of_770GBs_if_transfer_alone": nv_bytes / (t * 1e-3) / 1e9 / 770.0}
+                    "nvlink_GBs_if_transfer_alone": nv_bytes / (t * 1e-3) / 1e9}
                 barrier()
                 sp.close()
-            del blk, rows
+            best = min(extras[k]["ms_per_step"] for k in extras if k.startswith("cheb2d_16384_sharded_peer"))
+            strong["cheb2d_16384"] = {"ms_per_step": best, "elements_per_s": float(n2d) * n2d / (best * 1e-3), "scaling": "strong"}
+            del blk, rows, want_rows
+        else:
+            strong["cheb2d_16384"] = {"ms_per_step": extras["cheb2d_16384"]["ms_per_step"],
+                                      "elements_per_s": extras["cheb2d_16384"]["elements_per_s"], "scaling": "strong"}
+        extras["strong_scaling"] = strong
+        del p2
+
+        # ---- ONE process driving all N GPUs through the C ABI (afb_init(devices, N)): rank 0 only, the others wait on the CPU
+        if world > 1 and cpu_group is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+            if rank == 0:
+                sp_out = {}
+                try:
+                    nb1 = B
+                    hv1 = torch.empty(nb1, n, dtype=torch.float64).pin_memory()
+                    hc1 = torch.empty(nb1, n, dtype=torch.float64).pin_memory()
+                    hv1.normal_()
+                    pl = af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb1, n)
+                    ref_rows = np.empty((nb1, n))
+                    pl.execute_host(hv1.numpy(), ref_rows)                      # one device
+                    af.api.use_devices(list(range(world)))
+                    pl.execute_host(hv1.numpy(), hc1.numpy())                   # warm: replicas, pipes
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        pl.execute_host(hv1.numpy(), hc1.numpy())
+                    el1 = (time.perf_counter() - t0) / 3
+                    sp_out["cheb_65536x4096_host_call"] = {
+                        "ms_per_step": el1 * 1e3, "coefficients_per_s": float(nb1) * n / el1,
+                        "bit_identical_to_one_device": bool(np.array_equal(ref_rows, hc1.numpy())), "buffers": "pinned host"}
+                    pl.close()
+                    del hv1, hc1, ref_rows
+                    m2 = 16384
+                    hm = torch.empty(m2, m2, dtype=torch.float64).pin_memory()
+                    hm.normal_()
+                    ho = torch.empty(m2, m2, dtype=torch.float64).pin_memory()
+                    p2h = af.api.DevicePlan(L.CHEB1_2D_FWD, m2, m2, 1, m2)
+                    p2h.execute_host(hm.numpy(), ho.numpy())
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        p2h.execute_host(hm.numpy(), ho.numpy())
+                    el2 = (time.perf_counter() - t0) / 2
+                    af.api.use_devices(0)
+                    ref2 = np.empty((m2, m2))
+                    p2h.execute_host(hm.numpy(), ref2)
+                    sp_out["cheb2d_16384_host_call"] = {
+                        "ms_per_step": el2 * 1e3, "elements_per_s": float(m2) * m2 / el2,
+                        "max_abs_err_vs_one_device": float(np.max(np.abs(ref2 - ho.numpy()))), "buffers": "pinned host"}
+                    p2h.close()
+                    del hm, ho, ref2
+                except Exception as exc:  # noqa: BLE001  (an extra must not take the headline down)
+                    sp_out["error"] = f"{type(exc).__name__}: {exc}"
+                finally:
+                    af.api.use_devices(0)
+                sp_out["note"] = (f"rank 0 alone drives all {world} GPUs from one process through afb_init(devices, {world}) + "
+                                  "afb_plan_execute_host (host threads + per-device streams inside the library; the other "
+                                  "ranks idle on a CPU barrier)")
+                extras["single_process_multi_gpu"] = sp_out
+            dist.barrier(group=cpu_group)
 
     # the CPU legs run at N = 1 only: at N > 1 the other ranks busy-wait in the barrier on the same host cores
     # (measured: the 32-thread port drops from 8.7e8 to 2.0e8 coefficients/s beside seven waiting ranks)
     cpu_baseline = None if world == 1 else {"value": None, "unit": "coefficients/s", "cores": 0, "kind": "port",
                                             "sample": "not timed at N > 1 (rank 0 at N = 1 only); see the N = 1 line"}
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        val, el, reps = cpu_transform_sample(2048, 10.0, cores)
+        cores = host_threads()
+        cpu = CpuChebTransform(cores)
+        sb = min(B, 8192)                                   # bounded sample: 8192 x 4096 doubles = 256 MiB per pass
+        hv_s = np.random.default_rng(0).standard_normal((sb, n))
+        ho_s = np.empty_like(hv_s)
+        cpu(hv_s, ho_s)                                     # warm
+        reps = 0
+        t0 = time.perf_counter()
+        c0 = time.process_time()
+        while time.perf_counter() - t0 < 10.0 and reps < 200:
+            cpu(hv_s, ho_s)
+            reps += 1
+        el = time.perf_counter() - t0
+        busy = (time.process_time() - c0) / el
+        val = reps * sb * n / el
         from oracle import approxfun_oracle as orc
         want = orc.cheb_transform(chk_in, axis=1)
         cpu_baseline = {"value": val, "unit": "coefficients/s", "cores": cores, "kind": "port",
-                        "sample": f"{reps} x (2048 x {n}) f64 in {el:.1f} s, scipy.fft.dct(type=2, workers={cores}) + /n, c0/2 "
+                        "threads_effective": round(busy, 2),
+                        "sample": f"{reps} x ({sb} x {n}) f64 in {el:.1f} s, scipy.fft.dct(type=2) + /n, c0/2 on {cores} pool threads "
                                   "(oracle port; the Julia/FFTW reference cannot run in this image)",
                         "gpu_max_abs_err_vs_this_baseline": float(np.max(np.abs(chk_out - want))),
                         "e2e_max_abs_err_vs_this_baseline": None if chk_e2e is None else float(np.max(np.abs(chk_e2e - want)))}
@@ -506,10 +701,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "coefficients/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"batched Chebyshev transform: {B} functions x n={n} Float64 per GPU "
-                                   "(BASELINE.json configs[1]), plan_transform(Chebyshev(), n) forward",
-                       "batch_per_gpu": B, "n": n, "sharding": "by function batch, no collective",
-                       "l2": "inputs (2 GiB per step) are larger than the 126 MB L2; no flush needed"},
+            "config": workload_config(B, n),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "extras": extras,
         }

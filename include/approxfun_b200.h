@@ -17,7 +17,9 @@
  * handle (cudaStream_t passed as void*, NULL = legacy default stream) and are asynchronous.
  *
  * Threading: plan creation / destruction and table construction are mutex protected; executing
- * different plans concurrently is allowed; one plan must not be executed concurrently with itself.
+ * different plans concurrently (from different threads) is allowed -- every host-pointer call leases its own
+ * streams and staging buffers from a per-device pool; a plan executed concurrently with itself is serialised
+ * by a per-plan mutex.
  */
 #ifndef APPROXFUN_B200_H
 #define APPROXFUN_B200_H
@@ -86,8 +88,20 @@ typedef struct afb_plan_s* afb_plan;
 int32_t afb_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its status code */
 int32_t afb_last_error(char* buf, size_t len);
-/* Select the CUDA device of this process (one process per GPU).  device < 0 keeps the current one. */
-int32_t afb_init(int32_t device);
+/* Select the CUDA devices of this process.
+ *   ndev == 0 (devices may be NULL): keep the calling thread's current device.
+ *   ndev == 1: make devices[0] current (the one-process-per-GPU layout of torchrun / MPI launches).
+ *   ndev  > 1: ONE process drives several GPUs (what a Julia session does): devices[0] becomes current, peer access is
+ *              enabled between all pairs, and the host-pointer entry points fan out over the set with one internal host
+ *              thread and one stream set per device, joined before the call returns -- afb_plan_execute_host shards the
+ *              batch of a 1-D plan by contiguous blocks of functions and runs a 2-D plan as column slabs -> peer-memory
+ *              transpose over NVLink -> row slabs; afb_clenshaw_cheb / afb_clenshaw_rec / afb_cheb_bisect /
+ *              afb_samplecdf_cheb / afb_sample_cheb shard their point sets.  Results are bit-identical to one device.
+ * At most 16 devices (ordinals 0..15, one node).  Plans, tables and staging buffers belong to the device that was current
+ * when they were created; a plan may be executed from any thread.  *_device entry points always run on ONE device (the
+ * plan's, or the calling thread's current device for the plain functions). */
+int32_t afb_init(const int32_t* devices, int32_t ndev);
+/* Frees the staging buffers and cached device blocks of every device.  Plans stay valid. */
 int32_t afb_shutdown(void);
 int32_t afb_device_info(int32_t* sm_count, int64_t* hbm_bytes, char* name, size_t name_len);
 
@@ -193,6 +207,19 @@ int32_t afb_sample_cheb_device(const double* d_cdf_c, int64_t N, double a, doubl
 /* the uniforms afb_sample_cheb_device draws, for parity checks */
 int32_t afb_philox_uniform_device(uint64_t seed, uint64_t offset, double* d_out, int64_t P, void* stream);
 
+/* Piecewise Chebyshev Funs (a Fun on a PiecewiseSpace of Chebyshev segments, e.g. abs(Fun(sin, -5..5))): piece k lives on
+ * breaks[k]..breaks[k+1] (increasing) with coefficients coef[offsets[k] .. offsets[k+1]).
+ * afb_piecewise_clenshaw: y[i] = f(x[i]) in the domain variable -- the FIRST piece whose closed interval contains x[i],
+ *   evaluated at tocanonical = (2x - lo - hi)/(hi - lo); zero outside the domain (replaces evaluate(f::Fun{<:PiecewiseSpace}, x)).
+ * afb_piecewise_bisect: the GENERIC bisectioninv(f::Fun, x; numits = 47) of src/Extras/sample.jl:23-36 with genmidpoint
+ *   (sample.jl:11-21): a, b = minimum / maximum of the domain; numits x { m = genmidpoint(a,b); f(m) <= u ? a = m : b = m };
+ *   returns .5(a+b) per entry of u.  This is the route sample(f, n) takes for piecewise Funs (test/PiecewiseSampleTest.jl:5-10);
+ *   with npieces == 1 it is the generic bisection of a plain Chebyshev Fun. */
+int32_t afb_piecewise_clenshaw(const double* coef, const int64_t* offsets, const double* breaks, int64_t npieces, const double* x,
+                               double* y, int64_t P);
+int32_t afb_piecewise_bisect(const double* coef, const int64_t* offsets, const double* breaks, int64_t npieces, const double* u,
+                             double* out, int64_t P, int32_t numits);
+
 /* Bivariate evaluation f(x_p, y_p) = sum_{i,j} C[i,j] T_i(x_p) T_j(y_p) of a Chebyshev (x) Chebyshev coefficient matrix
  * (n1 x n2 column-major; canonical variables), in the order a ProductFun is evaluated upstream (columns in x by the
  * 1-D recurrence, then the recurrence over columns in y).  Replaces f(x, y) / evaluate for TensorSpace / ProductFun Funs
@@ -241,6 +268,9 @@ int32_t afb_sharded2d_destroy(void* handle);
  * all-gathers them (world x 64 bytes) and passes the array to afb_sharded2d_ipc_open on every rank. */
 int32_t afb_sharded2d_ipc_export(void* handle, void* handle64);
 int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world);
+/* Peer-memory mode only: run the column pass in `chunks` (1..8) pieces and send each finished piece to the peers on a side
+ * stream while the next is transformed (default 1 = one column pass, one exchange kernel). */
+int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks);
 
 #ifdef __cplusplus
 }

@@ -798,3 +798,54 @@ def sin_itransform_generic(x: np.ndarray) -> np.ndarray:
 def sinpoints(n: int) -> np.ndarray:
     """Grid of the SinSpace plans above: theta_j = pi j/(n+1), j = 1..n (f_k <-> sin(k theta), k = 1..n)."""
     return np.pi * np.arange(1, n + 1) / (n + 1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# generic bisection and piecewise Funs  (/root/reference/src/Extras/sample.jl:8-36; test/PiecewiseSampleTest.jl:5-10)
+# ------------------------------------------------------------------------------------------------------
+def genmidpoint(a: float, b: float) -> float:
+    """sample.jl:11-21, verbatim: a midpoint that also works for infinite end points."""
+    if math.isinf(a) and math.isinf(b):
+        return 0.0
+    if math.isinf(a):
+        return b - 100
+    if math.isinf(b):
+        return a + 100
+    return (a + b) / 2
+
+
+def piecewise_eval(pieces, breaks, x, clenshaw_fn=None):
+    """Evaluation of a Fun on a PiecewiseSpace of Chebyshev segments: the FIRST piece whose closed interval contains x
+    (UPSTREAM ApproxFunBase evaluate for PiecewiseSpace loops over the components in order), evaluated at
+    tocanonical(piece, x) = (2x - lo - hi)/(hi - lo); zero outside the domain."""
+    cl = clenshaw_fn or clenshaw
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    out = np.zeros_like(x)
+    done = ~((x >= breaks[0]) & (x <= breaks[-1]))
+    for k, c in enumerate(pieces):
+        lo, hi = breaks[k], breaks[k + 1]
+        sel = (~done) & (x <= hi)
+        if np.any(sel):
+            c = np.asarray(c, dtype=np.float64)
+            xc = (2.0 * x[sel] - lo - hi) / (hi - lo)
+            out[sel] = 0.0 if c.size == 0 else (c[0] if c.size == 1 else cl(c, xc))
+            done |= sel
+    return out
+
+
+def bisectioninv_generic(pieces, breaks, u, numits: int = 47, clenshaw_fn=None) -> np.ndarray:
+    """sample.jl:23-36 applied entry by entry (sample.jl:36), all entries advanced together:
+    a = minimum(d); b = maximum(d); numits x { m = genmidpoint(a,b); val = f(m); (val <= x) ? a = m : b = m }; .5*(a+b)."""
+    u = np.atleast_1d(np.asarray(u, dtype=np.float64))
+    a = np.full_like(u, breaks[0])
+    b = np.full_like(u, breaks[-1])
+    for _ in range(numits):
+        if np.isinf(a).any() or np.isinf(b).any():
+            m = np.array([genmidpoint(ai, bi) for ai, bi in zip(a, b)])
+        else:
+            m = (a + b) / 2
+        val = piecewise_eval(pieces, breaks, m, clenshaw_fn)
+        le = val <= u
+        a = np.where(le, m, a)
+        b = np.where(le, b, m)
+    return 0.5 * (a + b)

@@ -1,6 +1,8 @@
 /* Plain-C caller of libapproxfun_b200.so: what a non-Python host (Julia's ccall, a C program) does with the ABI of
  * include/approxfun_b200.h.  Exit codes: 0 = all checks passed, 3 = no CUDA device (the library has no CPU fallback),
- * 1 = a check failed.  Built and run by tests/test_abi.py (no GPU: expects 3) and tests/test_gpu_parity.py (expects 0). */
+ * 1 = a check failed.  Built and run by tests/test_abi.py (no GPU: expects 3) and tests/test_gpu_parity.py (expects 0).
+ * With two or more GPUs visible it also drives TWO of them from this one process (afb_init(devices, 2)): the batch of a 1-D
+ * plan and a 2-D transform are sharded inside the library and must reproduce the one-device results. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,10 +16,51 @@ static int die(const char* what, int32_t st) {
     return st == AFB_NO_DEVICE ? 3 : 1;
 }
 
+/* one process, two GPUs: same calls, the library fans out */
+static int two_gpus(void) {
+    const int32_t one[1] = {0}, two[2] = {0, 1};
+    int32_t st = afb_init(two, 2);
+    if (st == AFB_BAD_ARG) { printf("one GPU visible: multi-device section skipped\n"); return 0; }
+    if (st != AFB_OK) return die("afb_init(two devices)", st);
+    enum { N1 = 1024, B1 = 2048, R2 = 1024, C2 = 2048 };
+    double* v = (double*)malloc(sizeof(double) * N1 * B1);
+    double* c1 = (double*)malloc(sizeof(double) * N1 * B1);
+    double* c2 = (double*)malloc(sizeof(double) * N1 * B1);
+    if (!v || !c1 || !c2) return 1;
+    unsigned long long s = 88172645463325252ull;
+    for (long i = 0; i < (long)N1 * B1; ++i) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v[i] = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
+    afb_plan p = NULL, q = NULL;
+    int rc = 0;
+    /* (1) batched 1-D: 2048 functions x 1024 (16 MiB) over two devices vs one device: bit-identical */
+    if ((st = afb_plan_create(&p, AFB_CHEB1_FWD, N1, 0, B1, N1, 0)) != AFB_OK) return die("afb_plan_create", st);
+    if ((st = afb_plan_execute_host(p, v, c2)) != AFB_OK) return die("afb_plan_execute_host (2 GPUs)", st);
+    if ((st = afb_init(one, 1)) != AFB_OK) return die("afb_init(one device)", st);
+    if ((st = afb_plan_execute_host(p, v, c1)) != AFB_OK) return die("afb_plan_execute_host (1 GPU)", st);
+    for (long i = 0; i < (long)N1 * B1; ++i)
+        if (c1[i] != c2[i]) { fprintf(stderr, "batch sharding over 2 GPUs differs at %ld\n", i); rc = 1; break; }
+    /* (2) 2-D 1024 x 2048: slabs + peer-memory transpose over NVLink vs the one-device plan */
+    if (!rc) {
+        if ((st = afb_plan_create(&q, AFB_CHEB1_2D_FWD, R2, C2, 1, R2, 0)) != AFB_OK) return die("afb_plan_create(2D)", st);
+        if ((st = afb_plan_execute_host(q, v, c1)) != AFB_OK) return die("2D (1 GPU)", st);
+        if ((st = afb_init(two, 2)) != AFB_OK) return die("afb_init(two devices)", st);
+        for (int rep = 0; rep < 3 && !rc; ++rep) {   /* repeated calls alternate the receive buffers */
+            if ((st = afb_plan_execute_host(q, v, c2)) != AFB_OK) return die("2D (2 GPUs)", st);
+            for (long i = 0; i < (long)R2 * C2; ++i)
+                if (fabs(c1[i] - c2[i]) > 1e-13) { fprintf(stderr, "2-D over 2 GPUs differs at %ld: %.17g vs %.17g\n", i, c2[i], c1[i]); rc = 1; break; }
+        }
+    }
+    afb_plan_destroy(p);
+    afb_plan_destroy(q);
+    free(v); free(c1); free(c2);
+    if ((st = afb_init(one, 1)) != AFB_OK) return die("afb_init(one device)", st);
+    if (!rc) printf("two GPUs from one process: batch sharding bit-identical, 2-D within 1e-13\n");
+    return rc;
+}
+
 int main(void) {
     enum { N = 64, P = 5 };
     double x[N], v[N], c[N], back[N], xs[P] = {-1.0, -0.3, 0.0, 0.7, 1.0}, ys[P];
-    int32_t st = afb_init(-1);
+    int32_t st = afb_init(NULL, 0);
     if (st != AFB_OK) return die("afb_init", st);
     printf("libapproxfun_b200 version %d\n", (int)afb_version());
     if ((st = afb_chebpoints(x, N, -1.0, 1.0)) != AFB_OK) return die("afb_chebpoints", st);
@@ -47,6 +90,10 @@ int main(void) {
     }
     afb_plan_destroy(fwd);
     afb_plan_destroy(inv);
+    {
+        int rc = two_gpus();
+        if (rc) return rc;
+    }
     afb_shutdown();
     printf("abi smoke ok\n");
     return 0;

@@ -35,7 +35,7 @@ def _worker(rank, world, port, q):
         from approxfun_b200 import parallel as par
 
         lib = L.load()
-        L.check(lib, lib.afb_init(rank))
+        L.init(lib, rank)
         st = torch.cuda.current_stream().cuda_stream
         # (1) batch sharding, no collective on the data path
         n, B = 4096, 1024
@@ -91,3 +91,53 @@ def test_two_gpu_sharding_and_alltoall():
         p.join(60)
     assert all(r[1] for r in res), res          # bit-identical under batch sharding
     assert all(r[2] < 1e-13 for r in res), res  # 2-D all-to-all path equals the 1-GPU path
+
+
+def test_single_process_two_gpus_through_the_c_abi():
+    """afb_init(devices, 2): ONE process (what a Julia session is) drives two GPUs; the host-pointer calls shard inside
+    the library (host threads + per-device streams, peer-memory transpose for the 2-D plan; no torch.distributed, no IPC)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import approxfun_b200 as af
+    from approxfun_b200 import _lib as L
+    from oracle import approxfun_oracle as orc
+    from oracle import oracle_c as orcc
+
+    rng = np.random.default_rng(3)
+    n, B = 4096, 4096
+    v = rng.standard_normal((B, n))
+    M = rng.standard_normal((2048, 1024))            # column-major 1024 x 2048
+    c10k = rng.standard_normal(3000) / (1 + np.arange(3000))
+    x = rng.uniform(-1, 1, 1 << 21)
+    f = af.Fun(lambda t: np.exp(-t * t), af.Chebyshev(-5, 5))
+    cdf = af.normalizedcumsum(f).coefficients
+    u = rng.random(1 << 22)
+    plan = af.api.DevicePlan(L.CHEB1_FWD, n, 0, B, n)
+    plan2 = af.api.DevicePlan(L.CHEB1_2D_FWD, 1024, 2048, 1, 1024)
+    ll = af.api.lowlevel()
+    try:
+        af.api.use_devices(0)
+        one, one2 = np.empty_like(v), np.empty_like(M)
+        plan.execute_host(v, one)
+        plan2.execute_host(M, one2)
+        y1 = ll.clenshaw(c10k, x)
+        s1 = ll.samplecdf(cdf, -5.0, 5.0, u)
+        r1 = ll.sample_cheb(cdf, -5.0, 5.0, 99, 1 << 22)
+        af.api.use_devices([0, 1])
+        two, two2 = np.empty_like(v), np.empty_like(M)
+        for _ in range(3):                           # repeated calls alternate the 2-D receive buffers
+            plan.execute_host(v, two)
+            plan2.execute_host(M, two2)
+            assert np.array_equal(one, two)          # batch sharding: bit-identical to one device
+            assert np.max(np.abs(one2 - two2)) <= 1e-13 * 11 * np.max(np.abs(M))
+        assert np.max(np.abs(two2.T - orc.cheb2_transform(M.T))) <= 1e-13 * 11 * np.max(np.abs(M))
+        assert np.array_equal(ll.clenshaw(c10k, x), y1)
+        assert np.array_equal(ll.samplecdf(cdf, -5.0, 5.0, u), s1)
+        assert np.array_equal(ll.sample_cheb(cdf, -5.0, 5.0, 99, 1 << 22), r1)   # Philox counters do not depend on the device count
+        assert np.array_equal(y1[:5000], orcc.clenshaw(c10k, x[:5000]))
+    finally:
+        af.api.use_devices(0)
+        plan.close()
+        plan2.close()

@@ -73,7 +73,7 @@ def test_long_lines_persistent_tma_staged(af):
             assert np.max(np.abs(ll.transform(kind, v) - want)) <= coef_tol(n, want), (kind, n)
 
 
-@pytest.mark.parametrize("n", SIZES[:-1])
+@pytest.mark.parametrize("n", SIZES)
 def test_laurent_transform_pair(af, n):
     nb = 2 if n <= 8192 else 1
     v = RNG.standard_normal((n, nb)) + 1j * RNG.standard_normal((n, nb))
@@ -516,3 +516,160 @@ def test_plain_c_caller(af, tmp_path):
     from tests.test_abi import _build_c_smoke
     out = subprocess.run([_build_c_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "abi smoke ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: cases the first round only covered on the CPU emulator, generic / piecewise sampling, host-call pipelines
+# ---------------------------------------------------------------------------------------------------------------------
+def test_laurent_n65536(af):
+    # largest in-CTA complex length + 1 step: the generic path for the complex kinds
+    n = 65536
+    v = RNG.standard_normal((n, 1)) + 1j * RNG.standard_normal((n, 1))
+    c = af.transform(af.Laurent(), v)
+    assert np.max(np.abs(c - orc.laurent_transform(v, axis=0))) <= coef_tol(n, v)
+    vi = af.itransform(af.Laurent(), v)
+    wanti = orc.laurent_itransform(v, axis=0)
+    assert np.max(np.abs(vi - wanti)) <= coef_tol(n, wanti)
+
+
+@pytest.mark.parametrize("n,stride", [(64, 70), (256, 256 + 34), (4096, 4096 + 2), (1000, 1003), (16384, 16384 + 16)])
+def test_strided_and_inplace_device_plans(af, n, stride):
+    # stride > n (a column range of a larger Julia matrix) and in == out on the device, every real kind
+    import torch
+    from approxfun_b200 import _lib as L
+    nb = 37
+    st = torch.cuda.current_stream().cuda_stream
+    host = RNG.standard_normal((nb, stride))
+    for kind, ref in ((L.CHEB1_FWD, orc.cheb_transform), (L.CHEB1_INV, orc.cheb_itransform),
+                      (L.FOURIER_FWD, orc.fourier_transform), (L.FOURIER_INV, orc.fourier_itransform)):
+        want = ref(host[:, :n], axis=1)
+        plan = af.api.DevicePlan(kind, n, 0, nb, stride)
+        d_in = torch.tensor(host, device="cuda")
+        d_out = torch.full_like(d_in, -7.0)
+        plan.execute(d_in.data_ptr(), d_out.data_ptr(), st)          # out of place
+        plan.execute(d_in.data_ptr(), d_in.data_ptr(), st)           # in place
+        torch.cuda.synchronize()
+        got, got_ip = d_out.cpu().numpy(), d_in.cpu().numpy()
+        assert np.max(np.abs(got[:, :n] - want)) <= coef_tol(n, want), (kind, n)
+        assert np.array_equal(got[:, n:], np.full((nb, stride - n), -7.0))       # the padding is never written
+        assert np.array_equal(got_ip[:, :n], got[:, :n]) and np.array_equal(got_ip[:, n:], host[:, n:])
+        # the host-pointer call takes the same strided layout
+        hout = np.full_like(host, -7.0)
+        plan.execute_host(host, hout)
+        assert np.array_equal(hout[:, :n], got[:, :n]) and np.array_equal(hout[:, n:], np.full((nb, stride - n), -7.0))
+        plan.close()
+
+
+@pytest.mark.parametrize("n,batch", [(32, 300000), (8, 1100000), (31, 290000)])
+def test_tiny_lines_multi_chunk_host_pipeline(af, n, batch):
+    # n <= 32 runs the O(n^2) kernel, which is not in-place safe; batch * n * 8 B > 64 MiB makes afb_plan_execute_host
+    # pipeline several chunks over several streams (the round-1 advisor's race: every chunk now has its own in / out halves)
+    v = RNG.standard_normal((batch, n))
+    from approxfun_b200 import _lib as L
+    plan = af.api.DevicePlan(L.CHEB1_FWD, n, 0, batch, n)
+    out = np.empty_like(v)
+    for _ in range(2):
+        plan.execute_host(v, out)
+        assert np.max(np.abs(out - orc.cheb_transform(v, axis=1))) <= coef_tol(n, v)
+    plan.execute_host(v, v)                                              # in == out on the host
+    assert np.array_equal(v, out)
+    plan.close()
+
+
+def test_concurrent_host_calls_on_different_plans(af):
+    # include/approxfun_b200.h "Threading": different plans may execute concurrently from different threads
+    import threading
+    from approxfun_b200 import _lib as L
+    n, B = 4096, 8192     # 256 MiB per call: several pipeline chunks each
+    va, vb = RNG.standard_normal((B, n)), RNG.standard_normal((B, n))
+    pa, pb = af.api.DevicePlan(L.CHEB1_FWD, n, 0, B, n), af.api.DevicePlan(L.FOURIER_FWD, n, 0, B, n)
+    oa, ob = np.empty_like(va), np.empty_like(vb)
+    errs = []
+
+    def run(plan, src, dst):
+        try:
+            for _ in range(3):
+                plan.execute_host(src, dst)
+        except Exception as exc:  # noqa: BLE001
+            errs.append(exc)
+
+    ts = [threading.Thread(target=run, args=(pa, va, oa)), threading.Thread(target=run, args=(pb, vb, ob))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    sa, sb = np.empty_like(va), np.empty_like(vb)
+    pa.execute_host(va, sa)
+    pb.execute_host(vb, sb)
+    assert np.array_equal(oa, sa) and np.array_equal(ob, sb)             # same bits as the serial calls
+    idx = [0, 17, B - 1]
+    assert np.max(np.abs(oa[idx] - orc.cheb_transform(va[idx], axis=1))) <= coef_tol(n, va)
+    assert np.max(np.abs(ob[idx] - orc.fourier_transform(vb[idx], axis=1))) <= coef_tol(n, vb)
+    pa.close()
+    pb.close()
+
+
+def test_generic_bisection_and_genmidpoint(af):
+    # src/Extras/sample.jl:8-36: bisectioninv(f::Fun, x) in the domain variable between minimum(d) and maximum(d)
+    f = af.Fun(lambda x: np.exp(-x * x), af.Chebyshev(-5, 5))
+    cf = af.normalizedcumsum(f)
+    u = np.concatenate([RNG.random(20000), [0.0, 1.0, 0.5, 1e-300, 1 - 2.0 ** -53]])
+    got = af.api.bisectioninv_generic(cf, u)
+    want = orc.bisectioninv_generic([cf.coefficients], [-5.0, 5.0], u, clenshaw_fn=lambda c, x: orcc.clenshaw(c, x))
+    assert np.array_equal(got, want)                                      # bit exact against the fma oracle
+    # the Chebyshev dispatch (sample.jl:103-109) bisects the canonical variable: same root, bracket 10 * 2^-47 wide
+    assert np.max(np.abs(got - af.bisectioninv(cf, u))) <= 10 * 2.0 ** -45
+    assert isinstance(af.api.bisectioninv_generic(cf, 0.5), float)
+    assert abs(af.api.bisectioninv_generic(cf, 0.5)) < 1e-12             # median of the Gaussian
+    for numits in (0, 1, 5):
+        assert np.array_equal(af.api.bisectioninv_generic(cf, u[:100], numits=numits),
+                              orc.bisectioninv_generic([cf.coefficients], [-5.0, 5.0], u[:100], numits=numits,
+                                                       clenshaw_fn=lambda c, x: orcc.clenshaw(c, x)))
+    # genmidpoint (sample.jl:11-21), host mirror and oracle
+    inf = float("inf")
+    for a, b, w in ((-inf, inf, 0.0), (-inf, 3.0, -97.0), (2.0, inf, 102.0), (1.0, 4.0, 2.5)):
+        assert af.api.genmidpoint(a, b) == w == orc.genmidpoint(a, b)
+
+
+def test_piecewise_sample(af):
+    # test/PiecewiseSampleTest.jl:5-10 (#635)
+    f = af.api.abs_fun(af.Fun(np.sin, af.Chebyshev(-5, 5)))
+    assert len(f.pieces) == 4 and np.allclose(f.breaks, [-5, -math.pi, 0, math.pi, 5], atol=1e-13)
+    F = af.api.integrate(f)
+    assert abs(F(-4.0) - (-(math.cos(-4.0) - math.cos(-5.0)))) < 1e-13
+    assert abs(F(-3.0) - (-(math.cos(-math.pi) - math.cos(-5.0)) + math.cos(-3.0) - math.cos(-math.pi))) < 1e-13
+    r = af.sample(f, 10)
+    assert r.shape == (10,) and r.max() <= 5 and r.min() >= -5
+    # parity on caller-supplied uniforms: GPU generic bisection of the piecewise CDF against the oracle, bit for bit
+    cf = af.normalizedcumsum(f)
+    u = RNG.random(50000)
+    got = af.sample(f, u.size, uniforms=u)
+    pieces = [p.coefficients for p in cf.pieces]
+    want = orc.bisectioninv_generic(pieces, cf.breaks, u, clenshaw_fn=lambda c, x: orcc.clenshaw(c, x))
+    assert np.array_equal(got, want)
+    x = RNG.uniform(-6, 6, 10000)                                         # evaluation, including outside the domain
+    assert np.array_equal(f(x), orc.piecewise_eval([p.coefficients for p in f.pieces], f.breaks, x,
+                                                   clenshaw_fn=lambda c, xx: orcc.clenshaw(c, xx)))
+    assert np.max(np.abs(f(x) - np.where(np.abs(x) <= 5, np.abs(np.sin(x)), 0.0))) < 1e-13
+    # the samples follow |sin| / 4(ish): the CDF at the samples is uniform
+    assert abs(np.mean(cf(got)) - 0.5) < 0.01
+
+
+def test_sampling_2d_long_b_factors(af):
+    # B factors with more than 198 coefficients: the fused conditional kernel's column tile no longer fits shared memory and
+    # the library runs the reference's own sequence (sample.jl:208-213) as separate kernels; same bits as the C oracle
+    rng = np.random.default_rng(5)
+    NA, N, R, n = 40, 300, 3, 20000
+    decay = np.exp(-0.05 * np.arange(N))[:, None]
+    A = rng.standard_normal((NA, R)) * np.exp(-0.3 * np.arange(NA))[:, None]
+    B = np.abs(rng.standard_normal((N, R))) * decay
+    B[0] += 5.0                                                          # a positive density in x for every y
+    A[0] = np.abs(A[0]) + 3.0
+    A[1:] *= 0.05
+    ry, u = rng.uniform(-1, 1, n), rng.random(n)
+    got = af.api.lowlevel().sample2d_lowrank(A, B, -1.0, 1.0, -2.0, 3.0, ry, u)
+    want = orcc.sample2d_lowrank(A, B, -1.0, 1.0, -2.0, 3.0, ry, u, threads=8)
+    assert np.array_equal(got, want)
+    small = af.api.lowlevel().sample2d_lowrank(A, B[:150], -1.0, 1.0, -2.0, 3.0, ry, u)      # fused kernel, same formulae
+    assert np.array_equal(small, orcc.sample2d_lowrank(A, B[:150], -1.0, 1.0, -2.0, 3.0, ry, u, threads=8))
