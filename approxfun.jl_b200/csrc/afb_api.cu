@@ -3,7 +3,9 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
@@ -136,11 +138,105 @@ using namespace afb;
 // Staging pipes of the host-pointer entry points: NPIPE streams with grow-only device buffers.  Every device keeps a
 // free list of pipes; a call leases one (or makes a new one), so calls on different plans -- and on different devices --
 // never wait for each other (include/approxfun_b200.h "Threading").
+// Pageable host arrays (a Julia Vector{Float64}, a NumPy array) cannot be DMA-ed directly: the driver would stage them through
+// its own bounce buffers with ONE copying thread (measured: 65536 x 4096 doubles 317 ms per call against 45 ms for pinned
+// buffers).  The library stages them itself: a small team of host threads copies chunk c+1 into a pinned ring slot (and chunk
+// c-2 out of one) while the GPU and the DMA engines work on the chunks in between.
+class CopyTeam {
+  public:
+    // dst / src rows of `width` bytes, `height` rows, pitches in bytes; returns when every row is copied
+    void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t height) {
+        if (width == dpitch && width == spitch) { width *= height; height = 1; dpitch = spitch = width; }
+        const size_t total = width * height;
+        const int parts = (total < ((size_t)1 << 20)) ? 1 : nthreads() + 1;
+        if (parts == 1) { rows(dst, dpitch, src, spitch, width, 0, height, 0, width); return; }
+        start();
+        Batch b;
+        b.left = parts - 1;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int i = 1; i < parts; ++i) jobs_.push_back(Job{dst, dpitch, src, spitch, width, height, i, parts, &b});
+        }
+        cv_.notify_all();
+        run_part(Job{dst, dpitch, src, spitch, width, height, 0, parts, &b});
+        std::unique_lock<std::mutex> lk(b.mu);
+        b.cv.wait(lk, [&] { return b.left == 0; });
+    }
+
+  private:
+    struct Batch { std::mutex mu; std::condition_variable cv; int left = 0; };
+    struct Job { char* dst; size_t dpitch; const char* src; size_t spitch, width, height; int part, parts; Batch* batch; };
+    static void rows(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t r0, size_t r1, size_t c0, size_t c1) {
+        for (size_t r = r0; r < r1; ++r) std::memcpy(dst + r * dpitch + c0, src + r * spitch + c0, c1 - c0);
+    }
+    static void run_part(const Job& j) {
+        if (j.height >= (size_t)j.parts) {      // split by rows
+            const size_t r0 = j.height * (size_t)j.part / (size_t)j.parts, r1 = j.height * (size_t)(j.part + 1) / (size_t)j.parts;
+            rows(j.dst, j.dpitch, j.src, j.spitch, j.width, r0, r1, 0, j.width);
+        } else {                                // few long rows: split every row by columns (64-byte granules)
+            size_t c0 = (j.width * (size_t)j.part / (size_t)j.parts) & ~(size_t)63, c1 = (j.width * (size_t)(j.part + 1) / (size_t)j.parts) & ~(size_t)63;
+            if (j.part + 1 == j.parts) c1 = j.width;
+            rows(j.dst, j.dpitch, j.src, j.spitch, j.width, 0, j.height, c0, c1);
+        }
+    }
+    int nthreads() {
+        static const int n = [] {
+            unsigned hw = std::thread::hardware_concurrency();
+            int t = (int)(hw ? hw : 8) / 2 - 1;
+            return t < 1 ? 1 : (t > 7 ? 7 : t);
+        }();
+        return n;
+    }
+    void start() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (started_) return;
+        started_ = true;
+        for (int i = 0; i < nthreads(); ++i) {
+            std::thread([this] {
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk2(mu_);
+                        cv_.wait(lk2, [&] { return !jobs_.empty(); });
+                        j = jobs_.front();
+                        jobs_.pop_front();
+                    }
+                    run_part(j);
+                    { std::lock_guard<std::mutex> bl(j.batch->mu); --j.batch->left; }
+                    j.batch->cv.notify_one();
+                }
+            }).detach();   // workers live as long as the process and sleep on the queue
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Job> jobs_;
+    bool started_ = false;
+};
+static CopyTeam& copy_team() {
+    static CopyTeam* t = new CopyTeam();   // never destroyed: its detached workers may outlive static destruction
+    return *t;
+}
+static bool host_pageable(const void* p) {
+#ifdef AFB_HOST_EMU
+    (void)p;
+    return false;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+#endif
+}
+
 struct HostPipe {
     static constexpr int NPIPE = 3;
     cudaStream_t stream[NPIPE] = {nullptr, nullptr, nullptr};
     void* buf[NPIPE] = {nullptr, nullptr, nullptr};
     size_t cap[NPIPE] = {0, 0, 0};
+    // pinned ring for pageable callers: one input and one output slot per stream
+    void* hin[NPIPE] = {nullptr, nullptr, nullptr};
+    void* hout[NPIPE] = {nullptr, nullptr, nullptr};
+    size_t hin_cap[NPIPE] = {0, 0, 0}, hout_cap[NPIPE] = {0, 0, 0};
     int32_t ensure(int nbuf, size_t bytes) {
         for (int i = 0; i < nbuf; ++i) {
             if (!stream[i]) AFB_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
@@ -152,11 +248,31 @@ struct HostPipe {
         }
         return AFB_OK;
     }
+    int32_t ensure_pinned(int nbuf, size_t bytes, bool in, bool out) {
+        for (int i = 0; i < nbuf; ++i) {
+            if (in && hin_cap[i] < bytes) {
+                if (hin[i]) cudaFreeHost(hin[i]);
+                hin[i] = nullptr; hin_cap[i] = 0;
+                AFB_CUDA(cudaHostAlloc(&hin[i], bytes, cudaHostAllocDefault));
+                hin_cap[i] = bytes;
+            }
+            if (out && hout_cap[i] < bytes) {
+                if (hout[i]) cudaFreeHost(hout[i]);
+                hout[i] = nullptr; hout_cap[i] = 0;
+                AFB_CUDA(cudaHostAlloc(&hout[i], bytes, cudaHostAllocDefault));
+                hout_cap[i] = bytes;
+            }
+        }
+        return AFB_OK;
+    }
     void release() {
         for (int i = 0; i < NPIPE; ++i) {
             if (buf[i]) cudaFree(buf[i]);
+            if (hin[i]) cudaFreeHost(hin[i]);
+            if (hout[i]) cudaFreeHost(hout[i]);
             if (stream[i]) cudaStreamDestroy(stream[i]);
             buf[i] = nullptr; stream[i] = nullptr; cap[i] = 0;
+            hin[i] = hout[i] = nullptr; hin_cap[i] = hout_cap[i] = 0;
         }
     }
 };
@@ -904,7 +1020,12 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
 static int32_t host_pipeline_1d(afb_plan_s* p, const void* in, void* out, int64_t batch) {
     const int64_t n = p->n;
     const size_t line_bytes = (size_t)p->elem * (size_t)n;
-    int64_t ch = std::max<int64_t>(1, (int64_t)(64ll << 20) / (int64_t)line_bytes);
+    const size_t pitch = (size_t)p->elem * (size_t)p->stride;
+    // pageable caller arrays of some size go through the pinned ring (see CopyTeam); pinned / registered ones are DMA-ed directly
+    const bool big = line_bytes * (size_t)batch >= ((size_t)4 << 20);
+    const bool bounce_in = big && host_pageable(in), bounce_out = big && host_pageable(out);
+    const int64_t chunk_target = (bounce_in || bounce_out) ? ((int64_t)32 << 20) : ((int64_t)64 << 20);
+    int64_t ch = std::max<int64_t>(1, chunk_target / (int64_t)line_bytes);
     ch = std::min(ch, batch);
     if (p->path == PATH_GENERIC || p->path == PATH_EXT) ch = std::min(ch, p->gbatch);
     // the generic paths share one work buffer between chunks: keep them on a single stream
@@ -916,32 +1037,50 @@ static int32_t host_pipeline_1d(afb_plan_s* p, const void* in, void* out, int64_
     const size_t chunk_bytes = line_bytes * (size_t)ch;
     PipeLease pipe;
     AFB_TRY(pipe->ensure(nbuf, chunk_bytes * (direct ? 2 : 1)));
-    int64_t c = 0;
+    if (bounce_in || bounce_out) AFB_TRY(pipe->ensure_pinned(nbuf, chunk_bytes, bounce_in, bounce_out));
+    struct Pending { char* dst = nullptr; int64_t nb = 0; bool busy = false; } pend[HostPipe::NPIPE];
     int32_t st = AFB_OK;
+    // finish slot si: wait for its stream and, for a pageable destination, copy the finished chunk out of the ring
+    auto drain = [&](int si) -> int32_t {
+        if (!pend[si].busy) return AFB_OK;
+        AFB_CUDA(cudaStreamSynchronize(pipe->stream[si]));
+        if (bounce_out) copy_team().copy2d(pend[si].dst, pitch, (const char*)pipe->hout[si], line_bytes, line_bytes, (size_t)pend[si].nb);
+        pend[si].busy = false;
+        return AFB_OK;
+    };
+    int64_t c = 0;
     for (int64_t b0 = 0; b0 < batch && st == AFB_OK; b0 += ch, ++c) {
         const int si = (int)(c % nbuf);
         cudaStream_t s = pipe->stream[si];
         void* dbuf = pipe->buf[si];
         void* dout = direct ? (void*)((char*)dbuf + chunk_bytes) : dbuf;
         const int64_t nb = std::min(ch, batch - b0);
-        const char* src = reinterpret_cast<const char*>(in) + (size_t)p->elem * (size_t)(b0 * p->stride);
-        char* dst = reinterpret_cast<char*>(out) + (size_t)p->elem * (size_t)(b0 * p->stride);
+        const char* src = reinterpret_cast<const char*>(in) + pitch * (size_t)b0;
+        char* dst = reinterpret_cast<char*>(out) + pitch * (size_t)b0;
         cudaError_t e;
-        if (p->stride == n) e = cudaMemcpyAsync(dbuf, src, line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s);
-        else e = cudaMemcpy2DAsync(dbuf, line_bytes, src, (size_t)p->elem * (size_t)p->stride, line_bytes, (size_t)nb,
-                                   cudaMemcpyHostToDevice, s);
+        if (bounce_in || bounce_out) { st = drain(si); if (st != AFB_OK) break; }   // the slot's ring buffers are free again
+        if (bounce_in) {
+            copy_team().copy2d((char*)pipe->hin[si], line_bytes, src, pitch, line_bytes, (size_t)nb);
+            e = cudaMemcpyAsync(dbuf, pipe->hin[si], line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s);
+        } else if (p->stride == n) {
+            e = cudaMemcpyAsync(dbuf, src, line_bytes * (size_t)nb, cudaMemcpyHostToDevice, s);
+        } else {
+            e = cudaMemcpy2DAsync(dbuf, line_bytes, src, pitch, line_bytes, (size_t)nb, cudaMemcpyHostToDevice, s);
+        }
         if (e != cudaSuccess) { st = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
         st = exec_1d_device(p, dbuf, dout, nb, n, n, s);
         if (st != AFB_OK) break;
-        if (p->stride == n) e = cudaMemcpyAsync(dst, dout, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s);
-        else e = cudaMemcpy2DAsync(dst, (size_t)p->elem * (size_t)p->stride, dout, line_bytes, line_bytes, (size_t)nb,
-                                   cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+        if (bounce_out) e = cudaMemcpyAsync(pipe->hout[si], dout, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s);
+        else if (p->stride == n) e = cudaMemcpyAsync(dst, dout, line_bytes * (size_t)nb, cudaMemcpyDeviceToHost, s);
+        else e = cudaMemcpy2DAsync(dst, pitch, dout, line_bytes, line_bytes, (size_t)nb, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { st = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
+        pend[si].dst = dst; pend[si].nb = nb; pend[si].busy = true;
     }
-    // the pipe goes back to the pool only when its streams are idle (also on the error path)
-    for (int i = 0; i < nbuf; ++i) {
-        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
-        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    // the pipe goes back to the pool only when its streams are idle (also on the error path); chunks drain in issue order
+    for (int k = 0; k < nbuf; ++k) {
+        const int si = (int)((c + k) % nbuf);
+        if (st == AFB_OK) st = drain(si);
+        else { cudaStreamSynchronize(pipe->stream[si]); cudaGetLastError(); }
     }
     return st;
 }

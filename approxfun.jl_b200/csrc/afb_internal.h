@@ -58,6 +58,12 @@ int32_t cfft_launches(const CfftPlan* p);
 bool cfft_real_fused_ok(const CfftPlan* p);
 int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
                          const cplx* qtab, void* stream);
+// mixed-radix engine (afb_mixed.cu): n = 2^a 3^b 5^c 7^d, not a power of two, 6 <= n <= 6144
+bool mixed_radix_ok(int64_t n);
+int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale,
+                          void* stream);
+int32_t launch_mixed_real(int kind, int64_t n, const cplx* tw, const cplx* qtab, const double* in, int64_t istride, double* out,
+                          int64_t ostride, int64_t batch, void* stream);
 // four-step only: real DCT-ordered input (io_mode bit 0) / output (bit 1); see LineParams::io_mode
 int32_t cfft_exec_dctorder(CfftPlan* p, const void* in, void* out, bool conj_in, bool conj_out, double scale, int io_mode,
                            void* stream);

@@ -20,7 +20,7 @@ namespace afb {
 
 struct CfftPlan {
     int64_t n = 0, max_batch = 0;
-    int mode = 0;  // 0 line, 1 four-step, 2 Bluestein
+    int mode = 0;  // 0 line, 1 four-step, 2 Bluestein, 3 mixed radix (2^a 3^b 5^c 7^d in one CTA, afb_mixed.cu)
     const cplx* tw = nullptr;
     // four-step
     int n1 = 0, n2 = 0;
@@ -218,6 +218,9 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
             if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(four-step tmp)", __FILE__, __LINE__);
             p->tmp = reinterpret_cast<cplx*>(d);
         }
+    } else if (mixed_radix_ok(n)) {
+        p->mode = 3;
+        st = root_table(n, &p->tw);
     } else if (n >= 1) {
         p->mode = 2;
         int64_t M = 32;
@@ -270,6 +273,7 @@ int32_t cfft_launches(const CfftPlan* p) {
     switch (p->mode) {
         case 0: return 1;
         case 1: return 2;
+        case 3: return 1;
         default: return (p->M <= LINE_MAX_N) ? 1 : 3 + 2 * cfft_launches(p->sub);
     }
 }
@@ -297,6 +301,7 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
         }
         return AFB_OK;
     }
+    if (p->mode == 3) return launch_mixed_cfft(n, p->tw, in, out, batch, inverse, scale, stream);
     // Bluestein: X_k = chirp_k * sum_j (x_j chirp_j) conj(chirp)_{k-j}
     if (p->M <= LINE_MAX_N) {  // one kernel; in place is safe (a CTA reads its whole lines before it writes them)
         BlueParams bp{in, out, n, batch, p->chirp, p->bhat, p->sub->tw, inverse ? 1 : 0, inverse ? 1 : 0,
@@ -548,10 +553,12 @@ template <int KIND> static int32_t launch_blue_real_k(int64_t M, const BlueRealP
     }
 }
 // true when plan p is a Bluestein plan whose padded length fits one CTA: the real kinds then run in a single kernel
-bool cfft_real_fused_ok(const CfftPlan* p) { return p && p->mode == 2 && p->M <= LINE_MAX_N; }
+// ... or a mixed-radix plan (one length-n FFT in shared memory, afb_mixed.cu)
+bool cfft_real_fused_ok(const CfftPlan* p) { return p && ((p->mode == 2 && p->M <= LINE_MAX_N) || p->mode == 3); }
 int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
                          const cplx* qtab, void* stream) {
     if (batch == 0) return AFB_OK;
+    if (p->mode == 3) return launch_mixed_real(kind, p->n, p->tw, qtab, in, istride, out, ostride, batch, stream);
     BlueRealParams bp{in, out, p->n, batch, istride, ostride, p->chirp, p->bhat, p->sub->tw, qtab, 1.0 / (double)p->M};
     switch (kind) {
         case AFB_CHEB1_FWD: return launch_blue_real_k<AFB_CHEB1_FWD>(p->M, bp, stream);

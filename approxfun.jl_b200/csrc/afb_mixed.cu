@@ -1,0 +1,347 @@
+// Mixed-radix (2, 3, 4, 5, 7, 8) Stockham FFT in shared memory for lengths n = 2^a 3^b 5^c 7^d that are not powers of two:
+// n = 1000, the plot sizes 3n + 50 of /root/reference/src/Plot/Plot.jl:16,24 when they are smooth, chopped coefficient
+// counts, Padua grids.  One length-n complex FFT replaces the two padded (M >= 2n - 1) FFTs of Bluestein's algorithm.
+//
+//   * Radices are run-time data (any smooth n goes through ONE compiled kernel per kind); every pass is a switch onto a
+//     compile-time butterfly.  The butterflies of all lines of a CTA are pooled and dealt to the threads round robin, so
+//     odd butterfly counts (n / 5 = 200 on 256 threads) do not idle half a CTA.
+//   * Autosort needs out-of-place passes when a thread runs a run-time number of butterflies: two buffers per line
+//     (ping-pong), indexed through a pad of one 16-byte slot every eight so that the stride-R scatter of a pass and the
+//     stride-1 gather of the next are both conflict free.
+//   * The four real kinds ride TWO real lines per complex FFT (z = line 2q + i line 2q+1), with the kind's pre-processing in
+//     the load loop and the spectrum split + post-processing in the store loop, exactly as the fused Bluestein kernel
+//     (afb_large.cu) does: one read and one write of the data, 16 B per coefficient.
+#include <algorithm>
+#include <vector>
+
+#include "afb_fft.cuh"
+#include "afb_internal.h"
+
+namespace afb {
+
+constexpr int MX_MAXPASS = 14;
+constexpr int MX_CT = 256;
+constexpr int64_t MX_MAX_N = 6144;   // two padded buffers of 16 B * 9/8 n: 216 KB at n = 6144
+
+struct MixedSched {
+    int n, npass, lpc, npad;
+    int radix[MX_MAXPASS];
+    int ns[MX_MAXPASS];          // product of the radices of the earlier passes
+    float inv_nr[MX_MAXPASS];    // 1 / (n / radix)
+    float inv_ns[MX_MAXPASS];
+};
+
+__device__ __forceinline__ int mx_pad(int i) { return i + (i >> 3); }
+// floor(a / d) for 0 <= a < 2^20 through a float reciprocal, corrected to be exact
+__device__ __forceinline__ int mx_div(int a, int d, float inv) {
+    int q = (int)(((float)a + 0.5f) * inv);
+    int r = a - q * d;
+    if (r < 0) --q;
+    else if (r >= d) ++q;
+    return q;
+}
+
+// ---- odd-radix butterflies (forward sign): X_m = x0 + sum_k c_{mk} a_k - i sum_k s_{mk} b_k, a_k = x_k + x_{R-k}, b_k = x_k - x_{R-k}
+// cos / sin of 2 pi i / R, i = 0..R-1 (compile-time index after unrolling, so these fold to immediates)
+template <int R> __host__ __device__ constexpr double odd_cos(int i);
+template <int R> __host__ __device__ constexpr double odd_sin(int i);
+template <> __host__ __device__ constexpr double odd_cos<3>(int i) { return i == 0 ? 1.0 : -0.5; }
+template <> __host__ __device__ constexpr double odd_sin<3>(int i) {
+    return i == 0 ? 0.0 : i == 1 ? 0.86602540378443864676 : -0.86602540378443864676;
+}
+template <> __host__ __device__ constexpr double odd_cos<5>(int i) {
+    return i == 0 ? 1.0 : (i == 1 || i == 4) ? 0.30901699437494742410 : -0.80901699437494742410;
+}
+template <> __host__ __device__ constexpr double odd_sin<5>(int i) {
+    return i == 0 ? 0.0 : i == 1 ? 0.95105651629515357212 : i == 2 ? 0.58778525229247312917
+         : i == 3 ? -0.58778525229247312917 : -0.95105651629515357212;
+}
+template <> __host__ __device__ constexpr double odd_cos<7>(int i) {
+    return i == 0 ? 1.0 : (i == 1 || i == 6) ? 0.62348980185873353053 : (i == 2 || i == 5) ? -0.22252093395631440429
+         : -0.90096886790241912624;
+}
+template <> __host__ __device__ constexpr double odd_sin<7>(int i) {
+    return i == 0 ? 0.0 : i == 1 ? 0.78183148246802980871 : i == 2 ? 0.97492791218182360702 : i == 3 ? 0.43388373911755812048
+         : i == 4 ? -0.43388373911755812048 : i == 5 ? -0.97492791218182360702 : -0.78183148246802980871;
+}
+template <int R> __device__ __forceinline__ void dft_odd(cplx* x) {
+    constexpr int H = (R - 1) / 2;
+    cplx a[H], b[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) { a[k] = cadd(x[k + 1], x[R - 1 - k]); b[k] = csub(x[k + 1], x[R - 1 - k]); }
+    cplx x0 = x[0];
+    cplx sum = x0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) sum = cadd(sum, a[k]);
+    x[0] = sum;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        cplx re = x0, im = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const double cc = odd_cos<R>(((m + 1) * (k + 1)) % R), ss = odd_sin<R>(((m + 1) * (k + 1)) % R);
+            re.x = fma(cc, a[k].x, re.x); re.y = fma(cc, a[k].y, re.y);
+            im.x = fma(ss, b[k].x, im.x); im.y = fma(ss, b[k].y, im.y);
+        }
+        // X_{m+1} = re - i im ; X_{R-1-m} = re + i im
+        x[m + 1] = make_double2(re.x + im.y, re.y - im.x);
+        x[R - 1 - m] = make_double2(re.x - im.y, re.y + im.x);
+    }
+}
+template <int R> struct MxDft { static __device__ __forceinline__ void run(cplx* x) { Dft<R>::run(x); } };
+template <> struct MxDft<3> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<3>(x); } };
+template <> struct MxDft<5> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<5>(x); } };
+template <> struct MxDft<7> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<7>(x); } };
+
+// one pass of radix R over the pooled butterflies of the CTA's `lines` lines: src -> dst (both padded, stride `lstride` slots)
+template <int R>
+__device__ __forceinline__ void mx_pass(const MixedSched& sc, int pass, const cplx* __restrict__ src, cplx* __restrict__ dst,
+                                        int lines, int lstride, const cplx* __restrict__ tw) {
+    const int n = sc.n, nr = n / R, NS = sc.ns[pass];
+    const int twstep = n / (NS * R);
+    const int total = lines * nr;
+    for (int b = threadIdx.x; b < total; b += MX_CT) {
+        const int l = (lines == 1) ? 0 : mx_div(b, nr, sc.inv_nr[pass]);
+        const int j = b - l * nr;
+        const cplx* s = src + l * lstride;
+        cplx* d = dst + l * lstride;
+        cplx x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = s[mx_pad(j + r * nr)];
+        int k = 0;
+        if (NS > 1) {
+            k = j - mx_div(j, NS, sc.inv_ns[pass]) * NS;
+            apply_powers<R>(x, ldg2(tw + k * twstep));
+        }
+        MxDft<R>::run(x);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) d[mx_pad(base + q * NS)] = x[q];
+    }
+}
+// all passes; returns the buffer holding the natural-order result
+__device__ __forceinline__ cplx* mx_fft(const MixedSched& sc, cplx* a, cplx* b, int lines, int lstride, const cplx* __restrict__ tw) {
+    cplx *src = a, *dst = b;
+    for (int p = 0; p < sc.npass; ++p) {
+        switch (sc.radix[p]) {
+            case 2: mx_pass<2>(sc, p, src, dst, lines, lstride, tw); break;
+            case 3: mx_pass<3>(sc, p, src, dst, lines, lstride, tw); break;
+            case 4: mx_pass<4>(sc, p, src, dst, lines, lstride, tw); break;
+            case 5: mx_pass<5>(sc, p, src, dst, lines, lstride, tw); break;
+            case 7: mx_pass<7>(sc, p, src, dst, lines, lstride, tw); break;
+            default: mx_pass<8>(sc, p, src, dst, lines, lstride, tw); break;
+        }
+        __syncthreads();
+        cplx* t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+// ---- complex lines: out[b*n + k] = scale * sum_j in[b*n + j] exp(-/+ 2 pi i jk/n) ----------------------------------
+struct MixedCParams {
+    const cplx* in;
+    cplx* out;
+    int64_t batch;
+    const cplx* tw;
+    int inverse;
+    double scale;
+    MixedSched sc;
+};
+__global__ void __launch_bounds__(MX_CT) mixed_cfft_kernel(const __grid_constant__ MixedCParams p) {
+    AFB_DYN_SMEM(cplx, smem);
+    const MixedSched& sc = p.sc;
+    const int n = sc.n, lstride = sc.npad;
+    const int64_t line0 = (int64_t)blockIdx.x * sc.lpc;
+    const int lines = (int)((p.batch - line0 < sc.lpc) ? (p.batch - line0) : sc.lpc);
+    cplx* A = smem;
+    cplx* B = smem + (size_t)sc.lpc * lstride;
+    for (int l = 0; l < lines; ++l) {
+        const cplx* src = p.in + (line0 + l) * n;
+        for (int j = threadIdx.x; j < n; j += MX_CT) {
+            cplx z = src[j];
+            if (p.inverse) z.y = -z.y;
+            A[l * lstride + mx_pad(j)] = z;
+        }
+    }
+    __syncthreads();
+    const cplx* R = mx_fft(sc, A, B, lines, lstride, p.tw);
+    for (int l = 0; l < lines; ++l) {
+        cplx* dst = p.out + (line0 + l) * n;
+        for (int j = threadIdx.x; j < n; j += MX_CT) {
+            cplx z = cscale(R[l * lstride + mx_pad(j)], p.scale);
+            if (p.inverse) z.y = -z.y;
+            dst[j] = z;
+        }
+    }
+}
+
+// ---- the four real kinds, two real lines per complex FFT ------------------------------------------------------------
+struct MixedRParams {
+    const double* in;
+    double* out;
+    int64_t batch, istride, ostride;  // batch = real lines
+    const cplx *tw, *qtab;
+    MixedSched sc;
+};
+// pre-processing value of element j of one real line (same formulae as generic_pre_value in afb_large.cu)
+template <int KIND>
+__device__ __forceinline__ cplx mx_pre(const double* __restrict__ v, int n, int nh, int j, const cplx* __restrict__ qtab) {
+    cplx z = make_double2(0.0, 0.0);
+    if (KIND == AFB_CHEB1_FWD) {
+        z.x = (j < nh) ? v[2 * j] : v[2 * (n - 1 - j) + 1];
+    } else if (KIND == AFB_CHEB1_INV) {       // X'_k = conj(w^k) (c'_k - i c'_{n-k}) / 2,  c'_0 = 2 c_0, c'_n = 0
+        if (j == 0) z.x = v[0];
+        else {
+            const cplx w = ldg2(qtab + j);
+            z = cmul(make_double2(0.5 * v[j], -0.5 * v[n - j]), make_double2(w.x, -w.y));
+        }
+    } else if (KIND == AFB_FOURIER_FWD) {
+        z.x = v[j];
+    } else {                                  // AFB_FOURIER_INV
+        if (j == 0) z.x = v[0];
+        else if ((n % 2 == 0) && j == n / 2) z.x = -v[n - 1];
+        else if (j < nh) z = make_double2(0.5 * v[2 * j], -0.5 * v[2 * j - 1]);
+        else { const int k = n - j; z = make_double2(0.5 * v[2 * k], 0.5 * v[2 * k - 1]); }
+    }
+    return z;
+}
+template <int KIND>
+__global__ void __launch_bounds__(MX_CT) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
+    constexpr bool INV = (KIND & 1) != 0;
+    AFB_DYN_SMEM(cplx, smem);
+    const MixedSched& sc = p.sc;
+    const int n = sc.n, nh = (n + 1) / 2, lstride = sc.npad;
+    const int64_t npairs = (p.batch + 1) / 2;
+    const int64_t pair0 = (int64_t)blockIdx.x * sc.lpc;
+    const int lines = (int)((npairs - pair0 < sc.lpc) ? (npairs - pair0) : sc.lpc);
+    cplx* A = smem;
+    cplx* B = smem + (size_t)sc.lpc * lstride;
+    for (int l = 0; l < lines; ++l) {
+        const int64_t q = pair0 + l;
+        const bool has2 = 2 * q + 1 < p.batch;
+        const double* l0 = p.in + (2 * q) * p.istride;
+        const double* l1 = has2 ? l0 + p.istride : l0;
+        for (int j = threadIdx.x; j < n; j += MX_CT) {
+            const cplx z1 = mx_pre<KIND>(l0, n, nh, j, p.qtab);
+            cplx z2 = mx_pre<KIND>(l1, n, nh, j, p.qtab);
+            if (!has2) z2 = make_double2(0.0, 0.0);
+            cplx z = make_double2(z1.x - z2.y, z1.y + z2.x);  // z1 + i z2
+            if (INV) z.y = -z.y;                              // inverse DFT = conj FFT conj
+            A[l * lstride + mx_pad(j)] = z;
+        }
+    }
+    __syncthreads();
+    const cplx* R = mx_fft(sc, A, B, lines, lstride, p.tw);
+    const double dn = (double)n;
+    for (int l = 0; l < lines; ++l) {
+        const int64_t q = pair0 + l;
+        const bool has2 = 2 * q + 1 < p.batch;
+        const cplx* W = R + l * lstride;
+        double* o0 = p.out + (2 * q) * p.ostride;
+        double* o1 = o0 + p.ostride;
+        for (int o = threadIdx.x; o < n; o += MX_CT) {
+            double ve, vo;
+            if (KIND == AFB_CHEB1_INV) {
+                const cplx z = W[mx_pad((o & 1) ? n - 1 - (o - 1) / 2 : o / 2)];
+                ve = z.x; vo = -z.y;
+            } else if (KIND == AFB_FOURIER_INV) {
+                const cplx z = W[mx_pad(o)];
+                ve = z.x; vo = -z.y;
+            } else {
+                const bool nyq = (KIND == AFB_FOURIER_FWD) && (n % 2 == 0) && o == n - 1;
+                const int k = (KIND == AFB_CHEB1_FWD) ? o : (o == 0 ? 0 : nyq ? n / 2 : (o & 1) ? (o + 1) / 2 : o / 2);
+                const cplx Av = W[mx_pad(k)], Bc = W[mx_pad(k == 0 ? 0 : n - k)];
+                const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));    // (A + conj B) / 2
+                const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));   // (A - conj B) / (2i)
+                if (KIND == AFB_CHEB1_FWD) {
+                    const cplx w = ldg2(p.qtab + o);
+                    const double s = (o == 0) ? 1.0 / dn : 2.0 / dn;
+                    ve = cmul(Ye, w).x * s; vo = cmul(Yo, w).x * s;
+                } else if (o == 0) { ve = Ye.x / dn; vo = Yo.x / dn; }
+                else if (nyq) { ve = -Ye.x / dn; vo = -Yo.x / dn; }
+                else if (o & 1) { ve = -Ye.y * (2.0 / dn); vo = -Yo.y * (2.0 / dn); }
+                else { ve = Ye.x * (2.0 / dn); vo = Yo.x * (2.0 / dn); }
+            }
+            o0[o] = ve;
+            if (has2) o1[o] = vo;
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+bool mixed_radix_ok(int64_t n) {
+    if (n < 6 || n > MX_MAX_N || is_pow2(n)) return false;
+    for (int f : {2, 3, 5, 7}) while (n % f == 0) n /= f;
+    return n == 1;
+}
+static bool mixed_schedule(int64_t n, MixedSched* sc) {
+    if (!mixed_radix_ok(n)) return false;
+    int e2 = 0, e3 = 0, e5 = 0, e7 = 0;
+    int64_t m = n;
+    while (m % 2 == 0) { m /= 2; ++e2; }
+    while (m % 3 == 0) { m /= 3; ++e3; }
+    while (m % 5 == 0) { m /= 5; ++e5; }
+    while (m % 7 == 0) { m /= 7; ++e7; }
+    std::vector<int> r;
+    // the first pass has no twiddles: give it the largest radix
+    while (e2 >= 3) { r.push_back(8); e2 -= 3; }
+    for (int i = 0; i < e7; ++i) r.push_back(7);
+    for (int i = 0; i < e5; ++i) r.push_back(5);
+    if (e2 == 2) r.push_back(4);
+    for (int i = 0; i < e3; ++i) r.push_back(3);
+    if (e2 == 1) r.push_back(2);
+    if ((int)r.size() > MX_MAXPASS) return false;
+    sc->n = (int)n;
+    sc->npass = (int)r.size();
+    sc->npad = (int)(n + (n >> 3) + 1);
+    int ns = 1;
+    for (int p = 0; p < sc->npass; ++p) {
+        sc->radix[p] = r[(size_t)p];
+        sc->ns[p] = ns;
+        sc->inv_nr[p] = 1.0f / (float)(n / r[(size_t)p]);
+        sc->inv_ns[p] = 1.0f / (float)ns;
+        ns *= r[(size_t)p];
+    }
+    // lines per CTA: about 64 KB of shared memory (three CTAs per SM), at most 16 lines, at least one
+    const size_t per_line = 2 * sizeof(cplx) * (size_t)sc->npad;
+    int lpc = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)64 << 10) / per_line));
+    sc->lpc = lpc;
+    return true;
+}
+static size_t mixed_smem(const MixedSched& sc) { return 2 * sizeof(cplx) * (size_t)sc.npad * (size_t)sc.lpc; }
+
+int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale,
+                          void* stream) {
+    if (batch == 0) return AFB_OK;
+    MixedCParams p{in, out, batch, tw, inverse ? 1 : 0, scale, {}};
+    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
+    auto k = mixed_cfft_kernel;
+    AFB_SMEM_OPTIN(k, 220 * 1024);
+    AFB_LAUNCH(k, (unsigned)((batch + p.sc.lpc - 1) / p.sc.lpc), MX_CT, mixed_smem(p.sc), stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, void* stream) {
+    auto k = mixed_real_kernel<KIND>;
+    AFB_SMEM_OPTIN(k, 220 * 1024);
+    const int64_t npairs = (p.batch + 1) / 2;
+    AFB_LAUNCH(k, (unsigned)((npairs + p.sc.lpc - 1) / p.sc.lpc), MX_CT, mixed_smem(p.sc), stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+int32_t launch_mixed_real(int kind, int64_t n, const cplx* tw, const cplx* qtab, const double* in, int64_t istride, double* out,
+                          int64_t ostride, int64_t batch, void* stream) {
+    if (batch == 0) return AFB_OK;
+    MixedRParams p{in, out, batch, istride, ostride, tw, qtab, {}};
+    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
+    switch (kind) {
+        case AFB_CHEB1_FWD: return launch_mixed_real_k<AFB_CHEB1_FWD>(p, stream);
+        case AFB_CHEB1_INV: return launch_mixed_real_k<AFB_CHEB1_INV>(p, stream);
+        case AFB_FOURIER_FWD: return launch_mixed_real_k<AFB_FOURIER_FWD>(p, stream);
+        case AFB_FOURIER_INV: return launch_mixed_real_k<AFB_FOURIER_INV>(p, stream);
+        default: return fail(AFB_BAD_ARG, "mixed-radix real transform: kind");
+    }
+}
+
+}  // namespace afb

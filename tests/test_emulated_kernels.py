@@ -354,3 +354,31 @@ def test_host_sampler_with_device_uniforms():
     assert np.array_equal(s, orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cf, u)))
     assert np.array_equal(ll.sample_cheb(cf, -5.0, 5.0, 42, 10), s[:10])      # reproducible prefix
     assert not np.array_equal(ll.sample_cheb(cf, -5.0, 5.0, 43, 10), s[:10])  # seed matters
+
+
+# mixed-radix engine (afb_mixed.cu): n = 2^a 3^b 5^c 7^d in one shared-memory FFT instead of Bluestein
+MIXED_SIZES = [6, 10, 12, 14, 15, 21, 35, 36, 48, 60, 63, 70, 96, 100, 105, 120, 125, 243, 245, 343, 360, 500, 1000, 1029,
+               1536, 2187, 2400, 3000, 3125, 5000, 6000, 6144]
+
+
+@pytest.mark.parametrize("n", MIXED_SIZES)
+def test_mixed_radix_real_and_complex(n):
+    nb = 5 if n <= 1000 else 3        # odd line counts: the last pair of a CTA is half empty
+    v = RNG.standard_normal((n, nb))
+    for kind, ref in REAL_KINDS:
+        want = ref(v)
+        got = ll.transform(kind, v)
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
+    z = RNG.standard_normal((n, 2)) + 1j * RNG.standard_normal((n, 2))
+    for kind, ref in CPLX_KINDS:
+        want = ref(z)
+        got = ll.transform(kind, z)
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(z)))), (kind, n)
+
+
+def test_mixed_radix_many_lines_per_cta():
+    # short smooth lengths pack up to 16 pairs of lines into a CTA: pooled butterflies cross line boundaries
+    for n, nb in ((12, 67), (60, 41), (100, 33)):
+        v = RNG.standard_normal((n, nb))
+        assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) <= tol(n, np.max(np.abs(v)))
+        assert np.max(np.abs(ll.transform(B.FOURIER_INV, v) - orc.fourier_itransform(v, axis=0))) <= tol(n, 20 * np.max(np.abs(v)))

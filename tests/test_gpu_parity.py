@@ -673,3 +673,48 @@ def test_sampling_2d_long_b_factors(af):
     assert np.array_equal(got, want)
     small = af.api.lowlevel().sample2d_lowrank(A, B[:150], -1.0, 1.0, -2.0, 3.0, ry, u)      # fused kernel, same formulae
     assert np.array_equal(small, orcc.sample2d_lowrank(A, B[:150], -1.0, 1.0, -2.0, 3.0, ry, u, threads=8))
+
+
+MIXED_SIZES = [36, 48, 60, 96, 100, 120, 243, 245, 343, 360, 500, 1000, 1029, 1536, 2187, 2400, 3000, 3125, 5000, 6000, 6144]
+
+
+@pytest.mark.parametrize("n", MIXED_SIZES)
+def test_mixed_radix_lengths(af, n):
+    # n = 2^a 3^b 5^c 7^d (not a power of two): ONE shared-memory mixed-radix FFT per pair of lines (afb_mixed.cu)
+    from approxfun_b200 import _lib as L
+    nb = 37
+    v = RNG.standard_normal((n, nb))
+    for S, fwd, inv in ((af.Chebyshev(), orc.cheb_transform, orc.cheb_itransform),
+                        (af.Fourier(), orc.fourier_transform, orc.fourier_itransform)):
+        c = af.transform(S, v)
+        assert np.max(np.abs(c - fwd(v, axis=0))) <= coef_tol(n, v), (type(S).__name__, n)
+        wi = inv(v, axis=0)
+        assert np.max(np.abs(af.itransform(S, v) - wi)) <= coef_tol(n, wi), (type(S).__name__, n)
+        assert np.max(np.abs(af.itransform(S, c) - v)) <= coef_tol(n, v)
+    z = RNG.standard_normal((n, 5)) + 1j * RNG.standard_normal((n, 5))
+    assert np.max(np.abs(af.transform(af.Laurent(), z) - orc.laurent_transform(z, axis=0))) <= coef_tol(n, z)
+    wi = orc.laurent_itransform(z, axis=0)
+    assert np.max(np.abs(af.itransform(af.Laurent(), z) - wi)) <= coef_tol(n, wi)
+    assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 1
+
+
+def test_pageable_strided_host_arrays_through_the_pinned_ring(af):
+    # a pageable caller array with stride > n, large enough (> 4 MiB, several 32 MiB chunks) for the library's own staging:
+    # host copy team -> pinned ring -> DMA; the padding columns of the destination must stay untouched
+    from approxfun_b200 import _lib as L
+    n, stride, nb = 4096, 4096 + 6, 9000         # 295 MB
+    host = RNG.standard_normal((nb, stride))
+    out = np.full_like(host, -3.0)
+    plan = af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, stride)
+    plan.execute_host(host, out)
+    idx = RNG.integers(0, nb, 64)
+    assert np.max(np.abs(out[idx, :n] - orc.cheb_transform(host[idx, :n], axis=1))) <= coef_tol(n, host)
+    assert np.array_equal(out[:, n:], np.full((nb, stride - n), -3.0))
+    ref = np.empty((nb, n))
+    plan2 = af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n)
+    plan2.execute_host(np.ascontiguousarray(host[:, :n]), ref)
+    assert np.array_equal(out[:, :n], ref)
+    plan.execute_host(host, host)               # in place on the host
+    assert np.array_equal(host[:, :n], ref)
+    plan.close()
+    plan2.close()
