@@ -19,6 +19,7 @@ CHEB1_FWD, CHEB1_INV, FOURIER_FWD, FOURIER_INV, LAURENT_FWD, LAURENT_INV, CHEB1_
 CHEB2_FWD, CHEB2_INV, SIN_FWD, SIN_INV = 8, 9, 10, 11
 TAYLOR_FWD, TAYLOR_INV, HARDYM_FWD, HARDYM_INV = 12, 13, 14, 15
 PADUA_FWD, PADUA_INV = 16, 17
+FOURIER_CHEB1_2D_FWD, FOURIER_CHEB1_2D_INV, LAURENT_CHEB1_2D_FWD, LAURENT_CHEB1_2D_INV = 18, 19, 20, 21
 PLAN_2D_TRANSPOSE = 1  # afb_plan_create flag: explicit-transpose row pass for 2D kinds
 
 # every symbol include/approxfun_b200.h declares (tests check the .so exports each of them)
@@ -34,6 +35,7 @@ SYMBOLS = [
     "afb_cheb_bisect_cols", "afb_cheb_bisect_cols_device", "afb_samplecdf_cheb", "afb_sample_cheb", "afb_sample_cheb_device",
     "afb_philox_uniform_device", "afb_fp64_probe_device",
     "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device", "afb_piecewise_clenshaw", "afb_piecewise_bisect",
+    "afb_clenshaw_fourier_cheb2d", "afb_clenshaw_fourier_cheb2d_device",
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
@@ -100,6 +102,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_piecewise_clenshaw": [vp, vp, vp, i64, vp, vp, i64],
         "afb_piecewise_bisect": [vp, vp, vp, i64, vp, vp, i64, i32],
         "afb_clenshaw_cheb2d": [vp, i64, i64, vp, vp, vp, i64],
+        "afb_clenshaw_fourier_cheb2d": [vp, i64, i64, vp, vp, vp, i64],
+        "afb_clenshaw_fourier_cheb2d_device": [vp, i64, i64, vp, vp, vp, i64, vp],
         "afb_clenshaw_cheb2d_device": [vp, i64, i64, vp, vp, vp, i64, vp],
         "afb_sample2d_cheb_lowrank": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64],
         "afb_sample2d_cheb_lowrank_device": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64, vp],
@@ -355,6 +359,18 @@ class LowLevel:
             check(self.lib, self.lib.afb_piecewise_bisect(_ptr(coef), _ptr(offs), _ptr(brk), len(pieces), _ptr(xu), _ptr(out), xu.size, numits))
         else:
             check(self.lib, self.lib.afb_piecewise_clenshaw(_ptr(coef), _ptr(offs), _ptr(brk), len(pieces), _ptr(xu), _ptr(out), xu.size))
+        return out
+
+    def fourier_cheb2d(self, Cm, t, y) -> np.ndarray:
+        """Cm[i, j]: coefficient of F_i(t) T_j(y) (Fourier order in i); t in [0, 2 pi), y in [-1, 1]."""
+        Cm = np.asarray(Cm, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if t.size != y.size:
+            raise DimensionMismatch(AFB_BAD_SIZE, "fourier_cheb2d: t and y differ in length")
+        flat = np.ascontiguousarray(Cm.T)
+        out = np.empty_like(t)
+        check(self.lib, self.lib.afb_clenshaw_fourier_cheb2d(_ptr(flat), Cm.shape[0], Cm.shape[1], _ptr(t), _ptr(y), _ptr(out), t.size))
         return out
 
     def sample2d_lowrank(self, A, CB, ya, yb, xa, xb, ry, u) -> np.ndarray:

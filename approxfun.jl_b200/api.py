@@ -124,10 +124,24 @@ class Fourier(Space):
     def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
         self.a, self.b = float(a), float(b)
 
+    def tocanonical(self, x):
+        """PeriodicSegment(a, b) -> [0, 2 pi)"""
+        return 2.0 * math.pi * (np.asarray(x, dtype=np.float64) - self.a) / (self.b - self.a)
+
+    def __mul__(self, other):
+        return TensorSpace(self, other)
+
 
 class Laurent(Space):
     def __init__(self, a: float = 0.0, b: float = 2.0 * math.pi):
         self.a, self.b = float(a), float(b)
+
+    def tocanonical(self, x):
+        """PeriodicSegment(a, b) -> [0, 2 pi)"""
+        return 2.0 * math.pi * (np.asarray(x, dtype=np.float64) - self.a) / (self.b - self.a)
+
+    def __mul__(self, other):
+        return TensorSpace(self, other)
 
 
 class CosSpace(Space):
@@ -161,10 +175,21 @@ class Hardy(Space):
 
 
 class TensorSpace(Space):
-    def __init__(self, s1: Chebyshev, s2: Chebyshev):
-        if not (isinstance(s1, Chebyshev) and isinstance(s2, Chebyshev)):
-            raise TypeError("TensorSpace: only Chebyshev (x) Chebyshev has a GPU path")
+    """`S1 ⊗ S2` (`S1 * S2` here): Chebyshev ⊗ Chebyshev, and the periodic-times-interval spaces Fourier ⊗ Chebyshev and
+    Laurent ⊗ Chebyshev (`PeriodicSegment() × ChebyshevInterval()`, test/PeriodicXIntervalTest.jl:22, LaplaceInAStripTest.jl:5)."""
+
+    def __init__(self, s1: Space, s2: Space):
+        if not (isinstance(s1, (Chebyshev, Fourier, Laurent)) and isinstance(s2, Chebyshev)):
+            raise TypeError("TensorSpace: GPU paths exist for (Chebyshev | Fourier | Laurent) (x) Chebyshev")
         self.factors = (s1, s2)
+
+    def kinds(self):
+        s1 = self.factors[0]
+        if isinstance(s1, Fourier):
+            return L.FOURIER_CHEB1_2D_FWD, L.FOURIER_CHEB1_2D_INV
+        if isinstance(s1, Laurent):
+            return L.LAURENT_CHEB1_2D_FWD, L.LAURENT_CHEB1_2D_INV
+        return L.CHEB1_2D_FWD, L.CHEB1_2D_INV
 
 
 _FWD = {Chebyshev: L.CHEB1_FWD, Fourier: L.FOURIER_FWD, Laurent: L.LAURENT_FWD, TensorSpace: L.CHEB1_2D_FWD,
@@ -238,12 +263,14 @@ class TransformPlan:
             if len(self.shape) != 2:
                 raise L.DimensionMismatch(L.AFB_BAD_SIZE, "TensorSpace plans take an n x m matrix or a Padua vector")
             n, n2 = self.shape
+            self.kind = space.kinds()[1 if self.inverse else 0]
             self._h = self._ll.plan_create(self.kind, n, n2, 1, n)
         else:
             n = self.shape[0]
             batch = int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
             self._h = self._ll.plan_create(self.kind, n, 0, batch, n)
-        self.dtype = np.complex128 if isinstance(space, (Laurent, Taylor, Hardy)) else np.float64
+        cplx = isinstance(space, (Laurent, Taylor, Hardy)) or (isinstance(space, TensorSpace) and isinstance(space.factors[0], Laurent))
+        self.dtype = np.complex128 if cplx else np.float64
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -372,7 +399,8 @@ class Fun:
 
     def __init__(self, *args):
         if len(args) == 2 and isinstance(args[0], Space):
-            self.space, self.coefficients = args[0], np.array(args[1], dtype=np.float64 if not isinstance(args[0], Laurent) else np.complex128)
+            cplx = isinstance(args[0], Laurent) or (isinstance(args[0], TensorSpace) and isinstance(args[0].factors[0], Laurent))
+            self.space, self.coefficients = args[0], np.array(args[1], dtype=np.complex128 if cplx else np.float64)
         elif len(args) == 3:
             f, space, n = args
             self.space = space
@@ -414,6 +442,12 @@ class Fun:
             s1, s2 = sp.factors
             xs, ys = np.broadcast_arrays(np.atleast_1d(np.asarray(x, dtype=np.float64)),
                                          np.atleast_1d(np.asarray(y, dtype=np.float64)))
+            if isinstance(s1, Fourier):
+                out = lowlevel().fourier_cheb2d(self.coefficients, s1.tocanonical(xs.ravel()), s2.tocanonical(ys.ravel()))
+                out = out.reshape(xs.shape)
+                return float(out.ravel()[0]) if (np.ndim(x) == 0 and np.ndim(y) == 0) else out
+            if isinstance(s1, Laurent):
+                raise NotImplementedError("evaluation of Laurent (x) Chebyshev Funs: transform plans only")
             cm = self.coefficients if self.coefficients.ndim == 2 else totaldegree_to_matrix(self.coefficients)
             out = lowlevel().clenshaw2d(cm, s1.tocanonical(xs.ravel()), s2.tocanonical(ys.ravel()))
             out = out.reshape(xs.shape)

@@ -939,22 +939,31 @@ int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int6
                         uint32_t flags) {
     if (!out) return fail(AFB_BAD_ARG, "afb_plan_create: null out pointer");
     *out = nullptr;
-    if (kind < AFB_CHEB1_FWD || kind > AFB_PADUA_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
+    if (kind < AFB_CHEB1_FWD || kind > AFB_LAURENT_CHEB1_2D_INV) return fail(AFB_BAD_ARG, "afb_plan_create: unknown kind");
     if (n < 0 || n2 < 0 || batch < 0) return fail(AFB_BAD_SIZE, "afb_plan_create: negative size");
     AFB_TRY(ensure_device());
-    if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV) {
+    if (kind == AFB_CHEB1_2D_FWD || kind == AFB_CHEB1_2D_INV || kind >= AFB_FOURIER_CHEB1_2D_FWD) {
         if (batch != 1) return fail(AFB_BAD_SIZE, "afb_plan_create: 2D plans take batch == 1");
+        // factor-1 plan on the columns, Chebyshev plan on the rows.  A complex (Laurent) matrix is a real 2n x n2 matrix whose
+        // rows are the real and imaginary parts of the complex rows, and the row transform is real-linear.
+        const bool inv = (kind & 1) != 0;
+        const int32_t kcol = (kind <= AFB_CHEB1_2D_INV) ? (inv ? AFB_CHEB1_INV : AFB_CHEB1_FWD)
+                           : (kind <= AFB_FOURIER_CHEB1_2D_INV) ? (inv ? AFB_FOURIER_INV : AFB_FOURIER_FWD)
+                                                                : (inv ? AFB_LAURENT_INV : AFB_LAURENT_FWD);
+        const int32_t krow = inv ? AFB_CHEB1_INV : AFB_CHEB1_FWD;
         afb_plan_s* p = new afb_plan_s();
         p->kind = kind; p->n = n; p->n2 = n2; p->batch = 1; p->stride = n; p->flags = flags;
+        p->elem = (kcol == AFB_LAURENT_FWD || kcol == AFB_LAURENT_INV) ? 16 : 8;
         p->path = (n == 0 || n2 == 0) ? PATH_EMPTY : PATH_TENSOR2D;
         if (p->path == PATH_TENSOR2D) {
-            const int32_t k1 = (kind == AFB_CHEB1_2D_FWD) ? AFB_CHEB1_FWD : AFB_CHEB1_INV;
-            int32_t st = plan_create_1d(&p->col_plan, k1, n, n2, n, flags);
+            const int64_t nreal = n * (p->elem / 8);
+            int32_t st = plan_create_1d(&p->col_plan, kcol, n, n2, n, flags);
             // row pass: strided four-step on row pairs when the shape allows, else transpose + lines + transpose
-            if (st == AFB_OK && ((flags & AFB_PLAN_2D_TRANSPOSE) || !rows_cheb_supported(n, n2))) st = plan_create_1d(&p->row_plan, k1, n2, n, n2, flags);
+            if (st == AFB_OK && ((flags & AFB_PLAN_2D_TRANSPOSE) || !rows_cheb_supported(nreal, n2)))
+                st = plan_create_1d(&p->row_plan, krow, n2, nreal, n2, flags);
             if (st == AFB_OK) {
                 void* d = nullptr;
-                const int64_t tdoubles = p->row_plan ? n * n2 : rows_tmp_doubles(n, n2);
+                const int64_t tdoubles = p->row_plan ? nreal * n2 : rows_tmp_doubles(nreal, n2);
                 cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)tdoubles);
                 if (e != cudaSuccess) st = cuda_fail(e, "cudaMalloc(2D transpose buffer)", __FILE__, __LINE__);
                 p->t2buf = reinterpret_cast<double*>(d);
@@ -996,16 +1005,17 @@ int32_t afb_plan_execute_device(afb_plan p, const void* d_in, void* d_out, void*
     DeviceGuard guard(p->dev);
     if (p->path == PATH_TENSOR2D) {
         // C = T_x V T_y^T on a column-major n x n2 matrix.
-        const int64_t n = p->n, n2 = p->n2;
+        const int64_t n = p->n, n2 = p->n2, nreal = n * (p->elem / 8);
+        const bool inv = (p->kind & 1) != 0;
         // Column pass on contiguous lines, then the row pass.  (Fusing the transposes into the line kernels' stores --
         // 8-byte scatters with a 128 KB stride -- was measured 1.5x SLOWER at 16384^2: 6.06 ms vs 3.97 ms.)
         AFB_TRY(exec_1d_device(p->col_plan, d_in, d_out, n2, n, n, stream));
         if (!p->row_plan)
-            return launch_rows_cheb(p->kind == AFB_CHEB1_2D_INV, reinterpret_cast<const double*>(d_out), p->t2buf,
-                                    reinterpret_cast<double*>(d_out), n, n2, stream);
-        AFB_TRY(launch_transpose(reinterpret_cast<const double*>(d_out), p->t2buf, n, n2, stream));
-        AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, n, n2, n2, stream));
-        AFB_TRY(launch_transpose(p->t2buf, reinterpret_cast<double*>(d_out), n2, n, stream));
+            return launch_rows_cheb(inv, reinterpret_cast<const double*>(d_out), p->t2buf, reinterpret_cast<double*>(d_out),
+                                    nreal, n2, stream);
+        AFB_TRY(launch_transpose(reinterpret_cast<const double*>(d_out), p->t2buf, nreal, n2, stream));
+        AFB_TRY(exec_1d_device(p->row_plan, p->t2buf, p->t2buf, nreal, n2, n2, stream));
+        AFB_TRY(launch_transpose(p->t2buf, reinterpret_cast<double*>(d_out), n2, nreal, stream));
         return AFB_OK;
     }
     if (p->path == PATH_PADUA)
@@ -1115,7 +1125,7 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
             return mdev2d_execute_host(p->mdev2d, reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out));
         }
         DeviceGuard guard(p->dev);
-        const size_t bytes = sizeof(double) * (size_t)(p->path == PATH_PADUA ? p->n : p->n * p->n2);
+        const size_t bytes = (size_t)p->elem * (size_t)(p->path == PATH_PADUA ? p->n : p->n * p->n2);
         void* d = nullptr;
         AFB_CUDA(cudaMalloc(&d, bytes));
         int32_t st = AFB_OK;
@@ -1495,6 +1505,28 @@ int32_t afb_clenshaw_cheb2d(const double* C, int64_t n1, int64_t n2, const doubl
     AFB_TRY(dout.alloc(8 * (size_t)P));
     AFB_TRY(dc.put(C, 8 * (size_t)(n1 * n2))); AFB_TRY(dx.put(x, 8 * (size_t)P)); AFB_TRY(dy.put(y, 8 * (size_t)P));
     AFB_TRY(launch_clenshaw2d(dc.as<double>(), n1, n2, dx.as<double>(), dy.as<double>(), dout.as<double>(), P, nullptr));
+    return dout.get(out, 8 * (size_t)P);
+}
+
+int32_t afb_clenshaw_fourier_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_t, const double* d_y,
+                                           double* d_out, int64_t P, void* stream) {
+    if (n1 < 0 || n2 < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_fourier_cheb2d: negative size");
+    if (P == 0) return AFB_OK;
+    if ((n1 * n2 && !d_C) || !d_t || !d_y || !d_out) return fail(AFB_BAD_ARG, "afb_clenshaw_fourier_cheb2d: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_fourier_cheb2d(d_C, n1, n2, d_t, d_y, d_out, P, stream);
+}
+int32_t afb_clenshaw_fourier_cheb2d(const double* C, int64_t n1, int64_t n2, const double* t, const double* y, double* out,
+                                    int64_t P) {
+    if (n1 < 0 || n2 < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_clenshaw_fourier_cheb2d: negative size");
+    if (P == 0) return AFB_OK;
+    if ((n1 * n2 && !C) || !t || !y || !out) return fail(AFB_BAD_ARG, "afb_clenshaw_fourier_cheb2d: null buffer");
+    AFB_TRY(ensure_device());
+    DevBuf dc, dx, dy, dout;
+    AFB_TRY(dc.alloc(8 * (size_t)(n1 * n2))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(dc.put(C, 8 * (size_t)(n1 * n2))); AFB_TRY(dx.put(t, 8 * (size_t)P)); AFB_TRY(dy.put(y, 8 * (size_t)P));
+    AFB_TRY(launch_fourier_cheb2d(dc.as<double>(), n1, n2, dx.as<double>(), dy.as<double>(), dout.as<double>(), P, nullptr));
     return dout.get(out, 8 * (size_t)P);
 }
 

@@ -383,6 +383,70 @@ int32_t launch_clenshaw2d(const double* d_C, int64_t n1, int64_t n2, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fourier (x) Chebyshev evaluation: column j of C (length n1, Fourier order [a0, b1, a1, b2, a2, ...]) is the trigonometric
+// series g_j(t) = a0 + sum_k (b_k sin kt + a_k cos kt), summed by the two Clenshaw recurrences in c = cos t
+// (sum a_k T_k(c)  and  sin t * sum b_k U_{k-1}(c)); the g_j are then the coefficients of the Chebyshev recurrence in y.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fourier_cheb2d_kernel(const double* __restrict__ C, int64_t n1, int64_t n2, const double* __restrict__ t,
+                      const double* __restrict__ y, double* __restrict__ out, int64_t P, int use_smem) {
+    AFB_DYN_SMEM(double, sc);
+    const double* cc = C;
+    if (use_smem) {
+        for (int64_t k = threadIdx.x; k < n1 * n2; k += blockDim.x) sc[k] = C[k];
+        __syncthreads();
+        cc = sc;
+    }
+    const int64_t K = n1 / 2;          // highest frequency with a sine slot (slot 2K-1)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        double sn, cs;
+        sincos(t[i], &sn, &cs);
+        const double c2 = __dmul_rn(2.0, cs), y2 = __dmul_rn(2.0, y[i]);
+        double B1 = 0.0, B2 = 0.0, res = 0.0;
+        for (int64_t j = n2 - 1; j >= 0; --j) {
+            const double* cj = cc + j * n1;
+            double g = 0.0;
+            if (n1 >= 1) {
+                // cosine part: a_k = cj[2k], k = 0..(n1-1)/2
+                double b1 = 0.0, b2 = 0.0;
+                for (int64_t k = (n1 - 1) / 2; k >= 1; --k) {
+                    const double tt = __fma_rn(c2, b1, __dsub_rn(cj[2 * k], b2));
+                    b2 = b1; b1 = tt;
+                }
+                g = __fma_rn(cs, b1, __dsub_rn(cj[0], b2));
+                // sine part: b_k = cj[2k-1], k = 1..K:  d_k = b_k + 2c d_{k+1} - d_{k+2};  sum = sin t * d_1
+                double d1 = 0.0, d2 = 0.0;
+                for (int64_t k = K; k >= 1; --k) {
+                    const double tt = __fma_rn(c2, d1, __dsub_rn(cj[2 * k - 1], d2));
+                    d2 = d1; d1 = tt;
+                }
+                g = __fma_rn(sn, d1, g);
+            }
+            if (j >= 1) {
+                const double tt = __fma_rn(y2, B1, __dsub_rn(g, B2));
+                B2 = B1; B1 = tt;
+            } else {
+                res = (n2 == 1) ? g : __fma_rn(__dmul_rn(y2, 0.5), B1, __dsub_rn(g, B2));
+            }
+        }
+        out[i] = res;
+    }
+}
+int32_t launch_fourier_cheb2d(const double* d_C, int64_t n1, int64_t n2, const double* d_t, const double* d_y, double* d_out,
+                              int64_t P, void* stream) {
+    if (P == 0) return AFB_OK;
+    int64_t grid = (P + 255) / 256;
+    if (grid > 8 * (int64_t)sm_count()) grid = 8 * (int64_t)sm_count();
+    const size_t need = sizeof(double) * (size_t)(n1 * n2);
+    const int use_smem = (n1 * n2 > 0 && need <= 96 * 1024) ? 1 : 0;
+    auto k = fourier_cheb2d_kernel;
+    AFB_SMEM_OPTIN(k, 96 * 1024);
+    AFB_LAUNCH(k, (unsigned)grid, 256, use_smem ? need : 8, stream, d_C, n1, n2, d_t, d_y, d_out, P, use_smem);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9: chebnormalizedcumsum! per column (sample.jl:170-175), sequential per column to keep the
 // reference's summation order; one thread per column.
 // ------------------------------------------------------------------------------------------------

@@ -44,6 +44,8 @@ int32_t launch_sample2d(const double* d_A, int64_t NA, const double* d_CB, int64
                         void* stream);
 int32_t launch_clenshaw2d(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y, double* d_out,
                           int64_t P, void* stream);
+int32_t launch_fourier_cheb2d(const double* d_C, int64_t n1, int64_t n2, const double* d_t, const double* d_y, double* d_out,
+                              int64_t P, void* stream);
 int32_t launch_fp64_probe(int mode, int iters, int blocks, double* d_out, void* stream);
 int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream);
 

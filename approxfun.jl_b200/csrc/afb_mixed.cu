@@ -88,7 +88,27 @@ template <int R> __device__ __forceinline__ void dft_odd(cplx* x) {
         x[R - 1 - m] = make_double2(re.x - im.y, re.y + im.x);
     }
 }
+// radix 2H (H = 3, 5): H-point transforms of the even and odd inputs, twiddle w_{2H}^k on the odd ones, radix-2 combine
+template <int H> __device__ __forceinline__ void dft_two_odd(cplx* x) {
+    cplx e[H], o[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+    dft_odd<H>(e);
+    dft_odd<H>(o);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        // w_{2H}^k = -w_H^{(k + H) / 2} for odd k, w_H^{k/2} for even k
+        const int idx = (k & 1) ? ((k + H) / 2) % H : k / 2;
+        const double sg = (k & 1) ? -1.0 : 1.0;
+        const cplx w = make_double2(sg * odd_cos<H>(idx), -sg * odd_sin<H>(idx));
+        const cplx t = (k == 0) ? o[0] : cmul(o[k], w);
+        x[k] = cadd(e[k], t);
+        x[k + H] = csub(e[k], t);
+    }
+}
 template <int R> struct MxDft { static __device__ __forceinline__ void run(cplx* x) { Dft<R>::run(x); } };
+template <> struct MxDft<6> { static __device__ __forceinline__ void run(cplx* x) { dft_two_odd<3>(x); } };
+template <> struct MxDft<10> { static __device__ __forceinline__ void run(cplx* x) { dft_two_odd<5>(x); } };
 template <> struct MxDft<3> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<3>(x); } };
 template <> struct MxDft<5> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<5>(x); } };
 template <> struct MxDft<7> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<7>(x); } };
@@ -119,7 +139,9 @@ __device__ __forceinline__ void mx_pass(const MixedSched& sc, int pass, const cp
         for (int q = 0; q < R; ++q) d[mx_pad(base + q * NS)] = x[q];
     }
 }
-// all passes; returns the buffer holding the natural-order result
+// all passes; returns the buffer holding the natural-order result.  BIG = the schedule uses radix 16 (a separate instantiation:
+// the radix-16 butterfly needs ~120 registers, the others fit 80 and keep three CTAs per SM)
+template <bool BIG>
 __device__ __forceinline__ cplx* mx_fft(const MixedSched& sc, cplx* a, cplx* b, int lines, int lstride, const cplx* __restrict__ tw) {
     cplx *src = a, *dst = b;
     for (int p = 0; p < sc.npass; ++p) {
@@ -128,8 +150,11 @@ __device__ __forceinline__ cplx* mx_fft(const MixedSched& sc, cplx* a, cplx* b, 
             case 3: mx_pass<3>(sc, p, src, dst, lines, lstride, tw); break;
             case 4: mx_pass<4>(sc, p, src, dst, lines, lstride, tw); break;
             case 5: mx_pass<5>(sc, p, src, dst, lines, lstride, tw); break;
+            case 6: mx_pass<6>(sc, p, src, dst, lines, lstride, tw); break;
             case 7: mx_pass<7>(sc, p, src, dst, lines, lstride, tw); break;
-            default: mx_pass<8>(sc, p, src, dst, lines, lstride, tw); break;
+            case 8: mx_pass<8>(sc, p, src, dst, lines, lstride, tw); break;
+            case 10: mx_pass<10>(sc, p, src, dst, lines, lstride, tw); break;
+            default: if (BIG) mx_pass<16>(sc, p, src, dst, lines, lstride, tw); break;
         }
         __syncthreads();
         cplx* t = src; src = dst; dst = t;
@@ -147,7 +172,8 @@ struct MixedCParams {
     double scale;
     MixedSched sc;
 };
-__global__ void __launch_bounds__(MX_CT) mixed_cfft_kernel(const __grid_constant__ MixedCParams p) {
+template <bool BIG>
+__global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_cfft_kernel(const __grid_constant__ MixedCParams p) {
     AFB_DYN_SMEM(cplx, smem);
     const MixedSched& sc = p.sc;
     const int n = sc.n, lstride = sc.npad;
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(MX_CT) mixed_cfft_kernel(const __grid_constant
         }
     }
     __syncthreads();
-    const cplx* R = mx_fft(sc, A, B, lines, lstride, p.tw);
+    const cplx* R = mx_fft<BIG>(sc, A, B, lines, lstride, p.tw);
     for (int l = 0; l < lines; ++l) {
         cplx* dst = p.out + (line0 + l) * n;
         for (int j = threadIdx.x; j < n; j += MX_CT) {
@@ -205,8 +231,8 @@ __device__ __forceinline__ cplx mx_pre(const double* __restrict__ v, int n, int 
     }
     return z;
 }
-template <int KIND>
-__global__ void __launch_bounds__(MX_CT) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
+template <int KIND, bool BIG>
+__global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
     constexpr bool INV = (KIND & 1) != 0;
     AFB_DYN_SMEM(cplx, smem);
     const MixedSched& sc = p.sc;
@@ -216,22 +242,43 @@ __global__ void __launch_bounds__(MX_CT) mixed_real_kernel(const __grid_constant
     const int lines = (int)((npairs - pair0 < sc.lpc) ? (npairs - pair0) : sc.lpc);
     cplx* A = smem;
     cplx* B = smem + (size_t)sc.lpc * lstride;
+    // forward kinds read every line as coalesced 128-bit chunks when the lines are 16-byte aligned: chunk m = (v[2m], v[2m+1])
+    // feeds slots m and n-1-m (Chebyshev: Makhoul's even / odd split) or 2m and 2m+1 (Fourier)
+    const bool vec = !INV && (n % 2 == 0) && (p.istride % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
     for (int l = 0; l < lines; ++l) {
         const int64_t q = pair0 + l;
         const bool has2 = 2 * q + 1 < p.batch;
         const double* l0 = p.in + (2 * q) * p.istride;
         const double* l1 = has2 ? l0 + p.istride : l0;
+        cplx* Al = A + l * lstride;
+        if (vec) {
+            const double2* c0 = reinterpret_cast<const double2*>(l0);
+            const double2* c1 = reinterpret_cast<const double2*>(l1);
+            for (int m = threadIdx.x; m < n / 2; m += MX_CT) {
+                const double2 a = c0[m];
+                double2 b = c1[m];
+                if (!has2) b = make_double2(0.0, 0.0);
+                if (KIND == AFB_CHEB1_FWD) {
+                    Al[mx_pad(m)] = make_double2(a.x, b.x);
+                    Al[mx_pad(n - 1 - m)] = make_double2(a.y, b.y);
+                } else {
+                    Al[mx_pad(2 * m)] = make_double2(a.x, b.x);
+                    Al[mx_pad(2 * m + 1)] = make_double2(a.y, b.y);
+                }
+            }
+            continue;
+        }
         for (int j = threadIdx.x; j < n; j += MX_CT) {
             const cplx z1 = mx_pre<KIND>(l0, n, nh, j, p.qtab);
             cplx z2 = mx_pre<KIND>(l1, n, nh, j, p.qtab);
             if (!has2) z2 = make_double2(0.0, 0.0);
             cplx z = make_double2(z1.x - z2.y, z1.y + z2.x);  // z1 + i z2
             if (INV) z.y = -z.y;                              // inverse DFT = conj FFT conj
-            A[l * lstride + mx_pad(j)] = z;
+            Al[mx_pad(j)] = z;
         }
     }
     __syncthreads();
-    const cplx* R = mx_fft(sc, A, B, lines, lstride, p.tw);
+    const cplx* R = mx_fft<BIG>(sc, A, B, lines, lstride, p.tw);
     const double dn = (double)n;
     for (int l = 0; l < lines; ++l) {
         const int64_t q = pair0 + l;
@@ -274,23 +321,23 @@ bool mixed_radix_ok(int64_t n) {
     for (int f : {2, 3, 5, 7}) while (n % f == 0) n /= f;
     return n == 1;
 }
+// fewest passes over the available radices (depth-first over the divisors; n <= 6144 so this is instant)
+static void mixed_factor(int64_t m, std::vector<int>& cur, std::vector<int>& best) {
+    if (m == 1) { if (best.empty() || cur.size() < best.size()) best = cur; return; }
+    if (!best.empty() && cur.size() + 1 >= best.size() && m > 16) return;
+    for (int r : {16, 10, 8, 6, 7, 5, 4, 3, 2}) {
+        if (m % r) continue;
+        cur.push_back(r);
+        mixed_factor(m / r, cur, best);
+        cur.pop_back();
+    }
+}
 static bool mixed_schedule(int64_t n, MixedSched* sc) {
     if (!mixed_radix_ok(n)) return false;
-    int e2 = 0, e3 = 0, e5 = 0, e7 = 0;
-    int64_t m = n;
-    while (m % 2 == 0) { m /= 2; ++e2; }
-    while (m % 3 == 0) { m /= 3; ++e3; }
-    while (m % 5 == 0) { m /= 5; ++e5; }
-    while (m % 7 == 0) { m /= 7; ++e7; }
-    std::vector<int> r;
-    // the first pass has no twiddles: give it the largest radix
-    while (e2 >= 3) { r.push_back(8); e2 -= 3; }
-    for (int i = 0; i < e7; ++i) r.push_back(7);
-    for (int i = 0; i < e5; ++i) r.push_back(5);
-    if (e2 == 2) r.push_back(4);
-    for (int i = 0; i < e3; ++i) r.push_back(3);
-    if (e2 == 1) r.push_back(2);
-    if ((int)r.size() > MX_MAXPASS) return false;
+    std::vector<int> cur, r;
+    mixed_factor(n, cur, r);
+    if (r.empty() || (int)r.size() > MX_MAXPASS) return false;
+    std::sort(r.begin(), r.end(), [](int a, int b) { return a > b; });   // the first pass has no twiddles: largest radix first
     sc->n = (int)n;
     sc->npass = (int)r.size();
     sc->npad = (int)(n + (n >> 3) + 1);
@@ -302,10 +349,12 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
         sc->inv_ns[p] = 1.0f / (float)ns;
         ns *= r[(size_t)p];
     }
-    // lines per CTA: about 64 KB of shared memory (three CTAs per SM), at most 16 lines, at least one
+    // lines per CTA: the pooled butterflies of the thinnest pass (n / largest radix per line) should fill the 256 threads,
+    // within ~76 KB of shared memory (three CTAs per SM) when one line fits that at all; at most 16 lines
     const size_t per_line = 2 * sizeof(cplx) * (size_t)sc->npad;
-    int lpc = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)64 << 10) / per_line));
-    sc->lpc = lpc;
+    const int fit = (int)std::max<size_t>(1, ((size_t)76 << 10) / per_line);
+    const int want = (int)((MX_CT + n / r[0] - 1) / (n / r[0]));
+    sc->lpc = std::max(1, std::min({16, fit, std::max(want, 1)}));
     return true;
 }
 static size_t mixed_smem(const MixedSched& sc) { return 2 * sizeof(cplx) * (size_t)sc.npad * (size_t)sc.lpc; }
@@ -315,18 +364,32 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
     if (batch == 0) return AFB_OK;
     MixedCParams p{in, out, batch, tw, inverse ? 1 : 0, scale, {}};
     if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
-    auto k = mixed_cfft_kernel;
-    AFB_SMEM_OPTIN(k, 220 * 1024);
-    AFB_LAUNCH(k, (unsigned)((batch + p.sc.lpc - 1) / p.sc.lpc), MX_CT, mixed_smem(p.sc), stream, p);
+    const unsigned grid = (unsigned)((batch + p.sc.lpc - 1) / p.sc.lpc);
+    if (p.sc.radix[0] == 16) {
+        auto k = mixed_cfft_kernel<true>;
+        AFB_SMEM_OPTIN(k, 220 * 1024);
+        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
+    } else {
+        auto k = mixed_cfft_kernel<false>;
+        AFB_SMEM_OPTIN(k, 220 * 1024);
+        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
+    }
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
 
 template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, void* stream) {
-    auto k = mixed_real_kernel<KIND>;
-    AFB_SMEM_OPTIN(k, 220 * 1024);
     const int64_t npairs = (p.batch + 1) / 2;
-    AFB_LAUNCH(k, (unsigned)((npairs + p.sc.lpc - 1) / p.sc.lpc), MX_CT, mixed_smem(p.sc), stream, p);
+    const unsigned grid = (unsigned)((npairs + p.sc.lpc - 1) / p.sc.lpc);
+    if (p.sc.radix[0] == 16) {
+        auto k = mixed_real_kernel<KIND, true>;
+        AFB_SMEM_OPTIN(k, 220 * 1024);
+        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
+    } else {
+        auto k = mixed_real_kernel<KIND, false>;
+        AFB_SMEM_OPTIN(k, 220 * 1024);
+        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
+    }
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }

@@ -581,7 +581,7 @@ def main():
             nc, nr = n2d // world, n2d // world
             gs2 = torch.Generator(device="cuda").manual_seed(4242)
             Vfull = torch.randn(n2d, n2d, dtype=torch.float64, device="cuda", generator=gs2)   # same on every rank
-            blk = Vfull[rank * nc:(rank + 1) * nc].contiguous()                               # column-major n x nc
+            blk = Vfull[rank * nc:(rank + 1) * nc].clone()                                    # column-major n x nc (a copy: Vfull is transformed in place below)
             p2.execute(Vfull.data_ptr(), Vfull.data_ptr(), stream)                            # 1-GPU result, in place
             want_rows = Vfull[:, rank * nr:(rank + 1) * nr].t().contiguous()                  # out[il, j] = C[rank nr + il, j]
             vmax = 6.0

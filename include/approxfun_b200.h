@@ -79,7 +79,13 @@ enum afb_kind {
                              (UPSTREAM; NEWS.md:85): N = (d+1)(d+2)/2 values at afb_paduapoints -> N coefficients in the
                              order T0T0, T0(x)T1(y), T1(x)T0(y), ... (docs/src/usage/constructors.md:98-116).
                              afb_plan_create(kind, n = N, 0, 1, N, 0); AFB_BAD_SIZE unless N is triangular.        */
-    AFB_PADUA_INV = 17    /* plan_itransform(Chebyshev()^2, c::Vector) = plan_ipaduatransform!: coefficients -> values */
+    AFB_PADUA_INV = 17,   /* plan_itransform(Chebyshev()^2, c::Vector) = plan_ipaduatransform!: coefficients -> values */
+    /* mixed tensor spaces (UPSTREAM ApproxFunBase transform!(::TensorSpace, M): factor-1 plan on every column, factor-2 plan
+     * on every row): PeriodicSegment x Interval as in test/PeriodicXIntervalTest.jl:22-24, test/LaplaceInAStripTest.jl:6-8 */
+    AFB_FOURIER_CHEB1_2D_FWD = 18, /* Fourier (x) Chebyshev: real n x n2 matrix                                   */
+    AFB_FOURIER_CHEB1_2D_INV = 19,
+    AFB_LAURENT_CHEB1_2D_FWD = 20, /* Laurent (x) Chebyshev: complex n x n2 matrix (interleaved complex double)   */
+    AFB_LAURENT_CHEB1_2D_INV = 21
 };
 
 typedef struct afb_plan_s* afb_plan;
@@ -228,6 +234,14 @@ int32_t afb_clenshaw_cheb2d(const double* C, int64_t n1, int64_t n2, const doubl
                             int64_t P);
 int32_t afb_clenshaw_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_x, const double* d_y,
                                    double* d_out, int64_t P, void* stream);
+
+/* The same for a Fourier (x) Chebyshev coefficient matrix (rows in the Fourier order [1, sin t, cos t, sin 2t, ...],
+ * docs/src/usage/spaces.md:86-98): f(t_p, y_p) = sum_{i,j} C[i,j] F_i(t_p) T_j(y_p), t canonical in [0, 2 pi), y in [-1, 1].
+ * Replaces f(x, y) for Funs on PeriodicSegment x Interval (test/PeriodicXIntervalTest.jl:22-24). */
+int32_t afb_clenshaw_fourier_cheb2d(const double* C, int64_t n1, int64_t n2, const double* t, const double* y, double* out,
+                                    int64_t P);
+int32_t afb_clenshaw_fourier_cheb2d_device(const double* d_C, int64_t n1, int64_t n2, const double* d_t, const double* d_y,
+                                           double* d_out, int64_t P, void* stream);
 
 /* ---- 2-D sampling (sample(f::LowRankFun{Chebyshev,Chebyshev}, n), src/Extras/sample.jl:205-214) -------------
  * Fused replacement of lines 208-213: fA = evaluate.(f.A, ry'); AB = CB*fA; chebnormalizedcumsum!(AB);

@@ -849,3 +849,45 @@ def bisectioninv_generic(pieces, breaks, u, numits: int = 47, clenshaw_fn=None) 
         a = np.where(le, m, a)
         b = np.where(le, b, m)
     return 0.5 * (a + b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# mixed tensor spaces: factor-1 plan on every column, factor-2 (Chebyshev) plan on every row
+# (UPSTREAM ApproxFunBase transform!(::TensorSpace, M); callers /root/reference/test/PeriodicXIntervalTest.jl:22-24,
+#  test/LaplaceInAStripTest.jl:5-8)
+# ------------------------------------------------------------------------------------------------------
+def fourier_cheb_transform(V: np.ndarray) -> np.ndarray:
+    return cheb_transform(fourier_transform(V, axis=0), axis=1)
+
+
+def fourier_cheb_itransform(C: np.ndarray) -> np.ndarray:
+    return fourier_itransform(cheb_itransform(C, axis=1), axis=0)
+
+
+def laurent_cheb_transform(V: np.ndarray) -> np.ndarray:
+    A = laurent_transform(V, axis=0)
+    return cheb_transform(A.real, axis=1) + 1j * cheb_transform(A.imag, axis=1)
+
+
+def laurent_cheb_itransform(C: np.ndarray) -> np.ndarray:
+    A = cheb_itransform(C.real, axis=1) + 1j * cheb_itransform(C.imag, axis=1)
+    return laurent_itransform(A, axis=0)
+
+
+def fourier_basis(n: int, t: np.ndarray) -> np.ndarray:
+    """[1, sin t, cos t, sin 2t, cos 2t, ...] (docs/src/usage/spaces.md:86-98), shape (n, len(t))."""
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    F = np.empty((n, t.size))
+    for i in range(n):
+        k = (i + 1) // 2
+        F[i] = np.sin(k * t) if (i % 2 == 1) else np.cos(k * t)
+    return F
+
+
+def fourier_cheb_eval(Cm: np.ndarray, t, y) -> np.ndarray:
+    """sum_{i,j} C[i,j] F_i(t) T_j(y), direct summation (t canonical in [0, 2 pi), y in [-1, 1])."""
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    y = np.atleast_1d(np.asarray(y, dtype=np.float64))
+    F = fourier_basis(Cm.shape[0], t)                                  # n1 x P
+    T = np.cos(np.arange(Cm.shape[1])[:, None] * np.arccos(np.clip(y, -1, 1))[None, :])   # n2 x P
+    return np.einsum("ip,ij,jp->p", F, Cm, T)

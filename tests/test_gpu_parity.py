@@ -718,3 +718,45 @@ def test_pageable_strided_host_arrays_through_the_pinned_ring(af):
     assert np.array_equal(host[:, :n], ref)
     plan.close()
     plan2.close()
+
+
+@pytest.mark.parametrize("shape", [(5, 7), (20, 33), (64, 1024), (100, 60), (1000, 256), (4096, 2048)])
+def test_mixed_tensor_spaces_transform(af, shape):
+    # Fourier (x) Chebyshev and Laurent (x) Chebyshev: factor-1 plan on the columns, Chebyshev plan on the rows
+    n, n2 = shape
+    V = RNG.standard_normal(shape)
+    S = af.Fourier() * af.Chebyshev()
+    C = af.transform(S, V)
+    want = orc.fourier_cheb_transform(V)
+    tol = 1e-13 * np.max(np.abs(V)) * (math.log2(max(n, 2)) + math.log2(max(n2, 2)))
+    assert np.max(np.abs(C - want)) <= tol
+    assert np.max(np.abs(af.itransform(S, C) - V)) <= tol
+    wi = orc.fourier_cheb_itransform(V)
+    assert np.max(np.abs(af.itransform(S, V) - wi)) <= tol * max(1.0, np.max(np.abs(wi)))
+    Z = V + 1j * RNG.standard_normal(shape)
+    SL = af.Laurent() * af.Chebyshev()
+    CL = af.transform(SL, Z)
+    assert np.max(np.abs(CL - orc.laurent_cheb_transform(Z))) <= 2 * tol
+    assert np.max(np.abs(af.itransform(SL, CL) - Z)) <= 2 * tol
+
+
+def test_periodic_x_interval_fun(af):
+    # test/PeriodicXIntervalTest.jl:22-24 and test/LaplaceInAStripTest.jl:5-8:
+    #   d = PeriodicSegment() x ChebyshevInterval(); u_ex = Fun((x,y) -> real(cos(x + im*y)), d)
+    #   u_ex(1.0, 0.1) ~ real(cos(1.0 + 0.1im))  atol = 10 eps
+    S = af.Fourier() * af.Chebyshev()
+    f = lambda x, y: np.cos(x) * np.cosh(y)              # real(cos(x + i y))
+    u = af.Fun(f, S, (16, 24))
+    assert abs(u(1.0, 0.1) - math.cos(1.0) * math.cosh(0.1)) <= 10 * EPS
+    assert abs(u(0.1, 1.0) - math.cos(0.1) * math.cosh(1.0)) <= 10 * EPS       # LaplaceInAStripTest.jl:7
+    assert abs(u(0.1, -1.0) - math.cos(0.1) * math.cosh(-1.0)) <= 10 * EPS
+    # a periodic segment that is not the default one, many points, against direct summation of the series
+    S2 = af.Fourier(-2.0, 2.0) * af.Chebyshev(0.0, 1.0)                         # PeriodicXIntervalTest.jl:8-10
+    g = lambda th, t: np.exp(-20 * np.sin(math.pi * th / 4) ** 2) * (1 + t * t)
+    w = af.Fun(g, S2, (101, 20))
+    x, y = RNG.uniform(-2, 2, 5000), RNG.uniform(0, 1, 5000)
+    got = w(x, y)
+    s1, s2 = S2.factors
+    want = orc.fourier_cheb_eval(w.coefficients, s1.tocanonical(x), s2.tocanonical(y))
+    assert np.max(np.abs(got - want)) <= 1e-13 * 20
+    assert np.max(np.abs(got - g(x, y))) <= 1e-12
