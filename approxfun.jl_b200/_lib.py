@@ -36,7 +36,7 @@ SYMBOLS = [
     "afb_philox_uniform_device", "afb_fp64_probe_device",
     "afb_clenshaw_cheb2d", "afb_clenshaw_cheb2d_device", "afb_piecewise_clenshaw", "afb_piecewise_bisect",
     "afb_clenshaw_fourier_cheb2d", "afb_clenshaw_fourier_cheb2d_device",
-    "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device",
+    "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device", "afb_dgemm_nn_dmma_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
     "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open", "afb_sharded2d_set_chunks",
@@ -109,6 +109,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_sample2d_cheb_lowrank_device": [vp, i64, vp, i64, i64, dbl, dbl, dbl, dbl, vp, vp, vp, i64, vp],
         "afb_dgemm_nn": [vp, vp, vp, i64, i64, i64],
         "afb_dgemm_nn_device": [vp, vp, vp, i64, i64, i64, vp],
+        "afb_dgemm_nn_dmma_device": [vp, vp, vp, i64, i64, i64, vp],
         "afb_comm_unique_id": [vp],
         "afb_comm_create": [vp, i32, i32],
         "afb_comm_destroy": [],

@@ -341,7 +341,7 @@ _plan_cache: dict = {}
 def _cached_plan(cls, space: Space, shape):
     """`transform(S, v)` builds a plan per call in the reference (FFTW ESTIMATE plans are cheap); here plans own
     device tables, so the convenience entry points keep the most recent ones."""
-    key = (cls, type(space), tuple(shape))
+    key = (cls, type(space), tuple(type(f) for f in getattr(space, "factors", ())), tuple(shape))
     p = _plan_cache.get(key)
     if p is None:
         if len(_plan_cache) >= 64:

@@ -1580,9 +1580,19 @@ int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, 
 }
 
 
+// measurement variant of afb_dgemm_nn_device on the FP64 tensor cores (DMMA); agrees with it to rounding, not bit for bit
+int32_t afb_dgemm_nn_dmma_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
+                                 void* stream) {
+    if (N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_dgemm_nn_dmma: negative size");
+    if (N * P == 0) return AFB_OK;
+    if ((N * R && !d_CB) || (R * P && !d_fA) || !d_AB) return fail(AFB_BAD_ARG, "afb_dgemm_nn_dmma: null buffer");
+    AFB_TRY(ensure_device());
+    return launch_gemm_nn_dmma(d_CB, d_fA, d_AB, N, R, P, stream);
+}
+
 // measurement helper for bench.py (not a reference entry point): see fp64_probe_kernel
 int32_t afb_fp64_probe_device(int32_t mode, int32_t iters, int32_t blocks, double* d_out, void* stream) {
-    if (mode < 0 || mode > 3 || iters < 0 || blocks <= 0 || !d_out) return fail(AFB_BAD_ARG, "afb_fp64_probe: bad argument");
+    if (mode < 0 || mode > 4 || iters < 0 || blocks <= 0 || !d_out) return fail(AFB_BAD_ARG, "afb_fp64_probe: bad argument");
     AFB_TRY(ensure_device());
     return launch_fp64_probe(mode, iters, blocks, d_out, stream);
 }

@@ -979,6 +979,74 @@ int32_t launch_sample2d(const double* d_A, int64_t NA, const double* d_CB, int64
     return AFB_OK;
 }
 
+// FP64 tensor-core instruction (DMMA): D(8x8) = A(8x4, row) * B(4x8, col) + C.  Per thread: a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], c/d = {C[lane/4][2(lane%4)], C[lane/4][2(lane%4)+1]}.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+#ifndef AFB_HOST_EMU
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#else
+    (void)a; (void)b; (void)d0; (void)d1;
+#endif
+}
+// The same contraction on the FP64 tensor cores (DMMA m8n8k4), written to MEASURE the tensor-core route BASELINE.json asks
+// about (DESIGN.md 4b has the numbers): a warp owns 32 samples (four 8-sample A fragments of fA^T, loaded once) and walks the
+// N coefficients in tiles of 8; CB sits in shared memory (one LDS.64 feeds four DMMAs); D = AB^T tiles are stored as 16-byte
+// pairs of consecutive coefficients.  The accumulation order inside a DMMA is the hardware's, not the scalar loop's, so the
+// result agrees with gemm_nn_kernel to rounding only -- the product path of the sampler keeps the bit-exact FMA kernels.
+constexpr int DG_WARPS = 8, DG_MI = 4;
+__global__ void __launch_bounds__(32 * DG_WARPS) gemm_nn_dmma_kernel(const double* __restrict__ CB, const double* __restrict__ fA,
+                                                                     double* __restrict__ AB, int64_t N, int64_t R, int64_t P) {
+    AFB_DYN_SMEM(double, sCB);   // Np x Rp, zero padded to multiples of 8 and 4, row k contiguous in r (+1 pad)
+    const int64_t Np = (N + 7) & ~(int64_t)7, Rp = (R + 3) & ~(int64_t)3;
+    const int ldc = (int)Rp + 1;
+    for (int64_t g = threadIdx.x; g < Np * Rp; g += blockDim.x) {
+        const int64_t k = g / Rp, r = g % Rp;
+        sCB[k * ldc + r] = (k < N && r < R) ? CB[k + N * r] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int64_t nkt = Rp / 4;
+    for (int64_t j0 = ((int64_t)blockIdx.x * DG_WARPS + warp) * (8 * DG_MI); j0 < P; j0 += (int64_t)gridDim.x * DG_WARPS * 8 * DG_MI) {
+        for (int64_t nt = 0; nt < Np / 8; ++nt) {
+            double d[DG_MI][2];
+#pragma unroll
+            for (int mi = 0; mi < DG_MI; ++mi) { d[mi][0] = 0.0; d[mi][1] = 0.0; }
+            for (int64_t kt = 0; kt < nkt; ++kt) {
+                const int64_t r = 4 * kt + tig;
+                const double b = sCB[(8 * nt + grp) * ldc + r];            // B[k = r][n = coefficient 8 nt + grp]
+#pragma unroll
+                for (int mi = 0; mi < DG_MI; ++mi) {
+                    const int64_t j = j0 + 8 * mi + grp;                    // A[m = sample][k = r] = fA[r, j]
+                    const double a = (j < P && r < R) ? __ldg(fA + r + R * j) : 0.0;
+                    dmma_m8n8k4(d[mi][0], d[mi][1], a, b);
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < DG_MI; ++mi) {
+                const int64_t j = j0 + 8 * mi + grp, k = 8 * nt + 2 * tig;
+                if (j < P) {
+                    if (k < N) AB[k + N * j] = d[mi][0];
+                    if (k + 1 < N) AB[k + 1 + N * j] = d[mi][1];
+                }
+            }
+        }
+    }
+}
+int32_t launch_gemm_nn_dmma(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream) {
+    if (N * P == 0) return AFB_OK;
+    const int64_t Np = (N + 7) & ~(int64_t)7, Rp = (R + 3) & ~(int64_t)3;
+    const size_t smem = sizeof(double) * (size_t)(Np * (Rp + 1));
+    if (smem > 200 * 1024) return fail(AFB_UNSUPPORTED, "DMMA GEMM: CB does not fit shared memory");
+    int64_t grid = (P + DG_WARPS * 8 * DG_MI - 1) / (DG_WARPS * 8 * DG_MI);
+    if (grid > 8 * (int64_t)sm_count()) grid = 8 * (int64_t)sm_count();
+    auto k = gemm_nn_dmma_kernel;
+    AFB_SMEM_OPTIN(k, 200 * 1024);
+    AFB_LAUNCH(k, (unsigned)grid, 32 * DG_WARPS, smem, stream, d_CB, d_fA, d_AB, N, R, P);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+
 int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream) {
     if (N * P == 0) return AFB_OK;
     int64_t grid = (N * P + 255) / 256;
@@ -1000,6 +1068,22 @@ int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int
 // flops counted by the caller: modes 0/1: 2 per step and chain, mode 2: 3.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_probe_kernel(int mode, int iters, double seed, double* __restrict__ out) {
+    if (mode == 4) {
+        // DMMA issue rate: 8 independent accumulator tiles per warp, 512 flop per instruction and warp
+        double d[8][2];
+        double av = 0.999 + 1e-9 * (double)threadIdx.x, bv = 1e-3 + 1e-12 * (double)threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d[i][0] = seed * (double)(i + 1); d[i][1] = seed * (double)(i + 9); }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma_m8n8k4(d[i][0], d[i][1], av, bv);
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += d[i][0] + d[i][1];
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+        return;
+    }
     double x[8], a[8], c[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

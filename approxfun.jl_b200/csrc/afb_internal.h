@@ -47,6 +47,7 @@ int32_t launch_clenshaw2d(const double* d_C, int64_t n1, int64_t n2, const doubl
 int32_t launch_fourier_cheb2d(const double* d_C, int64_t n1, int64_t n2, const double* d_t, const double* d_y, double* d_out,
                               int64_t P, void* stream);
 int32_t launch_fp64_probe(int mode, int iters, int blocks, double* d_out, void* stream);
+int32_t launch_gemm_nn_dmma(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream);
 int32_t launch_gemm_nn(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P, void* stream);
 
 // ---- generic complex FFT engine (afb_large.cu): any length, batched, contiguous lines ---------------

@@ -20,11 +20,10 @@
 namespace afb {
 
 constexpr int MX_MAXPASS = 14;
-constexpr int MX_CT = 256;
 constexpr int64_t MX_MAX_N = 6144;   // two padded buffers of 16 B * 9/8 n: 216 KB at n = 6144
 
 struct MixedSched {
-    int n, npass, lpc, npad;
+    int n, npass, lpc, npad, ct;   // ct = threads per CTA (128 or 256)
     int radix[MX_MAXPASS];
     int ns[MX_MAXPASS];          // product of the radices of the earlier passes
     float inv_nr[MX_MAXPASS];    // 1 / (n / radix)
@@ -114,7 +113,7 @@ template <> struct MxDft<5> { static __device__ __forceinline__ void run(cplx* x
 template <> struct MxDft<7> { static __device__ __forceinline__ void run(cplx* x) { dft_odd<7>(x); } };
 
 // one pass of radix R over the pooled butterflies of the CTA's `lines` lines: src -> dst (both padded, stride `lstride` slots)
-template <int R>
+template <int R, int MX_CT>
 __device__ __forceinline__ void mx_pass(const MixedSched& sc, int pass, const cplx* __restrict__ src, cplx* __restrict__ dst,
                                         int lines, int lstride, const cplx* __restrict__ tw) {
     const int n = sc.n, nr = n / R, NS = sc.ns[pass];
@@ -141,20 +140,20 @@ __device__ __forceinline__ void mx_pass(const MixedSched& sc, int pass, const cp
 }
 // all passes; returns the buffer holding the natural-order result.  BIG = the schedule uses radix 16 (a separate instantiation:
 // the radix-16 butterfly needs ~120 registers, the others fit 80 and keep three CTAs per SM)
-template <bool BIG>
+template <bool BIG, int MX_CT>
 __device__ __forceinline__ cplx* mx_fft(const MixedSched& sc, cplx* a, cplx* b, int lines, int lstride, const cplx* __restrict__ tw) {
     cplx *src = a, *dst = b;
     for (int p = 0; p < sc.npass; ++p) {
         switch (sc.radix[p]) {
-            case 2: mx_pass<2>(sc, p, src, dst, lines, lstride, tw); break;
-            case 3: mx_pass<3>(sc, p, src, dst, lines, lstride, tw); break;
-            case 4: mx_pass<4>(sc, p, src, dst, lines, lstride, tw); break;
-            case 5: mx_pass<5>(sc, p, src, dst, lines, lstride, tw); break;
-            case 6: mx_pass<6>(sc, p, src, dst, lines, lstride, tw); break;
-            case 7: mx_pass<7>(sc, p, src, dst, lines, lstride, tw); break;
-            case 8: mx_pass<8>(sc, p, src, dst, lines, lstride, tw); break;
-            case 10: mx_pass<10>(sc, p, src, dst, lines, lstride, tw); break;
-            default: if (BIG) mx_pass<16>(sc, p, src, dst, lines, lstride, tw); break;
+            case 2: mx_pass<2, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 3: mx_pass<3, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 4: mx_pass<4, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 5: mx_pass<5, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 6: mx_pass<6, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 7: mx_pass<7, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 8: mx_pass<8, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            case 10: mx_pass<10, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
+            default: if (BIG) mx_pass<16, MX_CT>(sc, p, src, dst, lines, lstride, tw); break;
         }
         __syncthreads();
         cplx* t = src; src = dst; dst = t;
@@ -172,8 +171,8 @@ struct MixedCParams {
     double scale;
     MixedSched sc;
 };
-template <bool BIG>
-__global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_cfft_kernel(const __grid_constant__ MixedCParams p) {
+template <bool BIG, int MX_CT>
+__global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_cfft_kernel(const __grid_constant__ MixedCParams p) {
     AFB_DYN_SMEM(cplx, smem);
     const MixedSched& sc = p.sc;
     const int n = sc.n, lstride = sc.npad;
@@ -190,7 +189,7 @@ __global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_cfft_kernel(const __
         }
     }
     __syncthreads();
-    const cplx* R = mx_fft<BIG>(sc, A, B, lines, lstride, p.tw);
+    const cplx* R = mx_fft<BIG, MX_CT>(sc, A, B, lines, lstride, p.tw);
     for (int l = 0; l < lines; ++l) {
         cplx* dst = p.out + (line0 + l) * n;
         for (int j = threadIdx.x; j < n; j += MX_CT) {
@@ -231,8 +230,8 @@ __device__ __forceinline__ cplx mx_pre(const double* __restrict__ v, int n, int 
     }
     return z;
 }
-template <int KIND, bool BIG>
-__global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
+template <int KIND, bool BIG, int MX_CT>
+__global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
     constexpr bool INV = (KIND & 1) != 0;
     AFB_DYN_SMEM(cplx, smem);
     const MixedSched& sc = p.sc;
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(MX_CT, BIG ? 2 : 3) mixed_real_kernel(const __
         }
     }
     __syncthreads();
-    const cplx* R = mx_fft<BIG>(sc, A, B, lines, lstride, p.tw);
+    const cplx* R = mx_fft<BIG, MX_CT>(sc, A, B, lines, lstride, p.tw);
     const double dn = (double)n;
     for (int l = 0; l < lines; ++l) {
         const int64_t q = pair0 + l;
@@ -349,12 +348,16 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
         sc->inv_ns[p] = 1.0f / (float)ns;
         ns *= r[(size_t)p];
     }
-    // lines per CTA: the pooled butterflies of the thinnest pass (n / largest radix per line) should fill the 256 threads,
-    // within ~76 KB of shared memory (three CTAs per SM) when one line fits that at all; at most 16 lines
+    // threads and lines per CTA: the pooled butterflies of the thinnest pass (n / largest radix per line) should fill ONE round
+    // of the CTA's threads; short butterfly counts take 128-thread CTAs (twice as many resident CTAs in different phases).
+    // Shared memory: ~36 KB per 128 threads (six / three CTAs per SM) when one line fits that at all; at most 16 lines.
+    const int nr0 = (int)(n / r[0]);
+    sc->ct = (nr0 <= 160) ? 128 : 256;
     const size_t per_line = 2 * sizeof(cplx) * (size_t)sc->npad;
-    const int fit = (int)std::max<size_t>(1, ((size_t)76 << 10) / per_line);
-    const int want = (int)((MX_CT + n / r[0] - 1) / (n / r[0]));
-    sc->lpc = std::max(1, std::min({16, fit, std::max(want, 1)}));
+    const size_t budget = (sc->ct == 128) ? ((size_t)37 << 10) : ((size_t)74 << 10);
+    const int fit = (int)std::max<size_t>(1, budget / per_line);
+    const int want = std::max(1, sc->ct / nr0);
+    sc->lpc = std::max(1, std::min({16, fit, want}));
     return true;
 }
 static size_t mixed_smem(const MixedSched& sc) { return 2 * sizeof(cplx) * (size_t)sc.npad * (size_t)sc.lpc; }
@@ -365,15 +368,15 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
     MixedCParams p{in, out, batch, tw, inverse ? 1 : 0, scale, {}};
     if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
     const unsigned grid = (unsigned)((batch + p.sc.lpc - 1) / p.sc.lpc);
-    if (p.sc.radix[0] == 16) {
-        auto k = mixed_cfft_kernel<true>;
-        AFB_SMEM_OPTIN(k, 220 * 1024);
-        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
-    } else {
-        auto k = mixed_cfft_kernel<false>;
-        AFB_SMEM_OPTIN(k, 220 * 1024);
-        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
-    }
+#define AFB_MX_LAUNCH(BIG_, CT_)                                               \
+    do {                                                                       \
+        auto k = mixed_cfft_kernel<BIG_, CT_>;                                 \
+        AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
+        AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
+    } while (0)
+    if (p.sc.radix[0] == 16) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
+    else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
+#undef AFB_MX_LAUNCH
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
@@ -381,15 +384,15 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
 template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, void* stream) {
     const int64_t npairs = (p.batch + 1) / 2;
     const unsigned grid = (unsigned)((npairs + p.sc.lpc - 1) / p.sc.lpc);
-    if (p.sc.radix[0] == 16) {
-        auto k = mixed_real_kernel<KIND, true>;
-        AFB_SMEM_OPTIN(k, 220 * 1024);
-        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
-    } else {
-        auto k = mixed_real_kernel<KIND, false>;
-        AFB_SMEM_OPTIN(k, 220 * 1024);
-        AFB_LAUNCH(k, grid, MX_CT, mixed_smem(p.sc), stream, p);
-    }
+#define AFB_MX_LAUNCH(BIG_, CT_)                                               \
+    do {                                                                       \
+        auto k = mixed_real_kernel<KIND, BIG_, CT_>;                           \
+        AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
+        AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
+    } while (0)
+    if (p.sc.radix[0] == 16) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
+    else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
+#undef AFB_MX_LAUNCH
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }

@@ -259,8 +259,14 @@ int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, 
 int32_t afb_dgemm_nn_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
                             void* stream);
 
+/* Measurement variant of afb_dgemm_nn_device on the FP64 tensor cores (DMMA m8n8k4), kept to answer with numbers whether the
+ * one dense contraction of the path (sample.jl:210) belongs on them; same result to rounding. */
+int32_t afb_dgemm_nn_dmma_device(const double* d_CB, const double* d_fA, double* d_AB, int64_t N, int64_t R, int64_t P,
+                                 void* stream);
+
 /* Measurement helper (no reference counterpart): runs `blocks` x 256 threads x 8 chains x `iters` FP64 steps;
- * mode 0 = DFMA with three distinct register operands, 1 = DFMA with a repeated operand, 2 = the Clenshaw DADD+DFMA step.
+ * mode 0 = DFMA with three distinct register operands, 1 = DFMA with a repeated operand, 2 = the Clenshaw DADD+DFMA step,
+ * 3 = the reassociated step with a warp-uniform coefficient, 4 = DMMA m8n8k4 (8 accumulator tiles per warp, 512 flop each).
  * d_out needs blocks*256 doubles.  bench.py times it to report a MEASURED FP64 rate next to the nominal peak. */
 int32_t afb_fp64_probe_device(int32_t mode, int32_t iters, int32_t blocks, double* d_out, void* stream);
 
