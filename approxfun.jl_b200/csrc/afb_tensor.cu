@@ -283,6 +283,7 @@ struct Sharded2D {
     bool p2p = false, ipc = false;
     uint64_t epoch = 0;
     int chunks = 1;               // column-pass / exchange pipeline depth (see slab_execute)
+    int phases = 7;               // measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass
     cudaStream_t side = nullptr;  // the exchange runs here while the next column chunk is transformed
     cudaEvent_t ev_col[8] = {nullptr}, ev_x = nullptr;
     size_t recv_bytes() const { return sizeof(double) * (size_t)((n / G) * n2); }
@@ -352,6 +353,22 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
     int K = s.chunks;
     while (K > 1 && (nc / K) % XT_J) --K;
     if (K > 8) K = 8;
+    if (s.phases != 7) {   // measurement of the single phases (results are meaningless unless all three run)
+        if (s.phases & 1) AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
+        if (s.phases & 2) {
+            const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
+            const int64_t grid = std::min<int64_t>(tiles, 8 * (int64_t)sm_count());
+            const int vec = (nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+            AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
+                       s.ctr(), epoch, 1);
+            AFB_KERNEL_CHECK();
+            auto kw0 = xchg_wait_kernel;
+            AFB_LAUNCH(kw0, 1, 32, 0, st, s.flags(), (int)G, epoch);
+            AFB_KERNEL_CHECK();
+        }
+        if (s.phases & 4) AFB_TRY(afb_plan_execute_device(s.row_plan, s.recv(par), d_out, stream));
+        return AFB_OK;
+    }
     if (K == 1) {
         AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
         const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
@@ -515,6 +532,13 @@ int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h || h->magic != 0x5348415244324421ull || chunks < 1 || chunks > 8) return fail(AFB_BAD_ARG, "afb_sharded2d_set_chunks: bad argument");
     h->s.chunks = chunks;
+    return AFB_OK;
+}
+
+int32_t afb_sharded2d_set_phases(void* handle, int32_t mask) {
+    ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
+    if (!h || h->magic != 0x5348415244324421ull || mask < 1 || mask > 7) return fail(AFB_BAD_ARG, "afb_sharded2d_set_phases: bad argument");
+    h->s.phases = mask;
     return AFB_OK;
 }
 

@@ -102,6 +102,10 @@ class Sharded2DPlan:
         """Peer-memory mode: column pass in `chunks` pieces, each sent on a side stream while the next is transformed."""
         L.check(self.lib, self.lib.afb_sharded2d_set_chunks(self._h, int(chunks)))
 
+    def set_phases(self, mask: int):
+        """Measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass (7 = everything)."""
+        L.check(self.lib, self.lib.afb_sharded2d_set_phases(self._h, int(mask)))
+
     def execute(self, in_ptr: int, out_ptr: int, stream: int = 0):
         L.check(self.lib, self.lib.afb_sharded2d_execute_device(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_void_p(stream)))
 

@@ -603,6 +603,16 @@ def main():
                     "rows_checked": "every row of every rank's block (16384 x 16384 elements in total)",
                     "nvlink_bytes_per_rank": nv_bytes,
                     "nvlink_GBs_if_transfer_alone": nv_bytes / (t * 1e-3) / 1e9}
+                if mode == "peer_memory_fused":
+                    # where the time goes: the three phases alone (same plan, same buffers)
+                    ph = {}
+                    for nm, mask in (("column_pass", 1), ("exchange_and_wait", 2), ("row_pass", 4)):
+                        sp.set_phases(mask)
+                        barrier()
+                        ph[nm + "_ms"] = time_loop(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), stream), 8, 3)
+                    sp.set_phases(7)
+                    ph["exchange_nvlink_GBs"] = nv_bytes / (ph["exchange_and_wait_ms"] * 1e-3) / 1e9
+                    extras[f"cheb2d_16384_sharded_{mode}"]["phases"] = ph
                 barrier()
                 sp.close()
             best = min(extras[k]["ms_per_step"] for k in extras if k.startswith("cheb2d_16384_sharded_peer"))

@@ -291,6 +291,9 @@ int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world)
 /* Peer-memory mode only: run the column pass in `chunks` (1..8) pieces and send each finished piece to the peers on a side
  * stream while the next is transformed (default 1 = one column pass, one exchange kernel). */
 int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks);
+/* Measurement only (peer-memory mode): run a subset of the phases -- bit 0 column pass, bit 1 exchange + arrival wait,
+ * bit 2 row pass; 7 = the transform.  Every rank must use the same mask. */
+int32_t afb_sharded2d_set_phases(void* handle, int32_t mask);
 
 #ifdef __cplusplus
 }
