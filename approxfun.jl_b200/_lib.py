@@ -39,7 +39,7 @@ SYMBOLS = [
     "afb_sample2d_cheb_lowrank", "afb_sample2d_cheb_lowrank_device", "afb_dgemm_nn", "afb_dgemm_nn_device", "afb_dgemm_nn_dmma_device",
     "afb_comm_unique_id", "afb_comm_create", "afb_comm_destroy",
     "afb_sharded2d_create", "afb_sharded2d_execute_device", "afb_sharded2d_destroy",
-    "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open", "afb_sharded2d_set_chunks", "afb_sharded2d_set_phases",
+    "afb_sharded2d_ipc_export", "afb_sharded2d_ipc_open", "afb_sharded2d_set_chunks", "afb_sharded2d_set_phases", "afb_sharded2d_set_tuning",
 ]
 
 
@@ -120,6 +120,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_sharded2d_ipc_open": [vp, vp, i32],
         "afb_sharded2d_set_chunks": [vp, i32],
         "afb_sharded2d_set_phases": [vp, i32],
+        "afb_sharded2d_set_tuning": [vp, i32, i32, i32],
     }
     assert sorted(sig) == sorted(SYMBOLS)
     for name, args in sig.items():

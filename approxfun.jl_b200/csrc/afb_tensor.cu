@@ -141,15 +141,21 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 // nr-row share are sent (r0 = 0, r1 = nr: everything).  signal != 0: the last CTA publishes `epoch`.
 __global__ void __launch_bounds__(256) xchg_transpose_kernel(const double* __restrict__ in, XchgPeers peers, int64_t n, int64_t nc,
                                                              int64_t nr, int64_t n2, int G, int rank, int64_t c0, int64_t c1,
-                                                             int vec, unsigned* ctr, uint64_t epoch, int signal) {
+                                                             int vec, unsigned* ctr, uint64_t epoch, int signal, int order) {
     AFB_DYN_SMEM(double, tile);  // XT_J x (XT_I + 1)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const int64_t ti_per = (nr + XT_I - 1) / XT_I, tj_cnt = (c1 - c0 + XT_J - 1) / XT_J;
     const int64_t per_dest = ti_per * tj_cnt;
     for (int64_t b = blockIdx.x; b < per_dest * G; b += gridDim.x) {
-        const int k = (int)(b / per_dest);
-        const int d = (rank + 1 + k) % G;             // rotated destination order; the local share goes last
-        const int64_t w = b - (int64_t)k * per_dest;
+        // order 0: destination by destination, rotated (rank + 1 first, the local share last);
+        // order 1: consecutive CTAs go to consecutive destinations (all peers in flight at once), rotated;
+        // order 2: row tiles fastest over the whole matrix (unrotated)
+        int k;
+        int64_t w;
+        if (order == 0) { k = (int)(b / per_dest); w = b - (int64_t)k * per_dest; }
+        else if (order == 1) { k = (int)(b % G); w = b / G; }
+        else { const int64_t it = b % (ti_per * G); k = (int)(it / ti_per); w = (it % ti_per) + ti_per * (b / (ti_per * G)); }
+        const int d = (order == 2) ? k : (rank + 1 + k) % G;
         const int64_t il0 = (w % ti_per) * XT_I, j0 = c0 + (w / ti_per) * XT_J;
         const int64_t i0 = (int64_t)d * nr + il0;
 #pragma unroll
@@ -283,6 +289,7 @@ struct Sharded2D {
     bool p2p = false, ipc = false;
     uint64_t epoch = 0;
     int chunks = 1;               // column-pass / exchange pipeline depth (see slab_execute)
+    int order = 0, grid_mult = 8, novec = 0;   // exchange kernel tuning (afb_sharded2d_set_tuning)
     int phases = 7;               // measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass
     cudaStream_t side = nullptr;  // the exchange runs here while the next column chunk is transformed
     cudaEvent_t ev_col[8] = {nullptr}, ev_x = nullptr;
@@ -357,10 +364,10 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
         if (s.phases & 1) AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
         if (s.phases & 2) {
             const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
-            const int64_t grid = std::min<int64_t>(tiles, 8 * (int64_t)sm_count());
-            const int vec = (nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+            const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+            const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
             AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
-                       s.ctr(), epoch, 1);
+                       s.ctr(), epoch, 1, s.order);
             AFB_KERNEL_CHECK();
             auto kw0 = xchg_wait_kernel;
             AFB_LAUNCH(kw0, 1, 32, 0, st, s.flags(), (int)G, epoch);
@@ -372,10 +379,10 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
     if (K == 1) {
         AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
         const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
-        const int64_t grid = std::min<int64_t>(tiles, 8 * (int64_t)sm_count());
-        const int vec = (nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+        const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+        const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
         AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
-                   s.ctr(), epoch, 1);
+                   s.ctr(), epoch, 1, s.order);
         AFB_KERNEL_CHECK();
     } else {
         if (!s.side) AFB_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
@@ -390,7 +397,7 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
             // a few CTAs per chunk: the exchange is NVLink-bound and must leave the SMs to the next column chunk
             const int64_t grid = std::min<int64_t>(tiles, c + 1 < K ? 2 * (int64_t)sm_count() : 8 * (int64_t)sm_count());
             AFB_LAUNCH(kt, (unsigned)grid, 256, smem, s.side, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, c * cw, (c + 1) * cw, 1,
-                       s.ctr(), epoch, c + 1 == K ? 1 : 0);
+                       s.ctr(), epoch, c + 1 == K ? 1 : 0, s.order);
             AFB_KERNEL_CHECK();
         }
         AFB_CUDA(cudaEventRecord(s.ev_x, s.side));
@@ -535,6 +542,13 @@ int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks) {
     return AFB_OK;
 }
 
+int32_t afb_sharded2d_set_tuning(void* handle, int32_t order, int32_t grid_mult, int32_t novec) {
+    ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
+    if (!h || h->magic != 0x5348415244324421ull || order < 0 || order > 2 || grid_mult < 1 || grid_mult > 64)
+        return fail(AFB_BAD_ARG, "afb_sharded2d_set_tuning: bad argument");
+    h->s.order = order; h->s.grid_mult = grid_mult; h->s.novec = novec ? 1 : 0;
+    return AFB_OK;
+}
 int32_t afb_sharded2d_set_phases(void* handle, int32_t mask) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
     if (!h || h->magic != 0x5348415244324421ull || mask < 1 || mask > 7) return fail(AFB_BAD_ARG, "afb_sharded2d_set_phases: bad argument");

@@ -102,6 +102,9 @@ class Sharded2DPlan:
         """Peer-memory mode: column pass in `chunks` pieces, each sent on a side stream while the next is transformed."""
         L.check(self.lib, self.lib.afb_sharded2d_set_chunks(self._h, int(chunks)))
 
+    def set_tuning(self, order: int = 0, grid_mult: int = 8, novec: int = 0):
+        L.check(self.lib, self.lib.afb_sharded2d_set_tuning(self._h, int(order), int(grid_mult), int(novec)))
+
     def set_phases(self, mask: int):
         """Measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass (7 = everything)."""
         L.check(self.lib, self.lib.afb_sharded2d_set_phases(self._h, int(mask)))
