@@ -9,3 +9,5 @@ from . import _lib
 from ._lib import AfbError, DimensionMismatch, LIB_PATH
 from .api import *  # noqa: F401,F403
 from . import api
+from . import device
+from .device import DeviceArray, DeviceFun

@@ -28,6 +28,9 @@ SYMBOLS = [
     "afb_malloc", "afb_free", "afb_host_alloc", "afb_host_free", "afb_memcpy_h2d", "afb_memcpy_d2h",
     "afb_memcpy_d2d", "afb_stream_sync",
     "afb_plan_create", "afb_plan_execute_host", "afb_plan_execute_device", "afb_plan_destroy", "afb_plan_launches",
+    "afb_plan_io_doubles", "afb_plan_execute_buf",
+    "afb_buf_create", "afb_buf_destroy", "afb_buf_size", "afb_buf_ptr", "afb_buf_upload", "afb_buf_download", "afb_buf_unary",
+    "afb_buf_binary", "afb_buf_pad", "afb_buf_chebpoints", "afb_buf_clenshaw", "afb_buf_tail",
     "afb_chebpoints", "afb_chebpoints_device", "afb_fourierpoints", "afb_paduapoints",
     "afb_clenshaw_cheb", "afb_clenshaw_cheb_device", "afb_clenshaw_cheb_cols", "afb_clenshaw_cheb_cols_device",
     "afb_clenshaw_cheb_multi", "afb_clenshaw_cheb_multi_device", "afb_clenshaw_rec", "afb_clenshaw_rec_device",
@@ -76,6 +79,20 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_plan_execute_device": [vp, vp, vp, vp],
         "afb_plan_destroy": [vp],
         "afb_plan_launches": [vp, C.POINTER(i32)],
+        "afb_plan_io_doubles": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "afb_plan_execute_buf": [vp, vp, vp],
+        "afb_buf_create": [C.POINTER(vp), i64],
+        "afb_buf_destroy": [vp],
+        "afb_buf_size": [vp, C.POINTER(i64)],
+        "afb_buf_ptr": [vp, C.POINTER(vp)],
+        "afb_buf_upload": [vp, vp, i64, i64],
+        "afb_buf_download": [vp, vp, i64, i64],
+        "afb_buf_unary": [i32, vp, vp, i64, dbl, dbl],
+        "afb_buf_binary": [i32, vp, vp, vp, i64],
+        "afb_buf_pad": [vp, i64, vp, i64],
+        "afb_buf_chebpoints": [vp, i64, dbl, dbl],
+        "afb_buf_clenshaw": [vp, i64, vp, vp, i64],
+        "afb_buf_tail": [vp, i64, i64, dbl, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)],
         "afb_chebpoints": [vp, i64, dbl, dbl],
         "afb_chebpoints_device": [vp, i64, dbl, dbl, vp],
         "afb_fourierpoints": [vp, i64, dbl, dbl],

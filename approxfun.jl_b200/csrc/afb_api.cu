@@ -990,6 +990,17 @@ int32_t afb_plan_destroy(afb_plan plan) {
     return AFB_OK;
 }
 
+int32_t afb_plan_io_doubles(afb_plan p, int64_t* in_doubles, int64_t* out_doubles) {
+    if (!p || !in_doubles || !out_doubles) return fail(AFB_BAD_ARG, "afb_plan_io_doubles: null argument");
+    int64_t elems;
+    if (p->path == PATH_EMPTY) elems = 0;
+    else if (p->path == PATH_TENSOR2D) elems = p->n * p->n2;
+    else if (p->path == PATH_PADUA) elems = p->n;
+    else elems = (p->batch - 1) * p->stride + p->n;
+    *in_doubles = *out_doubles = elems * (p->elem / 8);
+    return AFB_OK;
+}
+
 int32_t afb_plan_launches(afb_plan plan, int32_t* launches) {
     if (!plan || !launches) return fail(AFB_BAD_ARG, "afb_plan_launches: null argument");
     *launches = plan_launch_count(plan);

@@ -154,9 +154,13 @@ __global__ void __launch_bounds__(256) xchg_transpose_kernel(const double* __res
         int64_t w;
         if (order == 0) { k = (int)(b / per_dest); w = b - (int64_t)k * per_dest; }
         else if (order == 1) { k = (int)(b % G); w = b / G; }
-        else { const int64_t it = b % (ti_per * G); k = (int)(it / ti_per); w = (it % ti_per) + ti_per * (b / (ti_per * G)); }
+        else if (order == 2) { const int64_t it = b % (ti_per * G); k = (int)(it / ti_per); w = (it % ti_per) + ti_per * (b / (ti_per * G)); }
+        else { k = (int)(b / per_dest); w = b - (int64_t)k * per_dest; }   // order 3: as 0, column tiles fastest
         const int d = (order == 2) ? k : (rank + 1 + k) % G;
-        const int64_t il0 = (w % ti_per) * XT_I, j0 = c0 + (w / ti_per) * XT_J;
+        // orders 0-2: consecutive CTAs walk down the rows of one column tile; order 3: along one band of 32 rows, so that the
+        // CTAs in flight write one contiguous span of the destination (nc * 8 bytes per row)
+        const int64_t il0 = (order == 3) ? (w / tj_cnt) * XT_I : (w % ti_per) * XT_I;
+        const int64_t j0 = c0 + ((order == 3) ? (w % tj_cnt) : (w / ti_per)) * XT_J;
         const int64_t i0 = (int64_t)d * nr + il0;
 #pragma unroll
         for (int r = 0; r < XT_J; r += 8) {
@@ -289,7 +293,7 @@ struct Sharded2D {
     bool p2p = false, ipc = false;
     uint64_t epoch = 0;
     int chunks = 1;               // column-pass / exchange pipeline depth (see slab_execute)
-    int order = 0, grid_mult = 8, novec = 0;   // exchange kernel tuning (afb_sharded2d_set_tuning)
+    int order = 3, grid_mult = 8, novec = 0;   // exchange kernel tuning (afb_sharded2d_set_tuning); measured best at 8 GPUs
     int phases = 7;               // measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass
     cudaStream_t side = nullptr;  // the exchange runs here while the next column chunk is transformed
     cudaEvent_t ev_col[8] = {nullptr}, ev_x = nullptr;
@@ -544,7 +548,7 @@ int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks) {
 
 int32_t afb_sharded2d_set_tuning(void* handle, int32_t order, int32_t grid_mult, int32_t novec) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
-    if (!h || h->magic != 0x5348415244324421ull || order < 0 || order > 2 || grid_mult < 1 || grid_mult > 64)
+    if (!h || h->magic != 0x5348415244324421ull || order < 0 || order > 3 || grid_mult < 1 || grid_mult > 64)
         return fail(AFB_BAD_ARG, "afb_sharded2d_set_tuning: bad argument");
     h->s.order = order; h->s.grid_mult = grid_mult; h->s.novec = novec ? 1 : 0;
     return AFB_OK;

@@ -520,6 +520,67 @@ def main():
         extras["padua_degree2047"] = {"ms_per_step": t, "coefficients_per_s": float(npad) / (t * 1e-3),
                                       "launches": pp.launches}
         del vp
+        # ---- device-resident Fun chains: the same chain three ways -- buffers that never leave the GPU,
+        # host arrays through the library (one PCIe round trip per step), and the CPU port (rank 0, N = 1 only)
+        if world == 1:
+            from approxfun_b200 import device as dv
+            Sd = af.Chebyshev(0, 10)
+            nbig = 1 << 20
+
+            def chain_device():
+                x_ = dv.chebpoints_device(Sd, nbig)
+                f_ = dv.transform_device(dv.sin(x_ ** 2), nbig)                         # Fun(x -> sin(x^2), 0..10, 2^20)
+                g_ = dv.transform_device(dv.exp(x_ * (-0.3)) + 2.0, nbig)
+                vf = dv.transform_device(f_, nbig, inverse=True)                        # values(f), values(g)
+                vg = dv.transform_device(g_, nbig, inverse=True)
+                return dv.transform_device(vf * vg, nbig)                               # coefficients of f * g
+
+            def chain_host():
+                x_ = af.points(Sd, nbig)
+                f_ = af.transform(Sd, np.sin(x_ ** 2))
+                g_ = af.transform(Sd, np.exp(-0.3 * x_) + 2.0)
+                return af.transform(Sd, af.itransform(Sd, f_) * af.itransform(Sd, g_))
+
+            def wall(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    r_ = fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / reps * 1e3, r_
+
+            td, rd = wall(lambda: chain_device().to_host(), 5)
+            th, rh = wall(chain_host, 3)
+            fc = {"n": nbig, "device_resident_ms": td, "host_arrays_ms": th,
+                  "max_abs_diff_device_vs_host_arrays": float(np.max(np.abs(rd - rh))),
+                  "chain": "points -> sin(x^2), exp(-0.3x)+2 -> 2 transforms -> 2 itransforms -> product -> transform; "
+                           "device-resident: zero uploads, one 8 MiB download"}
+            ta, fa = wall(lambda: dv.DeviceFun.from_function(lambda x_: dv.sin(x_ ** 2), Sd), 5)
+            tah, fah = wall(lambda: af.Fun(lambda x_: np.sin(x_ ** 2), Sd), 5)
+            fc["adaptive_ladder_device_ms"] = ta
+            fc["adaptive_ladder_host_arrays_ms"] = tah
+            fc["adaptive_ncoefficients"] = [int(fa.n), int(len(fah.coefficients))]
+            if not args.no_cpu:
+                from oracle import approxfun_oracle as orc
+
+                def chain_cpu():
+                    x_ = orc.chebpoints(nbig, 0.0, 10.0)
+                    f_ = orc.cheb_transform(np.sin(x_ ** 2), workers=host_threads())
+                    g_ = orc.cheb_transform(np.exp(-0.3 * x_) + 2.0, workers=host_threads())
+                    return orc.cheb_transform(orc.cheb_itransform(f_, workers=host_threads()) * orc.cheb_itransform(g_, workers=host_threads()),
+                                              workers=host_threads())
+
+                t0 = time.perf_counter()
+                rc = chain_cpu()
+                fc["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+                fc["max_abs_diff_device_vs_cpu_port"] = float(np.max(np.abs(rd - rc)))
+                t0 = time.perf_counter()
+                ca = orc.adaptive_fun_coefficients(lambda x_: np.sin(x_ ** 2), 0.0, 10.0)
+                fc["adaptive_ladder_cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+                fc["adaptive_ncoefficients"].append(int(len(ca)))
+            extras["fun_chain_2pow20"] = fc
+
         # ---- strong scaling (total work fixed, shared by the ranks) with parity checks on the record ------------------
         from approxfun_b200 import parallel as par
         strong = {}

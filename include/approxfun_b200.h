@@ -140,6 +140,8 @@ int32_t afb_plan_execute_host(afb_plan plan, const void* in, void* out);
 /* device buffers; in == out allowed; asynchronous on `stream` */
 int32_t afb_plan_execute_device(afb_plan plan, const void* d_in, void* d_out, void* stream);
 int32_t afb_plan_destroy(afb_plan plan);
+/* doubles a plan reads / writes per execution (complex kinds count two per element; strided batches include the gaps) */
+int32_t afb_plan_io_doubles(afb_plan plan, int64_t* in_doubles, int64_t* out_doubles);
 /* number of kernels one afb_plan_execute_device call launches (bench.py gpu_launches) */
 int32_t afb_plan_launches(afb_plan plan, int32_t* launches);
 
@@ -269,6 +271,39 @@ int32_t afb_dgemm_nn_dmma_device(const double* d_CB, const double* d_fA, double*
  * 3 = the reassociated step with a warp-uniform coefficient, 4 = DMMA m8n8k4 (8 accumulator tiles per warp, 512 flop each).
  * d_out needs blocks*256 doubles.  bench.py times it to report a MEASURED FP64 rate next to the nominal peak. */
 int32_t afb_fp64_probe_device(int32_t mode, int32_t iters, int32_t blocks, double* d_out, void* stream);
+
+/* ---- device-resident Fun algebra ------------------------------------------------------------
+ * Opaque device buffers of doubles plus point-wise kernels, so that the chains the reference builds from host arrays --
+ *   Fun(f, S, n):   vals = f.(points(S, n)); transform(S, vals)            (ext/ApproxFunDualNumbersExt.jl:79-82)
+ *   adaptive Fun:   the ladder n = 2^4 .. 2^20, 2^21 with its tail test     (ext/ApproxFunDualNumbersExt.jl:96-111)
+ *   f * g, sin(f):  values(pad(f, n)) -> point-wise op -> transform -> chop (UPSTREAM ApproxFunBase)
+ * -- stay on the GPU between steps: at most one upload of samples and one download of the final coefficients.
+ * All calls run on the legacy default stream of the buffer's device, in call order. */
+typedef struct afb_buf_s* afb_buf;
+int32_t afb_buf_create(afb_buf* out, int64_t n_doubles);
+int32_t afb_buf_destroy(afb_buf buf);
+int32_t afb_buf_size(afb_buf buf, int64_t* n_doubles);
+int32_t afb_buf_ptr(afb_buf buf, void** dptr);     /* raw device pointer, for the *_device entry points */
+int32_t afb_buf_upload(afb_buf buf, const double* host, int64_t n, int64_t offset);
+int32_t afb_buf_download(afb_buf buf, double* host, int64_t n, int64_t offset);
+/* plan * v with v and the result on the device (in == out allowed) */
+int32_t afb_plan_execute_buf(afb_plan plan, afb_buf in, afb_buf out);
+/* out[i] = op(alpha * a[i] + beta), i < n   (in place allowed) */
+enum afb_unary_op { AFB_OP_IDENT = 0, AFB_OP_SIN, AFB_OP_COS, AFB_OP_EXP, AFB_OP_ABS, AFB_OP_SQRT, AFB_OP_SQUARE, AFB_OP_RECIP,
+                    AFB_OP_LOG, AFB_OP_TANH };
+int32_t afb_buf_unary(int32_t op, afb_buf a, afb_buf out, int64_t n, double alpha, double beta);
+/* out[i] = a[i] (+, -, *, /) b[i] */
+enum afb_binary_op { AFB_OP_ADD = 0, AFB_OP_SUB, AFB_OP_MUL, AFB_OP_DIV };
+int32_t afb_buf_binary(int32_t op, afb_buf a, afb_buf b, afb_buf out, int64_t n);
+/* out[0..n_out) = in[0..min(n_in, n_out)) then zeros: pad(f, n) / truncation of a coefficient vector */
+int32_t afb_buf_pad(afb_buf in, int64_t n_in, afb_buf out, int64_t n_out);
+/* points(::Chebyshev, n) into a buffer (same kernel as afb_chebpoints) */
+int32_t afb_buf_chebpoints(afb_buf out, int64_t n, double a, double b);
+/* y = clenshaw(c[0..N), x[0..P)) on buffers (canonical variable) */
+int32_t afb_buf_clenshaw(afb_buf c, int64_t N, afb_buf x, afb_buf y, int64_t P);
+/* The ladder's tail test and chop on the device: *maxabs = max |c|, *tailmax = max |c[n-ntail..n)|, and (chop_len != NULL)
+ * *chop_len = 1 + the last index with |c| > rel_thresh * max |c| (0 if none).  Transfers 24 bytes. */
+int32_t afb_buf_tail(afb_buf c, int64_t n, int64_t ntail, double rel_thresh, double* maxabs, double* tailmax, int64_t* chop_len);
 
 /* ---- multi-GPU 2D transform (one process per GPU) ----------------------------------------------------
  * The n x n2 matrix is sharded by contiguous column blocks; the plan performs local column transforms,

@@ -382,3 +382,24 @@ def test_mixed_radix_many_lines_per_cta():
         v = RNG.standard_normal((n, nb))
         assert np.max(np.abs(ll.transform(B.CHEB1_FWD, v) - orc.cheb_transform(v, axis=0))) <= tol(n, np.max(np.abs(v)))
         assert np.max(np.abs(ll.transform(B.FOURIER_INV, v) - orc.fourier_itransform(v, axis=0))) <= tol(n, 20 * np.max(np.abs(v)))
+
+
+def test_device_resident_fun_layer_on_the_emulator():
+    # host logic of approxfun_b200.device (ladder, tail test, chop, product) with the kernels running in the emulator
+    import approxfun_b200 as af
+    from approxfun_b200 import api, device as dv
+    keep = api._ll
+    api._ll = ll
+    try:
+        S = af.Chebyshev(0, 3)
+        f = dv.DeviceFun.from_function(lambda x: dv.sin(x ** 2), S)
+        want = orc.adaptive_fun_coefficients(lambda x: np.sin(x ** 2), 0.0, 3.0)
+        assert f.n == len(want) and np.max(np.abs(f.coefficients - want)) < 1e-14
+        g = dv.DeviceFun.from_function(lambda x: dv.exp(-x), S)
+        x = np.linspace(0, 3, 50)
+        assert np.max(np.abs((f * g)(x) - np.sin(x ** 2) * np.exp(-x))) < 1e-13
+        assert np.max(np.abs(dv.exp_fun(f)(x) - np.exp(np.sin(x ** 2)))) < 1e-13
+        assert np.max(np.abs((f + g)(x) - np.sin(x ** 2) - np.exp(-x))) < 1e-13
+    finally:
+        api._ll = keep
+        dv._plans.clear()

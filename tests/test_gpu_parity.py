@@ -760,3 +760,44 @@ def test_periodic_x_interval_fun(af):
     want = orc.fourier_cheb_eval(w.coefficients, s1.tocanonical(x), s2.tocanonical(y))
     assert np.max(np.abs(got - want)) <= 1e-13 * 20
     assert np.max(np.abs(got - g(x, y))) <= 1e-12
+
+
+def test_device_resident_fun_chains(af):
+    # Fun(x -> sin(x^2), 0..10) built by the adaptive ladder ON the device (points, point-wise ops,
+    # transforms, tail test and chop), f * g and exp(f) without a PCIe round trip per step
+    from approxfun_b200 import device as dv
+    S = af.Chebyshev(0, 10)
+    dv.traffic["h2d"] = dv.traffic["d2h"] = 0
+    f = dv.DeviceFun.from_function(lambda x: dv.sin(x ** 2), S)
+    ladder_d2h = dv.traffic["d2h"]
+    assert dv.traffic["h2d"] == 0 and ladder_d2h <= 24 * 17            # 24 bytes of scalars per rung, no samples, no coefficients
+    want = orc.adaptive_fun_coefficients(lambda x: np.sin(x ** 2), 0.0, 10.0)
+    host = af.Fun(lambda x: np.sin(x ** 2), S)                          # the host-array route through the same library
+    c = f.coefficients                                                  # the ONE download of the result
+    assert dv.traffic["d2h"] == ladder_d2h + 8 * f.n
+    assert f.n == len(want) == len(host.coefficients)
+    assert np.max(np.abs(c - want)) <= 1e-13 * math.log2(256) and np.max(np.abs(c - host.coefficients)) <= 1e-13 * 8
+    assert abs(f(0.1) - math.sin(0.01)) < 1000 * EPS                    # test/ReadmeTest.jl:19-23 on the device-built Fun
+    # f * g: values on n_f + n_g - 1 points, multiplied and transformed on the device
+    g = dv.DeviceFun.from_function(lambda x: dv.exp(-0.3 * x) + 2.0, S)
+    before = dict(dv.traffic)
+    h = f * g
+    assert dv.traffic["h2d"] == before["h2d"] and dv.traffic["d2h"] - before["d2h"] == 24
+    x = RNG.uniform(0, 10, 2000)
+    assert np.max(np.abs(h(x) - np.sin(x ** 2) * (np.exp(-0.3 * x) + 2.0))) <= 1e-13 * 3 * 10
+    hc = orc.adaptive_fun_coefficients(lambda t: np.sin(t ** 2) * (np.exp(-0.3 * t) + 2.0), 0.0, 10.0)
+    assert abs(h.n - len(hc)) <= 8 and np.max(np.abs(h.coefficients[:min(h.n, len(hc))] - hc[:min(h.n, len(hc))])) <= 1e-13 * 30
+    # composition exp(f) (adaptive) and linear algebra of Funs
+    e = dv.exp_fun(f)
+    assert np.max(np.abs(e(x) - np.exp(np.sin(x ** 2)))) <= 1e-13 * 3 * 10
+    s = f + g - f
+    assert np.max(np.abs(s(x) - (np.exp(-0.3 * x) + 2.0))) <= 1e-13 * 30
+    # a Fun built on the host moves to the device once and back once
+    hf = dv.DeviceFun.from_fun(host)
+    assert np.array_equal(hf.coefficients, host.coefficients)
+    # fixed-length constructor Fun(f, S, n) and values(f) round trip on the device
+    f1k = dv.DeviceFun.from_function(lambda t: dv.cos(3.0 * t) * t, S, 1024)
+    assert np.max(np.abs(f1k.coefficients - orc.fun_coefficients(lambda t: np.cos(3 * t) * t, 1024, 0.0, 10.0))) <= 1e-13 * 10 * 10
+    v = f1k.values_device().to_host()
+    xs = orc.chebpoints(1024, 0.0, 10.0)
+    assert np.max(np.abs(v - np.cos(3 * xs) * xs)) <= 1e-13 * 10 * 10

@@ -45,10 +45,10 @@ def timeit(fn, reps=10, warm=3):
 
 sp = par.Sharded2DPlan(L.CHEB1_2D_FWD, n, n, p2p=True)
 nv = 8.0 * n * nc * (world - 1) / world
-for order in (0, 1, 2):
-    for gm in (2, 4, 8, 16):
+for order in (0, 3):
+    for gm in (1, 2, 4, 8):
         for novec in (0, 1):
-            if novec and gm != 8:
+            if novec:
                 continue
             sp.set_tuning(order, gm, novec)
             sp.set_phases(2)
@@ -57,7 +57,7 @@ for order in (0, 1, 2):
             tt = timeit(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), st))
             if rank == 0:
                 print(f"order {order} grid {gm}x novec {novec}: exchange {tx:.3f} ms ({nv / tx / 1e6:.0f} GB/s)  total {tt:.3f} ms", flush=True)
-sp.set_tuning(0, 8, 0)
+sp.set_tuning(3, 8, 0)
 for ch in (2, 4):
     sp.set_chunks(ch)
     tt = timeit(lambda: sp.execute(blk.data_ptr(), rows.data_ptr(), st))
