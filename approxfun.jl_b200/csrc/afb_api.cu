@@ -1576,7 +1576,7 @@ int32_t afb_dgemm_nn_device(const double* d_CB, const double* d_fA, double* d_AB
     if (N * P == 0) return AFB_OK;
     if ((N * R && !d_CB) || (R * P && !d_fA) || !d_AB) return fail(AFB_BAD_ARG, "afb_dgemm_nn: null buffer");
     AFB_TRY(ensure_device());
-    return launch_gemm_nn(d_CB, d_fA, d_AB, N, R, P, stream);
+    return launch_gemm_nn(d_CB, d_fA, d_AB, N, R, P, stream);   // bit-exact FMA order; afb_dgemm_nn_dmma_device: tensor cores
 }
 int32_t afb_dgemm_nn(const double* CB, const double* fA, double* AB, int64_t N, int64_t R, int64_t P) {
     if (N < 0 || R < 0 || P < 0) return fail(AFB_BAD_SIZE, "afb_dgemm_nn: negative size");

@@ -20,7 +20,10 @@
 namespace afb {
 
 constexpr int CL_THREADS = 512;        // threads per CTA
-constexpr int CL_R = 4;                // points per thread (independent recurrences)
+#ifndef AFB_CL_R
+#define AFB_CL_R 4
+#endif
+constexpr int CL_R = AFB_CL_R;         // points per thread (independent recurrences); 8 was measured in round 2
 constexpr int CL_CHUNK = 12288;        // coefficients staged per shared-memory chunk (96 KB)
 
 // Runs the recurrence over coefficients c[klo..khi) (khi exclusive), from high to low, with klo >= 1.
@@ -993,7 +996,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // N coefficients in tiles of 8; CB sits in shared memory (one LDS.64 feeds four DMMAs); D = AB^T tiles are stored as 16-byte
 // pairs of consecutive coefficients.  The accumulation order inside a DMMA is the hardware's, not the scalar loop's, so the
 // result agrees with gemm_nn_kernel to rounding only -- the product path of the sampler keeps the bit-exact FMA kernels.
-constexpr int DG_WARPS = 8, DG_MI = 4;
+constexpr int DG_WARPS = 8, DG_MI = 4, DG_KT = 8;
 __global__ void __launch_bounds__(32 * DG_WARPS) gemm_nn_dmma_kernel(const double* __restrict__ CB, const double* __restrict__ fA,
                                                                      double* __restrict__ AB, int64_t N, int64_t R, int64_t P) {
     AFB_DYN_SMEM(double, sCB);   // Np x Rp, zero padded to multiples of 8 and 4, row k contiguous in r (+1 pad)
@@ -1008,6 +1011,40 @@ __global__ void __launch_bounds__(32 * DG_WARPS) gemm_nn_dmma_kernel(const doubl
     const int grp = lane >> 2, tig = lane & 3;
     const int64_t nkt = Rp / 4;
     for (int64_t j0 = ((int64_t)blockIdx.x * DG_WARPS + warp) * (8 * DG_MI); j0 < P; j0 += (int64_t)gridDim.x * DG_WARPS * 8 * DG_MI) {
+        if (nkt <= DG_KT) {
+            // the warp's fA fragments stay in registers while it walks the coefficient tiles (R <= 32)
+            double a[DG_MI][DG_KT];
+#pragma unroll
+            for (int mi = 0; mi < DG_MI; ++mi)
+#pragma unroll
+                for (int kt = 0; kt < DG_KT; ++kt) {
+                    const int64_t j = j0 + 8 * mi + grp, r = 4 * kt + tig;
+                    a[mi][kt] = (kt < nkt && j < P && r < R) ? __ldg(fA + r + R * j) : 0.0;
+                }
+            for (int64_t nt = 0; nt < Np / 8; ++nt) {
+                double d[DG_MI][2];
+#pragma unroll
+                for (int mi = 0; mi < DG_MI; ++mi) { d[mi][0] = 0.0; d[mi][1] = 0.0; }
+                const double* brow = sCB + (8 * nt + grp) * ldc + tig;
+#pragma unroll
+                for (int kt = 0; kt < DG_KT; ++kt) {
+                    if (kt < nkt) {
+                        const double b = brow[4 * kt];
+#pragma unroll
+                        for (int mi = 0; mi < DG_MI; ++mi) dmma_m8n8k4(d[mi][0], d[mi][1], a[mi][kt], b);
+                    }
+                }
+#pragma unroll
+                for (int mi = 0; mi < DG_MI; ++mi) {
+                    const int64_t j = j0 + 8 * mi + grp, k = 8 * nt + 2 * tig;
+                    if (j < P) {
+                        if (k + 1 < N && (N & 1) == 0) *reinterpret_cast<double2*>(AB + k + N * j) = make_double2(d[mi][0], d[mi][1]);
+                        else { if (k < N) AB[k + N * j] = d[mi][0]; if (k + 1 < N) AB[k + 1 + N * j] = d[mi][1]; }
+                    }
+                }
+            }
+            continue;
+        }
         for (int64_t nt = 0; nt < Np / 8; ++nt) {
             double d[DG_MI][2];
 #pragma unroll
