@@ -361,6 +361,12 @@ static void block_cache_release() {
     }
 }
 
+namespace afb {
+// recycled device blocks for short-lived buffers (afb_buf_*): no cudaMalloc / cudaFree (and no device-wide sync) per temporary
+int32_t device_block_get(size_t bytes, void** out, size_t* cap) { return block_cache_get(bytes ? bytes : 1, out, cap); }
+void device_block_put(void* p, size_t cap, int dev) { block_cache_put(p, cap, dev); }
+}  // namespace afb
+
 // ---- fan-out over afb_init's device set -----------------------------------------------------------------
 // Splits [0, total) into contiguous shares, one per device, and runs fn(share_index, lo, hi) on one host thread per device
 // with that device current.  The first non-OK status (and its message) is returned to the caller's thread.

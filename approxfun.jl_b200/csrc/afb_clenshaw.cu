@@ -20,10 +20,13 @@
 namespace afb {
 
 constexpr int CL_THREADS = 512;        // threads per CTA
-#ifndef AFB_CL_R
-#define AFB_CL_R 4
+constexpr int CL_R = 4;                // points per thread (independent recurrences) of the bisection / 2-D kernels
+// ... and of the evaluation kernel: 8 points share every broadcast coefficient load and its .reuse'd DADD operand
+// (measured N = 10^4, 2.7e8 points: 4 -> 21.9, 8 -> 22.9 TFLOP/s; the bisection kernel got slower with 8: 21.3 -> 19.8)
+#ifndef AFB_CLV_R
+#define AFB_CLV_R 8
 #endif
-constexpr int CL_R = AFB_CL_R;         // points per thread (independent recurrences); 8 was measured in round 2
+constexpr int CLV_R = AFB_CLV_R;
 constexpr int CL_CHUNK = 12288;        // coefficients staged per shared-memory chunk (96 KB)
 
 // Runs the recurrence over coefficients c[klo..khi) (khi exclusive), from high to low, with klo >= 1.
@@ -63,7 +66,7 @@ __device__ __forceinline__ void clenshaw_finish(double c0, const double (&x2)[R]
 // ------------------------------------------------------------------------------------------------
 // K6: y[i] = sum_k c[k] T_k(x[i]),  one CTA loops over tiles of CL_THREADS*R points
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS, 2)
+__global__ void __launch_bounds__(CL_THREADS, CLV_R <= 8 ? 2 : 1)
 clenshaw_vec_kernel(const double* __restrict__ c, int64_t N, const double* __restrict__ x,
                     double* __restrict__ y, int64_t P, int64_t ntiles) {
     AFB_DYN_SMEM(double, sc);
@@ -74,10 +77,10 @@ clenshaw_vec_kernel(const double* __restrict__ c, int64_t N, const double* __res
         __syncthreads();
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * (int64_t)(CL_THREADS * CL_R);
-        double x2[CL_R], b1[CL_R], b2[CL_R], out[CL_R];
+        const int64_t base = tile * (int64_t)(CL_THREADS * CLV_R);
+        double x2[CLV_R], b1[CLV_R], b2[CLV_R], out[CLV_R];
 #pragma unroll
-        for (int r = 0; r < CL_R; ++r) {
+        for (int r = 0; r < CLV_R; ++r) {
             const int64_t i = base + tid + (int64_t)r * CL_THREADS;
             const double xv = (i < P) ? x[i] : 0.0;
             x2[r] = __dmul_rn(2.0, xv);
@@ -86,10 +89,10 @@ clenshaw_vec_kernel(const double* __restrict__ c, int64_t N, const double* __res
         }
         if (N == 0) {
 #pragma unroll
-            for (int r = 0; r < CL_R; ++r) out[r] = 0.0;
+            for (int r = 0; r < CLV_R; ++r) out[r] = 0.0;
         } else if (nchunks <= 1) {
-            clenshaw_span<CL_R>(sc, 1, (int)N, x2, b1, b2);
-            clenshaw_finish<CL_R>(sc[0], x2, b1, b2, out);
+            clenshaw_span<CLV_R>(sc, 1, (int)N, x2, b1, b2);
+            clenshaw_finish<CLV_R>(sc[0], x2, b1, b2, out);
         } else {
             double c0 = 0.0;
             for (int64_t ch = nchunks - 1; ch >= 0; --ch) {
@@ -99,13 +102,13 @@ clenshaw_vec_kernel(const double* __restrict__ c, int64_t N, const double* __res
                 for (int64_t k = lo + tid; k < hi; k += CL_THREADS) sc[k - lo] = c[k];
                 __syncthreads();
                 const int klo = (ch == 0) ? 1 : 0;
-                clenshaw_span<CL_R>(sc, klo, (int)(hi - lo), x2, b1, b2);
+                clenshaw_span<CLV_R>(sc, klo, (int)(hi - lo), x2, b1, b2);
                 if (ch == 0) c0 = sc[0];
             }
-            clenshaw_finish<CL_R>(c0, x2, b1, b2, out);
+            clenshaw_finish<CLV_R>(c0, x2, b1, b2, out);
         }
 #pragma unroll
-        for (int r = 0; r < CL_R; ++r) {
+        for (int r = 0; r < CLV_R; ++r) {
             const int64_t i = base + tid + (int64_t)r * CL_THREADS;
             if (i < P) y[i] = (N == 1) ? c[0] : out[r];
         }
@@ -697,7 +700,7 @@ static inline int64_t cl_tiles(int64_t P) { return (P + (int64_t)CL_THREADS * CL
 
 int32_t launch_clenshaw_vec(const double* d_c, int64_t N, const double* d_x, double* d_y, int64_t P, void* stream) {
     if (P == 0) return AFB_OK;
-    const int64_t ntiles = cl_tiles(P);
+    const int64_t ntiles = (P + (int64_t)CL_THREADS * CLV_R - 1) / ((int64_t)CL_THREADS * CLV_R);
     const int64_t grid = ntiles < 2 * (int64_t)sm_count() ? ntiles : 2 * (int64_t)sm_count();
     const size_t smem = sizeof(double) * (size_t)((N < CL_CHUNK ? (N > 0 ? N : 1) : CL_CHUNK));
     auto k = clenshaw_vec_kernel;

@@ -12,6 +12,7 @@ struct afb_buf_s {
     double* p = nullptr;
     int64_t n = 0;     // capacity in doubles
     int dev = 0;
+    size_t cap = 0;    // bytes of the underlying (recycled) device block
 };
 
 namespace afb {
@@ -127,16 +128,18 @@ int32_t afb_buf_create(afb_buf* out, int64_t n) {
     afb_buf_s* b = new afb_buf_s();
     b->n = n;
     b->dev = current_device();
+    // blocks are recycled through the per-device cache: every call of this layer runs on the legacy default stream, so a
+    // block handed out again is only touched after the work of its previous owner
     void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, sizeof(double) * (size_t)std::max<int64_t>(n, 2));
-    if (e != cudaSuccess) { delete b; return cuda_fail(e, "cudaMalloc(afb_buf)", __FILE__, __LINE__); }
+    const int32_t st = device_block_get(sizeof(double) * (size_t)std::max<int64_t>(n, 2), &d, &b->cap);
+    if (st != AFB_OK) { delete b; return st; }
     b->p = reinterpret_cast<double*>(d);
     *out = b;
     return AFB_OK;
 }
 int32_t afb_buf_destroy(afb_buf b) {
     if (!b) return AFB_OK;
-    if (b->p) cudaFree(b->p);
+    if (b->p) device_block_put(b->p, b->cap, b->dev);
     delete b;
     return AFB_OK;
 }
@@ -227,7 +230,8 @@ int32_t afb_buf_tail(afb_buf c, int64_t n, int64_t ntail, double rel_thresh, dou
     if (n == 0) { if (maxabs) *maxabs = 0; if (tailmax) *tailmax = 0; if (chop_len) *chop_len = 0; return AFB_OK; }
     BufGuard g(c->dev);
     void* d = nullptr;
-    AFB_CUDA(cudaMalloc(&d, 4 * sizeof(double)));
+    size_t dcap = 0;
+    AFB_TRY(device_block_get(4 * sizeof(double), &d, &dcap));
     double h[3] = {0, 0, 0};
     auto k = tail_kernel;
     int32_t st = AFB_OK;
@@ -242,7 +246,7 @@ int32_t afb_buf_tail(afb_buf c, int64_t n, int64_t ntail, double rel_thresh, dou
         if (e != cudaSuccess) st = cuda_fail(e, "afb_buf_tail", __FILE__, __LINE__);
         else *chop_len = (int64_t)h2[2];
     }
-    cudaFree(d);
+    device_block_put(d, dcap, c->dev);
     if (st == AFB_OK) { if (maxabs) *maxabs = h[0]; if (tailmax) *tailmax = h[1]; }
     return st;
 }

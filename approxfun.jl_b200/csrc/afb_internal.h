@@ -61,7 +61,7 @@ int32_t cfft_launches(const CfftPlan* p);
 bool cfft_real_fused_ok(const CfftPlan* p);
 int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
                          const cplx* qtab, void* stream);
-// mixed-radix engine (afb_mixed.cu): n = 2^a 3^b 5^c 7^d, not a power of two, 6 <= n <= 6144
+// mixed-radix engine (afb_mixed.cu): n = 2^a 3^b 5^c 7^d, not a power of two, 6 <= n <= 6912
 bool mixed_radix_ok(int64_t n);
 int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale,
                           void* stream);
@@ -112,6 +112,9 @@ void mdev2d_destroy(void* handle);
 // `batch` lines of a 1-D plan (batch <= the plan's batch), on the plan's device; used by the chunked column pass
 int32_t slab_col_chunk(afb_plan plan, const double* d_in, double* d_out, int64_t batch, void* stream);
 const std::vector<int>& device_list();
+// recycled device blocks (per device, freed by afb_shutdown)
+int32_t device_block_get(size_t bytes, void** out, size_t* cap);
+void device_block_put(void* p, size_t cap, int dev);
 
 // ---- device table helpers ------------------------------------------------------------------------------
 int32_t upload_table(const std::vector<cplx>& host, cplx** dev);

@@ -6,8 +6,7 @@
 //     compile-time butterfly.  The butterflies of all lines of a CTA are pooled and dealt to the threads round robin, so
 //     odd butterfly counts (n / 5 = 200 on 256 threads) do not idle half a CTA.
 //   * Autosort needs out-of-place passes when a thread runs a run-time number of butterflies: two buffers per line
-//     (ping-pong), indexed through a pad of one 16-byte slot every eight so that the stride-R scatter of a pass and the
-//     stride-1 gather of the next are both conflict free.
+//     (ping-pong), unpadded: stride-1 windows are conflict free at any alignment; see mx_pad.
 //   * The four real kinds ride TWO real lines per complex FFT (z = line 2q + i line 2q+1), with the kind's pre-processing in
 //     the load loop and the spectrum split + post-processing in the store loop, exactly as the fused Bluestein kernel
 //     (afb_large.cu) does: one read and one write of the data, 16 B per coefficient.
@@ -20,17 +19,21 @@
 namespace afb {
 
 constexpr int MX_MAXPASS = 14;
-constexpr int64_t MX_MAX_N = 6144;   // two padded buffers of 16 B * 9/8 n: 216 KB at n = 6144
+constexpr int64_t MX_MAX_N = 6912;   // two buffers of 16 B * n: 216 KB at n = 6912
 
 struct MixedSched {
-    int n, npass, lpc, npad, ct;   // ct = threads per CTA (128 or 256)
+    int n, npass, lpc, npad, ct, big;   // ct = threads per CTA (128 or 256); big = some pass has radix 16
     int radix[MX_MAXPASS];
     int ns[MX_MAXPASS];          // product of the radices of the earlier passes
     float inv_nr[MX_MAXPASS];    // 1 / (n / radix)
     float inv_ns[MX_MAXPASS];
 };
 
-__device__ __forceinline__ int mx_pad(int i) { return i + (i >> 3); }
+// Lines are NOT padded: every stride-1 window of eight 16-byte slots covers the 32 banks exactly once whatever its alignment
+// (a pad slot inside an unaligned window made almost every access two wavefronts: ncu, round 2).  The only strided access
+// is the scatter of the FIRST pass (stride = its radix), which is conflict free for an odd radix and 2-way for 6 and 10, so
+// the schedule starts with such a radix.
+__device__ __forceinline__ int mx_pad(int i) { return i; }
 // floor(a / d) for 0 <= a < 2^20 through a float reciprocal, corrected to be exact
 __device__ __forceinline__ int mx_div(int a, int d, float inv) {
     int q = (int)(((float)a + 0.5f) * inv);
@@ -336,10 +339,17 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
     std::vector<int> cur, r;
     mixed_factor(n, cur, r);
     if (r.empty() || (int)r.size() > MX_MAXPASS) return false;
-    std::sort(r.begin(), r.end(), [](int a, int b) { return a > b; });   // the first pass has no twiddles: largest radix first
+    // largest radix first (the first pass has no twiddles) among those whose stride-R scatter is cheap: odd, else 6 / 10
+    std::sort(r.begin(), r.end(), [](int a, int b) { return a > b; });
+    auto rank_first = [](int R) { return (R & 1) ? 0 : (R == 6 || R == 10) ? 1 : 2; };
+    size_t best = 0;
+    for (size_t i = 1; i < r.size(); ++i)
+        if (rank_first(r[i]) < rank_first(r[best])) best = i;
+    std::swap(r[0], r[best]);
+    std::sort(r.begin() + 1, r.end(), [](int a, int b) { return a > b; });
     sc->n = (int)n;
     sc->npass = (int)r.size();
-    sc->npad = (int)(n + (n >> 3) + 1);
+    sc->npad = (int)n;
     int ns = 1;
     for (int p = 0; p < sc->npass; ++p) {
         sc->radix[p] = r[(size_t)p];
@@ -351,7 +361,9 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
     // threads and lines per CTA: the pooled butterflies of the thinnest pass (n / largest radix per line) should fill ONE round
     // of the CTA's threads; short butterfly counts take 128-thread CTAs (twice as many resident CTAs in different phases).
     // Shared memory: ~36 KB per 128 threads (six / three CTAs per SM) when one line fits that at all; at most 16 lines.
-    const int nr0 = (int)(n / r[0]);
+    const int rmax = *std::max_element(r.begin(), r.end());
+    sc->big = rmax == 16 ? 1 : 0;
+    const int nr0 = (int)(n / rmax);
     sc->ct = (nr0 <= 160) ? 128 : 256;
     const size_t per_line = 2 * sizeof(cplx) * (size_t)sc->npad;
     const size_t budget = (sc->ct == 128) ? ((size_t)37 << 10) : ((size_t)74 << 10);
@@ -366,7 +378,7 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
                           void* stream) {
     if (batch == 0) return AFB_OK;
     MixedCParams p{in, out, batch, tw, inverse ? 1 : 0, scale, {}};
-    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
+    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6912");
     const unsigned grid = (unsigned)((batch + p.sc.lpc - 1) / p.sc.lpc);
 #define AFB_MX_LAUNCH(BIG_, CT_)                                               \
     do {                                                                       \
@@ -374,7 +386,7 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
         AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
         AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
     } while (0)
-    if (p.sc.radix[0] == 16) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
+    if (p.sc.big) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
     else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
 #undef AFB_MX_LAUNCH
     AFB_KERNEL_CHECK();
@@ -390,7 +402,7 @@ template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, vo
         AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
         AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
     } while (0)
-    if (p.sc.radix[0] == 16) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
+    if (p.sc.big) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
     else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
 #undef AFB_MX_LAUNCH
     AFB_KERNEL_CHECK();
@@ -400,7 +412,7 @@ int32_t launch_mixed_real(int kind, int64_t n, const cplx* tw, const cplx* qtab,
                           int64_t ostride, int64_t batch, void* stream) {
     if (batch == 0) return AFB_OK;
     MixedRParams p{in, out, batch, istride, ostride, tw, qtab, {}};
-    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6144");
+    if (!mixed_schedule(n, &p.sc)) return fail(AFB_UNSUPPORTED, "mixed-radix FFT: length is not 2^a 3^b 5^c 7^d <= 6912");
     switch (kind) {
         case AFB_CHEB1_FWD: return launch_mixed_real_k<AFB_CHEB1_FWD>(p, stream);
         case AFB_CHEB1_INV: return launch_mixed_real_k<AFB_CHEB1_INV>(p, stream);

@@ -775,8 +775,13 @@ def test_device_resident_fun_chains(af):
     host = af.Fun(lambda x: np.sin(x ** 2), S)                          # the host-array route through the same library
     c = f.coefficients                                                  # the ONE download of the result
     assert dv.traffic["d2h"] == ladder_d2h + 8 * f.n
-    assert f.n == len(want) == len(host.coefficients)
-    assert np.max(np.abs(c - want)) <= 1e-13 * math.log2(256) and np.max(np.abs(c - host.coefficients)) <= 1e-13 * 8
+    # the chop point sits in the rounding noise (coefficients ~ 1e-16 relative), where the device's sin and NumPy's differ by
+    # an ulp: lengths agree to a few terms, coefficients to tolerance once zero-extended
+    assert abs(f.n - len(want)) <= 24 and len(want) == len(host.coefficients)
+    m = max(f.n, len(want))
+    ext = lambda v: np.concatenate([v, np.zeros(m - len(v))])
+    assert np.max(np.abs(ext(c) - ext(want))) <= 1e-13 * math.log2(256)
+    assert np.max(np.abs(ext(c) - ext(host.coefficients))) <= 1e-13 * 8
     assert abs(f(0.1) - math.sin(0.01)) < 1000 * EPS                    # test/ReadmeTest.jl:19-23 on the device-built Fun
     # f * g: values on n_f + n_g - 1 points, multiplied and transformed on the device
     g = dv.DeviceFun.from_function(lambda x: dv.exp(-0.3 * x) + 2.0, S)
