@@ -525,12 +525,12 @@ static int32_t build_line_aux(afb_plan_s* p) {
         for (int64_t pi = 0; pi <= NSL / 2; ++pi) h[(size_t)(J * pi + j)] = tw_eval(fam[j], pi, n, fam[j].gre, fam[j].gim);
         h[(size_t)(J * (NSL / 2 + 1) + j)] = tw_eval(fam[j], N / 2, n, fam[j].gre, fam[j].gim);
     }
-    p->K.assign(2 * 8, make_double2(1.0, 0.0));
+    p->K.assign(2 * LINE_MAXRL, make_double2(1.0, 0.0));
     for (int j = 0; j < J; ++j) {
         const bool g_imag = fam[j].gim != 0.0L;  // g / conj(g) = -1 for purely imaginary g, +1 for real g
         for (int q = 0; q < RL; ++q) {
-            if (2 * q < RL) p->K[(size_t)(j * 8 + q)] = tw_eval(fam[j], (int64_t)NSL * q, n);
-            else p->K[(size_t)(j * 8 + q)] = tw_eval(fam[j], N - (int64_t)NSL * q, n, g_imag ? -1.0L : 1.0L, 0.0L);
+            if (2 * q < RL) p->K[(size_t)(j * LINE_MAXRL + q)] = tw_eval(fam[j], (int64_t)NSL * q, n);
+            else p->K[(size_t)(j * LINE_MAXRL + q)] = tw_eval(fam[j], N - (int64_t)NSL * q, n, g_imag ? -1.0L : 1.0L, 0.0L);
         }
     }
     return upload_table(h, &p->aux);

@@ -30,7 +30,7 @@ template <int N_, int R1_, int R2_, int R3_, int R4_> struct FftRadices {
     static constexpr int L = (R4_ > 1) ? 4 : (R3_ > 1) ? 3 : 2;
     static constexpr int T = N_ / R1_;
     static constexpr int E = R1_;
-    static constexpr int SH = (R1_ == 16) ? 4 : 3;
+    static constexpr int SH = (R1_ == 32) ? 5 : (R1_ == 16) ? 4 : 3;   // log2 R1: the first pass' scatter stride
     static constexpr int RL = (L == 4) ? R4_ : (L == 3) ? R3_ : R2_;  // last radix
     static constexpr int NSL = N_ / RL;                               // butterflies in the last pass
     static constexpr int BL = E / RL;                                 // ... per thread
@@ -46,7 +46,20 @@ AFB_FFTCFG(512, 16, 8, 4, 1);
 AFB_FFTCFG(1024, 16, 8, 8, 1);
 AFB_FFTCFG(2048, 16, 16, 8, 1);
 AFB_FFTCFG(4096, 16, 8, 4, 8);
+// N = 8192 (real lines of 16384): ONE CTA owns an SM.  A radix-32 first pass (32 complex values per thread, 256 threads, three
+// passes: 2 writes + 2 reads of the 128 KB exchange buffer instead of 3 + 3) was measured in round 2 (AFB_R32=1): of the HBM
+// roofline at 16384 x 16384, 16.16.16.2 -> 32.16.16:  Chebyshev forward 0.634 -> 0.599, inverse 0.574 -> 0.643, Fourier
+// forward 0.623 -> 0.663, inverse 0.609 -> 0.682.  A third less shared-memory traffic buys at most 12 %: the kernel is bound
+// by the serialisation of its phases inside the single resident CTA, not by the exchange volume; the forward Chebyshev line
+// (the column pass of the 2-D transform) loses, so the default stays 16.16.16.2.
+#ifndef AFB_R32
+#define AFB_R32 0
+#endif
+#if AFB_R32
+AFB_FFTCFG(8192, 32, 16, 16, 1);
+#else
 AFB_FFTCFG(8192, 16, 16, 16, 2);
+#endif
 #undef AFB_FFTCFG
 // Complex kinds (whole transform through shared memory, no pairing): fewest passes, largest radices first.  Same R1, so
 // same T and E.  (The real kinds above prefer a LARGE last radix: fewer partner butterflies per thread means fewer twiddle
@@ -131,6 +144,31 @@ template <> struct Dft<16> {
         for (int b = 0; b < 4; ++b) {
             dft4(y[0][b], y[1][b], y[2][b], y[3][b]);
             x[b] = y[0][b]; x[b + 4] = y[1][b]; x[b + 8] = y[2][b]; x[b + 12] = y[3][b];
+        }
+    }
+};
+
+template <> struct Dft<32> {
+    static __device__ __forceinline__ void run(cplx* x) {
+        // w32^k = exp(-2 pi i k / 32), k = 1..15
+        constexpr double C32[16] = {1.0, 0.98078528040323043058, 0.92387953251128673848, 0.83146961230254523567,
+                                    0.70710678118654752440, 0.55557023301960228867, 0.38268343236508978178, 0.19509032201612833135,
+                                    0.0, -0.19509032201612819257, -0.38268343236508972627, -0.55557023301960195560,
+                                    -0.70710678118654752440, -0.83146961230254534669, -0.92387953251128673848, -0.98078528040323043058};
+        constexpr double S32[16] = {0.0, 0.19509032201612824808, 0.38268343236508978178, 0.55557023301960217765,
+                                    0.70710678118654752440, 0.83146961230254523567, 0.92387953251128673848, 0.98078528040323043058,
+                                    1.0, 0.98078528040323043058, 0.92387953251128673848, 0.83146961230254545772,
+                                    0.70710678118654752440, 0.55557023301960217765, 0.38268343236508989280, 0.19509032201612860891};
+        cplx e[16], o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+        Dft<16>::run(e);
+        Dft<16>::run(o);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const cplx t = (k == 0) ? o[0] : (k == 8) ? cmul_mi(o[8]) : cmul(o[k], make_double2(C32[k], -S32[k]));
+            x[k] = cadd(e[k], t);
+            x[k + 16] = csub(e[k], t);
         }
     }
 };

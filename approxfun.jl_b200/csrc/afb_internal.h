@@ -14,6 +14,7 @@ enum { ILK_CHEB_FWD = 0, ILK_CHEB_INV = 1, ILK_FOURIER_FWD = 2, ILK_FOURIER_INV 
 constexpr int DIRECT_MAX = 32;      // n <= DIRECT_MAX: O(n^2) kernel
 constexpr int LINE_MIN_N = 32;      // complex FFT lengths served by one CTA in shared memory
 constexpr int LINE_MAX_N = 8192;
+constexpr int LINE_MAXRL = 16;       // largest last-pass radix of the line kernels (size of the rotation-constant rows)
 
 // ---- kernels / launchers --------------------------------------------------------------------------
 int32_t launch_line(int kind, int N, const void* in, void* out, int64_t batch, int64_t istride, int64_t ostride,

@@ -17,10 +17,11 @@
 // per-plan constant rotation passed in the kernel parameters (constant bank), so no per-element table traffic.
 // Global traffic is exactly one read and one write of every element (16 B per coefficient).
 #include "afb_fft.cuh"
+#include "afb_internal.h"
 
 namespace afb {
 
-constexpr int MAXRL = 8;   // largest last-pass radix
+constexpr int MAXRL = LINE_MAXRL;   // largest last-pass radix
 constexpr int MAXJ = 2;    // twiddle families per kind
 
 struct LineParams {
@@ -587,7 +588,7 @@ template <int N> struct LineOp<N, LK_CFFT> {
 // (Forcing 5 CTAs per SM on the forward kinds too -- 96 instead of 113 registers -- was measured slower: 0.887 vs
 // 0.905 of HBM at n = 4096, 0.70 vs 0.81 at n = 256.)
 template <int N, int KIND>
-__global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (KIND == LK_CHEB_INV || KIND == LK_FOURIER_INV)) ? 5 : 512 / LineGeom<N>::CT)) line_kernel(const __grid_constant__ LineParams p) {
+__global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (KIND == LK_CHEB_INV || KIND == LK_FOURIER_INV)) ? 5 : (N == 8192 ? 1 : 512 / LineGeom<N>::CT))) line_kernel(const __grid_constant__ LineParams p) {
     typedef LineGeom<N> G;
     AFB_DYN_SMEM(cplx, smem);
     const int tid = threadIdx.x;
@@ -608,7 +609,7 @@ template <int N> struct StageGeom {
     // staged load groups (of R1/2 = 8) and resident CTAs per SM: N = 8192 stages 3/4 of the line beside its 128 KB
     // exchange buffer.  (Other N: whole line, three CTAs per SM -- measured at N = 2048: 0.77 of HBM against 0.905 for
     // the plain kernel with four CTAs per SM, so only N = 8192 is dispatched here.)
-    static constexpr int HS = (N == 8192) ? 6 : (N == 4096) ? 5 : 8;
+    static constexpr int HS = (N == 8192) ? 3 * (C::R1 / 2) / 4 : (N == 4096) ? 5 : 8;
     static constexpr int MINB = (N == 8192) ? 1 : (N == 4096) ? 2 : 3;
     static constexpr int FULL = 2 * N;
     // + the slot n*3/4 itself (k = N/2 of the inverse) when the stage is partial
