@@ -145,6 +145,38 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 #endif
 }
+// TMA 1-D bulk copy shared -> global (also peer-mapped global memory over NVLink), tracked by bulk async-groups
+__device__ __forceinline__ void bulk_copy_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+#ifdef AFB_HOST_EMU
+    std::memcpy(gmem_dst, smem_src, bytes);
+#else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_commit_group() {
+#ifndef AFB_HOST_EMU
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+// waits until at most N of the thread's bulk groups are still READING their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+#ifndef AFB_HOST_EMU
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+#endif
+}
+// ... until at most N have not completed (writes performed)
+template <int N> __device__ __forceinline__ void bulk_wait_group() {
+#ifndef AFB_HOST_EMU
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+#ifndef AFB_HOST_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
 #ifndef AFB_HOST_EMU
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");

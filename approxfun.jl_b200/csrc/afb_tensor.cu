@@ -207,6 +207,57 @@ __global__ void __launch_bounds__(256) xchg_transpose_kernel(const double* __res
 #endif
     }
 }
+// TMA variant of the exchange: a 32 (rows) x 128 (columns) tile is transposed into shared memory as 32 contiguous rows of
+// 1 KB and every row leaves as ONE bulk copy (cp.async.bulk shared -> global, SASS UBLKCP.G.S) to the owner's receive
+// buffer -- whole-packet NVLink writes issued by the copy engine of the SM instead of 16-byte LSU stores.  Two tile buffers:
+// while the rows of tile k drain, tile k+1 is loaded and transposed.  Needs nr % 32 == 0, nc % 128 == 0, even n2.
+constexpr int XB_I = 32, XB_J = 128, XB_LD = XB_J + 2;   // row pitch 1040 B: 16-byte aligned rows
+__global__ void __launch_bounds__(256) xchg_bulk_kernel(const double* __restrict__ in, XchgPeers peers, int64_t n, int64_t nc,
+                                                        int64_t nr, int64_t n2, int G, int rank, int64_t c0, int64_t c1,
+                                                        unsigned* ctr, uint64_t epoch, int signal) {
+    AFB_DYN_SMEM(double, tiles);  // 2 x XB_I x XB_LD
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t ti_per = nr / XB_I, tj_cnt = (c1 - c0) / XB_J;
+    const int64_t per_dest = ti_per * tj_cnt;
+    int buf = 0;
+    for (int64_t b = blockIdx.x; b < per_dest * G; b += gridDim.x, buf ^= 1) {
+        const int k = (int)(b / per_dest);
+        const int64_t w = b - (int64_t)k * per_dest;
+        const int d = (rank + 1 + k) % G;
+        const int64_t il0 = (w / tj_cnt) * XB_I, j0 = c0 + (w % tj_cnt) * XB_J;   // column tiles fastest: contiguous destination
+        const int64_t i0 = (int64_t)d * nr + il0;
+        double v[XB_J / 8];
+#pragma unroll
+        for (int r = 0; r < XB_J / 8; ++r) v[r] = in[i0 + tx + (j0 + ty + 8 * r) * n];
+        // the rows that last used this buffer (two tiles ago) must have been read out by the copy engine
+        if (threadIdx.x < XB_I) bulk_wait_group_read<1>();
+        __syncthreads();
+        double* t = tiles + (size_t)buf * XB_I * XB_LD;
+#pragma unroll
+        for (int r = 0; r < XB_J / 8; ++r) t[tx * XB_LD + ty + 8 * r] = v[r];
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x < XB_I) {
+            double* dst = peers.recv[d] + (il0 + threadIdx.x) * n2 + (int64_t)rank * nc + j0;
+            bulk_copy_s2g(dst, t + threadIdx.x * XB_LD, (uint32_t)(sizeof(double) * XB_J));
+            bulk_commit_group();
+        }
+    }
+    if (threadIdx.x < XB_I) bulk_wait_group<0>();   // every row of this CTA has been written
+    if (!signal) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#ifndef AFB_HOST_EMU
+        __threadfence_system();
+        const unsigned prev = atomicAdd(ctr, 1u);
+        if (prev == gridDim.x - 1) {
+            *ctr = 0;
+            __threadfence_system();
+            for (int dd = 0; dd < G; ++dd) st_release_sys(peers.flags[dd] + rank, epoch);
+        }
+#endif
+    }
+}
 // One warp: lane s < G waits until sender s has published `epoch` (or a later one).  A peer that never arrives would hang
 // the stream; after ~10 s the kernel traps instead, which surfaces as a CUDA error at the caller's next synchronisation.
 __global__ void xchg_wait_kernel(const uint64_t* __restrict__ flags, int G, uint64_t epoch) {
@@ -344,6 +395,20 @@ static void slab_free(Sharded2D& s) {
     s = Sharded2D();
 }
 
+#ifndef AFB_HOST_EMU
+static int32_t launch_xchg_bulk(Sharded2D& s, const XchgPeers& pp, int64_t c0, int64_t c1, uint64_t epoch, int signal, cudaStream_t st) {
+    const int64_t G = s.G, nc = s.n2 / G, nr = s.n / G;
+    const int64_t tiles = G * (nr / XB_I) * ((c1 - c0) / XB_J);
+    const size_t smem = sizeof(double) * 2 * XB_I * XB_LD;
+    const int64_t grid = std::min<int64_t>(tiles, std::min(s.grid_mult, 3) * (int64_t)sm_count());
+    auto k = xchg_bulk_kernel;
+    AFB_SMEM_OPTIN(k, smem);
+    AFB_LAUNCH(k, (unsigned)grid, 256, smem, st, s.rbuf, pp, s.n, nc, nr, s.n2, (int)G, (int)s.rank, c0, c1, s.ctr(), epoch, signal);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+#endif
+
 // Peer-memory execution of one rank: column transforms -> fused transpose straight into the owners' receive buffers ->
 // wait for every sender's epoch flag -> row transforms.  With chunks > 1 the column pass runs in `chunks` pieces on the
 // caller's stream and each finished piece is sent on a side stream while the next is transformed.
@@ -368,11 +433,15 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
         if (s.phases & 1) AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
         if (s.phases & 2) {
             const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
-            const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
-            const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
-            AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
-                       s.ctr(), epoch, 1, s.order);
-            AFB_KERNEL_CHECK();
+            if (s.order == 4 && nr % XB_I == 0 && nc % XB_J == 0 && s.n2 % 2 == 0) {
+                AFB_TRY(launch_xchg_bulk(s, pp, 0, nc, epoch, 1, st));
+            } else {
+                const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+                const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+                AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
+                           s.ctr(), epoch, 1, s.order == 4 ? 3 : s.order);
+                AFB_KERNEL_CHECK();
+            }
             auto kw0 = xchg_wait_kernel;
             AFB_LAUNCH(kw0, 1, 32, 0, st, s.flags(), (int)G, epoch);
             AFB_KERNEL_CHECK();
@@ -383,11 +452,15 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
     if (K == 1) {
         AFB_TRY(afb_plan_execute_device(s.col_plan, d_in, s.rbuf, stream));
         const int64_t tiles = G * ((nr + XT_I - 1) / XT_I) * ((nc + XT_J - 1) / XT_J);
-        const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
-        const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
-        AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
-                   s.ctr(), epoch, 1, s.order);
-        AFB_KERNEL_CHECK();
+        if (s.order == 4 && nr % XB_I == 0 && nc % XB_J == 0 && s.n2 % 2 == 0) {
+            AFB_TRY(launch_xchg_bulk(s, pp, 0, nc, epoch, 1, st));
+        } else {
+            const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+            const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
+            AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
+                       s.ctr(), epoch, 1, s.order == 4 ? 3 : s.order);
+            AFB_KERNEL_CHECK();
+        }
     } else {
         if (!s.side) AFB_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
         if (!s.ev_x) AFB_CUDA(cudaEventCreateWithFlags(&s.ev_x, cudaEventDisableTiming));
@@ -548,7 +621,7 @@ int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks) {
 
 int32_t afb_sharded2d_set_tuning(void* handle, int32_t order, int32_t grid_mult, int32_t novec) {
     ShardHandle* h = reinterpret_cast<ShardHandle*>(handle);
-    if (!h || h->magic != 0x5348415244324421ull || order < 0 || order > 3 || grid_mult < 1 || grid_mult > 64)
+    if (!h || h->magic != 0x5348415244324421ull || order < 0 || order > 4 || grid_mult < 1 || grid_mult > 64)
         return fail(AFB_BAD_ARG, "afb_sharded2d_set_tuning: bad argument");
     h->s.order = order; h->s.grid_mult = grid_mult; h->s.novec = novec ? 1 : 0;
     return AFB_OK;

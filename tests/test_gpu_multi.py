@@ -66,6 +66,16 @@ def _worker(rank, world, port, q):
                 plan.execute(block.data_ptr(), out.data_ptr(), st)
             torch.cuda.synchronize()
             errs.append(float((out - want).abs().max()))
+            if p2p:
+                # every exchange-kernel variant: tile orders, the TMA bulk-store kernel (order 4), chunked column pass
+                for order, chunks in ((0, 1), (1, 1), (2, 1), (4, 1), (3, 2), (4, 4)):
+                    plan.set_tuning(order, 3, 0)
+                    plan.set_chunks(chunks)
+                    out.zero_()
+                    for _ in range(2):
+                        plan.execute(block.data_ptr(), out.data_ptr(), st)
+                    torch.cuda.synchronize()
+                    errs.append(float((out - want).abs().max()))
             dist.barrier()
             plan.close()
         q.put((rank, ok1, max(errs)))
