@@ -344,7 +344,9 @@ struct Sharded2D {
     bool p2p = false, ipc = false;
     uint64_t epoch = 0;
     int chunks = 1;               // column-pass / exchange pipeline depth (see slab_execute)
-    int order = 3, grid_mult = 8, novec = 0;   // exchange kernel tuning (afb_sharded2d_set_tuning); measured best at 8 GPUs
+    // exchange kernel tuning (afb_sharded2d_set_tuning).  Measured at 8 GPUs, 16384^2 (exchange alone, 235 MB per rank each way):
+    // order 0 0.49 ms, 1 0.73, 2 0.72, 3 0.39 (8 CTAs per SM), 4 = TMA bulk rows 0.383 (3 CTAs per SM; 0.40 with one)
+    int order = 4, grid_mult = 3, novec = 0;
     int phases = 7;               // measurement only: bit 0 column pass, bit 1 exchange + wait, bit 2 row pass
     cudaStream_t side = nullptr;  // the exchange runs here while the next column chunk is transformed
     cudaEvent_t ev_col[8] = {nullptr}, ev_x = nullptr;
@@ -436,7 +438,7 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
             if (s.order == 4 && nr % XB_I == 0 && nc % XB_J == 0 && s.n2 % 2 == 0) {
                 AFB_TRY(launch_xchg_bulk(s, pp, 0, nc, epoch, 1, st));
             } else {
-                const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+                const int64_t grid = std::min<int64_t>(tiles, (s.order == 4 ? 8 : s.grid_mult) * (int64_t)sm_count());
                 const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
                 AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
                            s.ctr(), epoch, 1, s.order == 4 ? 3 : s.order);
@@ -455,7 +457,7 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
         if (s.order == 4 && nr % XB_I == 0 && nc % XB_J == 0 && s.n2 % 2 == 0) {
             AFB_TRY(launch_xchg_bulk(s, pp, 0, nc, epoch, 1, st));
         } else {
-            const int64_t grid = std::min<int64_t>(tiles, s.grid_mult * (int64_t)sm_count());
+            const int64_t grid = std::min<int64_t>(tiles, (s.order == 4 ? 8 : s.grid_mult) * (int64_t)sm_count());
             const int vec = (!s.novec && nc % 2 == 0 && s.n2 % 2 == 0) ? 1 : 0;
             AFB_LAUNCH(kt, (unsigned)grid, 256, smem, st, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, (int64_t)0, nc, vec,
                        s.ctr(), epoch, 1, s.order == 4 ? 3 : s.order);

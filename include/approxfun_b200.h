@@ -329,9 +329,10 @@ int32_t afb_sharded2d_set_chunks(void* handle, int32_t chunks);
 /* Measurement only (peer-memory mode): run a subset of the phases -- bit 0 column pass, bit 1 exchange + arrival wait,
  * bit 2 row pass; 7 = the transform.  Every rank must use the same mask. */
 int32_t afb_sharded2d_set_phases(void* handle, int32_t mask);
-/* Tuning of the exchange kernel (defaults are the measured best): tile order 0 = one destination at a time, rotated by rank;
- * 1 = all destinations interleaved, rotated; 2 = row tiles fastest (unrotated).  grid_mult = CTAs per SM of its persistent
- * grid; novec != 0 = 8-byte instead of 16-byte remote stores. */
+/* Tuning of the exchange kernel (defaults are the measured best): tile order 0 = one destination at a time, rotated by rank,
+ * row tiles fastest; 1 = all destinations interleaved, rotated; 2 = row tiles fastest (unrotated); 3 = as 0 with column tiles
+ * fastest (contiguous spans at the destination); 4 = as 3 with every 1 KB row of a 32 x 128 tile sent as one TMA bulk copy
+ * (default).  grid_mult = CTAs per SM of its persistent grid; novec != 0 = 8-byte instead of 16-byte remote stores. */
 int32_t afb_sharded2d_set_tuning(void* handle, int32_t order, int32_t grid_mult, int32_t novec);
 
 #ifdef __cplusplus
