@@ -476,7 +476,7 @@ static int32_t slab_execute_p2p(Sharded2D& s, const double* d_in, double* d_out,
             // a few CTAs per chunk: the exchange is NVLink-bound and must leave the SMs to the next column chunk
             const int64_t grid = std::min<int64_t>(tiles, c + 1 < K ? 2 * (int64_t)sm_count() : 8 * (int64_t)sm_count());
             AFB_LAUNCH(kt, (unsigned)grid, 256, smem, s.side, s.rbuf, pp, n, nc, nr, s.n2, (int)G, (int)s.rank, c * cw, (c + 1) * cw, 1,
-                       s.ctr(), epoch, c + 1 == K ? 1 : 0, s.order);
+                       s.ctr(), epoch, c + 1 == K ? 1 : 0, s.order == 4 ? 3 : s.order);
             AFB_KERNEL_CHECK();
         }
         AFB_CUDA(cudaEventRecord(s.ev_x, s.side));
