@@ -806,3 +806,25 @@ def test_device_resident_fun_chains(af):
     v = f1k.values_device().to_host()
     xs = orc.chebpoints(1024, 0.0, 10.0)
     assert np.max(np.abs(v - np.cos(3 * xs) * xs)) <= 1e-13 * 10 * 10
+
+
+@pytest.mark.parametrize("N,R,P", [(66, 8, 5000), (198, 32, 3001), (100, 50, 4097), (7, 3, 33), (64, 64, 1000)])
+def test_dgemm_dmma_variant(af, N, R, P):
+    # AB = CB * fA (sample.jl:210) on the FP64 tensor cores (mma.sync m8n8k4) against the FMA kernel and NumPy
+    import ctypes as C
+    import torch
+    from approxfun_b200 import _lib as L
+    lib = af.api.lowlevel().lib
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + R)
+    CB = torch.randn(R, N, dtype=torch.float64, device="cuda", generator=g)        # column-major N x R
+    fA = torch.randn(P, R, dtype=torch.float64, device="cuda", generator=g)        # column-major R x P
+    a0 = torch.empty(P, N, dtype=torch.float64, device="cuda")
+    a1 = torch.full((P, N), 7.0, dtype=torch.float64, device="cuda")
+    vp = C.c_void_p
+    L.check(lib, lib.afb_dgemm_nn_device(vp(CB.data_ptr()), vp(fA.data_ptr()), vp(a0.data_ptr()), N, R, P, vp(0)))
+    L.check(lib, lib.afb_dgemm_nn_dmma_device(vp(CB.data_ptr()), vp(fA.data_ptr()), vp(a1.data_ptr()), N, R, P, vp(0)))
+    torch.cuda.synchronize()
+    want = fA.cpu().numpy() @ CB.cpu().numpy()
+    tol = 1e-13 * R * float(CB.abs().max()) * float(fA.abs().max())
+    assert np.max(np.abs(a0.cpu().numpy() - want)) <= tol
+    assert np.max(np.abs(a1.cpu().numpy() - want)) <= tol
