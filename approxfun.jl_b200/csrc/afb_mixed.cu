@@ -11,6 +11,7 @@
 //     the load loop and the spectrum split + post-processing in the store loop, exactly as the fused Bluestein kernel
 //     (afb_large.cu) does: one read and one write of the data, 16 B per coefficient.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "afb_fft.cuh"
@@ -23,6 +24,8 @@ constexpr int64_t MX_MAX_N = 6912;   // two buffers of 16 B * n: 216 KB at n = 6
 
 struct MixedSched {
     int n, npass, lpc, npad, ct, big;   // ct = threads per CTA (128 or 256); big = some pass has radix 16
+    int u0c, u0f, ul;                    // units per line pair: first pass (Chebyshev / Fourier pairing), last pass
+    float inv_u0c, inv_u0f, inv_ul;
     int radix[MX_MAXPASS];
     int ns[MX_MAXPASS];          // product of the radices of the earlier passes
     float inv_nr[MX_MAXPASS];    // 1 / (n / radix)
@@ -317,6 +320,196 @@ __global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_re
     }
 }
 
+// =====================================================================================================================
+// Forward kinds with the FIRST pass fed from global memory and the LAST pass finished in registers (round 2): the
+// shared-memory traffic of a transform drops from 9 passes over the line (pre-store, 3 x load + store, two post loads at
+// n = 1000) to 4 (first-pass store, one middle pass, last-pass load).
+//   first pass: a thread owns the partner butterflies (j, nr-1-j) (Chebyshev: the 16-byte chunk (v[2m], v[2m+1]) holds
+//               z[m] and its Makhoul mirror z[n-1-m], which are inputs r and R-1-r of the two partners) or (2a, 2a+1)
+//               (Fourier: the chunk holds z[2c], z[2c+1]); every global access is a coalesced 128-bit load;
+//   last pass:  a thread owns the partner butterflies (j, ns-j): their outputs are the pairs Z[k], Z[n-k] the spectrum
+//               split and the kind's post-processing need, so both run in registers and go straight to global memory.
+// Same arithmetic per output as mixed_real_kernel (bit-identical results).
+// =====================================================================================================================
+struct MxLines {   // the two real lines of a pair
+    const double2 *c0, *c1;
+    double *o0, *o1;
+    bool has2;
+};
+__device__ __forceinline__ MxLines mx_lines(const MixedRParams& p, int64_t q) {
+    MxLines L;
+    L.has2 = 2 * q + 1 < p.batch;
+    const double* l0 = p.in + (2 * q) * p.istride;
+    L.c0 = reinterpret_cast<const double2*>(l0);
+    L.c1 = reinterpret_cast<const double2*>(L.has2 ? l0 + p.istride : l0);
+    L.o0 = p.out + (2 * q) * p.ostride;
+    L.o1 = L.o0 + p.ostride;
+    return L;
+}
+// chunk c of both lines -> the complex values (even elements) and (odd elements)
+__device__ __forceinline__ void mx_chunk(const MxLines& L, int c, cplx& ev, cplx& od) {
+    const double2 a = L.c0[c];
+    double2 b = L.c1[c];
+    if (!L.has2) b = make_double2(0.0, 0.0);
+    ev = make_double2(a.x, b.x);
+    od = make_double2(a.y, b.y);
+}
+template <int R> __device__ __forceinline__ void mx_store_first(cplx* __restrict__ d, int j, cplx* x) {
+    MxDft<R>::run(x);
+#pragma unroll
+    for (int q = 0; q < R; ++q) d[j * R + q] = x[q];
+}
+template <int KIND, int R, int MX_CT>
+__device__ __forceinline__ void mx_first_fwd(const MixedSched& sc, const MixedRParams& p, int64_t pair0, int lines,
+                                             cplx* __restrict__ dst, int lstride) {
+    const int n = sc.n, nr = n / R;
+    const int upl = (KIND == AFB_CHEB1_FWD) ? sc.u0c : sc.u0f;
+    const float inv = (KIND == AFB_CHEB1_FWD) ? sc.inv_u0c : sc.inv_u0f;
+    const int total = lines * upl;
+    for (int b = threadIdx.x; b < total; b += MX_CT) {
+        const int l = (lines == 1) ? 0 : mx_div(b, upl, inv);
+        const int u = b - l * upl;
+        const MxLines L = mx_lines(p, pair0 + l);
+        cplx* d = dst + l * lstride;
+        cplx xa[R], xb[R];
+        if (KIND == AFB_CHEB1_FWD) {
+            const int j = u, jp = nr - 1 - u;
+            const bool self = jp == j;
+            constexpr int H = R / 2;
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                mx_chunk(L, j + r * nr, xa[r], xb[R - 1 - r]);
+                if (!self) mx_chunk(L, jp + r * nr, xb[r], xa[R - 1 - r]);
+                else xa[R - 1 - r] = xb[R - 1 - r];
+            }
+            if (R & 1) mx_chunk(L, j + H * nr, xa[H], xb[H]);   // odd R: the middle inputs of both partners share a chunk
+            mx_store_first<R>(d, j, xa);
+            if (!self) mx_store_first<R>(d, jp, xb);
+        } else {
+            const int nr2 = nr / 2;
+#pragma unroll
+            for (int r = 0; r < R; ++r) mx_chunk(L, u + r * nr2, xa[r], xb[r]);
+            mx_store_first<R>(d, 2 * u, xa);
+            mx_store_first<R>(d, 2 * u + 1, xb);
+        }
+    }
+}
+// post-processing of the pair A = W[k], B = W[n-k] (k == 0 or k == n/2: A == B)
+template <int KIND>
+__device__ __forceinline__ void mx_emit(const MxLines& L, const MixedRParams& p, int n, int k, cplx A, cplx B) {
+    const double dn = (double)n;
+    if (KIND == AFB_CHEB1_FWD) {
+        const int kk[2] = {k, (k == 0) ? 0 : n - k};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (t == 1 && (kk[1] == kk[0] || k == 0)) break;
+            const int o = kk[t];
+            const cplx Av = t ? B : A, Bc = t ? A : B;
+            const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));    // (A + conj B) / 2
+            const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));   // (A - conj B) / (2i)
+            const cplx w = ldg2(p.qtab + o);
+            const double s = (o == 0) ? 1.0 / dn : 2.0 / dn;
+            L.o0[o] = cmul(Ye, w).x * s;
+            if (L.has2) L.o1[o] = cmul(Yo, w).x * s;
+        }
+    } else {   // AFB_FOURIER_FWD: frequency kf = min(k, n-k)
+        const bool swap = (k != 0) && (2 * k > n);
+        const int kf = swap ? n - k : k;
+        const cplx Av = swap ? B : A, Bc = swap ? A : B;
+        const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));
+        const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));
+        if (kf == 0) {
+            L.o0[0] = Ye.x / dn;
+            if (L.has2) L.o1[0] = Yo.x / dn;
+        } else if (2 * kf == n) {
+            L.o0[n - 1] = -Ye.x / dn;
+            if (L.has2) L.o1[n - 1] = -Yo.x / dn;
+        } else {
+            L.o0[2 * kf - 1] = -Ye.y * (2.0 / dn);
+            L.o0[2 * kf] = Ye.x * (2.0 / dn);
+            if (L.has2) { L.o1[2 * kf - 1] = -Yo.y * (2.0 / dn); L.o1[2 * kf] = Yo.x * (2.0 / dn); }
+        }
+    }
+}
+template <int KIND, int R, int MX_CT>
+__device__ __forceinline__ void mx_last_fwd(const MixedSched& sc, const MixedRParams& p, int64_t pair0, int lines,
+                                            const cplx* __restrict__ src, int lstride) {
+    const int n = sc.n, ns = n / R;
+    const int upl = sc.ul;
+    const int total = lines * upl;
+    for (int b = threadIdx.x; b < total; b += MX_CT) {
+        const int l = (lines == 1) ? 0 : mx_div(b, upl, sc.inv_ul);
+        const int j = b - l * upl;
+        if (2 * j > ns) continue;                 // ns odd: upl = (ns + 1) / 2 covers j = 0 .. (ns - 1) / 2 exactly; guard only
+        const int jp = (j == 0) ? 0 : ns - j;
+        const bool self = jp == j;
+        const MxLines L = mx_lines(p, pair0 + l);
+        const cplx* s = src + l * lstride;
+        cplx xa[R], xb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xa[r] = s[j + r * ns];
+        if (j > 0) apply_powers<R>(xa, ldg2(p.tw + j));
+        MxDft<R>::run(xa);                        // xa[q] = Z[j + q ns]
+        if (!self) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) xb[r] = s[jp + r * ns];
+            apply_powers<R>(xb, ldg2(p.tw + jp));
+            MxDft<R>::run(xb);                    // xb[q] = Z[jp + q ns];  n - (j + q ns) = jp + (R-1-q) ns
+#pragma unroll
+            for (int q = 0; q < R; ++q) mx_emit<KIND>(L, p, n, j + q * ns, xa[q], xb[R - 1 - q]);
+        } else if (j == 0) {                      // Z[q ns] pairs with Z[(R - q) ns]
+            mx_emit<KIND>(L, p, n, 0, xa[0], xa[0]);
+#pragma unroll
+            for (int q = 1; 2 * q <= R; ++q) mx_emit<KIND>(L, p, n, q * ns, xa[q], xa[R - q]);
+        } else {                                  // j = ns / 2: Z[j + q ns] pairs with Z[j + (R-1-q) ns]
+#pragma unroll
+            for (int q = 0; 2 * q <= R - 1; ++q) mx_emit<KIND>(L, p, n, j + q * ns, xa[q], xa[R - 1 - q]);
+        }
+    }
+}
+template <int KIND, bool BIG, int MX_CT>
+// (two partner butterflies of radix 10 are 80 registers of data: 128 registers per thread, four 128-thread CTAs per SM)
+__global__ void __launch_bounds__(MX_CT, (BIG ? 1 : 2) * (256 / MX_CT)) mixed_fwd_kernel(const __grid_constant__ MixedRParams p) {
+    AFB_DYN_SMEM(cplx, smem);
+    const MixedSched& sc = p.sc;
+    const int lstride = sc.npad;
+    const int64_t npairs = (p.batch + 1) / 2;
+    const int64_t pair0 = (int64_t)blockIdx.x * sc.lpc;
+    const int lines = (int)((npairs - pair0 < sc.lpc) ? (npairs - pair0) : sc.lpc);
+    cplx* src = smem;
+    cplx* dst = smem + (size_t)sc.lpc * lstride;
+#define AFB_MX_FIRST(R_) case R_: mx_first_fwd<KIND, R_, MX_CT>(sc, p, pair0, lines, src, lstride); break
+    switch (sc.radix[0]) {
+        AFB_MX_FIRST(2); AFB_MX_FIRST(3); AFB_MX_FIRST(4); AFB_MX_FIRST(5); AFB_MX_FIRST(6); AFB_MX_FIRST(7); AFB_MX_FIRST(8);
+        AFB_MX_FIRST(10);
+        default: if (BIG) mx_first_fwd<KIND, 16, MX_CT>(sc, p, pair0, lines, src, lstride); break;
+    }
+#undef AFB_MX_FIRST
+    __syncthreads();
+    for (int ps = 1; ps + 1 < sc.npass; ++ps) {
+        switch (sc.radix[ps]) {
+            case 2: mx_pass<2, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 3: mx_pass<3, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 4: mx_pass<4, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 5: mx_pass<5, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 6: mx_pass<6, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 7: mx_pass<7, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 8: mx_pass<8, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            case 10: mx_pass<10, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+            default: if (BIG) mx_pass<16, MX_CT>(sc, ps, src, dst, lines, lstride, p.tw); break;
+        }
+        __syncthreads();
+        cplx* t = src; src = dst; dst = t;
+    }
+#define AFB_MX_LAST(R_) case R_: mx_last_fwd<KIND, R_, MX_CT>(sc, p, pair0, lines, src, lstride); break
+    switch (sc.radix[sc.npass - 1]) {
+        AFB_MX_LAST(2); AFB_MX_LAST(3); AFB_MX_LAST(4); AFB_MX_LAST(5); AFB_MX_LAST(6); AFB_MX_LAST(7); AFB_MX_LAST(8);
+        AFB_MX_LAST(10);
+        default: if (BIG) mx_last_fwd<KIND, 16, MX_CT>(sc, p, pair0, lines, src, lstride); break;
+    }
+#undef AFB_MX_LAST
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 bool mixed_radix_ok(int64_t n) {
     if (n < 6 || n > MX_MAX_N || is_pow2(n)) return false;
@@ -370,7 +563,16 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
     const int fit = (int)std::max<size_t>(1, budget / per_line);
     const int want = std::max(1, sc->ct / nr0);
     sc->lpc = std::max(1, std::min({16, fit, want}));
+    // register-resident first / last pass of the forward kinds: units = pairs of partner butterflies
+    const int nr_first = (int)(n / r[0]), ns_last = (int)(n / r.back());
+    sc->u0c = (nr_first + 1) / 2; sc->u0f = nr_first / 2; sc->ul = ns_last / 2 + 1;
+    sc->inv_u0c = 1.0f / (float)sc->u0c; sc->inv_u0f = 1.0f / (float)std::max(sc->u0f, 1); sc->inv_ul = 1.0f / (float)sc->ul;
     return true;
+}
+// AFB_MIXED_SMEM_PASSES=1 keeps every pass in shared memory (the round-2 first version; A/B runs and tests)
+static bool mixed_force_smem_passes() {
+    static const bool v = [] { const char* e = std::getenv("AFB_MIXED_SMEM_PASSES"); return e && e[0] == '1'; }();
+    return v;
 }
 static size_t mixed_smem(const MixedSched& sc) { return 2 * sizeof(cplx) * (size_t)sc.npad * (size_t)sc.lpc; }
 
@@ -396,6 +598,26 @@ int32_t launch_mixed_cfft(int64_t n, const cplx* tw, const cplx* in, cplx* out, 
 template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, void* stream) {
     const int64_t npairs = (p.batch + 1) / 2;
     const unsigned grid = (unsigned)((npairs + p.sc.lpc - 1) / p.sc.lpc);
+    // forward kinds: first pass from global memory, last pass in registers (needs 16-byte chunks that pair up: even n, even
+    // line stride, aligned base, >= 2 passes; Fourier additionally an even butterfly count in the first pass)
+    if constexpr (KIND == AFB_CHEB1_FWD || KIND == AFB_FOURIER_FWD) {
+        const int n = p.sc.n;
+        const bool ok = (n % 2 == 0) && (p.istride % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) && p.sc.npass >= 2 &&
+                        (KIND == AFB_CHEB1_FWD || (n / p.sc.radix[0]) % 2 == 0) && !mixed_force_smem_passes();
+        if (ok) {
+#define AFB_MX_LAUNCH(BIG_, CT_)                                               \
+    do {                                                                       \
+        auto k = mixed_fwd_kernel<KIND, BIG_, CT_>;                            \
+        AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
+        AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
+    } while (0)
+            if (p.sc.big) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
+            else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
+#undef AFB_MX_LAUNCH
+            AFB_KERNEL_CHECK();
+            return AFB_OK;
+        }
+    }
 #define AFB_MX_LAUNCH(BIG_, CT_)                                               \
     do {                                                                       \
         auto k = mixed_real_kernel<KIND, BIG_, CT_>;                           \
