@@ -24,7 +24,7 @@ constexpr int64_t MX_MAX_N = 6912;   // two buffers of 16 B * n: 216 KB at n = 6
 
 struct MixedSched {
     int n, npass, lpc, npad, ct, big;   // ct = threads per CTA (128 or 256); big = some pass has radix 16
-    int u0c, u0f, ul;                    // units per line pair: first pass (Chebyshev / Fourier pairing), last pass
+    int u0c, u0f, ul, lpc_f;             // units per line pair: first pass (Chebyshev / Fourier pairing), last pass; lines per CTA of the forward kernel
     float inv_u0c, inv_u0f, inv_ul;
     int radix[MX_MAXPASS];
     int ns[MX_MAXPASS];          // product of the radices of the earlier passes
@@ -474,10 +474,10 @@ __global__ void __launch_bounds__(MX_CT, (BIG ? 1 : 2) * (256 / MX_CT)) mixed_fw
     const MixedSched& sc = p.sc;
     const int lstride = sc.npad;
     const int64_t npairs = (p.batch + 1) / 2;
-    const int64_t pair0 = (int64_t)blockIdx.x * sc.lpc;
-    const int lines = (int)((npairs - pair0 < sc.lpc) ? (npairs - pair0) : sc.lpc);
+    const int64_t pair0 = (int64_t)blockIdx.x * sc.lpc_f;
+    const int lines = (int)((npairs - pair0 < sc.lpc_f) ? (npairs - pair0) : sc.lpc_f);
     cplx* src = smem;
-    cplx* dst = smem + (size_t)sc.lpc * lstride;
+    cplx* dst = smem + (size_t)sc.lpc_f * lstride;
 #define AFB_MX_FIRST(R_) case R_: mx_first_fwd<KIND, R_, MX_CT>(sc, p, pair0, lines, src, lstride); break
     switch (sc.radix[0]) {
         AFB_MX_FIRST(2); AFB_MX_FIRST(3); AFB_MX_FIRST(4); AFB_MX_FIRST(5); AFB_MX_FIRST(6); AFB_MX_FIRST(7); AFB_MX_FIRST(8);
@@ -567,11 +567,18 @@ static bool mixed_schedule(int64_t n, MixedSched* sc) {
     const int nr_first = (int)(n / r[0]), ns_last = (int)(n / r.back());
     sc->u0c = (nr_first + 1) / 2; sc->u0f = nr_first / 2; sc->ul = ns_last / 2 + 1;
     sc->inv_u0c = 1.0f / (float)sc->u0c; sc->inv_u0f = 1.0f / (float)std::max(sc->u0f, 1); sc->inv_ul = 1.0f / (float)sc->ul;
+    // (packing more lines per CTA to fill the halved unit count of the paired passes was measured slower: two 96 KB CTAs per
+    //  SM instead of six 32 KB ones; n = 1000 Fourier forward 0.417 -> 0.358 of HBM)
+    sc->lpc_f = sc->lpc;
     return true;
 }
 // AFB_MIXED_SMEM_PASSES=1 keeps every pass in shared memory (the round-2 first version; A/B runs and tests)
 static bool mixed_force_smem_passes() {
     static const bool v = [] { const char* e = std::getenv("AFB_MIXED_SMEM_PASSES"); return e && e[0] == '1'; }();
+    return v;
+}
+static bool mixed_force_reg_passes() {
+    static const bool v = [] { const char* e = std::getenv("AFB_MIXED_REG_PASSES"); return e && e[0] == '1'; }();
     return v;
 }
 static size_t mixed_smem(const MixedSched& sc) { return 2 * sizeof(cplx) * (size_t)sc.npad * (size_t)sc.lpc; }
@@ -602,14 +609,25 @@ template <int KIND> static int32_t launch_mixed_real_k(const MixedRParams& p, vo
     // line stride, aligned base, >= 2 passes; Fourier additionally an even butterfly count in the first pass)
     if constexpr (KIND == AFB_CHEB1_FWD || KIND == AFB_FOURIER_FWD) {
         const int n = p.sc.n;
-        const bool ok = (n % 2 == 0) && (p.istride % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) && p.sc.npass >= 2 &&
-                        (KIND == AFB_CHEB1_FWD || (n / p.sc.radix[0]) % 2 == 0) && !mixed_force_smem_passes();
+        // Where it pays (measured on one box, fraction of the HBM roofline, shared-memory passes -> register passes):
+        //   Fourier forward  n = 100 0.29 -> 0.43, 360 0.41 -> 0.50, 3000 0.37 -> 0.42, 5000 0.27 -> 0.33, 6000 0.26 -> 0.32,
+        //                    but n = 1000 0.52 -> 0.42 and n = 1536 (radix 16: 230+ registers, one CTA per SM) 0.51 -> 0.28;
+        //   Chebyshev forward loses everywhere (n = 1000 0.53 -> 0.25): two partner butterflies per thread halve the units of
+        //   the first and last pass (50 on 128 threads) and cost 128 registers, so fewer, emptier CTAs hide less latency
+        //   (ncu: warps active 10 %, issue 23 %, l1tex 19 %) -- the traffic saved was not the limiter.
+        // AFB_MIXED_REG_PASSES=1 forces the register passes wherever the layout allows (tests, A/B runs).
+        const bool layout = (n % 2 == 0) && (p.istride % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) && p.sc.npass >= 2 &&
+                            (KIND == AFB_CHEB1_FWD || (n / p.sc.radix[0]) % 2 == 0);
+        const bool pays = KIND == AFB_FOURIER_FWD && !p.sc.big && (n <= 512 || n >= 2048);
+        const bool ok = layout && !mixed_force_smem_passes() && (pays || mixed_force_reg_passes());
         if (ok) {
+            const unsigned gridf = (unsigned)((npairs + p.sc.lpc_f - 1) / p.sc.lpc_f);
+            const size_t smemf = 2 * sizeof(cplx) * (size_t)p.sc.npad * (size_t)p.sc.lpc_f;
 #define AFB_MX_LAUNCH(BIG_, CT_)                                               \
     do {                                                                       \
         auto k = mixed_fwd_kernel<KIND, BIG_, CT_>;                            \
         AFB_SMEM_OPTIN(k, 220 * 1024);                                         \
-        AFB_LAUNCH(k, grid, CT_, mixed_smem(p.sc), stream, p);                 \
+        AFB_LAUNCH(k, gridf, CT_, smemf, stream, p);                           \
     } while (0)
             if (p.sc.big) { if (p.sc.ct == 128) AFB_MX_LAUNCH(true, 128); else AFB_MX_LAUNCH(true, 256); }
             else { if (p.sc.ct == 128) AFB_MX_LAUNCH(false, 128); else AFB_MX_LAUNCH(false, 256); }
