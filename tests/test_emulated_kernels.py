@@ -403,3 +403,30 @@ def test_device_resident_fun_layer_on_the_emulator():
     finally:
         api._ll = keep
         dv._plans.clear()
+
+
+def test_mixed_radix_register_passes_match_shared_memory_passes():
+    # forward kinds: first pass from global memory / last pass in registers (AFB_MIXED_REG_PASSES=1) against the all-shared-
+    # memory passes (AFB_MIXED_SMEM_PASSES=1), in fresh processes because the switches are read once: same bits
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from tests.emu_harness import emu_lowlevel\n"
+        "B, ll = emu_lowlevel()\n"
+        "rng = np.random.default_rng(5)\n"
+        "out = []\n"
+        "for n in (36, 48, 96, 100, 360, 1000, 1536, 3000):\n"
+        "    v = rng.standard_normal((n, 5))\n"
+        "    out += [ll.transform(B.CHEB1_FWD, v).ravel(), ll.transform(B.FOURIER_FWD, v).ravel()]\n"
+        "np.save(__import__('sys').argv[1], np.concatenate(out))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for key in ("AFB_MIXED_REG_PASSES", "AFB_MIXED_SMEM_PASSES"):
+        path = f"/tmp/afb_mixed_{key}.npy"
+        env = dict(os.environ, **{key: "1"})
+        env.pop("AFB_MIXED_SMEM_PASSES" if key == "AFB_MIXED_REG_PASSES" else "AFB_MIXED_REG_PASSES", None)
+        subprocess.check_call([sys.executable, "-c", code, path], env=env, cwd=root)
+        res.append(np.load(path))
+    assert np.array_equal(res[0], res[1])
