@@ -1206,6 +1206,39 @@ static bool fan_points(int64_t P, int64_t work_per_point, std::vector<int>* devs
     return devs->size() > 1 && P >= ((int64_t)1 << 20) && (double)P * (double)std::max<int64_t>(work_per_point, 1) >= 1e9;
 }
 
+// Large point sets through host pointers: chunks of 2^22 points ping-pong over the streams of a leased pipe -- H2D of chunk
+// c+1 and D2H of chunk c-1 run under the kernel of chunk c, and the device never holds more than three chunks (a 10^9-point
+// call would otherwise need 16 GB of device memory and serialise 16 GB of copies around 1.3 s of arithmetic).
+// launch(d_in, d_out, np, stream) evaluates np points.
+static constexpr int64_t POINT_CHUNK = (int64_t)1 << 22;
+template <class Launch>
+static int32_t host_points_pipeline(const double* in, double* out, int64_t P, Launch launch) {
+    const int nbuf = (int)std::min<int64_t>(HostPipe::NPIPE, (P + POINT_CHUNK - 1) / POINT_CHUNK);
+    const size_t chunk_bytes = sizeof(double) * (size_t)std::min(P, POINT_CHUNK);
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(nbuf, 2 * chunk_bytes));   // input half, output half
+    int32_t st = AFB_OK;
+    int64_t c = 0;
+    for (int64_t p0 = 0; p0 < P && st == AFB_OK; p0 += POINT_CHUNK, ++c) {
+        const int si = (int)(c % nbuf);
+        const int64_t np = std::min(POINT_CHUNK, P - p0);
+        cudaStream_t s = pipe->stream[si];
+        double* din = reinterpret_cast<double*>(pipe->buf[si]);
+        double* dout = reinterpret_cast<double*>((char*)pipe->buf[si] + chunk_bytes);
+        cudaError_t e = cudaMemcpyAsync(din, in + p0, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { st = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
+        st = launch(din, dout, np, (void*)s);
+        if (st != AFB_OK) break;
+        e = cudaMemcpyAsync(out + p0, dout, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < nbuf; ++i) {
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
+        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    return st;
+}
+
 extern "C" {
 
 int32_t afb_chebpoints(double* out, int64_t n, double a, double b) {
@@ -1264,8 +1297,14 @@ int32_t afb_clenshaw_cheb(const double* c, int64_t N, const double* x, double* y
     if (fan_points(P, N, &devs))
         return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return afb_clenshaw_cheb(c, N, x + lo, y + lo, hi - lo); });
     DevBuf dc, dx, dy;
-    AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
-    AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(dx.put(x, 8 * (size_t)P));
+    AFB_TRY(dc.alloc(8 * (size_t)N));
+    AFB_TRY(dc.put(c, 8 * (size_t)N));
+    if (P > POINT_CHUNK)
+        return host_points_pipeline(x, y, P, [&](const double* din, double* dout, int64_t np, void* s) {
+            return launch_clenshaw_vec(dc.as<double>(), N, din, dout, np, s);
+        });
+    AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dx.put(x, 8 * (size_t)P));
     AFB_TRY(launch_clenshaw_vec(dc.as<double>(), N, dx.as<double>(), dy.as<double>(), P, nullptr));
     return dy.get(y, 8 * (size_t)P);
 }
@@ -1289,9 +1328,14 @@ int32_t afb_clenshaw_rec(const double* c, int64_t N, const double* A, const doub
         return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return afb_clenshaw_rec(c, N, A, B, C, x + lo, y + lo, hi - lo); });
     DevBuf dc, dA, dB, dC, dx, dy;
     AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(dA.alloc(8 * (size_t)N)); AFB_TRY(dB.alloc(8 * (size_t)N));
-    AFB_TRY(dC.alloc(8 * (size_t)(N + 1))); AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
+    AFB_TRY(dC.alloc(8 * (size_t)(N + 1)));
     AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(dA.put(A, 8 * (size_t)N)); AFB_TRY(dB.put(B, 8 * (size_t)N));
     if (N) AFB_TRY(dC.put(C, 8 * (size_t)(N + 1)));
+    if (P > POINT_CHUNK)
+        return host_points_pipeline(x, y, P, [&](const double* din, double* dout, int64_t np, void* s) {
+            return launch_clenshaw_rec(dc.as<double>(), N, dA.as<double>(), dB.as<double>(), dC.as<double>(), din, dout, np, s);
+        });
+    AFB_TRY(dx.alloc(8 * (size_t)P)); AFB_TRY(dy.alloc(8 * (size_t)P));
     AFB_TRY(dx.put(x, 8 * (size_t)P));
     AFB_TRY(launch_clenshaw_rec(dc.as<double>(), N, dA.as<double>(), dB.as<double>(), dC.as<double>(), dx.as<double>(),
                                 dy.as<double>(), P, nullptr));
@@ -1379,8 +1423,14 @@ static int32_t bisect_host(const double* c, int64_t N, const double* u, double* 
     if (fan_points(P, (int64_t)numits * N, &devs))
         return fanout(devs, P, [&](int, int64_t lo, int64_t hi) { return bisect_host(c, N, u + lo, out + lo, hi - lo, numits, a, b); });
     DevBuf dc, du, dout;
-    AFB_TRY(dc.alloc(8 * (size_t)N)); AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
-    AFB_TRY(dc.put(c, 8 * (size_t)N)); AFB_TRY(du.put(u, 8 * (size_t)P));
+    AFB_TRY(dc.alloc(8 * (size_t)N));
+    AFB_TRY(dc.put(c, 8 * (size_t)N));
+    if (P > POINT_CHUNK)
+        return host_points_pipeline(u, out, P, [&](const double* din, double* dres, int64_t np, void* s) {
+            return launch_bisect_vec(dc.as<double>(), N, din, false, 0, 0, dres, np, numits, a, b, s);
+        });
+    AFB_TRY(du.alloc(8 * (size_t)P)); AFB_TRY(dout.alloc(8 * (size_t)P));
+    AFB_TRY(du.put(u, 8 * (size_t)P));
     AFB_TRY(launch_bisect_vec(dc.as<double>(), N, du.as<double>(), false, 0, 0, dout.as<double>(), P, numits, a, b, nullptr));
     return dout.get(out, 8 * (size_t)P);
 }

@@ -828,3 +828,25 @@ def test_dgemm_dmma_variant(af, N, R, P):
     tol = 1e-13 * R * float(CB.abs().max()) * float(fA.abs().max())
     assert np.max(np.abs(a0.cpu().numpy() - want)) <= tol
     assert np.max(np.abs(a1.cpu().numpy() - want)) <= tol
+
+
+def test_host_point_sets_pipelined(af):
+    # more than 2^22 points through the host-pointer calls: chunks pipelined over three streams (H2D | kernel | D2H);
+    # results equal those of small calls, and the oracle on a subsample
+    ll = af.api.lowlevel()
+    P = 3 * (1 << 22) + 17
+    rng = np.random.default_rng(77)
+    c = rng.standard_normal(50) / (1 + np.arange(50))
+    x = rng.uniform(-1, 1, P)
+    y = ll.clenshaw(c, x)
+    idx = np.concatenate([np.arange(0, 3000), np.arange((1 << 22) - 1500, (1 << 22) + 1500), np.arange(P - 3000, P)])
+    assert np.array_equal(y[idx], orcc.clenshaw(c, x[idx]))
+    assert np.array_equal(y[5_000_000:5_010_000], ll.clenshaw(c, x[5_000_000:5_010_000]))
+    f = af.Fun(lambda t: np.exp(-t * t), af.Chebyshev(-5, 5))
+    cdf = af.normalizedcumsum(f).coefficients
+    u = rng.random(P)
+    s = ll.samplecdf(cdf, -5.0, 5.0, u)
+    assert np.array_equal(s[idx], orc.fromcanonical(-5.0, 5.0, orcc.cheb_bisect(cdf, u[idx], threads=8)))
+    A, Bv, Cv = af.Legendre().rec(50)
+    yr = ll.clenshaw_rec(c, A, Bv, Cv, x)
+    assert np.array_equal(yr[idx], orcc.clenshaw_rec(c, A, Bv, Cv, x[idx]))
