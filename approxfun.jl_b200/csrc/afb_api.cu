@@ -851,14 +851,14 @@ int32_t afb_last_error(char* buf, size_t len) {
 }
 
 int32_t afb_init(const int32_t* devices, int32_t ndev) {
+    if (ndev < 0 || (ndev > 0 && !devices)) return fail(AFB_BAD_ARG, "afb_init: bad device list");
+    if (ndev > MAX_DEVICES) return fail(AFB_UNSUPPORTED, "afb_init: at most 16 devices");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return fail(AFB_NO_DEVICE, "no CUDA device visible: libapproxfun_b200 has no CPU fallback");
     }
-    if (ndev < 0 || (ndev > 0 && !devices)) return fail(AFB_BAD_ARG, "afb_init: bad device list");
-    if (ndev > MAX_DEVICES) return fail(AFB_UNSUPPORTED, "afb_init: at most 16 devices");
     std::vector<int> list;
     for (int32_t i = 0; i < ndev; ++i) {
         if (devices[i] < 0 || devices[i] >= n || devices[i] >= MAX_DEVICES) return fail(AFB_BAD_ARG, "afb_init: device index out of range");

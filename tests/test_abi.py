@@ -55,6 +55,40 @@ def test_no_cpu_fallback_without_device(built):
         built.clenshaw(built.Chebyshev(), np.ones(3), 0.5)
 
 
+def test_round2_entry_points_fail_loudly_without_device(built):
+    # the multi-device init, device buffers, piecewise bisection, mixed tensor plans and the DMMA variant: no GPU => AFB_NO_DEVICE
+    # (or an argument error that is raised before the device is touched), never a CPU result
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = built._lib
+    lib = L.load()
+    ND = L.AFB_NO_DEVICE
+    devs = (ctypes.c_int32 * 2)(0, 1)
+    assert lib.afb_init(devs, 2) == ND and lib.afb_init(None, 0) == ND
+    h = ctypes.c_void_p()
+    assert lib.afb_buf_create(ctypes.byref(h), 16) == ND and not h.value
+    for kind in (L.FOURIER_CHEB1_2D_FWD, L.LAURENT_CHEB1_2D_INV):
+        assert lib.afb_plan_create(ctypes.byref(h), kind, 8, 8, 1, 8, 0) == ND
+    assert lib.afb_plan_create(ctypes.byref(h), L.CHEB1_FWD, 1000, 0, 4, 1000, 0) == ND          # mixed-radix length
+    c = np.ones(4); offs = np.array([0, 4], dtype=np.int64); brk = np.array([-1.0, 1.0]); u = np.full(3, 0.5); out = np.empty(3)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    assert lib.afb_piecewise_bisect(p(c), p(offs), p(brk), 1, p(u), p(out), 3, 47) == ND
+    assert lib.afb_piecewise_clenshaw(p(c), p(offs), p(brk), 1, p(u), p(out), 3) == ND
+    assert lib.afb_clenshaw_fourier_cheb2d(p(c), 2, 2, p(u), p(u), p(out), 3) == ND
+    assert lib.afb_dgemm_nn_dmma_device(p(c), p(c), p(out), 1, 1, 1, None) == ND
+    # argument errors come first
+    assert lib.afb_init(None, 2) == L.AFB_BAD_ARG
+    assert lib.afb_piecewise_bisect(p(c), p(offs), p(np.array([1.0, -1.0])), 1, p(u), p(out), 3, 47) == L.AFB_BAD_SIZE
+    assert lib.afb_buf_create(ctypes.byref(h), -1) == L.AFB_BAD_SIZE
+    assert lib.afb_sharded2d_set_chunks(None, 2) == L.AFB_BAD_ARG and lib.afb_sharded2d_set_tuning(None, 0, 8, 0) == L.AFB_BAD_ARG
+    with pytest.raises(built.AfbError):
+        built.device.DeviceArray(8)
+    with pytest.raises(built.AfbError):
+        built.api.use_devices([0])
+
+
 def test_argument_validation_needs_no_device(built):
     lib = built._lib.load()
     h = ctypes.c_void_p()
