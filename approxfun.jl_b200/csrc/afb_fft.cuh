@@ -45,7 +45,14 @@ AFB_FFTCFG(256, 16, 4, 4, 1);
 AFB_FFTCFG(512, 16, 8, 4, 1);
 AFB_FFTCFG(1024, 16, 8, 8, 1);
 AFB_FFTCFG(2048, 16, 16, 8, 1);
+#ifndef AFB_R32_4096
+#define AFB_R32_4096 0
+#endif
+#if AFB_R32_4096
+AFB_FFTCFG(4096, 32, 16, 8, 1);   // measurement variant: radix-32 first pass, 128 threads, three passes
+#else
 AFB_FFTCFG(4096, 16, 8, 4, 8);
+#endif
 // N = 8192 (real lines of 16384): ONE CTA owns an SM.  A radix-32 first pass (32 complex values per thread, 256 threads, three
 // passes: 2 writes + 2 reads of the 128 KB exchange buffer instead of 3 + 3) was measured in round 2 (AFB_R32=1): of the HBM
 // roofline at 16384 x 16384, 16.16.16.2 -> 32.16.16:  Chebyshev forward 0.634 -> 0.599, inverse 0.574 -> 0.643, Fourier
@@ -69,7 +76,11 @@ template <int N> struct FftCfgC : FftCfg<N> {};
 template <> struct FftCfgC<256> : FftRadices<256, 16, 16, 1, 1> {};
 template <> struct FftCfgC<512> : FftRadices<512, 16, 16, 2, 1> {};
 template <> struct FftCfgC<1024> : FftRadices<1024, 16, 16, 4, 1> {};
+#if AFB_R32_4096
+template <> struct FftCfgC<4096> : FftRadices<4096, 32, 16, 8, 1> {};
+#else
 template <> struct FftCfgC<4096> : FftRadices<4096, 16, 16, 8, 2> {};
+#endif
 // (4096 as 16.16.16 was measured slower than 16.16.8.2 for Laurent: 0.877 vs 0.847 ms at 32768 x 4096)
 
 // Slots per line in shared memory.  Short lines are packed many per CTA and two of them share a quarter-warp: a stride

@@ -91,7 +91,7 @@ template <int M> struct BlueGeom {
     static constexpr size_t SMEM = sizeof(cplx) * (size_t)LPC * FftLine<M>::STRIDE;
 };
 template <int M>
-__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : 512 / BlueGeom<M>::CT) blue_fused_kernel(const __grid_constant__ BlueParams p) {
+__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 && AFB_R32_4096 ? 2 : 512 / BlueGeom<M>::CT)) blue_fused_kernel(const __grid_constant__ BlueParams p) {
     typedef FftCfg<M> C;
     typedef BlueGeom<M> G;
     AFB_DYN_SMEM(cplx, smem);
@@ -446,7 +446,7 @@ struct BlueRealParams {
     double scale;  // 1/M
 };
 template <int M, int KIND>
-__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : 512 / BlueGeom<M>::CT) blue_real_kernel(const __grid_constant__ BlueRealParams p) {
+__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 && AFB_R32_4096 ? 2 : 512 / BlueGeom<M>::CT)) blue_real_kernel(const __grid_constant__ BlueRealParams p) {
     typedef FftCfg<M> C;
     typedef BlueGeom<M> G;
     constexpr bool INV = (KIND & 1) != 0;
@@ -630,7 +630,7 @@ struct ExtParams {
     double scale;  // 1/M (Bluestein)
 };
 template <int M, int KIND, bool BLUE>
-__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : 512 / BlueGeom<M>::CT) ext_fused_kernel(const __grid_constant__ ExtParams p) {
+__global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 && AFB_R32_4096 ? 2 : 512 / BlueGeom<M>::CT)) ext_fused_kernel(const __grid_constant__ ExtParams p) {
     typedef FftCfg<M> C;
     typedef BlueGeom<M> G;
     AFB_DYN_SMEM(cplx, smem);

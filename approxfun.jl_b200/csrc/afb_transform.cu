@@ -588,7 +588,7 @@ template <int N> struct LineOp<N, LK_CFFT> {
 // (Forcing 5 CTAs per SM on the forward kinds too -- 96 instead of 113 registers -- was measured slower: 0.887 vs
 // 0.905 of HBM at n = 4096, 0.70 vs 0.81 at n = 256.)
 template <int N, int KIND>
-__global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (KIND == LK_CHEB_INV || KIND == LK_FOURIER_INV)) ? 5 : (N == 8192 ? 1 : 512 / LineGeom<N>::CT))) line_kernel(const __grid_constant__ LineParams p) {
+__global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (KIND == LK_CHEB_INV || KIND == LK_FOURIER_INV)) ? (N == 4096 && AFB_R32_4096 ? 2 : 5) : (N == 8192 ? 1 : (N == 4096 && AFB_R32_4096 ? 2 : 512 / LineGeom<N>::CT)))) line_kernel(const __grid_constant__ LineParams p) {
     typedef LineGeom<N> G;
     AFB_DYN_SMEM(cplx, smem);
     const int tid = threadIdx.x;
