@@ -273,6 +273,37 @@ __global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_re
             }
             continue;
         }
+        if (INV) {
+            // inverse kinds: elements j and n-j are built from the SAME coefficients (c_j, c_{n-j} / a_j, b_j), so one thread
+            // makes both and every coefficient is loaded once (same arithmetic per element as mx_pre: same bits)
+            for (int j = threadIdx.x; 2 * j <= n; j += MX_CT) {
+                cplx za0, zb0, za1, zb1;   // line 0 / line 1, elements j (a) and n - j (b)
+                const bool twin = j > 0 && 2 * j < n;
+                if (KIND == AFB_CHEB1_INV) {
+                    if (j == 0) { za0 = make_double2(l0[0], 0.0); za1 = make_double2(l1[0], 0.0); }
+                    else {
+                        const cplx wj = ldg2(p.qtab + j), wn = ldg2(p.qtab + (n - j));
+                        const double c0j = l0[j], c0n = l0[n - j], c1j = l1[j], c1n = l1[n - j];
+                        za0 = cmul(make_double2(0.5 * c0j, -0.5 * c0n), make_double2(wj.x, -wj.y));
+                        za1 = cmul(make_double2(0.5 * c1j, -0.5 * c1n), make_double2(wj.x, -wj.y));
+                        zb0 = cmul(make_double2(0.5 * c0n, -0.5 * c0j), make_double2(wn.x, -wn.y));
+                        zb1 = cmul(make_double2(0.5 * c1n, -0.5 * c1j), make_double2(wn.x, -wn.y));
+                    }
+                } else {   // AFB_FOURIER_INV
+                    if (j == 0) { za0 = make_double2(l0[0], 0.0); za1 = make_double2(l1[0], 0.0); }
+                    else if (2 * j == n) { za0 = make_double2(-l0[n - 1], 0.0); za1 = make_double2(-l1[n - 1], 0.0); }
+                    else {
+                        const double a0 = l0[2 * j], b0 = l0[2 * j - 1], a1 = l1[2 * j], b1 = l1[2 * j - 1];
+                        za0 = make_double2(0.5 * a0, -0.5 * b0); zb0 = make_double2(0.5 * a0, 0.5 * b0);
+                        za1 = make_double2(0.5 * a1, -0.5 * b1); zb1 = make_double2(0.5 * a1, 0.5 * b1);
+                    }
+                }
+                if (!has2) { za1 = make_double2(0.0, 0.0); zb1 = make_double2(0.0, 0.0); }
+                Al[mx_pad(j)] = make_double2(za0.x - za1.y, -(za0.y + za1.x));            // conj(z0 + i z1)
+                if (twin) Al[mx_pad(n - j)] = make_double2(zb0.x - zb1.y, -(zb0.y + zb1.x));
+            }
+            continue;
+        }
         for (int j = threadIdx.x; j < n; j += MX_CT) {
             const cplx z1 = mx_pre<KIND>(l0, n, nh, j, p.qtab);
             cplx z2 = mx_pre<KIND>(l1, n, nh, j, p.qtab);
