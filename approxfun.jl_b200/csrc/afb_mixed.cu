@@ -236,6 +236,66 @@ __device__ __forceinline__ cplx mx_pre(const double* __restrict__ v, int n, int 
     }
     return z;
 }
+struct MxLines {   // the two real lines of a pair
+    const double2 *c0, *c1;
+    double *o0, *o1;
+    bool has2;
+};
+__device__ __forceinline__ MxLines mx_lines(const MixedRParams& p, int64_t q) {
+    MxLines L;
+    L.has2 = 2 * q + 1 < p.batch;
+    const double* l0 = p.in + (2 * q) * p.istride;
+    L.c0 = reinterpret_cast<const double2*>(l0);
+    L.c1 = reinterpret_cast<const double2*>(L.has2 ? l0 + p.istride : l0);
+    L.o0 = p.out + (2 * q) * p.ostride;
+    L.o1 = L.o0 + p.ostride;
+    return L;
+}
+// chunk c of both lines -> the complex values (even elements) and (odd elements)
+__device__ __forceinline__ void mx_chunk(const MxLines& L, int c, cplx& ev, cplx& od) {
+    const double2 a = L.c0[c];
+    double2 b = L.c1[c];
+    if (!L.has2) b = make_double2(0.0, 0.0);
+    ev = make_double2(a.x, b.x);
+    od = make_double2(a.y, b.y);
+}
+// post-processing of the pair A = W[k], B = W[n-k] (k == 0 or k == n/2: A == B)
+template <int KIND>
+__device__ __forceinline__ void mx_emit(const MxLines& L, const MixedRParams& p, int n, int k, cplx A, cplx B) {
+    const double dn = (double)n;
+    if (KIND == AFB_CHEB1_FWD) {
+        const int kk[2] = {k, (k == 0) ? 0 : n - k};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (t == 1 && (kk[1] == kk[0] || k == 0)) break;
+            const int o = kk[t];
+            const cplx Av = t ? B : A, Bc = t ? A : B;
+            const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));    // (A + conj B) / 2
+            const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));   // (A - conj B) / (2i)
+            const cplx w = ldg2(p.qtab + o);
+            const double s = (o == 0) ? 1.0 / dn : 2.0 / dn;
+            L.o0[o] = cmul(Ye, w).x * s;
+            if (L.has2) L.o1[o] = cmul(Yo, w).x * s;
+        }
+    } else {   // AFB_FOURIER_FWD: frequency kf = min(k, n-k)
+        const bool swap = (k != 0) && (2 * k > n);
+        const int kf = swap ? n - k : k;
+        const cplx Av = swap ? B : A, Bc = swap ? A : B;
+        const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));
+        const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));
+        if (kf == 0) {
+            L.o0[0] = Ye.x / dn;
+            if (L.has2) L.o1[0] = Yo.x / dn;
+        } else if (2 * kf == n) {
+            L.o0[n - 1] = -Ye.x / dn;
+            if (L.has2) L.o1[n - 1] = -Yo.x / dn;
+        } else {
+            L.o0[2 * kf - 1] = -Ye.y * (2.0 / dn);
+            L.o0[2 * kf] = Ye.x * (2.0 / dn);
+            if (L.has2) { L.o1[2 * kf - 1] = -Yo.y * (2.0 / dn); L.o1[2 * kf] = Yo.x * (2.0 / dn); }
+        }
+    }
+}
 template <int KIND, bool BIG, int MX_CT>
 __global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_real_kernel(const __grid_constant__ MixedRParams p) {
     constexpr bool INV = (KIND & 1) != 0;
@@ -315,38 +375,20 @@ __global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_re
     }
     __syncthreads();
     const cplx* R = mx_fft<BIG, MX_CT>(sc, A, B, lines, lstride, p.tw);
-    const double dn = (double)n;
     for (int l = 0; l < lines; ++l) {
         const int64_t q = pair0 + l;
-        const bool has2 = 2 * q + 1 < p.batch;
         const cplx* W = R + l * lstride;
-        double* o0 = p.out + (2 * q) * p.ostride;
-        double* o1 = o0 + p.ostride;
+        const MxLines L = mx_lines(p, q);
+        if (!INV) {
+            // forward kinds: the pair W[k], W[n-k] gives the outputs k and n-k (Chebyshev) / the sine and cosine slots of
+            // frequency k (Fourier) of both lines: one thread reads each element of the spectrum once
+            for (int k = threadIdx.x; 2 * k <= n; k += MX_CT) mx_emit<KIND>(L, p, n, k, W[mx_pad(k)], W[mx_pad(k == 0 ? 0 : n - k)]);
+            continue;
+        }
         for (int o = threadIdx.x; o < n; o += MX_CT) {
-            double ve, vo;
-            if (KIND == AFB_CHEB1_INV) {
-                const cplx z = W[mx_pad((o & 1) ? n - 1 - (o - 1) / 2 : o / 2)];
-                ve = z.x; vo = -z.y;
-            } else if (KIND == AFB_FOURIER_INV) {
-                const cplx z = W[mx_pad(o)];
-                ve = z.x; vo = -z.y;
-            } else {
-                const bool nyq = (KIND == AFB_FOURIER_FWD) && (n % 2 == 0) && o == n - 1;
-                const int k = (KIND == AFB_CHEB1_FWD) ? o : (o == 0 ? 0 : nyq ? n / 2 : (o & 1) ? (o + 1) / 2 : o / 2);
-                const cplx Av = W[mx_pad(k)], Bc = W[mx_pad(k == 0 ? 0 : n - k)];
-                const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));    // (A + conj B) / 2
-                const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));   // (A - conj B) / (2i)
-                if (KIND == AFB_CHEB1_FWD) {
-                    const cplx w = ldg2(p.qtab + o);
-                    const double s = (o == 0) ? 1.0 / dn : 2.0 / dn;
-                    ve = cmul(Ye, w).x * s; vo = cmul(Yo, w).x * s;
-                } else if (o == 0) { ve = Ye.x / dn; vo = Yo.x / dn; }
-                else if (nyq) { ve = -Ye.x / dn; vo = -Yo.x / dn; }
-                else if (o & 1) { ve = -Ye.y * (2.0 / dn); vo = -Yo.y * (2.0 / dn); }
-                else { ve = Ye.x * (2.0 / dn); vo = Yo.x * (2.0 / dn); }
-            }
-            o0[o] = ve;
-            if (has2) o1[o] = vo;
+            const cplx z = W[mx_pad(KIND == AFB_CHEB1_INV ? ((o & 1) ? n - 1 - (o - 1) / 2 : o / 2) : o)];
+            L.o0[o] = z.x;
+            if (L.has2) L.o1[o] = -z.y;
         }
     }
 }
@@ -362,29 +404,6 @@ __global__ void __launch_bounds__(MX_CT, (BIG ? 2 : 3) * (256 / MX_CT)) mixed_re
 //               split and the kind's post-processing need, so both run in registers and go straight to global memory.
 // Same arithmetic per output as mixed_real_kernel (bit-identical results).
 // =====================================================================================================================
-struct MxLines {   // the two real lines of a pair
-    const double2 *c0, *c1;
-    double *o0, *o1;
-    bool has2;
-};
-__device__ __forceinline__ MxLines mx_lines(const MixedRParams& p, int64_t q) {
-    MxLines L;
-    L.has2 = 2 * q + 1 < p.batch;
-    const double* l0 = p.in + (2 * q) * p.istride;
-    L.c0 = reinterpret_cast<const double2*>(l0);
-    L.c1 = reinterpret_cast<const double2*>(L.has2 ? l0 + p.istride : l0);
-    L.o0 = p.out + (2 * q) * p.ostride;
-    L.o1 = L.o0 + p.ostride;
-    return L;
-}
-// chunk c of both lines -> the complex values (even elements) and (odd elements)
-__device__ __forceinline__ void mx_chunk(const MxLines& L, int c, cplx& ev, cplx& od) {
-    const double2 a = L.c0[c];
-    double2 b = L.c1[c];
-    if (!L.has2) b = make_double2(0.0, 0.0);
-    ev = make_double2(a.x, b.x);
-    od = make_double2(a.y, b.y);
-}
 template <int R> __device__ __forceinline__ void mx_store_first(cplx* __restrict__ d, int j, cplx* x) {
     MxDft<R>::run(x);
 #pragma unroll
@@ -422,43 +441,6 @@ __device__ __forceinline__ void mx_first_fwd(const MixedSched& sc, const MixedRP
             for (int r = 0; r < R; ++r) mx_chunk(L, u + r * nr2, xa[r], xb[r]);
             mx_store_first<R>(d, 2 * u, xa);
             mx_store_first<R>(d, 2 * u + 1, xb);
-        }
-    }
-}
-// post-processing of the pair A = W[k], B = W[n-k] (k == 0 or k == n/2: A == B)
-template <int KIND>
-__device__ __forceinline__ void mx_emit(const MxLines& L, const MixedRParams& p, int n, int k, cplx A, cplx B) {
-    const double dn = (double)n;
-    if (KIND == AFB_CHEB1_FWD) {
-        const int kk[2] = {k, (k == 0) ? 0 : n - k};
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            if (t == 1 && (kk[1] == kk[0] || k == 0)) break;
-            const int o = kk[t];
-            const cplx Av = t ? B : A, Bc = t ? A : B;
-            const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));    // (A + conj B) / 2
-            const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));   // (A - conj B) / (2i)
-            const cplx w = ldg2(p.qtab + o);
-            const double s = (o == 0) ? 1.0 / dn : 2.0 / dn;
-            L.o0[o] = cmul(Ye, w).x * s;
-            if (L.has2) L.o1[o] = cmul(Yo, w).x * s;
-        }
-    } else {   // AFB_FOURIER_FWD: frequency kf = min(k, n-k)
-        const bool swap = (k != 0) && (2 * k > n);
-        const int kf = swap ? n - k : k;
-        const cplx Av = swap ? B : A, Bc = swap ? A : B;
-        const cplx Ye = make_double2(0.5 * (Av.x + Bc.x), 0.5 * (Av.y - Bc.y));
-        const cplx Yo = make_double2(0.5 * (Av.y + Bc.y), -0.5 * (Av.x - Bc.x));
-        if (kf == 0) {
-            L.o0[0] = Ye.x / dn;
-            if (L.has2) L.o1[0] = Yo.x / dn;
-        } else if (2 * kf == n) {
-            L.o0[n - 1] = -Ye.x / dn;
-            if (L.has2) L.o1[n - 1] = -Yo.x / dn;
-        } else {
-            L.o0[2 * kf - 1] = -Ye.y * (2.0 / dn);
-            L.o0[2 * kf] = Ye.x * (2.0 / dn);
-            if (L.has2) { L.o1[2 * kf - 1] = -Yo.y * (2.0 / dn); L.o1[2 * kf] = Yo.x * (2.0 / dn); }
         }
     }
 }
