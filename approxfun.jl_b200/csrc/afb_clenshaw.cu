@@ -20,7 +20,10 @@
 namespace afb {
 
 constexpr int CL_THREADS = 512;        // threads per CTA
-constexpr int CL_R = 4;                // points per thread (independent recurrences) of the bisection / 2-D kernels
+#ifndef AFB_CL_R
+#define AFB_CL_R 4
+#endif
+constexpr int CL_R = AFB_CL_R;         // points per thread (independent recurrences) of the bisection / 2-D kernels
 // ... and of the evaluation kernel: more points share every broadcast coefficient load and its .reuse'd DADD operand
 // (measured N = 10^4, 2.7e8 points: 4 -> 21.9, 6 -> 23.35, 8 -> 22.9, 12 -> 21.9, 16 -> 22.2 TFLOP/s; 6 is the largest count
 //  without spills at 64 registers.  The bisection kernel got slower with 8: 21.3 -> 19.8, it stays at 4.)
