@@ -321,6 +321,7 @@ int32_t afb_sharded2d_destroy(void* handle);
 /* Optional peer-memory mode: replaces pack + NCCL send/recv + unpack by ONE kernel that transposes tiles straight
  * into the owning rank's buffer over NVLink (CUDA IPC mapped peer memory).  Each rank exports 64 bytes, the host layer
  * all-gathers them (world x 64 bytes) and passes the array to afb_sharded2d_ipc_open on every rank. */
+/* world <= 16 (the peer-pointer tables are fixed size; one node). */
 int32_t afb_sharded2d_ipc_export(void* handle, void* handle64);
 int32_t afb_sharded2d_ipc_open(void* handle, const void* handles, int32_t world);
 /* Peer-memory mode only: run the column pass in `chunks` (1..8) pieces and send each finished piece to the peers on a side
