@@ -1138,6 +1138,7 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
     if (p->path == PATH_TENSOR2D || p->path == PATH_PADUA) {
         if (p->path == PATH_TENSOR2D && devs.size() > 1 && mdev2d_supported(p->kind, p->n, p->n2, (int)devs.size(), p->flags)) {
             std::lock_guard<std::mutex> lk(p->mu);
+            if (p->mdev2d && !mdev2d_matches(p->mdev2d, devs)) { mdev2d_destroy(p->mdev2d); p->mdev2d = nullptr; }   // afb_init changed the set
             if (!p->mdev2d) AFB_TRY(mdev2d_create(&p->mdev2d, p->kind, p->n, p->n2, devs));
             return mdev2d_execute_host(p->mdev2d, reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out));
         }

@@ -110,6 +110,7 @@ bool mdev2d_supported(int32_t kind, int64_t n, int64_t n2, int ndev, uint32_t fl
 int32_t mdev2d_create(void** out, int32_t kind, int64_t n, int64_t n2, const std::vector<int>& devs);
 int32_t mdev2d_execute_host(void* handle, const double* in, double* out);
 void mdev2d_destroy(void* handle);
+bool mdev2d_matches(void* handle, const std::vector<int>& devs);
 // `batch` lines of a 1-D plan (batch <= the plan's batch), on the plan's device; used by the chunked column pass
 int32_t slab_col_chunk(afb_plan plan, const double* d_in, double* d_out, int64_t batch, void* stream);
 const std::vector<int>& device_list();

@@ -702,6 +702,11 @@ bool mdev2d_supported(int32_t kind, int64_t n, int64_t n2, int ndev, uint32_t fl
     return ndev > 1 && ndev <= MAX_DEVICES && n > 0 && n2 > 0 && n % ndev == 0 && n2 % ndev == 0 && n * n2 >= ((int64_t)1 << 21);
 }
 
+bool mdev2d_matches(void* handle, const std::vector<int>& devs) {
+    MultiDev2D* m = reinterpret_cast<MultiDev2D*>(handle);
+    return m && m->devs == devs;
+}
+
 void mdev2d_destroy(void* handle) {
     MultiDev2D* m = reinterpret_cast<MultiDev2D*>(handle);
     if (!m) return;
