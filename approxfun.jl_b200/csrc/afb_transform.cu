@@ -16,6 +16,8 @@
 // Post/pre twiddles: one table load per pair-slot (index pi); the q-dependence k = pi + NSL q is a
 // per-plan constant rotation passed in the kernel parameters (constant bank), so no per-element table traffic.
 // Global traffic is exactly one read and one write of every element (16 B per coefficient).
+#include <cstdlib>
+
 #include "afb_fft.cuh"
 #include "afb_internal.h"
 
@@ -688,6 +690,135 @@ __global__ void __launch_bounds__(FftCfg<N>::T, StageGeom<N>::MINB) line_kernel_
         }
     }
 }
+// -------------------------------------------------------------------------------------------------
+// N = 8192 lines on a 2-CTA thread-block cluster (round 2; measured against line_kernel_staged).
+// One line = 128 KB = half an SM's register file, so a single CTA per SM serialises its FP64 and shared-memory phases.
+// Here CTA c of a cluster (c = 0, 1; two SMs) owns the samples z[2m + c] of a line: 256 threads, a 64 KB exchange buffer,
+// three radix-16 passes of a 4096-point transform -- the first three passes of the 16.16.16.2 schedule never mix the two
+// parity classes -- so two CTAs of DIFFERENT lines are resident per SM and overlap each other's phases.  The last (radix-2)
+// pass pairs E[k] = FFT(even)[k] with O[k] = FFT(odd)[k]: it reads one operand from its own shared memory and the other
+// from the partner's through distributed shared memory, and runs the same paired post-processing as dit_last_paired.
+// Makhoul's permutation puts z[q] and z[N-1-q] (opposite parities) in one 32-byte sector, so each CTA uses half of every
+// sector of the line (8-byte loads; the partner fetches the other half from L2 at about the same time).
+// -------------------------------------------------------------------------------------------------
+#ifndef AFB_HOST_EMU
+}  // namespace afb
+#include <cooperative_groups.h>
+namespace afb {
+namespace cg = cooperative_groups;
+
+struct FftCfgHalf : FftRadices<4096, 16, 16, 16, 1> {};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// x[r] = z[2 (t + 256 r) + c]: r < 8 are the first half of z (even elements of a quad), r >= 8 the mirrored half
+__device__ __forceinline__ void cluster_load_line(const double* __restrict__ v, int t, int c, cplx* x) {
+    constexpr int N = 8192;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = 2 * (t + 256 * r) + c;
+        x[r] = make_double2(v[4 * i], v[4 * i + 2]);
+    }
+#pragma unroll
+    for (int r = 8; r < 16; ++r) {
+        const int q = N - 1 - (2 * (t + 256 * r) + c);
+        x[r] = make_double2(v[4 * q + 3], v[4 * q + 1]);
+    }
+}
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) line_cluster_kernel(const __grid_constant__ LineParams p) {
+    static_assert(KIND == LK_CHEB_FWD, "cluster lines: Chebyshev forward");
+    constexpr int N = 8192, NH = 4096, NSL = 4096;
+    typedef FftCfgHalf C;
+    AFB_DYN_SMEM(cplx, s);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int t = threadIdx.x;
+    const cplx* sE = cluster.map_shared_rank(s, 0);
+    const cplx* sO = cluster.map_shared_rank(s, 1);
+    const cplx* tw4 = p.twA;   // root table of 4096 (the sub-transforms); p.tw = root table of 8192 (the last pass)
+    const int64_t nclusters = gridDim.x / 2;
+    bool first = true;
+    for (int64_t line = blockIdx.x / 2; line < p.batch; line += nclusters) {
+        const double* v = reinterpret_cast<const double*>(p.in) + line * p.istride;
+        // ---- first pass from registers; the global loads are in flight while the partner finishes reading this CTA's
+        //      buffer (second half of the previous line's barrier pair)
+        cplx x[C::E];
+        cluster_load_line(v, t, c, x);
+        if (!first) cluster_wait();
+        first = false;
+        dit_first<NH, C>(s, t, x);
+        dit_middle<NH, C>(s, t, x, tw4);
+        pass_dit<NH, C::RL, C::NSL, C>(s, t, x, tw4);     // Y_c in natural order
+        cluster_arrive();                                  // this half is complete ...
+        // ... meanwhile: pull the next line towards L2 and fetch this thread's post-processing twiddles
+        if (line + nclusters < p.batch) {
+            const double* vn = reinterpret_cast<const double*>(p.in) + (line + nclusters) * p.istride;
+            if (t == 0) bulk_prefetch_l2(vn + 8192 * c, 65536u);   // each CTA asks for half of the 128 KB line
+        }
+        cplx tb[4][2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) load_tw<2>(p.aux, 1024 * c + t + 256 * g, tb[g]);
+        cluster_wait();                                    // ... and so is the partner's
+        // ---- last pass (radix 2 across the CTAs) + paired post-processing, pairs pi = 1024 c + t + 256 g
+        ChebFwdPost<N> f{reinterpret_cast<double*>(p.out) + line * p.ostride, p.oes, p.scale, true};
+        cplx lo[4][2], hi[4][2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                      // every shared / distributed-shared load first
+            const int pi = 1024 * c + t + 256 * g;
+            const int jh = (pi == 0) ? NSL / 2 : NSL - pi;
+            lo[g][0] = sE[swz<C::SH>(pi)]; lo[g][1] = sO[swz<C::SH>(pi)];
+            hi[g][0] = sE[swz<C::SH>(jh)]; hi[g][1] = sO[swz<C::SH>(jh)];
+        }
+        cluster_arrive();                                  // done reading the partner's buffer (waited for at the next line)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int pi = 1024 * c + t + 256 * g;
+            const int jh = (pi == 0) ? NSL / 2 : NSL - pi;
+            cplx tq[2];
+            bfly_dit<N, 2, NSL>(pi, lo[g], p.tw);
+            bfly_dit<N, 2, NSL>(jh, hi[g], p.tw);
+            if (pi != 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tq[j] = cmul(tb[g][j], p.K[j][0]);
+                f.pair(pi, lo[g][0], hi[g][1], tq);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tq[j] = cmul(cconj(tb[g][j]), p.K[j][1]);
+                f.pair(NSL - pi, hi[g][0], lo[g][1], tq);
+            } else {
+                f.dc(lo[g][0]);
+                load_tw<2>(p.aux, NSL / 2 + 1, tq);
+                f.mid(lo[g][1], tq);
+                cplx tm[2];
+                load_tw<2>(p.aux, NSL / 2, tm);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tq[j] = cmul(tm[j], p.K[j][0]);
+                f.pair(NSL / 2, hi[g][0], hi[g][1], tq);
+            }
+        }
+    }
+    if (!first) cluster_wait();                            // no CTA exits while its partner may still read its shared memory
+}
+template <int KIND> static int32_t launch_line_cluster(const LineParams& p0, void* stream) {
+    LineParams p = p0;
+    AFB_TRY(root_table(4096, &p.twA));
+    auto k = line_cluster_kernel<KIND>;
+    const size_t smem = sizeof(cplx) * 4096;
+    AFB_SMEM_OPTIN(k, smem);
+    const int64_t cap = (int64_t)sm_count();              // two CTAs per SM = one cluster per SM on average
+    const int64_t nclusters = p.batch < cap ? p.batch : cap;
+    AFB_LAUNCH(k, (unsigned)(2 * nclusters), 256, smem, stream, p);
+    AFB_KERNEL_CHECK();
+    return AFB_OK;
+}
+static bool line_cluster_enabled() {
+    static const bool v = [] { const char* e = std::getenv("AFB_LINE_CLUSTER"); return e && e[0] == '1'; }();
+    return v;
+}
+#endif
+
 template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p, void* stream) {
     typedef StageGeom<N> SG;
     auto k = line_kernel_staged<N, KIND>;
@@ -706,6 +837,11 @@ template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, vo
     if constexpr (N == 8192 &&
                   (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV)) {
         // 16-byte aligned contiguous lines and more lines than resident CTAs, otherwise there is nothing to overlap
+#ifndef AFB_HOST_EMU
+        if constexpr (KIND == LK_CHEB_FWD && !AFB_R32) {
+            if (line_cluster_enabled() && p.batch >= 2) return launch_line_cluster<KIND>(p, stream);
+        }
+#endif
         if (p.oes == 1 && p.batch > (int64_t)StageGeom<N>::MINB * sm_count() && p.istride % 2 == 0 &&
             reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
             return launch_line_staged<N, KIND>(p, stream);

@@ -850,3 +850,26 @@ def test_host_point_sets_pipelined(af):
     A, Bv, Cv = af.Legendre().rec(50)
     yr = ll.clenshaw_rec(c, A, Bv, Cv, x)
     assert np.array_equal(yr[idx], orcc.clenshaw_rec(c, A, Bv, Cv, x[idx]))
+
+
+def test_cluster_line_kernel_variant(af):
+    # the 2-CTA cluster / distributed-shared-memory kernel for n = 16384 lines (AFB_LINE_CLUSTER=1; measured slower than the
+    # persistent TMA-staged kernel and therefore off by default): same results
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, sys\n"
+        "import approxfun_b200 as af\n"
+        "from approxfun_b200 import _lib as L\n"
+        "v = np.random.default_rng(9).standard_normal((16384, 151))\n"
+        "np.save(sys.argv[1], af.api.lowlevel().transform(L.CHEB1_FWD, v))\n")
+    res = []
+    for flag in ("0", "1"):
+        path = f"/tmp/afb_cluster_{flag}.npy"
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, AFB_LINE_CLUSTER=flag), cwd=root)
+        res.append(np.load(path))
+    v = np.random.default_rng(9).standard_normal((16384, 151))
+    assert np.max(np.abs(res[1] - orc.cheb_transform(v, axis=0))) <= coef_tol(16384, v)
+    assert np.array_equal(res[0], res[1])       # same radix schedule and twiddle tables: identical bits
