@@ -101,10 +101,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 def workload_config(B: int, n: int) -> dict:
     """The `config` object, identical in both arms (ours and `--impl reference`)."""
-    return {"workload": f"batched Chebyshev transform: {B} functions x n={n} Float64 per GPU "
-                        "(BASELINE.json configs[1]), plan_transform(Chebyshev(), n) forward",
-            "batch_per_gpu": B, "n": n, "sharding": "by function batch, no collective",
-            "l2": "inputs (2 GiB per step) are larger than the 126 MB L2; no flush needed"}
+    return {"workload": f"batched Chebyshev transform: {B} functions x n={n} Float64 IN TOTAL, sharded by function batch "
+                        "over the GPUs (BASELINE.json configs[1]), plan_transform(Chebyshev(), n) forward",
+            "batch_total": B, "n": n, "sharding": "by function batch (batch_total / n_gpus functions per GPU), no collective",
+            "l2": "one step reads and writes 4 GiB / n_gpus per GPU (512 MiB at 8 GPUs), larger than the 126 MB L2; no flush needed"}
 
 
 def host_threads() -> int:
@@ -170,7 +170,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "coefficients/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(B, N_LEN),
         "cpu_baseline": {"value": val, "unit": "coefficients/s", "cores": cores, "kind": "port",
                          "threads_requested": cores, "threads_effective": round(busy, 2),
@@ -260,7 +260,11 @@ def main():
 
     lib = L.load()
     L.init(lib, local)
-    n, B = N_LEN, args.batch
+    # strong scaling: the workload is args.batch functions IN TOTAL; this rank owns the contiguous shard [b_lo, b_hi)
+    n, Bt = N_LEN, args.batch
+    b_lo, b_hi = Bt * rank // world, Bt * (rank + 1) // world
+    B = b_hi - b_lo
+    total_coefs = float(Bt) * n
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -288,7 +292,7 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps  # ms per step, max over ranks
 
-    # ---- headline: device-resident batched Chebyshev transform (weak scaling: every rank owns B functions)
+    # ---- headline: device-resident batched Chebyshev transform (strong scaling: every rank owns Bt / world functions)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     v = torch.randn(B, n, dtype=torch.float64, device="cuda", generator=g)
     c = torch.empty_like(v)
@@ -318,7 +322,7 @@ def main():
         clocks["note"] = "sampled over the timed region plus a 1 s untimed continuation of the same kernel"
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     coefs_per_step = float(B) * n
-    value = world * coefs_per_step / (ms * 1e-3)
+    value = total_coefs / (ms * 1e-3)
 
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_COEF * coefs_per_step / (ms * 1e-3) / 1e9
@@ -384,10 +388,10 @@ def main():
         el_pg = max_over_ranks((time.perf_counter() - t0) / 2 * 1e3) * 1e-3
         pageable_ok = bool(np.array_equal(pc[idx], chk_e2e))
         del pv, pc
-        e2e_pageable = {"value": world * coefs_per_step / el_pg, "unit": "coefficients/s", "ms_per_step": el_pg * 1e3,
+        e2e_pageable = {"value": total_coefs / el_pg, "unit": "coefficients/s", "ms_per_step": el_pg * 1e3,
                         "same_bits_as_pinned": pageable_ok,
                         "note": "afb_plan_execute_host on plain (pageable) NumPy arrays, as a Julia Array would be passed"}
-        e2e = {"value": world * coefs_per_step / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
+        e2e = {"value": total_coefs / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
                "d2h_bytes_per_step": int(8 * B * n), "ms_per_step": el * 1e3, "steps": e2e_steps,
                "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)",
                "pcie_copy_only_ms": copy_ms, "frac_of_pcie_copy_only": copy_ms / (el * 1e3),
@@ -403,7 +407,7 @@ def main():
         fi = af.api.DevicePlan(L.FOURIER_INV, n, 0, B, n)
         for name, pl in (("chebyshev_itransform", inv), ("fourier_transform", ff), ("fourier_itransform", fi)):
             t = time_loop(lambda: pl.execute(v.data_ptr(), c.data_ptr(), stream), 5, 3)
-            extras[name] = {"coefficients_per_s": world * coefs_per_step / (t * 1e-3), "ms_per_step": t,
+            extras[name] = {"coefficients_per_s": total_coefs / (t * 1e-3), "ms_per_step": t,
                             "hbm_frac": ALG_BYTES_PER_COEF * coefs_per_step / (t * 1e-3) / 1e9 / peak}
         del c
         # Laurent (complex): 32 B per coefficient; same batch and length (4 GiB in, 4 GiB out)
@@ -413,7 +417,7 @@ def main():
             for name, kind in (("laurent_transform", L.LAURENT_FWD), ("laurent_itransform", L.LAURENT_INV)):
                 pz = af.api.DevicePlan(kind, n, 0, B, n)
                 t = time_loop(lambda: pz.execute(vz.data_ptr(), cz.data_ptr(), stream), 3, 3)
-                extras[name] = {"coefficients_per_s": world * coefs_per_step / (t * 1e-3), "ms_per_step": t,
+                extras[name] = {"coefficients_per_s": total_coefs / (t * 1e-3), "ms_per_step": t,
                                 "hbm_frac": 32.0 * coefs_per_step / (t * 1e-3) / 1e9 / peak}
                 pz.close()
             del vz, cz
@@ -587,11 +591,16 @@ def main():
         ok_all = lambda flag: bool(max_over_ranks(0.0 if flag else 1.0) == 0.0)   # true on every rank
         # config 2: 65536 x 4096 in total, 65536 / N functions per rank, bit-identical to the 1-GPU slices
         gs = torch.Generator(device="cuda").manual_seed(777)                      # the SAME global batch on every rank
-        Vg = torch.randn(B, n, dtype=torch.float64, device="cuda", generator=gs)
-        lo, hi = par.shard_range(B, rank, world)
+        Vg = torch.randn(Bt, n, dtype=torch.float64, device="cuda", generator=gs)
+        lo, hi = par.shard_range(Bt, rank, world)
         if world > 1:
             Cg = torch.empty_like(Vg)
-            fwd.execute(Vg.data_ptr(), Cg.data_ptr(), stream)                     # the 1-GPU result of the whole batch
+            pw = af.api.DevicePlan(L.CHEB1_FWD, n, 0, Bt, n)
+            pw.execute(Vg.data_ptr(), Cg.data_ptr(), stream)                      # the 1-GPU result of the whole batch
+            tw = time_loop(lambda: pw.execute(Vg.data_ptr(), Cg.data_ptr(), stream), 10, 3)
+            extras["weak_scaling_full_batch_per_gpu"] = {"ms_per_step": tw, "coefficients_per_s": world * total_coefs / (tw * 1e-3),
+                                                         "functions_per_rank": Bt, "scaling": "weak"}
+            pw.close()
             Cs = torch.empty(hi - lo, n, dtype=torch.float64, device="cuda")
             ps = af.api.DevicePlan(L.CHEB1_FWD, n, 0, hi - lo, n)
             t = time_loop(lambda: ps.execute(Vg[lo:hi].data_ptr(), Cs.data_ptr(), stream), 10, 3)
@@ -600,7 +609,7 @@ def main():
             del Cg, Cs
         else:
             t, same = ms, True
-        strong["cheb_65536x4096"] = {"ms_per_step": t, "coefficients_per_s": float(B) * n / (t * 1e-3), "functions_per_rank": hi - lo,
+        strong["cheb_65536x4096"] = {"ms_per_step": t, "coefficients_per_s": total_coefs / (t * 1e-3), "functions_per_rank": hi - lo,
                                      "bit_identical_to_1gpu_slices": same, "scaling": "strong"}
         del Vg
         # configs 3 and 5: 10^9 points / samples in total, 10^9 / N per rank (Philox counters = GLOBAL indices, so the union
@@ -745,14 +754,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_threads()
         cpu = CpuChebTransform(cores)
-        sb = min(B, 8192)                                   # bounded sample: 8192 x 4096 doubles = 256 MiB per pass
+        sb = min(Bt, 8192)                                  # bounded sample: 8192 x 4096 doubles = 256 MiB per pass
         hv_s = np.random.default_rng(0).standard_normal((sb, n))
         ho_s = np.empty_like(hv_s)
         cpu(hv_s, ho_s)                                     # warm
         reps = 0
         t0 = time.perf_counter()
         c0 = time.process_time()
-        while time.perf_counter() - t0 < 10.0 and reps < 200:
+        while time.perf_counter() - t0 < 10.0 and reps < 5000:
             cpu(hv_s, ho_s)
             reps += 1
         el = time.perf_counter() - t0
@@ -770,9 +779,9 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "coefficients/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(B, n),
+            "config": workload_config(Bt, n),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "extras": extras,
         }
