@@ -687,9 +687,9 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
                 const int64_t nb = std::min(p->gbatch, batch - b0);
                 const double* in = reinterpret_cast<const double*>(d_in) + b0 * istride;
                 double* out = reinterpret_cast<double*>(d_out) + b0 * ostride;
-                AFB_TRY(launch_ext_pre(p->kind, p->n, p->cn, in, istride, p->gwork, nb, stream));
-                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, (nb + 1) / 2, false, 1.0, stream));  // two lines per FFT
-                AFB_TRY(launch_ext_post(p->kind, p->n, p->cn, p->gwork, out, ostride, nb, stream));
+                AFB_TRY(launch_ext_pre(p->kind, p->n, p->cn, in, istride, p->gwork, nb, stream, p->cfft));
+                AFB_TRY(cfft_exec_work(p->cfft, p->gwork, (nb + 1) / 2, false, stream));  // two lines per FFT
+                AFB_TRY(launch_ext_post(p->kind, p->n, p->cn, p->gwork, out, ostride, nb, stream, p->cfft));
             }
             return AFB_OK;
         }
@@ -703,11 +703,11 @@ static int32_t exec_1d_device(afb_plan_s* p, const void* d_in, void* d_out, int6
                 const int64_t nb = std::min(p->gbatch, batch - b0);
                 const char* in = reinterpret_cast<const char*>(d_in) + (size_t)p->elem * (size_t)(b0 * istride);
                 char* out = reinterpret_cast<char*>(d_out) + (size_t)p->elem * (size_t)(b0 * ostride);
-                AFB_TRY(launch_generic_pre(p->kind, p->n, in, istride, p->gwork, nb, p->qtab, stream));
+                AFB_TRY(launch_generic_pre(p->kind, p->n, in, istride, p->gwork, nb, p->qtab, stream, p->cfft));
                 // the four real kinds ride two lines per complex FFT (see generic_pre_kernel)
                 const int64_t nfft = (p->kind <= AFB_FOURIER_INV) ? (nb + 1) / 2 : nb;
-                AFB_TRY(cfft_exec(p->cfft, p->gwork, p->gwork, nfft, inv, 1.0, stream));
-                AFB_TRY(launch_generic_post(p->kind, p->n, p->gwork, out, ostride, nb, p->qtab, stream));
+                AFB_TRY(cfft_exec_work(p->cfft, p->gwork, nfft, inv, stream));
+                AFB_TRY(launch_generic_post(p->kind, p->n, p->gwork, out, ostride, nb, p->qtab, stream, p->cfft));
             }
             return AFB_OK;
         }
@@ -726,12 +726,12 @@ static int32_t plan_launch_count(afb_plan_s* p) {
         case PATH_EXT: {
             if (cfft_ext_fused_ok(p->cfft)) return 1;
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
-            return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
+            return (int32_t)(reps * (2 + cfft_work_launches(p->cfft)));
         }
         case PATH_GENERIC: {
             if (p->kind <= AFB_FOURIER_INV && cfft_real_fused_ok(p->cfft)) return 1;
             const int64_t reps = (p->batch + p->gbatch - 1) / p->gbatch;
-            return (int32_t)(reps * (2 + cfft_launches(p->cfft)));
+            return (int32_t)(reps * (2 + cfft_work_launches(p->cfft)));
         }
         case PATH_TENSOR2D: {
             if (!p->row_plan) return plan_launch_count(p->col_plan) + 2;  // + outer and inner row kernels

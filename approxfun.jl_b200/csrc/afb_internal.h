@@ -58,6 +58,11 @@ void cfft_destroy(CfftPlan* p);
 // out[b*n + k] = scale * sum_j in[b*n + j] exp(-/+ 2 pi i jk/n)   (inverse = +, unnormalised); in == out allowed
 int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool inverse, double scale, void* stream);
 int32_t cfft_launches(const CfftPlan* p);
+// split plans (n = S h with h inside a one-CTA engine): S, else 1.  The pre / post launchers below take the plan and fuse
+// the radix-S pass / the de-interleave; cfft_exec_work runs the transform(s) of a work buffer they filled, in place.
+int cfft_split(const CfftPlan* p);
+int32_t cfft_exec_work(CfftPlan* p, cplx* work, int64_t nfft, bool inverse, void* stream);
+int32_t cfft_work_launches(const CfftPlan* p);
 // arbitrary-length real kinds in one kernel (Bluestein, padded length within one CTA's shared memory)
 bool cfft_real_fused_ok(const CfftPlan* p);
 int32_t launch_blue_real(CfftPlan* p, int kind, const double* in, int64_t istride, double* out, int64_t ostride, int64_t batch,
@@ -82,14 +87,14 @@ int32_t launch_ext_fused(CfftPlan* p, int kind, int64_t n, const double* in, int
 
 // pre/post kernels mapping the real transforms onto a length-n complex FFT (afb_large.cu)
 int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
-                           const cplx* qtab, void* stream);
+                           const cplx* qtab, void* stream, const CfftPlan* sp = nullptr);
 int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, int64_t ostride, int64_t batch,
-                            const cplx* qtab, void* stream);
+                            const cplx* qtab, void* stream, const CfftPlan* sp = nullptr);
 
 int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_t istride, cplx* work, int64_t batch,
-                       void* stream);
+                       void* stream, const CfftPlan* sp = nullptr);
 int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, double* out, int64_t ostride, int64_t batch,
-                        void* stream);
+                        void* stream, const CfftPlan* sp = nullptr);
 
 // ---- 2-D (afb_tensor.cu) -----------------------------------------------------------------------------
 int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, void* stream);

@@ -20,14 +20,18 @@ namespace afb {
 
 struct CfftPlan {
     int64_t n = 0, max_batch = 0;
-    int mode = 0;  // 0 line, 1 four-step, 2 Bluestein, 3 mixed radix (2^a 3^b 5^c 7^d in one CTA, afb_mixed.cu)
+    int mode = 0;  // 0 line, 1 four-step, 2 Bluestein, 3 mixed radix (2^a 3^b 5^c 7^d in one CTA, afb_mixed.cu),
+                   // 4 split: one radix-S decimation-in-frequency pass (S = 2, 4, 8, 16) in front of S one-CTA transforms of n / S
     const cplx* tw = nullptr;
     // four-step
     int n1 = 0, n2 = 0;
     const cplx *tw1 = nullptr, *tw2 = nullptr;
     cplx *twA = nullptr, *twB = nullptr;
     cplx* tmp = nullptr;
-    // Bluestein
+    // split
+    int S = 1;
+    const cplx* rootn = nullptr;   // exp(-2 pi i k / n), k < n
+    // Bluestein (sub: the padded power-of-two engine) / split (sub: the engine of length n / S)
     int64_t M = 0;
     CfftPlan* sub = nullptr;
     cplx *chirp = nullptr, *bhat = nullptr, *pad = nullptr;
@@ -170,6 +174,24 @@ static inline unsigned ew_grid(int64_t total) {
     return (unsigned)std::max<int64_t>(1, std::min(g, cap));
 }
 
+// lengths the one-CTA engines do not reach (smooth n > 6912, Bluestein with a padded length above 8192) but whose S-th part
+// they do: the smallest S in {2, 4, 8, 16} with n / S served by the mixed-radix kernel or the fused Bluestein kernel
+static bool one_cta_engine_ok(int64_t h) {
+    if (is_pow2(h)) return h >= LINE_MIN_N && h <= LINE_MAX_N;
+    return mixed_radix_ok(h) || (h >= 2 && 2 * h - 1 <= LINE_MAX_N);
+}
+static int split_factor(int64_t n) {
+    if (n < 2 || is_pow2(n) || one_cta_engine_ok(n)) return 1;
+    // the mixed-radix kernel runs at 0.4-0.55 of HBM up to h ~ 2000 (several CTAs per SM) and at 0.2-0.3 above: prefer the
+    // first S that brings a smooth h under 2048, else the first S any one-CTA engine accepts
+    for (int S = 2; S <= 16; S *= 2)
+        if (n % S == 0 && n / S <= 2048 && mixed_radix_ok(n / S)) return S;
+    for (int S = 2; S <= 16; S *= 2)
+        if (n % S == 0 && one_cta_engine_ok(n / S)) return S;
+    return 1;
+}
+int cfft_split(const CfftPlan* p) { return (p && p->mode == 4) ? p->S : 1; }
+
 void cfft_destroy(CfftPlan* p) {
     if (!p) return;
     if (p->twA) cudaFree(p->twA);
@@ -221,6 +243,11 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
     } else if (mixed_radix_ok(n)) {
         p->mode = 3;
         st = root_table(n, &p->tw);
+    } else if (split_factor(n) > 1) {
+        p->mode = 4;
+        p->S = split_factor(n);
+        st = root_table(n, &p->rootn);
+        if (st == AFB_OK) st = cfft_create(&p->sub, n / p->S, p->max_batch);
     } else if (n >= 1) {
         p->mode = 2;
         int64_t M = 32;
@@ -268,12 +295,20 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
     return AFB_OK;
 }
 
+// the transform(s) of a work buffer filled by launch_generic_pre / launch_ext_pre (S blocks per line for a split plan)
+int32_t cfft_exec_work(CfftPlan* p, cplx* work, int64_t nfft, bool inverse, void* stream) {
+    if (p->mode == 4) return cfft_exec(p->sub, work, work, nfft * p->S, inverse, 1.0, stream);
+    return cfft_exec(p, work, work, nfft, inverse, 1.0, stream);
+}
+int32_t cfft_work_launches(const CfftPlan* p) { return (p && p->mode == 4) ? cfft_launches(p->sub) : cfft_launches(p); }
+
 int32_t cfft_launches(const CfftPlan* p) {
     if (!p) return 0;
     switch (p->mode) {
         case 0: return 1;
         case 1: return 2;
         case 3: return 1;
+        case 4: return cfft_launches(p->sub);
         default: return (p->M <= LINE_MAX_N) ? 1 : 3 + 2 * cfft_launches(p->sub);
     }
 }
@@ -302,6 +337,8 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
         return AFB_OK;
     }
     if (p->mode == 3) return launch_mixed_cfft(n, p->tw, in, out, batch, inverse, scale, stream);
+    if (p->mode == 4)  // the element-wise halves of a split plan live in the callers' pre / post kernels
+        return fail(AFB_UNSUPPORTED, "split FFT plans run through launch_*_pre / cfft_exec_work / launch_*_post");
     // Bluestein: X_k = chirp_k * sum_j (x_j chirp_j) conj(chirp)_{k-j}
     if (p->M <= LINE_MAX_N) {  // one kernel; in place is safe (a CTA reads its whole lines before it writes them)
         BlueParams bp{in, out, n, batch, p->chirp, p->bhat, p->sub->tw, inverse ? 1 : 0, inverse ? 1 : 0,
@@ -369,41 +406,89 @@ __device__ __forceinline__ cplx generic_pre_value(int kind, int64_t n, int64_t n
     return z;
 }
 
+// element j of work line q: z(line 2q) + i z(line 2q + 1) for the real kinds, the line itself for the complex ones
+__device__ __forceinline__ cplx generic_packed_value(int kind, bool real, int64_t n, int64_t nh, const void* __restrict__ in,
+                                                     int64_t istride, int64_t batch, int64_t q, int64_t j,
+                                                     const cplx* __restrict__ qtab) {
+    if (!real) return generic_pre_value(kind, n, nh, reinterpret_cast<const cplx*>(in) + q * istride, j, qtab);
+    const double* base = reinterpret_cast<const double*>(in);
+    cplx z = generic_pre_value(kind, n, nh, base + (2 * q) * istride, j, qtab);
+    if (2 * q + 1 < batch) {
+        const cplx z2 = generic_pre_value(kind, n, nh, base + (2 * q + 1) * istride, j, qtab);
+        z = make_double2(z.x - z2.y, z.y + z2.x);  // z + i z2
+    }
+    return z;
+}
+
 __global__ void generic_pre_kernel(int kind, int64_t n, const void* __restrict__ in, int64_t istride,
                                    cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ qtab) {
     const bool real = generic_real_kind(kind);
     const int64_t total = (real ? (batch + 1) / 2 : batch) * n;
     const int64_t nh = (n + 1) / 2;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = g / n, j = g % n;
-        if (real) {
-            const double* base = reinterpret_cast<const double*>(in);
-            cplx z = generic_pre_value(kind, n, nh, base + (2 * q) * istride, j, qtab);
-            if (2 * q + 1 < batch) {
-                const cplx z2 = generic_pre_value(kind, n, nh, base + (2 * q + 1) * istride, j, qtab);
-                z = make_double2(z.x - z2.y, z.y + z2.x);  // z + i z2
-            }
-            work[g] = z;
-        } else {
-            work[g] = generic_pre_value(kind, n, nh, reinterpret_cast<const cplx*>(in) + q * istride, j, qtab);
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
+        work[g] = generic_packed_value(kind, real, n, nh, in, istride, batch, g / n, g % n, qtab);
+}
+
+// ---- split plans (mode 4): n = S h.  One radix-S decimation-in-frequency pass
+//        y_s[j] = w_n^(+-j s) sum_r z[j + r h] w_S^(+-r s),   j < h, s < S,
+// fused into the pre kernels, leaves S contiguous blocks of length h per line; their length-h transforms (one-CTA engines:
+// mixed radix or fused Bluestein) hold X[S k + s] = Y_s[k], which the post kernels read through SpecView.
+template <int S>
+__device__ __forceinline__ void split_dif(const cplx (&z)[S], int64_t j, int64_t h, const cplx* __restrict__ rootn, bool inv,
+                                          cplx* __restrict__ dst) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        cplx acc = z[0];
+#pragma unroll
+        for (int r = 1; r < S; ++r) {
+            cplx w = rootn[(int64_t)((r * s) % S) * h];
+            if (inv) w.y = -w.y;
+            acc = cadd(acc, cmul(z[r], w));
         }
+        if (s) {
+            cplx w = rootn[j * s];
+            if (inv) w.y = -w.y;
+            acc = cmul(acc, w);
+        }
+        dst[(int64_t)s * h + j] = acc;
+    }
+}
+struct SpecView {   // element k of a spectrum left as S blocks of length h
+    const cplx* base;
+    int64_t h;
+    int S;
+    __device__ __forceinline__ cplx operator[](int64_t k) const { return S == 1 ? base[k] : base[(k % S) * h + k / S]; }
+};
+
+template <int S>
+__global__ void generic_pre_split_kernel(int kind, int64_t n, const void* __restrict__ in, int64_t istride,
+                                         cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ qtab,
+                                         const cplx* __restrict__ rootn, int inv) {
+    const bool real = generic_real_kind(kind);
+    const int64_t h = n / S, total = (real ? (batch + 1) / 2 : batch) * h, nh = (n + 1) / 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = g / h, j = g % h;
+        cplx z[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) z[r] = generic_packed_value(kind, real, n, nh, in, istride, batch, q, j + r * h, qtab);
+        split_dif<S>(z, j, h, rootn, inv != 0, work + q * n);
     }
 }
 
 // spectrum of the real input riding in the real (odd = false) or imaginary (odd = true) part of the packed line
-__device__ __forceinline__ cplx pair_spectrum(const cplx* __restrict__ W, int64_t n, int64_t k, bool odd) {
+__device__ __forceinline__ cplx pair_spectrum(const SpecView& W, int64_t n, int64_t k, bool odd) {
     const cplx A = W[k], Bc = W[(n - k) % n];
     return odd ? make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x))   // (A - conj B) / (2i)
                : make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));   // (A + conj B) / 2
 }
 
 __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict__ work, void* __restrict__ out,
-                                    int64_t ostride, int64_t batch, const cplx* __restrict__ qtab) {
+                                    int64_t ostride, int64_t batch, const cplx* __restrict__ qtab, int S) {
     const int64_t total = batch * n;
     const bool real = generic_real_kind(kind);
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = g / n, o = g % n;
-        const cplx* W = work + (real ? (b >> 1) : b) * n;
+        const SpecView W{work + (real ? (b >> 1) : b) * n, n / S, S};
         const bool odd = b & 1;
         if (kind == AFB_CHEB1_FWD) {
             double* c = reinterpret_cast<double*>(out) + b * ostride;
@@ -432,6 +517,51 @@ __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict_
         } else {
             (reinterpret_cast<cplx*>(out) + b * ostride)[o] = W[o];
         }
+    }
+}
+
+// output o of the two real lines packed in one complex transform: W(k) = element k of the length-n (inverse) DFT of
+// z(line 2q) + i z(line 2q + 1); ve belongs to line 2q, vo to line 2q + 1
+template <class WF>
+__device__ __forceinline__ void real_pair_post(int kind, int64_t n, int64_t o, const WF& W, const cplx* __restrict__ qtab,
+                                               double& ve, double& vo) {
+    const double dn = (double)n;
+    if (kind == AFB_CHEB1_INV) {
+        const cplx z = W((o & 1) ? n - 1 - (o - 1) / 2 : o / 2);
+        ve = z.x; vo = z.y;
+    } else if (kind == AFB_FOURIER_INV) {
+        const cplx z = W(o);
+        ve = z.x; vo = z.y;
+    } else {
+        const bool nyq = (kind == AFB_FOURIER_FWD) && (n % 2 == 0) && o == n - 1;
+        const int64_t k = (kind == AFB_CHEB1_FWD) ? o : (o == 0 ? 0 : nyq ? n / 2 : (o & 1) ? (o + 1) / 2 : o / 2);
+        const cplx A = W(k), Bc = W((n - k) % n);
+        const cplx Ye = make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));    // (A + conj B) / 2
+        const cplx Yo = make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x));   // (A - conj B) / (2i)
+        if (kind == AFB_CHEB1_FWD) {
+            const cplx w = ldg2(qtab + o);
+            const double sc = (o == 0) ? 1.0 / dn : 2.0 / dn;
+            ve = cmul(Ye, w).x * sc; vo = cmul(Yo, w).x * sc;
+        } else if (o == 0) { ve = Ye.x / dn; vo = Yo.x / dn; }
+        else if (nyq) { ve = -Ye.x / dn; vo = -Yo.x / dn; }
+        else if (o & 1) { ve = -Ye.y * (2.0 / dn); vo = -Yo.y * (2.0 / dn); }
+        else { ve = Ye.x * (2.0 / dn); vo = Yo.x * (2.0 / dn); }
+    }
+}
+
+// the real kinds of the multi-kernel route: one thread per (pair of lines, output index) -- every spectrum element is read
+// for both lines at once
+__global__ void generic_post_pair_kernel(int kind, int64_t n, const cplx* __restrict__ work, double* __restrict__ out,
+                                         int64_t ostride, int64_t batch, const cplx* __restrict__ qtab, int S) {
+    const int64_t total = ((batch + 1) / 2) * n;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = g / n, o = g % n;
+        const SpecView V{work + q * n, n / S, S};
+        auto W = [&](int64_t k) -> cplx { return V[k]; };
+        double ve, vo;
+        real_pair_post(kind, n, o, W, qtab, ve, vo);
+        out[(2 * q) * ostride + o] = ve;
+        if (2 * q + 1 < batch) out[(2 * q + 1) * ostride + o] = vo;
     }
 }
 
@@ -498,33 +628,12 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 &&
     };
     double* o0 = p.out + (2 * q) * p.ostride;
     double* o1 = o0 + p.ostride;
-    const double dn = (double)n;
 #pragma unroll
     for (int r = 0; r < C::E; ++r) {
         const int64_t o = t2 + C::T * r;
         if (o >= n) continue;
         double ve, vo;
-        if (KIND == AFB_CHEB1_INV) {
-            const cplx z = W((o & 1) ? n - 1 - (o - 1) / 2 : o / 2);
-            ve = z.x; vo = z.y;
-        } else if (KIND == AFB_FOURIER_INV) {
-            const cplx z = W(o);
-            ve = z.x; vo = z.y;
-        } else {
-            const bool nyq = (KIND == AFB_FOURIER_FWD) && (n % 2 == 0) && o == n - 1;
-            const int64_t k = (KIND == AFB_CHEB1_FWD) ? o : (o == 0 ? 0 : nyq ? n / 2 : (o & 1) ? (o + 1) / 2 : o / 2);
-            const cplx A = W(k), Bc = W((n - k) % n);
-            const cplx Ye = make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));    // (A + conj B) / 2
-            const cplx Yo = make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x));   // (A - conj B) / (2i)
-            if (KIND == AFB_CHEB1_FWD) {
-                const cplx w = ldg2(p.qtab + o);
-                const double sc = (o == 0) ? 1.0 / dn : 2.0 / dn;
-                ve = cmul(Ye, w).x * sc; vo = cmul(Yo, w).x * sc;
-            } else if (o == 0) { ve = Ye.x / dn; vo = Yo.x / dn; }
-            else if (nyq) { ve = -Ye.x / dn; vo = -Yo.x / dn; }
-            else if (o & 1) { ve = -Ye.y * (2.0 / dn); vo = -Yo.y * (2.0 / dn); }
-            else { ve = Ye.x * (2.0 / dn); vo = Yo.x * (2.0 / dn); }
-        }
+        real_pair_post(KIND, n, o, W, p.qtab, ve, vo);
         o0[o] = ve;
         if (has2) o1[o] = vo;
     }
@@ -599,12 +708,28 @@ __global__ void ext_pre_kernel(int kind, int64_t n, int64_t cn, const double* __
         work[g] = make_double2(re, im);
     }
 }
+template <int S>
+__global__ void ext_pre_split_kernel(int kind, int64_t n, int64_t cn, const double* __restrict__ in, int64_t istride,
+                                     cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ rootn) {
+    const int64_t h = cn / S, total = ((batch + 1) / 2) * h;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = g / h, j = g % h;
+        const bool has2 = 2 * q + 1 < batch;
+        cplx z[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            z[r].x = ext_value(kind, n, cn, in + (2 * q) * istride, j + r * h);
+            z[r].y = has2 ? ext_value(kind, n, cn, in + (2 * q + 1) * istride, j + r * h) : 0.0;
+        }
+        split_dif<S>(z, j, h, rootn, false, work + q * cn);
+    }
+}
 __global__ void ext_post_kernel(int kind, int64_t n, int64_t cn, const cplx* __restrict__ work, double* __restrict__ out,
-                                int64_t ostride, int64_t batch) {
+                                int64_t ostride, int64_t batch, int S) {
     const int64_t total = batch * n;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = g / n, k = g % n;
-        const cplx* W = work + (b >> 1) * cn;
+        const SpecView W{work + (b >> 1) * cn, cn / S, S};
         const bool odd = b & 1;
         double r;
         if (kind == AFB_CHEB2_FWD) {
@@ -742,35 +867,71 @@ int32_t launch_ext_fused(CfftPlan* p, int kind, int64_t n, const double* in, int
 }
 
 int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_t istride, cplx* work, int64_t batch,
-                       void* stream) {
+                       void* stream, const CfftPlan* sp) {
     if (batch == 0) return AFB_OK;
+    const int S = cfft_split(sp);
+    if (S > 1) {
+        const unsigned grid = ew_grid(((batch + 1) / 2) * (cn / S));
+#define AFB_EXT_SPLIT(S_) \
+    case S_: { auto k = ext_pre_split_kernel<S_>; \
+               AFB_LAUNCH(k, grid, 256, 0, stream, kind, n, cn, in, istride, work, batch, sp->rootn); break; }
+        switch (S) {
+            AFB_EXT_SPLIT(2) AFB_EXT_SPLIT(4) AFB_EXT_SPLIT(8) AFB_EXT_SPLIT(16)
+            default: return fail(AFB_BAD_ARG, "split factor");
+        }
+#undef AFB_EXT_SPLIT
+        AFB_KERNEL_CHECK();
+        return AFB_OK;
+    }
     auto k = ext_pre_kernel;
     AFB_LAUNCH(k, ew_grid(((batch + 1) / 2) * cn), 256, 0, stream, kind, n, cn, in, istride, work, batch);
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
 int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, double* out, int64_t ostride, int64_t batch,
-                        void* stream) {
+                        void* stream, const CfftPlan* sp) {
     if (batch == 0) return AFB_OK;
     auto k = ext_post_kernel;
-    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, cn, work, out, ostride, batch);
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, cn, work, out, ostride, batch, cfft_split(sp));
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
 
 int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride, cplx* work, int64_t batch,
-                           const cplx* qtab, void* stream) {
+                           const cplx* qtab, void* stream, const CfftPlan* sp) {
     if (batch == 0) return AFB_OK;
+    const int S = cfft_split(sp);
+    if (S > 1) {
+        const unsigned grid = ew_grid(batch * (n / S));
+        const int inv = kind & 1;   // inverse kinds ask cfft_exec for the inverse transform
+#define AFB_GEN_SPLIT(S_) \
+    case S_: { auto k = generic_pre_split_kernel<S_>; \
+               AFB_LAUNCH(k, grid, 256, 0, stream, kind, n, in, istride, work, batch, qtab, sp->rootn, inv); break; }
+        switch (S) {
+            AFB_GEN_SPLIT(2) AFB_GEN_SPLIT(4) AFB_GEN_SPLIT(8) AFB_GEN_SPLIT(16)
+            default: return fail(AFB_BAD_ARG, "split factor");
+        }
+#undef AFB_GEN_SPLIT
+        AFB_KERNEL_CHECK();
+        return AFB_OK;
+    }
     auto k = generic_pre_kernel;
     AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, in, istride, work, batch, qtab);  // grid-stride: covers the packed count too
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }
 int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, int64_t ostride, int64_t batch,
-                            const cplx* qtab, void* stream) {
+                            const cplx* qtab, void* stream, const CfftPlan* sp) {
     if (batch == 0) return AFB_OK;
+    if (kind <= AFB_FOURIER_INV) {
+        auto kp = generic_post_pair_kernel;
+        AFB_LAUNCH(kp, ew_grid(((batch + 1) / 2) * n), 256, 0, stream, kind, n, work, reinterpret_cast<double*>(out), ostride, batch,
+                   qtab, cfft_split(sp));
+        AFB_KERNEL_CHECK();
+        return AFB_OK;
+    }
     auto k = generic_post_kernel;
-    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, work, out, ostride, batch, qtab);
+    AFB_LAUNCH(k, ew_grid(batch * n), 256, 0, stream, kind, n, work, out, ostride, batch, qtab, cfft_split(sp));
     AFB_KERNEL_CHECK();
     return AFB_OK;
 }

@@ -430,3 +430,25 @@ def test_mixed_radix_register_passes_match_shared_memory_passes():
         subprocess.check_call([sys.executable, "-c", code, path], env=env, cwd=root)
         res.append(np.load(path))
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("n", [8000, 8002, 16000])
+def test_split_plans(n):
+    # n = S h, h inside a one-CTA engine (8000 -> 2 x 4000 mixed radix, 8002 -> 2 x 4001 fused Bluestein, 16000 -> 4 x 4000):
+    # radix-S pass in the pre kernel, de-interleave in the post kernel (afb_large.cu, CfftPlan mode 4)
+    v = RNG.standard_normal((n, 3))
+    for kind, ref in REAL_KINDS:
+        want = ref(v)
+        got = ll.transform(kind, v)
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
+    z = RNG.standard_normal((n, 2)) + 1j * RNG.standard_normal((n, 2))
+    for kind, ref in CPLX_KINDS:
+        want = ref(z)
+        assert np.max(np.abs(ll.transform(kind, z) - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(z)))), (kind, n)
+    m = n // 2 + 1                      # extension kinds: 2 (m - 1) = n
+    w = RNG.standard_normal((m, 3))
+    c2 = ll.transform(B.CHEB2_FWD, w)
+    assert np.max(np.abs(c2 - orc.chebkind2_transform(w, axis=0))) <= tol(n, np.max(np.abs(w)))
+    assert np.max(np.abs(ll.transform(B.CHEB2_INV, c2) - w)) <= 50 * tol(n, np.max(np.abs(w)))
+    s = ll.transform(B.SIN_FWD, w[:m - 2])     # 2 (m - 2) + 2 = n
+    assert np.max(np.abs(ll.transform(B.SIN_INV, s) - w[:m - 2])) <= 50 * tol(n, np.max(np.abs(w)))

@@ -698,6 +698,39 @@ def test_mixed_radix_lengths(af, n):
     assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 1
 
 
+@pytest.mark.parametrize("n", [8000, 8002, 13824, 16000, 40000])
+def test_split_plan_lengths(af, n):
+    # n = S h with h inside a one-CTA engine (mixed radix h <= 6912 or fused Bluestein h <= 4096), S = 2, 4, 8: one radix-S
+    # pass fused into the pre kernel, S one-CTA transforms per line, de-interleave fused into the post kernel: 3 launches
+    # instead of Bluestein's padded multi-kernel route (8000 / 8002 are the Padua lengths of degree 4000)
+    from approxfun_b200 import _lib as L
+    nb = 9
+    v = RNG.standard_normal((n, nb))
+    for S, fwd, inv in ((af.Chebyshev(), orc.cheb_transform, orc.cheb_itransform),
+                        (af.Fourier(), orc.fourier_transform, orc.fourier_itransform)):
+        c = af.transform(S, v)
+        assert np.max(np.abs(c - fwd(v, axis=0))) <= coef_tol(n, v), (type(S).__name__, n)
+        wi = inv(v, axis=0)
+        assert np.max(np.abs(af.itransform(S, v) - wi)) <= coef_tol(n, wi), (type(S).__name__, n)
+    z = RNG.standard_normal((n, 3)) + 1j * RNG.standard_normal((n, 3))
+    assert np.max(np.abs(af.transform(af.Laurent(), z) - orc.laurent_transform(z, axis=0))) <= coef_tol(n, z)
+    wi = orc.laurent_itransform(z, axis=0)
+    assert np.max(np.abs(af.itransform(af.Laurent(), z) - wi)) <= coef_tol(n, wi)
+    assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 3
+
+
+@pytest.mark.parametrize("n", [4001, 4002, 6913])
+def test_split_plan_extension_kinds(af, n):
+    # second-kind points / SinSpace: the even / odd extension (length 2(n-1) / 2n+2) through a split plan
+    from approxfun_b200 import _lib as L
+    v = RNG.standard_normal((n, 5))
+    got = af.api.lowlevel().transform(L.CHEB2_FWD, v)
+    assert np.max(np.abs(got - orc.chebkind2_transform(v, axis=0))) <= coef_tol(n, v)
+    assert np.max(np.abs(af.api.lowlevel().transform(L.CHEB2_INV, got) - v)) <= 50 * coef_tol(n, v)
+    s = af.api.lowlevel().transform(L.SIN_FWD, v[:n - 2])
+    assert np.max(np.abs(af.api.lowlevel().transform(L.SIN_INV, s) - v[:n - 2])) <= 50 * coef_tol(n, v)
+
+
 def test_pageable_strided_host_arrays_through_the_pinned_ring(af):
     # a pageable caller array with stride > n, large enough (> 4 MiB, several 32 MiB chunks) for the library's own staging:
     # host copy team -> pinned ring -> DMA; the padding columns of the destination must stay untouched
