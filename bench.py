@@ -391,8 +391,8 @@ def main():
         e2e_pageable = {"value": total_coefs / el_pg, "unit": "coefficients/s", "ms_per_step": el_pg * 1e3,
                         "same_bits_as_pinned": pageable_ok,
                         "note": "afb_plan_execute_host on plain (pageable) NumPy arrays, as a Julia Array would be passed"}
-        e2e = {"value": total_coefs / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * B * n),
-               "d2h_bytes_per_step": int(8 * B * n), "ms_per_step": el * 1e3, "steps": e2e_steps,
+        e2e = {"value": total_coefs / el, "unit": "coefficients/s", "h2d_bytes_per_step": int(8 * Bt * n),
+               "d2h_bytes_per_step": int(8 * Bt * n), "bytes_per_step_note": "whole job (all ranks); each rank copies 1 / n_gpus of it", "ms_per_step": el * 1e3, "steps": e2e_steps,
                "api": "afb_plan_execute_host (plan*v through the C ABI, pinned host buffers)",
                "pcie_copy_only_ms": copy_ms, "frac_of_pcie_copy_only": copy_ms / (el * 1e3),
                "host_affinity": numa_note, "pageable": e2e_pageable}
@@ -701,7 +701,7 @@ def main():
             if rank == 0:
                 sp_out = {}
                 try:
-                    nb1 = B
+                    nb1 = Bt                                                   # the WHOLE batch from one process
                     hv1 = torch.empty(nb1, n, dtype=torch.float64).pin_memory()
                     hc1 = torch.empty(nb1, n, dtype=torch.float64).pin_memory()
                     hv1.normal_()
