@@ -25,7 +25,7 @@ PLAN_2D_TRANSPOSE = 1  # afb_plan_create flag: explicit-transpose row pass for 2
 # every symbol include/approxfun_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = [
     "afb_version", "afb_last_error", "afb_init", "afb_shutdown", "afb_device_info",
-    "afb_malloc", "afb_free", "afb_host_alloc", "afb_host_free", "afb_memcpy_h2d", "afb_memcpy_d2h",
+    "afb_malloc", "afb_free", "afb_host_alloc", "afb_host_free", "afb_host_register", "afb_host_unregister", "afb_memcpy_h2d", "afb_memcpy_d2h",
     "afb_memcpy_d2d", "afb_stream_sync",
     "afb_plan_create", "afb_plan_execute_host", "afb_plan_execute_device", "afb_plan_destroy", "afb_plan_launches",
     "afb_plan_io_doubles", "afb_plan_execute_buf",
@@ -70,6 +70,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "afb_free": [vp],
         "afb_host_alloc": [C.POINTER(vp), sz],
         "afb_host_free": [vp],
+        "afb_host_register": [vp, sz],
+        "afb_host_unregister": [vp],
         "afb_memcpy_h2d": [vp, vp, sz, vp],
         "afb_memcpy_d2h": [vp, vp, sz, vp],
         "afb_memcpy_d2d": [vp, vp, sz, vp],

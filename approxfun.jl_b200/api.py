@@ -38,6 +38,38 @@ def use_devices(devices=None) -> None:
     L.init(lowlevel().lib, devices)
 
 
+class pinned:
+    """`with pinned(a, b): ...` page-locks caller-owned NumPy arrays in place (`afb_host_register`) for the duration of the
+    block, so host-array calls DMA them directly instead of staging them through the library's pinned ring; they are
+    unregistered on exit.  Also usable without `with`: `h = pinned(a); ...; h.release()`."""
+
+    def __init__(self, *arrays):
+        import ctypes as C
+        self._lib = lowlevel().lib
+        self._ptrs = []
+        try:
+            for a in arrays:
+                if not (a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]):
+                    raise L.AfbError(L.AFB_BAD_ARG, "pinned: array must be contiguous")
+                L.check(self._lib, self._lib.afb_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+                self._ptrs.append(a.ctypes.data)
+        except Exception:
+            self.release()
+            raise
+
+    def release(self) -> None:
+        import ctypes as C
+        while self._ptrs:
+            L.check(self._lib, self._lib.afb_host_unregister(C.c_void_p(self._ptrs.pop())))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
+
+
 # ------------------------------------------------------------------------------------------------------
 # spaces
 # ------------------------------------------------------------------------------------------------------

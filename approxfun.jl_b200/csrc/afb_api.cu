@@ -926,6 +926,18 @@ int32_t afb_host_alloc(void** hptr, size_t bytes) {
     return AFB_OK;
 }
 int32_t afb_host_free(void* hptr) { if (hptr) AFB_CUDA(cudaFreeHost(hptr)); return AFB_OK; }
+int32_t afb_host_register(void* hptr, size_t bytes) {
+    if (!hptr || bytes == 0) return fail(AFB_BAD_ARG, "afb_host_register: null pointer or zero size");
+    AFB_TRY(ensure_device());
+    AFB_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterPortable));
+    return AFB_OK;
+}
+int32_t afb_host_unregister(void* hptr) {
+    if (!hptr) return fail(AFB_BAD_ARG, "afb_host_unregister: null pointer");
+    AFB_TRY(ensure_device());
+    AFB_CUDA(cudaHostUnregister(hptr));
+    return AFB_OK;
+}
 int32_t afb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
     AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return AFB_OK;

@@ -125,6 +125,9 @@ static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+enum { cudaHostRegisterPortable = 1 };
+static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { if (n) std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind k) { return cudaMemcpyAsync(d, s, n, k); }
 static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind,

@@ -39,6 +39,15 @@ function use_devices(devs = Int32[])
 end
 __init__() = use_devices()
 
+# Page-lock a work array in place so host calls DMA it directly (a pageable Array is staged through the library's pinned
+# ring at about 0.4x the speed).  The array must be unpinned before the GC frees it: pin!(A) installs that finalizer.
+function pin!(A::Array)
+    check(ccall((:afb_host_register, LIB), Int32, (Ptr{Cvoid}, Csize_t), A, sizeof(A)))
+    finalizer(a -> ccall((:afb_host_unregister, LIB), Int32, (Ptr{Cvoid},), a), A)
+    A
+end
+unpin!(A::Array) = check(ccall((:afb_host_unregister, LIB), Int32, (Ptr{Cvoid},), A))
+
 # ---- plan objects: what FastTransforms.ChebyshevTransformPlan / FFTW.r2rFFTWPlan are upstream -------
 mutable struct B200Plan{T}
     handle::Ptr{Cvoid}

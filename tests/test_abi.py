@@ -78,7 +78,9 @@ def test_round2_entry_points_fail_loudly_without_device(built):
     assert lib.afb_piecewise_clenshaw(p(c), p(offs), p(brk), 1, p(u), p(out), 3) == ND
     assert lib.afb_clenshaw_fourier_cheb2d(p(c), 2, 2, p(u), p(u), p(out), 3) == ND
     assert lib.afb_dgemm_nn_dmma_device(p(c), p(c), p(out), 1, 1, 1, None) == ND
+    assert lib.afb_host_register(p(c), c.nbytes) == ND and lib.afb_host_unregister(p(c)) == ND
     # argument errors come first
+    assert lib.afb_host_register(None, 8) == L.AFB_BAD_ARG and lib.afb_host_register(p(c), 0) == L.AFB_BAD_ARG
     assert lib.afb_init(None, 2) == L.AFB_BAD_ARG
     assert lib.afb_piecewise_bisect(p(c), p(offs), p(np.array([1.0, -1.0])), 1, p(u), p(out), 3, 47) == L.AFB_BAD_SIZE
     assert lib.afb_buf_create(ctypes.byref(h), -1) == L.AFB_BAD_SIZE

@@ -731,6 +731,29 @@ def test_split_plan_extension_kinds(af, n):
     assert np.max(np.abs(af.api.lowlevel().transform(L.SIN_INV, s) - v[:n - 2])) <= 50 * coef_tol(n, v)
 
 
+def test_registered_caller_arrays_take_the_direct_path(af):
+    # afb_host_register: a caller-owned NumPy array page-locked in place is DMA-ed directly (no pinned ring); same bits as the
+    # pageable route; registering twice is a CUDA error that comes back as a status, not a crash
+    import ctypes
+    from approxfun_b200 import _lib as L
+    n, nb = 4096, 4096                              # 128 MiB
+    host = RNG.standard_normal((nb, n))
+    want = np.empty_like(host)
+    pl = af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n)
+    pl.execute_host(host, want)                     # pageable: through the ring
+    got = np.empty_like(host)
+    with af.api.pinned(host, got) as h:
+        pl.execute_host(host, got)
+        lib = af.api.lowlevel().lib
+        assert lib.afb_host_register(ctypes.c_void_p(host.ctypes.data), ctypes.c_size_t(host.nbytes)) == L.AFB_CUDA_ERROR
+        assert len(h._ptrs) == 2
+    assert np.array_equal(got, want)
+    assert np.max(np.abs(got[:64] - orc.cheb_transform(host[:64], axis=1))) <= coef_tol(n, host)
+    pl.execute_host(host, got)                      # unregistered again: back through the ring
+    assert np.array_equal(got, want)
+    pl.close()
+
+
 def test_pageable_strided_host_arrays_through_the_pinned_ring(af):
     # a pageable caller array with stride > n, large enough (> 4 MiB, several 32 MiB chunks) for the library's own staging:
     # host copy team -> pinned ring -> DMA; the padding columns of the destination must stay untouched
