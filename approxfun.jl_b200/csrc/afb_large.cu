@@ -35,6 +35,8 @@ struct CfftPlan {
     int64_t M = 0;
     CfftPlan* sub = nullptr;
     cplx *chirp = nullptr, *bhat = nullptr, *pad = nullptr;
+    int bS = 1;                     // Bluestein with M = bS * 8192 > 8192: bhat holds bS blocks (element bS k + s at s h + k)
+    const cplx* rootM = nullptr;    // exp(-2 pi i m / M)
 };
 
 // ---- Bluestein element-wise kernels ------------------------------------------------------------------
@@ -84,9 +86,10 @@ struct BlueParams {
     const cplx* in;
     cplx* out;
     int64_t n, batch;
-    const cplx *chirp, *bhat, *tw;
+    const cplx *chirp, *bhat, *tw;   // chirp == nullptr: plain circular convolution core (FFT, filter, inverse FFT)
     int conj_in, conj_out;
     double scale;  // includes 1/M
+    int S = 1;     // filters: line L uses bhat + (L % S) M
 };
 template <int M> struct BlueGeom {
     static constexpr int T = FftCfg<M>::T;
@@ -110,16 +113,16 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 &&
         const int64_t j = t + C::T * r;
         const int64_t jc = j < p.n ? j : p.n - 1;
         cplx z = src[jc];
-        const cplx ch = ldg2(p.chirp + jc);
         if (p.conj_in) z.y = -z.y;
-        z = cmul(z, ch);
+        if (p.chirp) z = cmul(z, ldg2(p.chirp + jc));
         x[r] = (j < p.n) ? z : make_double2(0.0, 0.0);
     }
     fft_line<M>(s, t, x, p.tw);
+    const cplx* bh = p.bhat + (p.S > 1 ? (line % p.S) * M : 0);
 #pragma unroll
     for (int r = 0; r < C::E; ++r) {
         const int i = t + C::T * r;
-        const cplx z = cmul(line_get<M>(s, i), ldg2(p.bhat + i));
+        const cplx z = cmul(line_get<M>(s, i), ldg2(bh + i));
         x[r] = make_double2(z.x, -z.y);  // inverse FFT = conj FFT conj
     }
     __syncthreads();  // every read of the first result is done before the second transform reuses the buffer
@@ -139,7 +142,9 @@ __global__ void __launch_bounds__(BlueGeom<M>::CT, M == 8192 ? 1 : (M == 4096 &&
         const int64_t k = t2 + C::T * r;
         if (k < p.n) {
             const cplx y = line_get<M>(s2, (int)k);
-            cplx z = cscale(cmul(make_double2(y.x, -y.y), ldg2(p.chirp + k)), p.scale);
+            cplx z = make_double2(y.x, -y.y);
+            if (p.chirp) z = cmul(z, ldg2(p.chirp + k));
+            z = cscale(z, p.scale);
             if (p.conj_out) z.y = -z.y;
             dst[k] = z;
         }
@@ -173,6 +178,13 @@ static inline unsigned ew_grid(int64_t total) {
     const int64_t cap = 16 * (int64_t)sm_count();
     return (unsigned)std::max<int64_t>(1, std::min(g, cap));
 }
+
+template <int S>
+__global__ void blue_split_pre_kernel(const cplx* __restrict__ in, cplx* __restrict__ pad, int64_t n, int64_t h, int64_t batch,
+                                      const cplx* __restrict__ chirp, const cplx* __restrict__ rootM, int conj_in);
+template <int S>
+__global__ void blue_split_post_kernel(const cplx* __restrict__ pad, cplx* __restrict__ out, int64_t n, int64_t h, int64_t batch,
+                                       const cplx* __restrict__ chirp, const cplx* __restrict__ rootM, int conj_out, double scale);
 
 // lengths the one-CTA engines do not reach (smooth n > 6912, Bluestein with a padded length above 8192) but whose S-th part
 // they do: the smallest S in {2, 4, 8, 16} with n / S served by the mixed-radix kernel or the fused Bluestein kernel
@@ -253,7 +265,11 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
         int64_t M = 32;
         while (M < 2 * n - 1) M <<= 1;
         p->M = M;
-        st = cfft_create(&p->sub, M, p->max_batch);
+        // M above one CTA and at most 16 x 8192: FFT_M as a radix-bS pass around length-8192 one-CTA transforms (see
+        // blue_split_pre_kernel); the run-time engine is then the 8192 line plan, a length-M plan only builds the filter
+        const bool bsplit = M > LINE_MAX_N && M / LINE_MAX_N <= 16;
+        CfftPlan* full = nullptr;   // length-M engine
+        st = cfft_create(&full, M, bsplit ? 1 : p->max_batch);
         if (st == AFB_OK) {
             std::vector<cplx> h((size_t)n);
             for (int64_t j = 0; j < n; ++j) {
@@ -281,11 +297,31 @@ int32_t cfft_create(CfftPlan** out, int64_t n, int64_t max_batch) {
             AFB_LAUNCH(k, ew_grid(M), 256, 0, nullptr, p->bhat, n, M, p->chirp);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) st = cuda_fail(e, "fill_bfilter_kernel", __FILE__, __LINE__);
-            if (st == AFB_OK) st = cfft_exec(p->sub, p->bhat, p->bhat, 1, false, 1.0, nullptr);
+            if (st == AFB_OK) st = cfft_exec(full, p->bhat, p->bhat, 1, false, 1.0, nullptr);
             if (st == AFB_OK) {
                 e = cudaStreamSynchronize(nullptr);
                 if (e != cudaSuccess) st = cuda_fail(e, "sync(bhat)", __FILE__, __LINE__);
             }
+        }
+        if (st == AFB_OK && bsplit) {
+            // filter blocks: element bS k + s of the spectrum moves to s h + k
+            const int S = (int)(M / LINE_MAX_N);
+            const int64_t h = LINE_MAX_N;
+            std::vector<cplx> nat((size_t)M), blk((size_t)M);
+            cudaError_t e = cudaMemcpy(nat.data(), p->bhat, sizeof(cplx) * (size_t)M, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) st = cuda_fail(e, "cudaMemcpy(bhat)", __FILE__, __LINE__);
+            for (int64_t k = 0; k < h; ++k)
+                for (int sgm = 0; sgm < S; ++sgm) blk[(size_t)(sgm * h + k)] = nat[(size_t)(S * k + sgm)];
+            if (st == AFB_OK) {
+                e = cudaMemcpy(p->bhat, blk.data(), sizeof(cplx) * (size_t)M, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) st = cuda_fail(e, "cudaMemcpy(bhat blocks)", __FILE__, __LINE__);
+            }
+            if (st == AFB_OK) st = root_table(M, &p->rootM);
+            if (st == AFB_OK) st = cfft_create(&p->sub, h, 1);
+            p->bS = S;
+            cfft_destroy(full);
+        } else {
+            p->sub = full;
         }
     } else {
         st = fail(AFB_BAD_SIZE, "complex FFT length must be >= 1");
@@ -309,7 +345,7 @@ int32_t cfft_launches(const CfftPlan* p) {
         case 1: return 2;
         case 3: return 1;
         case 4: return cfft_launches(p->sub);
-        default: return (p->M <= LINE_MAX_N) ? 1 : 3 + 2 * cfft_launches(p->sub);
+        default: return (p->M <= LINE_MAX_N) ? 1 : (p->bS > 1 ? 3 : 3 + 2 * cfft_launches(p->sub));
     }
 }
 
@@ -344,6 +380,29 @@ int32_t cfft_exec(CfftPlan* p, const cplx* in, cplx* out, int64_t batch, bool in
         BlueParams bp{in, out, n, batch, p->chirp, p->bhat, p->sub->tw, inverse ? 1 : 0, inverse ? 1 : 0,
                       scale / (double)p->M};
         return launch_blue_fused(p->M, bp, stream);
+    }
+    if (p->bS > 1) {
+        const int64_t h = LINE_MAX_N, M = p->M;
+        for (int64_t b0 = 0; b0 < batch; b0 += p->max_batch) {
+            const int64_t nb = std::min(p->max_batch, batch - b0);
+            const unsigned g1 = ew_grid(nb * h), g2 = ew_grid(nb * n);
+            const int ci = inverse ? 1 : 0;
+#define AFB_BSPLIT(S_) \
+    case S_: { auto k1 = blue_split_pre_kernel<S_>; \
+               AFB_LAUNCH(k1, g1, 256, 0, stream, in + b0 * n, p->pad, n, h, nb, p->chirp, p->rootM, ci); break; }
+            switch (p->bS) { AFB_BSPLIT(2) AFB_BSPLIT(4) AFB_BSPLIT(8) AFB_BSPLIT(16) default: return fail(AFB_BAD_ARG, "split factor"); }
+#undef AFB_BSPLIT
+            AFB_KERNEL_CHECK();
+            BlueParams bp{p->pad, p->pad, h, nb * p->bS, nullptr, p->bhat, p->sub->tw, 0, 0, 1.0, p->bS};
+            AFB_TRY(launch_blue_fused(h, bp, stream));
+#define AFB_BSPLIT(S_) \
+    case S_: { auto k2 = blue_split_post_kernel<S_>; \
+               AFB_LAUNCH(k2, g2, 256, 0, stream, p->pad, out + b0 * n, n, h, nb, p->chirp, p->rootM, ci, scale / (double)M); break; }
+            switch (p->bS) { AFB_BSPLIT(2) AFB_BSPLIT(4) AFB_BSPLIT(8) AFB_BSPLIT(16) default: return fail(AFB_BAD_ARG, "split factor"); }
+#undef AFB_BSPLIT
+            AFB_KERNEL_CHECK();
+        }
+        return AFB_OK;
     }
     for (int64_t b0 = 0; b0 < batch; b0 += p->max_batch) {
         const int64_t nb = std::min(p->max_batch, batch - b0);
@@ -472,6 +531,49 @@ __global__ void generic_pre_split_kernel(int kind, int64_t n, const void* __rest
 #pragma unroll
         for (int r = 0; r < S; ++r) z[r] = generic_packed_value(kind, real, n, nh, in, istride, batch, q, j + r * h, qtab);
         split_dif<S>(z, j, h, rootn, inv != 0, work + q * n);
+    }
+}
+
+// ---- Bluestein with a padded length M = S h above one CTA (h = 8192): the radix-S DIF pass of FFT_M rides in the chirp
+// kernel, the blocks go through blue_fused_kernel<h> as plain circular convolutions (FFT_h, filter block, inverse FFT_h) and
+// the radix-S DIT pass of the inverse FFT_M rides in the final chirp kernel: three launches, 4 passes over the padded data
+// instead of 12.
+template <int S>
+__global__ void blue_split_pre_kernel(const cplx* __restrict__ in, cplx* __restrict__ pad, int64_t n, int64_t h, int64_t batch,
+                                      const cplx* __restrict__ chirp, const cplx* __restrict__ rootM, int conj_in) {
+    const int64_t total = batch * h;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / h, j = g % h;
+        cplx z[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            const int64_t i = j + r * h;
+            z[r] = make_double2(0.0, 0.0);
+            if (i < n) {
+                cplx v = in[b * n + i];
+                if (conj_in) v.y = -v.y;
+                z[r] = cmul(v, chirp[i]);
+            }
+        }
+        split_dif<S>(z, j, h, rootM, false, pad + b * (S * h));
+    }
+}
+template <int S>
+__global__ void blue_split_post_kernel(const cplx* __restrict__ pad, cplx* __restrict__ out, int64_t n, int64_t h, int64_t batch,
+                                       const cplx* __restrict__ chirp, const cplx* __restrict__ rootM, int conj_out, double scale) {
+    const int64_t total = batch * n, M = S * h;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / n, k = g % n;
+        const cplx* d = pad + b * M + (k % h);
+        cplx acc = d[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            const cplx w = rootM[(s * k) & (M - 1)];
+            acc = cadd(acc, cmul(d[(int64_t)s * h], make_double2(w.x, -w.y)));
+        }
+        cplx z = cscale(cmul(acc, chirp[k]), scale);
+        if (conj_out) z.y = -z.y;
+        out[g] = z;
     }
 }
 

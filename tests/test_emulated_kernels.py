@@ -452,3 +452,17 @@ def test_split_plans(n):
     assert np.max(np.abs(ll.transform(B.CHEB2_INV, c2) - w)) <= 50 * tol(n, np.max(np.abs(w)))
     s = ll.transform(B.SIN_FWD, w[:m - 2])     # 2 (m - 2) + 2 = n
     assert np.max(np.abs(ll.transform(B.SIN_INV, s) - w[:m - 2])) <= 50 * tol(n, np.max(np.abs(w)))
+
+
+@pytest.mark.parametrize("n", [4097, 10006])
+def test_bluestein_padded_length_above_one_cta(n):
+    # M = 16384 / 32768: radix-S pass in the chirp kernels around length-8192 one-CTA convolutions (blue_split_*_kernel)
+    v = RNG.standard_normal((n, 3))
+    for kind, ref in REAL_KINDS:
+        want = ref(v)
+        got = ll.transform(kind, v)
+        assert np.max(np.abs(got - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(v)))), (kind, n)
+    z = RNG.standard_normal((n, 2)) + 1j * RNG.standard_normal((n, 2))
+    for kind, ref in CPLX_KINDS:
+        want = ref(z)
+        assert np.max(np.abs(ll.transform(kind, z) - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(z)))), (kind, n)

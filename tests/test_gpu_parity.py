@@ -719,6 +719,28 @@ def test_split_plan_lengths(af, n):
     assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 3
 
 
+@pytest.mark.parametrize("n", [4097, 5003, 10006, 40009, 70001])
+def test_bluestein_beyond_one_cta(af, n):
+    # non-smooth n whose padded length M exceeds one CTA: M = S x 8192 (S <= 16) runs as chirp + radix-S pass, length-8192
+    # one-CTA convolutions, radix-S pass + chirp (5 launches with the real pre / post kernels); 70001 (M = 2^18) keeps the
+    # padded four-step route
+    from approxfun_b200 import _lib as L
+    nb = 7
+    v = RNG.standard_normal((n, nb))
+    for S, fwd, inv in ((af.Chebyshev(), orc.cheb_transform, orc.cheb_itransform),
+                        (af.Fourier(), orc.fourier_transform, orc.fourier_itransform)):
+        c = af.transform(S, v)
+        assert np.max(np.abs(c - fwd(v, axis=0))) <= coef_tol(n, v), (type(S).__name__, n)
+        wi = inv(v, axis=0)
+        assert np.max(np.abs(af.itransform(S, v) - wi)) <= coef_tol(n, wi), (type(S).__name__, n)
+    z = RNG.standard_normal((n, 3)) + 1j * RNG.standard_normal((n, 3))
+    assert np.max(np.abs(af.transform(af.Laurent(), z) - orc.laurent_transform(z, axis=0))) <= coef_tol(n, z)
+    wi = orc.laurent_itransform(z, axis=0)
+    assert np.max(np.abs(af.itransform(af.Laurent(), z) - wi)) <= coef_tol(n, wi)
+    if n < 70001:
+        assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 5
+
+
 @pytest.mark.parametrize("n", [4001, 4002, 6913])
 def test_split_plan_extension_kinds(af, n):
     # second-kind points / SinSpace: the even / odd extension (length 2(n-1) / 2n+2) through a split plan
