@@ -19,7 +19,13 @@ def load_binding_module():
 
 
 def emu_lowlevel():
-    subprocess.check_call(["make", "-C", EMU_DIR, "libafb_emu.so"], stdout=subprocess.DEVNULL)
+    so = os.environ.get("AFB_EMU_SO")            # e.g. the AddressSanitizer build (tests/emu/Makefile)
+    if so:
+        so = os.path.abspath(so)
+        subprocess.check_call(["make", "-C", EMU_DIR, os.path.basename(so)], stdout=subprocess.DEVNULL)
+    else:
+        so = EMU_SO
+        subprocess.check_call(["make", "-C", EMU_DIR, "libafb_emu.so"], stdout=subprocess.DEVNULL)
     B = load_binding_module()
-    lib = B.bind(ctypes.CDLL(EMU_SO))
+    lib = B.bind(ctypes.CDLL(so))
     return B, B.LowLevel(lib)
