@@ -577,47 +577,24 @@ __global__ void blue_split_post_kernel(const cplx* __restrict__ pad, cplx* __res
     }
 }
 
-// spectrum of the real input riding in the real (odd = false) or imaginary (odd = true) part of the packed line
-__device__ __forceinline__ cplx pair_spectrum(const SpecView& W, int64_t n, int64_t k, bool odd) {
-    const cplx A = W[k], Bc = W[(n - k) % n];
-    return odd ? make_double2(0.5 * (A.y + Bc.y), -0.5 * (A.x - Bc.x))   // (A - conj B) / (2i)
-               : make_double2(0.5 * (A.x + Bc.x), 0.5 * (A.y - Bc.y));   // (A + conj B) / 2
-}
-
+// post kernel of the COMPLEX kinds (the real kinds: generic_post_pair_kernel below)
 __global__ void generic_post_kernel(int kind, int64_t n, const cplx* __restrict__ work, void* __restrict__ out,
                                     int64_t ostride, int64_t batch, const cplx* __restrict__ qtab, int S) {
+    (void)qtab;
     const int64_t total = batch * n;
-    const bool real = generic_real_kind(kind);
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = g / n, o = g % n;
-        const SpecView W{work + (real ? (b >> 1) : b) * n, n / S, S};
-        const bool odd = b & 1;
-        if (kind == AFB_CHEB1_FWD) {
-            double* c = reinterpret_cast<double*>(out) + b * ostride;
-            const cplx P = cmul(pair_spectrum(W, n, o, odd), qtab[o]);
-            c[o] = (o == 0) ? P.x / (double)n : P.x * (2.0 / (double)n);
-        } else if (kind == AFB_CHEB1_INV) {
-            double* v = reinterpret_cast<double*>(out) + b * ostride;
-            const cplx z = (o & 1) ? W[n - 1 - (o - 1) / 2] : W[o / 2];
-            v[o] = odd ? z.y : z.x;
-        } else if (kind == AFB_FOURIER_FWD) {
-            double* c = reinterpret_cast<double*>(out) + b * ostride;
-            const double l = (double)n;
-            if (o == 0) c[o] = pair_spectrum(W, n, 0, odd).x / l;
-            else if ((n % 2 == 0) && o == n - 1) c[o] = -pair_spectrum(W, n, n / 2, odd).x / l;
-            else if (o & 1) c[o] = -pair_spectrum(W, n, (o + 1) / 2, odd).y * (2.0 / l);
-            else c[o] = pair_spectrum(W, n, o / 2, odd).x * (2.0 / l);
-        } else if (kind == AFB_FOURIER_INV) {
-            (reinterpret_cast<double*>(out) + b * ostride)[o] = odd ? W[o].y : W[o].x;
-        } else if (kind == AFB_LAURENT_FWD) {
+        const SpecView W{work + b * n, n / S, S};
+        cplx* dst = reinterpret_cast<cplx*>(out) + b * ostride;
+        if (kind == AFB_LAURENT_FWD) {
             const int64_t m = (o & 1) ? n - ((o + 1) >> 1) : (o >> 1);
-            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[m], 1.0 / (double)n);
+            dst[o] = cscale(W[m], 1.0 / (double)n);
         } else if (kind == AFB_TAYLOR_FWD) {        // f_k = F_k / n
-            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[o], 1.0 / (double)n);
+            dst[o] = cscale(W[o], 1.0 / (double)n);
         } else if (kind == AFB_HARDYM_FWD) {        // f_k = F_{n-1-k} / n   (mode -(k+1))
-            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = cscale(W[n - 1 - o], 1.0 / (double)n);
+            dst[o] = cscale(W[n - 1 - o], 1.0 / (double)n);
         } else {
-            (reinterpret_cast<cplx*>(out) + b * ostride)[o] = W[o];
+            dst[o] = W[o];
         }
     }
 }
