@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -222,6 +223,9 @@ static bool host_pageable(const void* p) {
     (void)p;
     return false;
 #else
+    // AFB_NO_RING=1: hand pageable pointers to the driver as they are (A/B runs of tools/time_host_paths.py)
+    static const bool no_ring = [] { const char* e = std::getenv("AFB_NO_RING"); return e && e[0] == '1'; }();
+    if (no_ring) return false;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
     return a.type == cudaMemoryTypeUnregistered;
@@ -299,6 +303,65 @@ struct PipeLease {
     }
     HostPipe* operator->() { return pipe; }
 };
+// ---- one large contiguous caller array to / from the device ---------------------------------------------------------
+// Page-locked (or registered) memory is DMA-ed directly.  PAGEABLE memory would go through the driver's own bounce buffer on
+// one thread (about 6-10 GB/s and synchronous); instead 32 MiB chunks go through the pinned ring of a leased pipe: the copy
+// team fills / drains one slot while the DMA engine works on the neighbouring ones.
+static constexpr size_t RING_CHUNK = (size_t)32 << 20;
+static int32_t big_h2d(void* d, const void* h, size_t bytes) {
+    if (bytes == 0) return AFB_OK;
+    if (bytes < ((size_t)4 << 20) || !host_pageable(h)) { AFB_CUDA(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); return AFB_OK; }
+    const int nbuf = (int)std::min<size_t>(HostPipe::NPIPE, (bytes + RING_CHUNK - 1) / RING_CHUNK);
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(nbuf, 1));                    // streams
+    AFB_TRY(pipe->ensure_pinned(nbuf, RING_CHUNK, true, false));
+    int32_t st = AFB_OK;
+    size_t c = 0;
+    for (size_t off = 0; off < bytes && st == AFB_OK; off += RING_CHUNK, ++c) {
+        const int si = (int)(c % nbuf);
+        const size_t nb = std::min(RING_CHUNK, bytes - off);
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[si]);      // the slot's previous DMA has read it
+        if (e != cudaSuccess) { st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); break; }
+        copy_team().copy2d((char*)pipe->hin[si], nb, (const char*)h + off, nb, nb, 1);
+        e = cudaMemcpyAsync((char*)d + off, pipe->hin[si], nb, cudaMemcpyHostToDevice, pipe->stream[si]);
+        if (e != cudaSuccess) st = cuda_fail(e, "H2D", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < nbuf; ++i) {
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
+        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    return st;
+}
+// `after`: a stream whose work produced d (nullptr: the legacy stream, already ordered with the synchronous copies)
+static int32_t big_d2h(void* h, const void* d, size_t bytes) {
+    if (bytes == 0) return AFB_OK;
+    if (bytes < ((size_t)4 << 20) || !host_pageable(h)) { AFB_CUDA(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); return AFB_OK; }
+    AFB_CUDA(cudaDeviceSynchronize());                 // the pipe's streams are non-blocking: order them after the producer
+    const size_t nchunks = (bytes + RING_CHUNK - 1) / RING_CHUNK;
+    const int nbuf = (int)std::min<size_t>(HostPipe::NPIPE, nchunks);
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(nbuf, 1));
+    AFB_TRY(pipe->ensure_pinned(nbuf, RING_CHUNK, false, true));
+    int32_t st = AFB_OK;
+    auto issue = [&](size_t c) -> int32_t {
+        const size_t off = c * RING_CHUNK, nb = std::min(RING_CHUNK, bytes - off);
+        AFB_CUDA(cudaMemcpyAsync(pipe->hout[c % nbuf], (const char*)d + off, nb, cudaMemcpyDeviceToHost, pipe->stream[c % nbuf]));
+        return AFB_OK;
+    };
+    for (size_t c = 0; c < (size_t)nbuf && st == AFB_OK; ++c) st = issue(c);
+    for (size_t c = 0; c < nchunks && st == AFB_OK; ++c) {
+        const int si = (int)(c % nbuf);
+        const size_t off = c * RING_CHUNK, nb = std::min(RING_CHUNK, bytes - off);
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[si]);
+        if (e != cudaSuccess) { st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); break; }
+        copy_team().copy2d((char*)h + off, nb, (const char*)pipe->hout[si], nb, nb, 1);
+        if (c + nbuf < nchunks) st = issue(c + nbuf);  // the slot is free again
+    }
+    for (int i = 0; i < nbuf; ++i) cudaStreamSynchronize(pipe->stream[i]);
+    if (st != AFB_OK) cudaGetLastError();
+    return st;
+}
+
 static void pipes_release_all() {
     int keep = 0;
     const bool have = cudaGetDevice(&keep) == cudaSuccess;
@@ -1158,14 +1221,9 @@ int32_t afb_plan_execute_host(afb_plan p, const void* in, void* out) {
         const size_t bytes = (size_t)p->elem * (size_t)(p->path == PATH_PADUA ? p->n : p->n * p->n2);
         void* d = nullptr;
         AFB_CUDA(cudaMalloc(&d, bytes));
-        int32_t st = AFB_OK;
-        cudaError_t e = cudaMemcpy(d, in, bytes, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) st = cuda_fail(e, "H2D", __FILE__, __LINE__);
+        int32_t st = big_h2d(d, in, bytes);            // pageable caller arrays: through the pinned ring
         if (st == AFB_OK) st = afb_plan_execute_device(p, d, d, nullptr);
-        if (st == AFB_OK) {
-            e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
-        }
+        if (st == AFB_OK) st = big_d2h(out, d, bytes);
         cudaFree(d);
         return st;
     }
@@ -1208,8 +1266,8 @@ struct DevBuf {
     int dev = 0;
     ~DevBuf() { if (p) block_cache_put(p, cap, dev); }
     int32_t alloc(size_t bytes) { dev = current_device(); return block_cache_get(bytes ? bytes : 1, &p, &cap); }
-    int32_t put(const void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice)); return AFB_OK; }
-    int32_t get(void* h, size_t bytes) { if (bytes) AFB_CUDA(cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost)); return AFB_OK; }
+    int32_t put(const void* h, size_t bytes) { return big_h2d(p, h, bytes); }
+    int32_t get(void* h, size_t bytes) { return big_d2h(h, p, bytes); }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
@@ -1228,26 +1286,46 @@ template <class Launch>
 static int32_t host_points_pipeline(const double* in, double* out, int64_t P, Launch launch) {
     const int nbuf = (int)std::min<int64_t>(HostPipe::NPIPE, (P + POINT_CHUNK - 1) / POINT_CHUNK);
     const size_t chunk_bytes = sizeof(double) * (size_t)std::min(P, POINT_CHUNK);
+    // pageable caller arrays go through the pinned ring (a pageable cudaMemcpyAsync is staged by the driver on one thread and
+    // blocks the host, which serialises the chunks: for cheap kernels -- sampling -- the call was D2H bound)
+    const bool big = sizeof(double) * (size_t)P >= ((size_t)4 << 20);
+    const bool bounce_in = big && host_pageable(in), bounce_out = big && host_pageable(out);
     PipeLease pipe;
     AFB_TRY(pipe->ensure(nbuf, 2 * chunk_bytes));   // input half, output half
+    if (bounce_in || bounce_out) AFB_TRY(pipe->ensure_pinned(nbuf, chunk_bytes, bounce_in, bounce_out));
+    struct Pending { double* dst = nullptr; int64_t np = 0; bool busy = false; } pend[HostPipe::NPIPE];
+    auto drain = [&](int si) -> int32_t {
+        if (!pend[si].busy) return AFB_OK;
+        AFB_CUDA(cudaStreamSynchronize(pipe->stream[si]));
+        const size_t nb = sizeof(double) * (size_t)pend[si].np;
+        if (bounce_out) copy_team().copy2d((char*)pend[si].dst, nb, (const char*)pipe->hout[si], nb, nb, 1);
+        pend[si].busy = false;
+        return AFB_OK;
+    };
     int32_t st = AFB_OK;
     int64_t c = 0;
     for (int64_t p0 = 0; p0 < P && st == AFB_OK; p0 += POINT_CHUNK, ++c) {
         const int si = (int)(c % nbuf);
         const int64_t np = std::min(POINT_CHUNK, P - p0);
+        const size_t nb = sizeof(double) * (size_t)np;
         cudaStream_t s = pipe->stream[si];
         double* din = reinterpret_cast<double*>(pipe->buf[si]);
         double* dout = reinterpret_cast<double*>((char*)pipe->buf[si] + chunk_bytes);
-        cudaError_t e = cudaMemcpyAsync(din, in + p0, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, s);
+        if (bounce_in || bounce_out) { st = drain(si); if (st != AFB_OK) break; }
+        const void* hsrc = in + p0;
+        if (bounce_in) { copy_team().copy2d((char*)pipe->hin[si], nb, (const char*)(in + p0), nb, nb, 1); hsrc = pipe->hin[si]; }
+        cudaError_t e = cudaMemcpyAsync(din, hsrc, nb, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { st = cuda_fail(e, "H2D", __FILE__, __LINE__); break; }
         st = launch(din, dout, np, (void*)s);
         if (st != AFB_OK) break;
-        e = cudaMemcpyAsync(out + p0, dout, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+        e = cudaMemcpyAsync(bounce_out ? pipe->hout[si] : (void*)(out + p0), dout, nb, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { st = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
+        pend[si].dst = out + p0; pend[si].np = np; pend[si].busy = true;
     }
-    for (int i = 0; i < nbuf; ++i) {
-        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
-        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    for (int k = 0; k < nbuf; ++k) {
+        const int si = (int)((c + k) % nbuf);
+        if (st == AFB_OK) st = drain(si);
+        else { cudaStreamSynchronize(pipe->stream[si]); cudaGetLastError(); }
     }
     return st;
 }
@@ -1491,23 +1569,42 @@ static int32_t sample_host_one(const double* cdf_c, int64_t N, double a, double 
     DevBuf dc;
     AFB_TRY(dc.alloc(8 * (size_t)N));
     AFB_TRY(dc.put(cdf_c, 8 * (size_t)N));
-    const int64_t chunk = std::min<int64_t>(P, (int64_t)1 << 23);
+    // a pageable destination (a Julia / NumPy array) is drained through the pinned ring: the driver's own pageable D2H runs at
+    // a fraction of PCIe speed on one thread and blocks the host, which made sample(f, 10^9) copy bound
+    const bool bounce = sizeof(double) * (size_t)P >= ((size_t)4 << 20) && host_pageable(out);
+    const int64_t chunk = std::min<int64_t>(P, bounce ? POINT_CHUNK : ((int64_t)1 << 23));
+    const int nbuf = (int)std::min<int64_t>(bounce ? HostPipe::NPIPE : 2, (P + chunk - 1) / chunk);
     PipeLease pipe;
-    AFB_TRY(pipe->ensure(2, sizeof(double) * (size_t)chunk));
+    AFB_TRY(pipe->ensure(nbuf, sizeof(double) * (size_t)chunk));
+    if (bounce) AFB_TRY(pipe->ensure_pinned(nbuf, sizeof(double) * (size_t)chunk, false, true));
+    struct Pending { double* dst = nullptr; int64_t np = 0; bool busy = false; } pend[HostPipe::NPIPE];
+    auto drain = [&](int si) -> int32_t {
+        if (!pend[si].busy) return AFB_OK;
+        AFB_CUDA(cudaStreamSynchronize(pipe->stream[si]));
+        const size_t nb = sizeof(double) * (size_t)pend[si].np;
+        if (bounce) copy_team().copy2d((char*)pend[si].dst, nb, (const char*)pipe->hout[si], nb, nb, 1);
+        pend[si].busy = false;
+        return AFB_OK;
+    };
     int64_t c = 0;
     int32_t st = AFB_OK;
     for (int64_t p0 = 0; p0 < P && st == AFB_OK; p0 += chunk, ++c) {
-        const int si = (int)(c & 1);
+        const int si = (int)(c % nbuf);
         const int64_t np = std::min(chunk, P - p0);
+        st = drain(si);                                // the slot's device and ring buffers are free again
+        if (st != AFB_OK) break;
         double* dbuf = reinterpret_cast<double*>(pipe->buf[si]);
         st = launch_bisect_vec(dc.as<double>(), N, nullptr, true, seed, offset + (uint64_t)p0, dbuf, np, 47, a, b, pipe->stream[si]);
         if (st != AFB_OK) break;
-        cudaError_t e = cudaMemcpyAsync(out + p0, dbuf, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, pipe->stream[si]);
-        if (e != cudaSuccess) st = cuda_fail(e, "D2H", __FILE__, __LINE__);
+        cudaError_t e = cudaMemcpyAsync(bounce ? pipe->hout[si] : (void*)(out + p0), dbuf, sizeof(double) * (size_t)np,
+                                        cudaMemcpyDeviceToHost, pipe->stream[si]);
+        if (e != cudaSuccess) { st = cuda_fail(e, "D2H", __FILE__, __LINE__); break; }
+        pend[si].dst = out + p0; pend[si].np = np; pend[si].busy = true;
     }
-    for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaStreamSynchronize(pipe->stream[i]);
-        if (e != cudaSuccess && st == AFB_OK) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    for (int k = 0; k < nbuf; ++k) {
+        const int si = (int)((c + k) % nbuf);
+        if (st == AFB_OK) st = drain(si);
+        else { cudaStreamSynchronize(pipe->stream[si]); cudaGetLastError(); }
     }
     return st;
 }

@@ -776,6 +776,24 @@ def test_registered_caller_arrays_take_the_direct_path(af):
     pl.close()
 
 
+def test_pageable_2d_and_padua_host_calls_through_the_pinned_ring(af):
+    # the 2-D / Padua host calls move one large array each way: pageable arrays go through the ring in 32 MiB chunks (with a
+    # ragged last chunk), registered ones directly -- same bits, and the oracle on a small corner
+    from approxfun_b200 import _lib as L
+    n1, n2 = 2048, 2306                               # 37.8 MB: one full chunk + a tail
+    M = RNG.standard_normal((n2, n1))                 # column-major n1 x n2
+    pl = af.api.DevicePlan(L.CHEB1_2D_FWD, n1, n2, 1, n1)
+    got = np.empty_like(M)
+    pl.execute_host(M, got)
+    reg = np.empty_like(M)
+    with af.api.pinned(M, reg):
+        pl.execute_host(M, reg)
+    assert np.array_equal(got, reg)
+    want = orc.cheb_transform(orc.cheb_transform(M, axis=1), axis=0)
+    assert np.max(np.abs(got - want)) <= coef_tol(max(n1, n2), M)
+    pl.close()
+
+
 def test_pageable_strided_host_arrays_through_the_pinned_ring(af):
     # a pageable caller array with stride > n, large enough (> 4 MiB, several 32 MiB chunks) for the library's own staging:
     # host copy team -> pinned ring -> DMA; the padding columns of the destination must stay untouched
