@@ -233,14 +233,17 @@ static bool host_pageable(const void* p) {
 }
 
 struct HostPipe {
-    static constexpr int NPIPE = 3;
-    cudaStream_t stream[NPIPE] = {nullptr, nullptr, nullptr};
-    void* buf[NPIPE] = {nullptr, nullptr, nullptr};
-    size_t cap[NPIPE] = {0, 0, 0};
+#ifndef AFB_NPIPE
+#define AFB_NPIPE 3          // slots of the pipeline (A/B: -DAFB_NPIPE=5 made no difference for the pageable ring)
+#endif
+    static constexpr int NPIPE = AFB_NPIPE;
+    cudaStream_t stream[NPIPE] = {};
+    void* buf[NPIPE] = {};
+    size_t cap[NPIPE] = {};
     // pinned ring for pageable callers: one input and one output slot per stream
-    void* hin[NPIPE] = {nullptr, nullptr, nullptr};
-    void* hout[NPIPE] = {nullptr, nullptr, nullptr};
-    size_t hin_cap[NPIPE] = {0, 0, 0}, hout_cap[NPIPE] = {0, 0, 0};
+    void* hin[NPIPE] = {};
+    void* hout[NPIPE] = {};
+    size_t hin_cap[NPIPE] = {}, hout_cap[NPIPE] = {};
     int32_t ensure(int nbuf, size_t bytes) {
         for (int i = 0; i < nbuf; ++i) {
             if (!stream[i]) AFB_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));

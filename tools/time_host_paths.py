@@ -8,8 +8,11 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import approxfun_b200 as af  # noqa: E402
 from approxfun_b200 import _lib as L  # noqa: E402
+
+if len(sys.argv) > 2 and sys.argv[1] == "--lib":
+    L.LIB_PATH = os.path.abspath(sys.argv[2])
+import approxfun_b200 as af  # noqa: E402
 
 tag = "driver-staged (AFB_NO_RING=1)" if os.environ.get("AFB_NO_RING") == "1" else "pinned ring"
 
@@ -25,6 +28,14 @@ def best(fn, reps=3):
 
 
 rng = np.random.default_rng(0)
+V = rng.standard_normal((65536, 4096))
+C = np.empty_like(V)
+pl = af.api.DevicePlan(L.CHEB1_FWD, 4096, 0, 65536, 4096)
+print(f"[{tag}] {os.path.basename(L.LIB_PATH)} batched 65536 x 4096 host call: {best(lambda: pl.execute_host(V, C)):.1f} ms", flush=True)
+pl.close()
+del V, C
+if "--only-1d" in sys.argv:
+    sys.exit(0)
 for m in (8192, 16384):
     M = rng.standard_normal((m, m))
     out = np.empty_like(M)
