@@ -303,13 +303,18 @@ template <int N> struct ChebFwdPost {
 template <int N> struct LineOp<N, LK_CHEB_FWD> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        const int64_t off = act ? line * p.istride : 0;
-        const double2* v2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + off);
+        run_io(p, reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0),
+               reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.oes, act, t, s);
+    }
+    // the line at `in` -> the line at `out` (global memory, or the shared-memory tile of line_kernel_tile)
+    static __device__ __forceinline__ void run_io(const LineParams& p, const double* in, double* out, int64_t oes, bool act, int t,
+                                                  cplx* s) {
+        const double2* v2 = reinterpret_cast<const double2*>(in);
         cplx x[C::E];
         cheb_exchange_load<N>(v2, act, t, x);
         dit_first<N>(s, PairMap<N>::col(t), x);
         dit_middle<N>(s, t, x, p.tw);
-        ChebFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.oes, p.scale, act};
+        ChebFwdPost<N> f{out, oes, p.scale, act};
         dit_last_paired<N, 2>(p, s, t, f);
     }
 };
@@ -365,13 +370,17 @@ template <int N, int STAGED> struct ChebInvPreStaged : ChebInvPre<N> {
 template <int N> struct LineOp<N, LK_CHEB_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        ChebInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), act};
+        run_io(p, reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0),
+               reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.oes, act, t, s);
+    }
+    static __device__ __forceinline__ void run_io(const LineParams& p, const double* in, double* out, int64_t oes, bool act, int t,
+                                                  cplx* s) {
+        ChebInvPre<N> f{in, act};
         dif_first_paired<N, 2>(p, s, t, f);
         cplx x[C::E];
         dif_middle<N>(s, t, x, p.tw);
         dif_last<N>(s, PairMap<N>::col(t), x);
-        double* v = reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0);
-        cheb_exchange_store<N>(v, p.oes, act, t, x);
+        cheb_exchange_store<N>(out, oes, act, t, x);
     }
 };
 
@@ -411,13 +420,18 @@ template <int N> struct FourierFwdPost {
 template <int N> struct LineOp<N, LK_FOURIER_FWD> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        const double2* v2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0));
+        run_io(p, reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0),
+               reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), 1, act, t, s);
+    }
+    static __device__ __forceinline__ void run_io(const LineParams& p, const double* in, double* out, int64_t, bool act, int t,
+                                                  cplx* s) {
+        const double2* v2 = reinterpret_cast<const double2*>(in);
         cplx x[C::E];
 #pragma unroll
         for (int r = 0; r < C::E; ++r) x[r] = act ? v2[t + C::T * r] : make_double2(0.0, 0.0);
         dit_first<N>(s, t, x);
         dit_middle<N>(s, t, x, p.tw);
-        FourierFwdPost<N> f{reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), p.scale, act};
+        FourierFwdPost<N> f{out, p.scale, act};
         dit_last_paired<N, 1>(p, s, t, f);
     }
 };
@@ -465,13 +479,18 @@ template <int N, int STAGED> struct FourierInvPreStaged : FourierInvPre<N> {
 template <int N> struct LineOp<N, LK_FOURIER_INV> {
     typedef FftCfg<N> C;
     static __device__ __forceinline__ void run(const LineParams& p, int64_t line, bool act, int t, cplx* s) {
-        FourierInvPre<N> f{reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0), act};
+        run_io(p, reinterpret_cast<const double*>(p.in) + (act ? line * p.istride : 0),
+               reinterpret_cast<double*>(p.out) + (act ? line * p.ostride : 0), 1, act, t, s);
+    }
+    static __device__ __forceinline__ void run_io(const LineParams& p, const double* in, double* out, int64_t, bool act, int t,
+                                                  cplx* s) {
+        FourierInvPre<N> f{in, act};
         dif_first_paired<N, 1>(p, s, t, f);
         cplx x[C::E];
         dif_middle<N>(s, t, x, p.tw);
         dif_last<N>(s, t, x);
         if (!act) return;
-        double2* v2 = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + line * p.ostride);
+        double2* v2 = reinterpret_cast<double2*>(out);
 #pragma unroll
         for (int r = 0; r < C::E; ++r) v2[t + C::T * r] = make_double2(x[r].x, -x[r].y);
     }
@@ -599,6 +618,43 @@ __global__ void __launch_bounds__(LineGeom<N>::CT, ((LineGeom<N>::CT == 128 && (
     const bool act = line < p.batch;
     cplx* s = smem + (size_t)l * FftLine<N>::STRIDE;
     LineOp<N, KIND>::run(p, line, act, t, s);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Short lines (n <= 256: four or eight threads per line, 16 or 32 lines per CTA).  The plain kernel's per-thread 8- and
+// 16-byte accesses touch eight lines per warp instruction and keep the L1 84-99 % busy (ncu, profiles/
+// r02_ncu_full_short_lines_summary.json).  Here the CTA's LPC contiguous lines move between global and shared memory as ONE
+// tile with 128-bit accesses of consecutive threads, and the line code of LineOp runs on the tile (in place: a line's inputs
+// are all in registers before the first barrier of its passes, its outputs are written after the last).
+// Needs packed lines (istride = ostride = n, oes = 1).
+// -------------------------------------------------------------------------------------------------
+template <int N> struct TileGeom {
+    typedef LineGeom<N> G;
+    static constexpr int LINE = 2 * N;                                  // doubles per line
+    static constexpr size_t FFT_BYTES = G::SMEM;
+    static constexpr size_t SMEM = G::SMEM + sizeof(double) * (size_t)G::LPC * LINE;
+};
+template <int N, int KIND>
+__global__ void __launch_bounds__(LineGeom<N>::CT, 3) line_kernel_tile(const __grid_constant__ LineParams p) {
+    typedef LineGeom<N> G;
+    typedef TileGeom<N> TG;
+    AFB_DYN_SMEM(cplx, smem);
+    double* tile = reinterpret_cast<double*>(smem + TG::FFT_BYTES / sizeof(cplx));
+    const int tid = threadIdx.x;
+    const int64_t line0 = (int64_t)blockIdx.x * G::LPC;
+    const int nl = (int)((p.batch - line0 < G::LPC) ? (p.batch - line0) : G::LPC);      // valid lines of this CTA
+    const int chunks = nl * (TG::LINE / 2);
+    const double2* src = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(p.in) + line0 * TG::LINE);
+    double2* t2 = reinterpret_cast<double2*>(tile);
+    for (int i = tid; i < chunks; i += G::CT) t2[i] = src[i];
+    __syncthreads();
+    const int l = tid / G::T, t = tid % G::T;
+    const bool act = l < nl;
+    double* mine = tile + (size_t)(act ? l : 0) * TG::LINE;
+    LineOp<N, KIND>::run_io(p, mine, mine, 1, act, t, smem + (size_t)l * FftLine<N>::STRIDE);
+    __syncthreads();
+    double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.out) + line0 * TG::LINE);
+    for (int i = tid; i < chunks; i += G::CT) dst[i] = t2[i];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -830,6 +886,12 @@ template <int N, int KIND> static int32_t launch_line_staged(const LineParams& p
     return AFB_OK;
 }
 
+// AFB_LINE_TILE=1 / 0 switches the tile kernel for short lines on / off (default: see line_tile_enabled)
+static bool line_tile_enabled() {
+    static const int v = [] { const char* e = std::getenv("AFB_LINE_TILE"); return e ? (e[0] == '1' ? 1 : 0) : 0; }();
+    return v != 0;
+}
+
 template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, void* stream) {
     typedef LineGeom<N> G;
     // (N = 4096 with two CTAs per SM and 5/8 of the line staged was measured SLOWER than the plain kernel: Chebyshev
@@ -845,6 +907,18 @@ template <int N, int KIND> static int32_t launch_line_nk(const LineParams& p, vo
         if (p.oes == 1 && p.batch > (int64_t)StageGeom<N>::MINB * sm_count() && p.istride % 2 == 0 &&
             reinterpret_cast<uintptr_t>(p.in) % 16 == 0)
             return launch_line_staged<N, KIND>(p, stream);
+    }
+    if constexpr (N <= 128 && (KIND == LK_CHEB_FWD || KIND == LK_CHEB_INV || KIND == LK_FOURIER_FWD || KIND == LK_FOURIER_INV)) {
+        // short packed lines: CTA-wide coalesced tile through shared memory (line_kernel_tile)
+        if (line_tile_enabled() && p.oes == 1 && p.istride == 2 * N && p.ostride == 2 * N &&
+            reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0) {
+            auto kt = line_kernel_tile<N, KIND>;
+            AFB_SMEM_OPTIN(kt, TileGeom<N>::SMEM);
+            const int64_t gridt = (p.batch + G::LPC - 1) / G::LPC;
+            AFB_LAUNCH(kt, (unsigned)gridt, G::CT, TileGeom<N>::SMEM, stream, p);
+            AFB_KERNEL_CHECK();
+            return AFB_OK;
+        }
     }
     auto k = line_kernel<N, KIND>;
     AFB_SMEM_OPTIN(k, G::SMEM);

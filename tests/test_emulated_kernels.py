@@ -466,3 +466,32 @@ def test_bluestein_padded_length_above_one_cta(n):
     for kind, ref in CPLX_KINDS:
         want = ref(z)
         assert np.max(np.abs(ll.transform(kind, z) - want)) <= tol(n, max(np.max(np.abs(want)), np.max(np.abs(z)))), (kind, n)
+
+
+def test_short_line_tile_kernel_variant():
+    # line_kernel_tile (AFB_LINE_TILE=1: the CTA's lines staged as one coalesced tile; measured slower on the B200 and therefore
+    # off by default) gives the same bits as the plain kernel; the switch is read once per process
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from tests.emu_harness import emu_lowlevel\n"
+        "B, ll = emu_lowlevel()\n"
+        "rng = np.random.default_rng(3)\n"
+        "out = []\n"
+        "for n in (64, 128, 256):\n"
+        "    for nb in (1, 37, 100):\n"
+        "        v = rng.standard_normal((n, nb))\n"
+        "        for kind in (B.CHEB1_FWD, B.CHEB1_INV, B.FOURIER_FWD, B.FOURIER_INV):\n"
+        "            out.append(ll.transform(kind, v).ravel())\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n" % root)
+    res = {}
+    for flag in ("0", "1"):
+        path = os.path.join(root, "tests", "emu", "_tile_%s.npy" % flag)
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, AFB_LINE_TILE=flag), cwd=root)
+        res[flag] = np.load(path)
+        os.remove(path)
+    assert np.array_equal(res["0"], res["1"])

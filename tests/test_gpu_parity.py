@@ -969,3 +969,31 @@ def test_cluster_line_kernel_variant(af):
     v = np.random.default_rng(9).standard_normal((16384, 151))
     assert np.max(np.abs(res[1] - orc.cheb_transform(v, axis=0))) <= coef_tol(16384, v)
     assert np.array_equal(res[0], res[1])       # same radix schedule and twiddle tables: identical bits
+
+
+def test_short_line_tile_kernel_variant(af):
+    # line_kernel_tile for n <= 256 (AFB_LINE_TILE=1: the CTA's lines move as one coalesced tile through shared memory; measured
+    # slower than the plain kernel -- n = 128: 0.53 against 0.755 of HBM -- and therefore off by default): same bits
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, sys\n"
+        "import approxfun_b200 as af\n"
+        "from approxfun_b200 import _lib as L\n"
+        "rng = np.random.default_rng(12)\n"
+        "out = []\n"
+        "for n in (64, 128, 256):\n"
+        "    v = rng.standard_normal((n, 1003))\n"
+        "    for kind in (L.CHEB1_FWD, L.CHEB1_INV, L.FOURIER_FWD, L.FOURIER_INV):\n"
+        "        out.append(af.api.lowlevel().transform(kind, v).ravel())\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n")
+    res = []
+    for flag in ("0", "1"):
+        path = f"/tmp/afb_tile_{flag}.npy"
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, AFB_LINE_TILE=flag), cwd=root)
+        res.append(np.load(path))
+    assert np.array_equal(res[0], res[1])
+    v = np.random.default_rng(12).standard_normal((64, 1003))
+    assert np.max(np.abs(res[1][:64 * 1003].reshape(64, 1003) - orc.cheb_transform(v, axis=0))) <= coef_tol(64, v)
