@@ -21,7 +21,7 @@ namespace afb {
 struct CfftPlan {
     int64_t n = 0, max_batch = 0;
     int mode = 0;  // 0 line, 1 four-step, 2 Bluestein, 3 mixed radix (2^a 3^b 5^c 7^d in one CTA, afb_mixed.cu),
-                   // 4 split: one radix-S decimation-in-frequency pass (S = 2, 4, 8, 16) in front of S one-CTA transforms of n / S
+                   // 4 split: one radix-S decimation-in-frequency pass (S = 2, 3, 4, 5, 7, 8, 16) in front of S one-CTA transforms of n / S
     const cplx* tw = nullptr;
     // four-step
     int n1 = 0, n2 = 0;
@@ -195,10 +195,12 @@ static bool one_cta_engine_ok(int64_t h) {
 static int split_factor(int64_t n) {
     if (n < 2 || is_pow2(n) || one_cta_engine_ok(n)) return 1;
     // the mixed-radix kernel runs at 0.4-0.55 of HBM up to h ~ 2000 (several CTAs per SM) and at 0.2-0.3 above: prefer the
-    // first S that brings a smooth h under 2048, else the first S any one-CTA engine accepts
-    for (int S = 2; S <= 16; S *= 2)
+    // first S that brings a smooth h under 2048, else the first S any one-CTA engine accepts (odd S serve the smooth odd
+    // lengths: 7875 = 3 x 2625, 15625 = 5 x 3125, 16807 = 7 x 2401)
+    static const int kS[] = {2, 3, 4, 5, 7, 8, 16};
+    for (int S : kS)
         if (n % S == 0 && n / S <= 2048 && mixed_radix_ok(n / S)) return S;
-    for (int S = 2; S <= 16; S *= 2)
+    for (int S : kS)
         if (n % S == 0 && one_cta_engine_ok(n / S)) return S;
     return 1;
 }
@@ -955,7 +957,7 @@ int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_
     case S_: { auto k = ext_pre_split_kernel<S_>; \
                AFB_LAUNCH(k, grid, 256, 0, stream, kind, n, cn, in, istride, work, batch, sp->rootn); break; }
         switch (S) {
-            AFB_EXT_SPLIT(2) AFB_EXT_SPLIT(4) AFB_EXT_SPLIT(8) AFB_EXT_SPLIT(16)
+            AFB_EXT_SPLIT(2) AFB_EXT_SPLIT(3) AFB_EXT_SPLIT(4) AFB_EXT_SPLIT(5) AFB_EXT_SPLIT(7) AFB_EXT_SPLIT(8) AFB_EXT_SPLIT(16)
             default: return fail(AFB_BAD_ARG, "split factor");
         }
 #undef AFB_EXT_SPLIT
@@ -987,7 +989,7 @@ int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride,
     case S_: { auto k = generic_pre_split_kernel<S_>; \
                AFB_LAUNCH(k, grid, 256, 0, stream, kind, n, in, istride, work, batch, qtab, sp->rootn, inv); break; }
         switch (S) {
-            AFB_GEN_SPLIT(2) AFB_GEN_SPLIT(4) AFB_GEN_SPLIT(8) AFB_GEN_SPLIT(16)
+            AFB_GEN_SPLIT(2) AFB_GEN_SPLIT(3) AFB_GEN_SPLIT(4) AFB_GEN_SPLIT(5) AFB_GEN_SPLIT(7) AFB_GEN_SPLIT(8) AFB_GEN_SPLIT(16)
             default: return fail(AFB_BAD_ARG, "split factor");
         }
 #undef AFB_GEN_SPLIT

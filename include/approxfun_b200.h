@@ -141,7 +141,7 @@ int32_t afb_stream_sync(void* stream);
  * Data type: double for Chebyshev / Fourier, interleaved complex double for Laurent.
  * Any n >= 0 is accepted, as FFTW accepts any length: n <= 32 a direct kernel; powers of two one shared-memory line kernel
  * (n <= 16384) or a four-step; n = 2^a 3^b 5^c 7^d <= 6912 one mixed-radix kernel; other n <= 4096 one fused Bluestein kernel;
- * n = S h (S = 2, 4, 8, 16) with h inside one of those engines three launches; remaining n Bluestein over a padded copy. */
+ * n = S h (S = 2, 3, 4, 5, 7, 8, 16) with h inside one of those engines three launches; remaining n Bluestein over a padded copy. */
 #define AFB_PLAN_2D_TRANSPOSE 1u
 int32_t afb_plan_create(afb_plan* out, int32_t kind, int64_t n, int64_t n2, int64_t batch, int64_t stride,
                         uint32_t flags);

@@ -698,9 +698,9 @@ def test_mixed_radix_lengths(af, n):
     assert af.api.DevicePlan(L.CHEB1_FWD, n, 0, nb, n).launches == 1
 
 
-@pytest.mark.parametrize("n", [8000, 8002, 13824, 16000, 40000])
+@pytest.mark.parametrize("n", [8000, 8002, 13824, 16000, 40000, 7875, 12003, 16807])
 def test_split_plan_lengths(af, n):
-    # n = S h with h inside a one-CTA engine (mixed radix h <= 6912 or fused Bluestein h <= 4096), S = 2, 4, 8: one radix-S
+    # n = S h with h inside a one-CTA engine (mixed radix h <= 6912 or fused Bluestein h <= 4096), S = 2, 3, 4, 5, 7, 8, 16: one radix-S
     # pass fused into the pre kernel, S one-CTA transforms per line, de-interleave fused into the post kernel: 3 launches
     # instead of Bluestein's padded multi-kernel route (8000 / 8002 are the Padua lengths of degree 4000)
     from approxfun_b200 import _lib as L
