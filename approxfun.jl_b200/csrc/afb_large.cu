@@ -178,13 +178,6 @@ static inline unsigned ew_grid(int64_t total) {
     const int64_t cap = 16 * (int64_t)sm_count();
     return (unsigned)std::max<int64_t>(1, std::min(g, cap));
 }
-// 2-D grid of 256-thread blocks for (len elements) x (lines): x covers one line (at most 64 blocks), y the lines
-static inline dim3 ew_grid2(int64_t len, int64_t lines) {
-    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>((len + 255) / 256, 64));
-    const int64_t cap = std::max<int64_t>(1, 16 * (int64_t)sm_count() / gx);
-    const int64_t gy = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(lines, cap), 65535));
-    return dim3((unsigned)gx, (unsigned)gy, 1);
-}
 
 template <int S>
 __global__ void blue_split_pre_kernel(const cplx* __restrict__ in, cplx* __restrict__ pad, int64_t n, int64_t h, int64_t batch,
@@ -528,20 +521,19 @@ struct SpecView {   // element k of a spectrum left as S blocks of length h
     __device__ __forceinline__ cplx operator[](int64_t k) const { return S == 1 ? base[k] : base[(k % S) * h + k / S]; }
 };
 
-// (2-D grids: blockIdx.y walks the work lines, so no 64-bit division per element)
 template <int S>
 __global__ void generic_pre_split_kernel(int kind, int64_t n, const void* __restrict__ in, int64_t istride,
                                          cplx* __restrict__ work, int64_t batch, const cplx* __restrict__ qtab,
                                          const cplx* __restrict__ rootn, int inv) {
     const bool real = generic_real_kind(kind);
-    const int64_t h = n / S, nq = real ? (batch + 1) / 2 : batch, nh = (n + 1) / 2;
-    for (int64_t q = blockIdx.y; q < nq; q += gridDim.y)
-        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < h; j += (int64_t)gridDim.x * blockDim.x) {
-            cplx z[S];
+    const int64_t h = n / S, total = (real ? (batch + 1) / 2 : batch) * h, nh = (n + 1) / 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = g / h, j = g % h;
+        cplx z[S];
 #pragma unroll
-            for (int r = 0; r < S; ++r) z[r] = generic_packed_value(kind, real, n, nh, in, istride, batch, q, j + r * h, qtab);
-            split_dif<S>(z, j, h, rootn, inv != 0, work + q * n);
-        }
+        for (int r = 0; r < S; ++r) z[r] = generic_packed_value(kind, real, n, nh, in, istride, batch, q, j + r * h, qtab);
+        split_dif<S>(z, j, h, rootn, inv != 0, work + q * n);
+    }
 }
 
 // ---- Bluestein with a padded length M = S h above one CTA (h = 8192): the radix-S DIF pass of FFT_M rides in the chirp
@@ -640,20 +632,17 @@ __device__ __forceinline__ void real_pair_post(int kind, int64_t n, int64_t o, c
 
 // the real kinds of the multi-kernel route: one thread per (pair of lines, output index) -- every spectrum element is read
 // for both lines at once
-template <int S>
 __global__ void generic_post_pair_kernel(int kind, int64_t n, const cplx* __restrict__ work, double* __restrict__ out,
-                                         int64_t ostride, int64_t batch, const cplx* __restrict__ qtab) {
-    const int64_t nq = (batch + 1) / 2, h = n / S;
-    for (int64_t q = blockIdx.y; q < nq; q += gridDim.y) {
-        const cplx* base = work + q * n;
-        auto W = [&](int64_t k) -> cplx { return S == 1 ? base[k] : base[(k % S) * h + k / S]; };   // S is a constant here
-        const bool has2 = 2 * q + 1 < batch;
-        for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-            double ve, vo;
-            real_pair_post(kind, n, o, W, qtab, ve, vo);
-            out[(2 * q) * ostride + o] = ve;
-            if (has2) out[(2 * q + 1) * ostride + o] = vo;
-        }
+                                         int64_t ostride, int64_t batch, const cplx* __restrict__ qtab, int S) {
+    const int64_t total = ((batch + 1) / 2) * n;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = g / n, o = g % n;
+        const SpecView V{work + q * n, n / S, S};
+        auto W = [&](int64_t k) -> cplx { return V[k]; };
+        double ve, vo;
+        real_pair_post(kind, n, o, W, qtab, ve, vo);
+        out[(2 * q) * ostride + o] = ve;
+        if (2 * q + 1 < batch) out[(2 * q + 1) * ostride + o] = vo;
     }
 }
 
@@ -994,7 +983,7 @@ int32_t launch_generic_pre(int kind, int64_t n, const void* in, int64_t istride,
     if (batch == 0) return AFB_OK;
     const int S = cfft_split(sp);
     if (S > 1) {
-        const dim3 grid = ew_grid2(n / S, (kind <= AFB_FOURIER_INV) ? (batch + 1) / 2 : batch);
+        const unsigned grid = ew_grid(batch * (n / S));
         const int inv = kind & 1;   // inverse kinds ask cfft_exec for the inverse transform
 #define AFB_GEN_SPLIT(S_) \
     case S_: { auto k = generic_pre_split_kernel<S_>; \
@@ -1016,17 +1005,9 @@ int32_t launch_generic_post(int kind, int64_t n, const cplx* work, void* out, in
                             const cplx* qtab, void* stream, const CfftPlan* sp) {
     if (batch == 0) return AFB_OK;
     if (kind <= AFB_FOURIER_INV) {
-        const dim3 grid = ew_grid2(n, (batch + 1) / 2);
-        double* o = reinterpret_cast<double*>(out);
-#define AFB_POST_SPLIT(S_) \
-    case S_: { auto kp = generic_post_pair_kernel<S_>; \
-               AFB_LAUNCH(kp, grid, 256, 0, stream, kind, n, work, o, ostride, batch, qtab); break; }
-        switch (cfft_split(sp)) {
-            AFB_POST_SPLIT(1) AFB_POST_SPLIT(2) AFB_POST_SPLIT(3) AFB_POST_SPLIT(4) AFB_POST_SPLIT(5) AFB_POST_SPLIT(7)
-            AFB_POST_SPLIT(8) AFB_POST_SPLIT(16)
-            default: return fail(AFB_BAD_ARG, "split factor");
-        }
-#undef AFB_POST_SPLIT
+        auto kp = generic_post_pair_kernel;
+        AFB_LAUNCH(kp, ew_grid(((batch + 1) / 2) * n), 256, 0, stream, kind, n, work, reinterpret_cast<double*>(out), ostride, batch,
+                   qtab, cfft_split(sp));
         AFB_KERNEL_CHECK();
         return AFB_OK;
     }
