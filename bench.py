@@ -174,6 +174,7 @@ def run_reference(args):
         "config": workload_config(B, N_LEN),
         "cpu_baseline": {"value": val, "unit": "coefficients/s", "cores": cores, "kind": "port",
                          "threads_requested": cores, "threads_effective": round(busy, 2),
+                         "threads_ok": bool(cores == 1 or busy > 1.5),   # more than one worker really ran (round 1: 1.0 at N > 1)
                          "sample": f"the full {B} x {N_LEN} f64 batch per step (2 GiB in, 2 GiB out, host memory): "
                                    f"scipy.fft.dct(type=2) + /n, c0/2 on {cores} pool threads, one contiguous block of "
                                    "functions per task (oracle port of FastTransforms.plan_chebyshevtransform; Julia/FFTW absent)"},
