@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/approxfun_b200.h"
 
@@ -90,6 +91,30 @@ int main(void) {
     }
     afb_plan_destroy(fwd);
     afb_plan_destroy(inv);
+    {   /* a caller-owned array page-locked in place, and a length served by a split plan (8000 = 4 x 2000): round trip */
+        enum { NS = 8000, NB = 600 };            /* 38 MB: above the 4 MiB threshold of the pageable ring */
+        double* a = (double*)malloc(sizeof(double) * NS * NB);
+        double* b = (double*)malloc(sizeof(double) * NS * NB);
+        double* r = (double*)malloc(sizeof(double) * NS * NB);
+        if (!a || !b || !r) return die("malloc", -1);
+        for (long i = 0; i < (long)NS * NB; ++i) a[i] = sin(0.001 * (double)i) + 0.25 * cos(0.37 * (double)(i % 911));
+        afb_plan f8 = NULL, i8 = NULL;
+        if ((st = afb_plan_create(&f8, AFB_CHEB1_FWD, NS, 0, NB, NS, 0)) != AFB_OK) return die("afb_plan_create(8000)", st);
+        if ((st = afb_plan_create(&i8, AFB_CHEB1_INV, NS, 0, NB, NS, 0)) != AFB_OK) return die("afb_plan_create(8000 inv)", st);
+        if ((st = afb_plan_execute_host(f8, a, b)) != AFB_OK) return die("execute_host(8000, pageable)", st);
+        if ((st = afb_host_register(a, sizeof(double) * NS * NB)) != AFB_OK) return die("afb_host_register", st);
+        if ((st = afb_host_register(r, sizeof(double) * NS * NB)) != AFB_OK) return die("afb_host_register", st);
+        if ((st = afb_plan_execute_host(f8, a, r)) != AFB_OK) return die("execute_host(8000, registered)", st);
+        if (memcmp(b, r, sizeof(double) * NS * NB) != 0) { fprintf(stderr, "registered and pageable results differ\n"); return 1; }
+        if ((st = afb_plan_execute_host(i8, b, r)) != AFB_OK) return die("execute_host(8000 inv)", st);
+        if ((st = afb_host_unregister(a)) != AFB_OK || (st = afb_host_unregister(r)) != AFB_OK) return die("afb_host_unregister", st);
+        for (long i = 0; i < (long)NS * NB; ++i)
+            if (fabs(r[i] - a[i]) > 1e-12) { fprintf(stderr, "n = 8000 round trip failed at %ld\n", i); return 1; }
+        afb_plan_destroy(f8);
+        afb_plan_destroy(i8);
+        free(a); free(b); free(r);
+        printf("split plan n = 8000 and afb_host_register: ok\n");
+    }
     {
         int rc = two_gpus();
         if (rc) return rc;
