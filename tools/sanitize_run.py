@@ -1,4 +1,6 @@
-"""Small-shape run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small-shape run of every kernel family, written as a workload for a memory / race checker.  The GPU pool of this project
+refuses compute-sanitizer, so it is not run under it there: the bounds checks that exist are the AddressSanitizer build of the
+emulator (tests/emu/Makefile, tests/test_emulator_asan.py); on a machine where the tool is allowed this script is the command."""
 import os
 import sys
 
