@@ -11,6 +11,7 @@
 // arbitrary n -- the fused power-of-two kernels of afb_transform.cu are the throughput path.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "afb_fft.cuh"
@@ -192,17 +193,33 @@ static bool one_cta_engine_ok(int64_t h) {
     if (is_pow2(h)) return h >= LINE_MIN_N && h <= LINE_MAX_N;
     return mixed_radix_ok(h) || (h >= 2 && 2 * h - 1 <= LINE_MAX_N);
 }
+// Cost model behind the choice of S (fitted to one box, 4.3 GB batches, ms: n = 8000 S = 2 / 4 / 8 -> 4.87 / 4.41 / 4.66;
+// 13 824 S = 4 / 8 / 16 -> 4.24 / 4.95 / 7.41; 16 000 S = 4 / 8 / 16 -> 5.06 / 5.31 / 6.98; 40 000 S = 8 / 16 -> 5.92 / 7.43):
+// the radix-S pass costs O(S) complex multiplies per element (S = 16 is expensive), the one-CTA transform gets cheaper per
+// element as h shrinks (more resident CTAs), a Bluestein block costs in proportion to its padding M / h.
+static double split_cost(int S, int64_t h) {
+    static const double pre[17] = {0, 0, 0.0, 0.05, 0.1, 0.3, 0, 0.6, 0.9, 0, 0, 0, 0, 0, 0, 0, 2.7};
+    double mid;
+    if (is_pow2(h)) mid = 0.7;
+    else if (mixed_radix_ok(h)) mid = h <= 1024 ? 1.0 : h <= 2048 ? 1.5 : h <= 4096 ? 2.05 : 3.0;
+    else {
+        int64_t M = 32;
+        while (M < 2 * h - 1) M <<= 1;
+        mid = 2.35 * (double)M / (double)h;
+    }
+    return pre[S] + mid;
+}
 static int split_factor(int64_t n) {
     if (n < 2 || is_pow2(n) || one_cta_engine_ok(n)) return 1;
-    // the mixed-radix kernel runs at 0.4-0.55 of HBM up to h ~ 2000 (several CTAs per SM) and at 0.2-0.3 above: prefer the
-    // first S that brings a smooth h under 2048, else the first S any one-CTA engine accepts (odd S serve the smooth odd
-    // lengths: 7875 = 3 x 2625, 15625 = 5 x 3125, 16807 = 7 x 2401)
-    static const int kS[] = {2, 3, 4, 5, 7, 8, 16};
-    for (int S : kS)
-        if (n % S == 0 && n / S <= 2048 && mixed_radix_ok(n / S)) return S;
-    for (int S : kS)
-        if (n % S == 0 && one_cta_engine_ok(n / S)) return S;
-    return 1;
+    static const int kS[] = {2, 3, 4, 5, 7, 8, 16};   // odd S serve smooth odd lengths: 7875 = 3 x 2625, 16807 = 7 x 2401
+    int best = 1;
+    double cbest = 0.0;
+    for (int S : kS) {
+        if (n % S != 0 || !one_cta_engine_ok(n / S)) continue;
+        const double c = split_cost(S, n / S);
+        if (best == 1 || c < cbest) { best = S; cbest = c; }
+    }
+    return best;
 }
 int cfft_split(const CfftPlan* p) { return (p && p->mode == 4) ? p->S : 1; }
 
