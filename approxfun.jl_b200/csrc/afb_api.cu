@@ -365,6 +365,47 @@ static int32_t big_d2h(void* h, const void* d, size_t bytes) {
     return st;
 }
 
+// pitched variant of big_d2h: `height` rows of `width` bytes, device pitch dpitch, host pitch hpitch
+static int32_t big_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height) {
+    if (width == 0 || height == 0) return AFB_OK;
+    if (width * height < ((size_t)4 << 20) || !host_pageable(h)) {
+        AFB_CUDA(cudaMemcpy2D(h, hpitch, d, dpitch, width, height, cudaMemcpyDeviceToHost));
+        return AFB_OK;
+    }
+    AFB_CUDA(cudaDeviceSynchronize());
+    const size_t rows_per = std::max<size_t>(1, RING_CHUNK / width);
+    const size_t nchunks = (height + rows_per - 1) / rows_per;
+    const int nbuf = (int)std::min<size_t>(HostPipe::NPIPE, nchunks);
+    PipeLease pipe;
+    AFB_TRY(pipe->ensure(nbuf, 1));
+    AFB_TRY(pipe->ensure_pinned(nbuf, rows_per * width, false, true));
+    int32_t st = AFB_OK;
+    auto issue = [&](size_t c) -> int32_t {
+        const size_t r0 = c * rows_per, nr = std::min(rows_per, height - r0);
+        AFB_CUDA(cudaMemcpy2DAsync(pipe->hout[c % nbuf], width, (const char*)d + r0 * dpitch, dpitch, width, nr,
+                                   cudaMemcpyDeviceToHost, pipe->stream[c % nbuf]));
+        return AFB_OK;
+    };
+    for (size_t c = 0; c < (size_t)nbuf && st == AFB_OK; ++c) st = issue(c);
+    for (size_t c = 0; c < nchunks && st == AFB_OK; ++c) {
+        const int si = (int)(c % nbuf);
+        const size_t r0 = c * rows_per, nr = std::min(rows_per, height - r0);
+        cudaError_t e = cudaStreamSynchronize(pipe->stream[si]);
+        if (e != cudaSuccess) { st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); break; }
+        copy_team().copy2d((char*)h + r0 * hpitch, hpitch, (const char*)pipe->hout[si], width, width, nr);
+        if (c + nbuf < nchunks) st = issue(c + nbuf);
+    }
+    for (int i = 0; i < nbuf; ++i) cudaStreamSynchronize(pipe->stream[i]);
+    if (st != AFB_OK) cudaGetLastError();
+    return st;
+}
+// for the multi-device 2-D plan (afb_tensor.cu): one device thread each, current device = the slab's
+bool host_is_pageable(const void* p) { return host_pageable(p); }
+int32_t host_big_h2d(void* d, const void* h, size_t bytes) { return big_h2d(d, h, bytes); }
+int32_t host_big_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height) {
+    return big_d2h_2d(h, hpitch, d, dpitch, width, height);
+}
+
 static void pipes_release_all() {
     int keep = 0;
     const bool have = cudaGetDevice(&keep) == cudaSuccess;

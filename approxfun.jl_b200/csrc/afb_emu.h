@@ -135,6 +135,9 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
     for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
     return 0;
 }
+static inline cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k) {
+    return cudaMemcpy2DAsync(d, dp, s, sp, w, h, k);
+}
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

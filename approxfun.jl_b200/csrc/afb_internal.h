@@ -96,6 +96,11 @@ int32_t launch_ext_pre(int kind, int64_t n, int64_t cn, const double* in, int64_
 int32_t launch_ext_post(int kind, int64_t n, int64_t cn, const cplx* work, double* out, int64_t ostride, int64_t batch,
                         void* stream, const CfftPlan* sp = nullptr);
 
+// large caller arrays to / from the current device (afb_api.cu): pageable memory goes through the pinned ring
+bool host_is_pageable(const void* p);
+int32_t host_big_h2d(void* d, const void* h, size_t bytes);
+int32_t host_big_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height);
+
 // ---- 2-D (afb_tensor.cu) -----------------------------------------------------------------------------
 int32_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, void* stream);
 
