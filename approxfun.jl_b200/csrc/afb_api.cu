@@ -400,11 +400,13 @@ static int32_t big_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, 
     return st;
 }
 // for the multi-device 2-D plan (afb_tensor.cu): one device thread each, current device = the slab's
+namespace afb {
 bool host_is_pageable(const void* p) { return host_pageable(p); }
 int32_t host_big_h2d(void* d, const void* h, size_t bytes) { return big_h2d(d, h, bytes); }
 int32_t host_big_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height) {
     return big_d2h_2d(h, hpitch, d, dpitch, width, height);
 }
+}  // namespace afb
 
 static void pipes_release_all() {
     int keep = 0;
