@@ -170,3 +170,17 @@ def test_host_side_index_helpers():
     assert dv.shape == (2,) and np.array_equal(af.realpart(dv), [1.0, 2.0]) and np.array_equal(af.dualpart(dv), [0.5, 0.25])
     with pytest.raises(af.DimensionMismatch):
         af.DualArray([1.0, 2.0], [1.0])
+
+
+def test_library_has_no_undefined_symbols_of_its_own(built):
+    # a helper declared in one translation unit and defined in the wrong namespace of another links fine into a shared
+    # object and only fails at dlopen on the GPU box: catch it here
+    import shutil
+    import subprocess
+
+    nm = shutil.which("nm")
+    if nm is None:
+        pytest.skip("nm not available")
+    out = subprocess.run([nm, "-D", "--undefined-only", built._lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    own = [ln for ln in out.splitlines() if "afb" in ln]
+    assert not own, own
